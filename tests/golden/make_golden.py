@@ -1,0 +1,106 @@
+"""Generates tests/golden/*.npz from the LIVE reference (run in the build container only).
+
+    PYTHONDONTWRITEBYTECODE=1 YOLO_CONFIG_DIR=/tmp/ulcfg python tests/golden/make_golden.py
+
+Imports /root/reference/ultralytics, builds each model through the reference's own
+DetectionModel/parse_model, fuses it, loads the synthetic state dict from
+fce_yolo_b200.weights (same keys - load is strict), runs the reference forward and stores what
+the parity tests compare against.  /root/reference does not exist on the GPU box, hence the
+committed fixtures.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from ultralytics.nn.tasks import DetectionModel, yaml_model_load  # noqa: E402
+from ultralytics.nn.modules import fce_block  # noqa: E402
+from ultralytics.utils import nms as ref_nms  # noqa: E402
+
+from fce_yolo_b200.weights import load_synthetic, synth_images, synth_predictions, synth_tensor  # noqa: E402
+
+from cases import FORWARD_CASES, MODULE_CASES, NMS_CASES, variant_cfg  # noqa: E402
+
+
+def build_ref(case):
+    d = yaml_model_load(case["yaml"])
+    d = variant_cfg(d, case.get("variant"))
+    m = DetectionModel(d, verbose=False).eval()
+    m.fuse()
+    load_synthetic(m, case["seed"])
+    return m
+
+
+def forward_case(name, case):
+    m = build_ref(case)
+    x = synth_images(case["img_seed"], case["batch"], case["size"], case["size"])
+    outs = []
+    hooks = [l.register_forward_hook(lambda mod, i, o: outs.append(o)) for l in m.model]
+    with torch.no_grad():
+        y, raw = m(x)
+    for h in hooks:
+        h.remove()
+    blob = {}
+    keep = case["layers"]
+    for i, o in enumerate(outs[:-1]):
+        if keep == "all" or i in keep:
+            blob[f"layer{i}"] = o.numpy()
+    sub = case.get("y_stride", 1)
+    blob["y"] = y.numpy()[:, :, ::sub]
+    for i, r in enumerate(raw):
+        blob[f"raw{i}_sum"] = np.array([r.double().sum().item(), r.double().abs().sum().item()])
+    np.savez_compressed(os.path.join(HERE, f"fwd_{name}.npz"), **blob)
+    print(name, {k: v.shape for k, v in blob.items() if k in ("y",)}, "layers:", len(blob))
+
+
+def module_case(name, case):
+    cls = getattr(fce_block, case["cls"])
+    mod = cls(*case["args"]).eval()
+    # realign Conv inside BiFPN_Concat / cv1 inside CoordAtt carry BN: fold it the reference way
+    from ultralytics.nn.modules.conv import Conv
+    from ultralytics.utils.torch_utils import fuse_conv_and_bn
+    for sub in mod.modules():
+        if isinstance(sub, Conv) and hasattr(sub, "bn"):
+            sub.conv = fuse_conv_and_bn(sub.conv, sub.bn)
+            delattr(sub, "bn")
+            sub.forward = sub.forward_fuse
+    sd = mod.state_dict()
+    for k, v in sd.items():
+        v.copy_(torch.from_numpy(synth_tensor(case["seed"], "mod." + k, v.shape)))
+    xs = [synth_images(case["img_seed"] + j, case["batch"], h, w, c) * 4 - 2 for j, (c, h, w) in enumerate(case["inputs"])]
+    with torch.no_grad():
+        y = mod(xs if case["cls"] == "BiFPN_Concat" else xs[0])
+    np.savez_compressed(os.path.join(HERE, f"mod_{name}.npz"), y=y.numpy())
+    print(name, tuple(y.shape))
+
+
+def nms_case(name, case):
+    p = case["make"]()
+    kw = dict(case["kw"])
+    out, idx = ref_nms.non_max_suppression(p.clone(), return_idxs=True, **kw)
+    blob = {}
+    for b, (o, i) in enumerate(zip(out, idx)):
+        blob[f"det{b}"] = o.numpy().astype(np.float32).reshape(-1, 6)
+        blob[f"idx{b}"] = i.numpy().astype(np.int64).reshape(-1)
+    np.savez_compressed(os.path.join(HERE, f"nms_{name}.npz"), **blob)
+    print(name, [v.shape[0] for k, v in blob.items() if k.startswith("idx")])
+
+
+if __name__ == "__main__":
+    import torchvision  # noqa: F401  (the branch ultralytics takes in practice: nms.py:151-154)
+    which = sys.argv[1:] or ["fwd", "mod", "nms"]
+    if "fwd" in which:
+        for n, c in FORWARD_CASES.items():
+            forward_case(n, c)
+    if "mod" in which:
+        for n, c in MODULE_CASES.items():
+            module_case(n, c)
+    if "nms" in which:
+        for n, c in NMS_CASES.items():
+            nms_case(n, c)
