@@ -90,5 +90,5 @@ NMS_CASES = {
     "empty": dict(make=_empty, kw=dict(conf_thres=0.25, iou_thres=0.7)),
     "maxdet20": dict(make=lambda: synth_predictions(14, 1, 8400), kw=dict(conf_thres=0.25, iou_thres=0.7, max_det=20)),
     "a33600": dict(make=lambda: synth_predictions(15, 1, 33600, imgsz=1280, sharp=1.5),
-                   kw=dict(conf_thres=0.25, iou_thres=0.7, max_det=300)),
+                   kw=dict(conf_thres=0.25, iou_thres=0.7, max_det=300), tie_perm=True),
 }
