@@ -1,0 +1,40 @@
+// C-ABI glue: version / error reporting and the convolution front door (kernel selection).
+#include "common.cuh"
+
+namespace fce {
+
+static thread_local cudaError_t g_last_err = cudaSuccess;
+void set_cuda_error(cudaError_t e) { g_last_err = e; }
+
+int conv2d_simt(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+int conv2d_tc(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+bool conv2d_tc_supported(const fce_conv_desc*, const void*, const void*, const void*, const void*);
+
+}  // namespace fce
+
+using namespace fce;
+
+extern "C" int fce_abi_version(void) { return 1; }
+
+extern "C" const char* fce_last_cuda_error(void) { return cudaGetErrorString(g_last_err); }
+
+extern "C" int fce_device_ok(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+    return p.major == 10 ? 1 : 0;
+}
+
+extern "C" int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res,
+                          void* y, void* stream) {
+    if (!d || !x || !w || !y) return FCE_ERR_BAD_ARG;
+    if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0) return FCE_ERR_BAD_ARG;
+    if ((d->k != 1 && d->k != 3) || (d->stride != 1 && d->stride != 2)) return FCE_ERR_UNSUPPORTED;
+    if (d->in_layout == FCE_NCHW && d->in_dtype == FCE_BF16) return FCE_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc_ok = conv2d_tc_supported(d, x, w, res, y);
+    if (d->impl == 2) return tc_ok ? conv2d_tc(d, x, w, bias, res, y, st) : FCE_ERR_UNSUPPORTED;
+    if (d->impl == 0 && tc_ok) return conv2d_tc(d, x, w, bias, res, y, st);
+    return conv2d_simt(d, x, w, bias, res, y, st);
+}

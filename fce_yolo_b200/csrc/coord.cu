@@ -1,0 +1,220 @@
+// Coordinate pooling and the strip cross-attention core of CoordAtt / CoordCrossAtt / BiCoordCrossAtt.
+//
+// fce_coord_pool: ONE pass over x producing both strips (mean over W per row, mean over H per
+// column), fp32 accumulation, deterministic (no atomics).  A CTA owns (image, 64-channel chunk)
+// [32 channels in fp32 mode]; a warp reads 4 pixels x 128 contiguous bytes per request.  Column sums
+// live in registers for the whole image, row sums are reduced once per 8-row block.
+// HBM-bound: algorithmic bytes = C*H*W*e read (+ (H+W)*C*4 written).
+//
+// fce_strip_attn: softmax(q k^T * scale) v over strips; the whole per-(image, head) K/V fits in
+// shared memory (L <= 160, dh <= 32 on this path), fp32 CUDA-core math - far too small for tensor cores.
+#include "common.cuh"
+
+namespace fce {
+namespace {
+
+constexpr int PT = 256;       // threads
+constexpr int CVT = 8;        // channel-vector lanes per CTA
+constexpr int SLOTS = 32;     // pixel slots along W
+constexpr int RB = 8;         // rows per block
+constexpr int BAND = 5;       // column groups held in registers -> band of 160 columns
+
+template <typename T>
+__global__ void __launch_bounds__(PT) coord_pool_kernel(const fce_pool_desc d, const T* __restrict__ x,
+                                                        float* __restrict__ strip) {
+    constexpr int N = Vec16<T>::N;
+    constexpr int CC = CVT * N;  // channels per CTA
+    __shared__ float red[PT / 32][RB][CC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cvt = tid & (CVT - 1);
+    const int slot = tid / CVT;  // 0..31 ; a warp holds 4 consecutive slots
+    const int chunks = (d.C + CC - 1) / CC;
+    const int b = blockIdx.x / chunks;
+    const int c0 = (blockIdx.x % chunks) * CC + cvt * N;
+    const bool c_ok = c0 < d.C;  // C is a multiple of N (checked on host)
+    const T* xb = x + (size_t)b * d.H * d.W * d.pitch + d.off + c0;
+    float* xh = strip + ((size_t)b * d.H) * d.C;                      // rows [b*H, b*H+H)
+    float* xw = strip + ((size_t)d.B * d.H + (size_t)b * d.W) * d.C;  // rows B*H + b*W + w
+    const float inv_w = 1.f / (float)d.W, inv_h = 1.f / (float)d.H;
+
+    for (int w_base = 0; w_base < d.W; w_base += SLOTS * BAND) {
+        float col[BAND][N];
+#pragma unroll
+        for (int g = 0; g < BAND; ++g)
+#pragma unroll
+            for (int j = 0; j < N; ++j) col[g][j] = 0.f;
+
+        for (int h_base = 0; h_base < d.H; h_base += RB) {
+            float row[RB][N];
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+#pragma unroll
+                for (int j = 0; j < N; ++j) row[r][j] = 0.f;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int h = h_base + r;
+#pragma unroll
+                for (int g = 0; g < BAND; ++g) {
+                    const int w = w_base + g * SLOTS + slot;
+                    if (c_ok && h < d.H && w < d.W) {
+                        Vec16<T> v;
+                        v.load_nc(xb + ((size_t)h * d.W + w) * d.pitch);
+                        float f[N];
+                        v.unpack(f);
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            row[r][j] += f[j];
+                            col[g][j] += f[j];
+                        }
+                    }
+                }
+            }
+            // reduce row sums over the 32 slots: 4 slots inside the warp (lanes differ by 8, 16), 8 warps via smem
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    float v = row[r][j];
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    row[r][j] = v;
+                }
+            __syncthreads();  // previous block's readers are done with red[]
+            if (lane < CVT) {
+#pragma unroll
+                for (int r = 0; r < RB; ++r)
+#pragma unroll
+                    for (int j = 0; j < N; ++j) red[warp][r][cvt * N + j] = row[r][j];
+            }
+            __syncthreads();
+            for (int o = tid; o < RB * CC; o += PT) {
+                const int r = o / CC, c = o % CC;
+                const int h = h_base + r;
+                const int cg = (blockIdx.x % chunks) * CC + c;
+                if (h < d.H && cg < d.C) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int wq = 0; wq < PT / 32; ++wq) s += red[wq][r][c];
+                    float* dst = xh + (size_t)h * d.C + cg;
+                    if (w_base > 0) s += *dst;  // later bands of very wide maps accumulate (same CTA, ordered)
+                    if (w_base + SLOTS * BAND >= d.W) s *= inv_w;
+                    *dst = s;
+                }
+            }
+        }
+        // column sums: every (slot, group) column is owned by exactly one thread
+        if (c_ok) {
+#pragma unroll
+            for (int g = 0; g < BAND; ++g) {
+                const int w = w_base + g * SLOTS + slot;
+                if (w < d.W) {
+                    float* dst = xw + (size_t)w * d.C + c0;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) dst[j] = col[g][j] * inv_h;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int AT = 256;
+
+__global__ void __launch_bounds__(AT) strip_attn_kernel(const fce_strip_attn_desc d, const float* __restrict__ q,
+                                                        const float* __restrict__ k, const float* __restrict__ v,
+                                                        float* __restrict__ out) {
+    extern __shared__ float sm[];
+    const int dh = d.dh, Lk = d.Lk;
+    float* Ks = sm;                    // [Lk][dh]
+    float* Vs = Ks + Lk * dh;          // [Lk][dh]
+    float* Ss = Vs + Lk * dh;          // [warps][Lk]
+    float* Qs = Ss + (AT / 32) * Lk;   // [warps][dh]
+    const int b = blockIdx.x / d.heads, head = blockIdx.x % d.heads;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* kb = k + b * d.k_bstride + head * dh;
+    const float* vb = v + b * d.v_bstride + head * dh;
+    for (int i = tid; i < Lk * dh; i += AT) {
+        const int m = i / dh, j = i % dh;
+        Ks[i] = kb[m * d.k_rstride + j];
+        Vs[i] = vb[m * d.v_rstride + j];
+    }
+    __syncthreads();
+    float* sw = Ss + warp * Lk;
+    float* qw = Qs + warp * dh;
+    for (int l = blockIdx.y * (AT / 32) + warp; l < d.Lq; l += gridDim.y * (AT / 32)) {
+        const float* qp = q + b * d.q_bstride + l * d.q_rstride + head * dh;
+        for (int j = lane; j < dh; j += 32) qw[j] = qp[j];
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int m = lane; m < Lk; m += 32) {
+            float s = 0.f;
+            for (int j = 0; j < dh; ++j) s = fmaf(qw[j], Ks[m * dh + j], s);
+            s *= d.scale;
+            sw[m] = s;
+            mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int m = lane; m < Lk; m += 32) {
+            const float e = expf(sw[m] - mx);
+            sw[m] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        const float inv = 1.f / sum;
+        float* op = out + b * d.o_bstride + l * d.o_rstride + head * dh;
+        for (int j = lane; j < dh; j += 32) {
+            float acc = 0.f;
+            for (int m = 0; m < Lk; ++m) acc = fmaf(sw[m], Vs[m * dh + j], acc);
+            op[j] = acc * inv;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+}  // namespace fce
+
+using namespace fce;
+
+extern "C" size_t fce_coord_pool_workspace(const fce_pool_desc*) { return 0; }
+
+extern "C" int fce_coord_pool(const fce_pool_desc* d, const void* x, float* strip, void* ws, size_t ws_bytes,
+                              void* stream) {
+    (void)ws; (void)ws_bytes;
+    if (!d || !x || !strip || d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0) return FCE_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = d->dtype == FCE_BF16 ? 8 : 4;
+    if (d->dtype != FCE_BF16 && d->dtype != FCE_F32) return FCE_ERR_UNSUPPORTED;
+    if ((d->C % n) || (d->pitch % n) || (d->off % n) || (((uintptr_t)x) & 15)) return FCE_ERR_ALIGNMENT;
+    const int cc = CVT * n;
+    const int chunks = (d->C + cc - 1) / cc;
+    const int grid = d->B * chunks;
+    if (d->dtype == FCE_BF16)
+        coord_pool_kernel<__nv_bfloat16><<<grid, PT, 0, st>>>(*d, (const __nv_bfloat16*)x, strip);
+    else
+        coord_pool_kernel<float><<<grid, PT, 0, st>>>(*d, (const float*)x, strip);
+    return check_launch();
+}
+
+extern "C" int fce_strip_attn(const fce_strip_attn_desc* d, const float* q, const float* k, const float* v,
+                              float* out, void* stream) {
+    if (!d || !q || !k || !v || !out || d->B <= 0 || d->heads <= 0 || d->dh <= 0 || d->Lq <= 0 || d->Lk <= 0)
+        return FCE_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(float) * ((size_t)2 * d->Lk * d->dh + (AT / 32) * (size_t)d->Lk + (AT / 32) * (size_t)d->dh);
+    if (smem > 200 * 1024) return FCE_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(strip_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_cuda_error(e); return FCE_ERR_CUDA; }
+    }
+    int qblocks = (d->Lq + (AT / 32) - 1) / (AT / 32);
+    // enough CTAs to cover the SMs, without re-loading K/V more often than needed
+    int want = (2 * kNumSMs + d->B * d->heads - 1) / (d->B * d->heads);
+    if (qblocks > want) qblocks = want;
+    if (qblocks < 1) qblocks = 1;
+    dim3 grid(d->B * d->heads, qblocks);
+    strip_attn_kernel<<<grid, AT, smem, st>>>(*d, q, k, v, out);
+    return check_launch();
+}

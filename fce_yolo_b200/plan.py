@@ -1,0 +1,571 @@
+"""Static plan compiler: nn.Module graph -> list of kernel launches over NHWC buffers.
+
+The reference executes ~350-590 ATen ops per forward from a Python loop
+(ultralytics/nn/tasks.py:160-188).  Here the same graph is compiled ONCE, for a fixed
+(batch, height, width, precision), into a flat list of C-ABI calls (include/fce_yolo_b200.h):
+
+ * every Conv/BN/SiLU (+ Bottleneck / PSABlock residual) is one fused conv launch;
+ * torch.cat / chunk / split never move data: producers write, consumers read, channel slices of
+   one NHWC buffer;
+ * nn.Upsample feeding BiFPN_Concat is folded into the fusion kernel's read pattern, and a 1x1
+   realign conv behind an Upsample runs at the low resolution (pointwise ops commute with nearest
+   upsampling);
+ * q/k/v strip projections that share an input are merged into one conv by stacking weights.
+
+The compiler walks modules by *class name* and attribute names only, so it accepts both the mirror
+classes in fce_yolo_b200.modules and the reference's own ultralytics instances (drop-in).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+DT_SIZE = {L.BF16: 2, L.F32: 4, L.U8: 1}
+TORCH_DT = {L.BF16: torch.bfloat16, L.F32: torch.float32, L.U8: torch.uint8}
+
+
+@dataclass
+class Buf:
+    """An NHWC activation buffer [B, H, W, C] (strips: [1, rows, 1, C])."""
+    id: int
+    B: int
+    H: int
+    W: int
+    C: int
+    dtype: int
+    persistent: bool = False
+    first: int = -1
+    last: int = -1
+    offset: int = -1  # byte offset in the arena
+
+    @property
+    def nbytes(self):
+        return self.B * self.H * self.W * self.C * DT_SIZE[self.dtype]
+
+
+@dataclass
+class View:
+    """Channel slice [c0, c0+C) and row range of a Buf."""
+    buf: Buf
+    c0: int
+    C: int
+    B: int
+    H: int
+    W: int
+    row0: int = 0  # first pixel-row (strips only)
+
+    @property
+    def pitch(self):
+        return self.buf.C
+
+    @property
+    def dtype(self):
+        return self.buf.dtype
+
+    def ch(self, c0, c1):
+        assert 0 <= c0 < c1 <= self.C
+        return View(self.buf, self.c0 + c0, c1 - c0, self.B, self.H, self.W, self.row0)
+
+    def rows(self, r0, r1):
+        """Row sub-range of a strip view (B == 1, W == 1)."""
+        assert self.B == 1 and self.W == 1 and 0 <= r0 < r1 <= self.H
+        return View(self.buf, self.c0, self.C, 1, r1 - r0, 1, self.row0 + r0)
+
+    def byte_offset(self):
+        return (self.row0 * self.buf.C + self.c0) * DT_SIZE[self.buf.dtype]
+
+
+@dataclass
+class LazyUp:
+    """A nearest-2x upsample that has not been materialised (consumer may fold it)."""
+    src: View
+    mat: View | None = None
+
+
+@dataclass
+class Node:
+    fn: str                 # C-ABI symbol
+    desc: object            # ctypes struct
+    ptrs: list              # entries: View | torch.Tensor | None | ("ws", nbytes) | int
+    reads: list = field(default_factory=list)
+    writes: list = field(default_factory=list)
+    tag: str = ""
+    flops: float = 0.0      # algorithmic FLOPs (2*MAC) for convs
+    bytes: float = 0.0      # algorithmic bytes for bandwidth kernels
+
+
+class PlanError(ValueError):
+    pass
+
+
+class Plan:
+    def __init__(self, batch: int, precision: str, device, impl: int = 0):
+        if precision not in ("bf16", "fp32"):
+            raise PlanError(f"precision must be 'bf16' or 'fp32', got {precision}")
+        self.B = batch
+        self.precision = precision
+        self.act_dt = L.BF16 if precision == "bf16" else L.F32
+        self.device = device
+        self.impl = impl
+        self.bufs: list[Buf] = []
+        self.nodes: list[Node] = []
+        self.weights: list[torch.Tensor] = []  # keeps packed device tensors alive
+        self.layer_out: dict[int, object] = {}
+        self.inputs: list[View] = []
+        self.outputs: dict[str, object] = {}
+
+    # ------------------------------------------------------------------ buffers
+    def new_buf(self, H, W, C, dtype=None, B=None, persistent=False) -> View:
+        b = Buf(len(self.bufs), self.B if B is None else B, H, W, C, self.act_dt if dtype is None else dtype,
+                persistent)
+        self.bufs.append(b)
+        return View(b, 0, C, b.B, H, W)
+
+    def strip_buf(self, rows, C) -> View:
+        return self.new_buf(rows, 1, C, dtype=L.F32, B=1)
+
+    def _w(self, t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+        t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        self.weights.append(t)
+        return t
+
+    def add(self, node: Node):
+        idx = len(self.nodes)
+        for v in node.reads + node.writes:
+            b = v.buf
+            if b.first < 0:
+                b.first = idx
+            b.last = idx
+        self.nodes.append(node)
+
+    # ------------------------------------------------------------------ conv family
+    @staticmethod
+    def conv_params(m):
+        """(weight[O,I,kh,kw] fp32, bias[O] fp32, k, stride, groups, act) of a Conv-like module or bare Conv2d,
+        with BatchNorm folded if still present (reference torch_utils.py:237-267)."""
+        if isinstance(m, nn.Conv2d):
+            conv, bn, act = m, None, L.ACT_NONE
+        else:
+            conv, bn = m.conv, getattr(m, "bn", None)
+            a = getattr(m, "act", None)
+            if isinstance(a, nn.SiLU):
+                act = L.ACT_SILU
+            elif a is None or isinstance(a, nn.Identity):
+                act = L.ACT_NONE
+            else:
+                raise PlanError(f"activation {type(a).__name__} has no fused epilogue (only SiLU / identity)")
+        w = conv.weight.detach().float()
+        b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+        if isinstance(bn, nn.BatchNorm2d):
+            s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            w = w * s.view(-1, 1, 1, 1)
+            b = bn.bias.detach().float() + (b - bn.running_mean.detach().float()) * s
+        k = conv.kernel_size[0]
+        if conv.kernel_size[0] != conv.kernel_size[1] or k not in (1, 3) or conv.dilation[0] != 1:
+            raise PlanError(f"conv kernel {conv.kernel_size} / dilation {conv.dilation} outside the path")
+        if conv.padding[0] != k // 2:
+            raise PlanError("only 'same' padding (k//2) is on the path")
+        return w, b, k, conv.stride[0], conv.groups, act
+
+    def conv(self, m, x: View, dst: View | None = None, res: View | None = None, out_dtype=None, act=None,
+             w_override=None, b_override=None, in_layout=L.NHWC, in_scale=1.0, tag="") -> View:
+        w, b, k, s, g, a = self.conv_params(m) if m is not None else (w_override, b_override, 1, 1, 1, L.ACT_NONE)
+        if w_override is not None:
+            w, b = w_override, b_override
+        if act is not None:
+            a = act
+        if g != 1:
+            raise PlanError("grouped conv goes through dwconv()")
+        Cout, Cin = w.shape[0], w.shape[1]
+        if Cin != x.C:
+            raise PlanError(f"{tag}: conv expects {Cin} input channels, view has {x.C}")
+        Ho = (x.H + 2 * (k // 2) - k) // s + 1
+        Wo = (x.W + 2 * (k // 2) - k) // s + 1
+        strip = x.dtype == L.F32 and self.act_dt != L.F32 and in_layout == L.NHWC  # fp32 strips in bf16 mode
+        if out_dtype is None:
+            out_dtype = L.F32 if strip else self.act_dt
+        if dst is None:
+            dst = self.new_buf(Ho, Wo, Cout, dtype=out_dtype, B=x.B)
+        if (dst.H, dst.W, dst.C, dst.B) != (Ho, Wo, Cout, x.B):
+            raise PlanError(f"{tag}: conv output {(x.B, Ho, Wo, Cout)} does not fit destination "
+                            f"{(dst.B, dst.H, dst.W, dst.C)}")
+        w_dt = L.F32 if (x.dtype == L.F32 and (strip or self.act_dt == L.F32)) else self.act_dt
+        if in_layout == L.NCHW:
+            w_dt = self.act_dt
+        wp = self._w(w.permute(0, 2, 3, 1), TORCH_DT[w_dt])  # OHWI
+        bp = self._w(b)
+        d = L.ConvDesc(B=x.B, H=x.H, W=x.W, Cin=Cin, Cout=Cout, in_pitch=x.pitch, in_off=0, out_pitch=dst.pitch,
+                       out_off=0, res_pitch=res.pitch if res is not None else 0, res_off=0, k=k, stride=s, act=a,
+                       in_dtype=x.dtype, w_dtype=w_dt, out_dtype=dst.dtype, in_layout=in_layout, in_scale=in_scale,
+                       impl=self.impl)
+        if res is not None and (res.C != Cout or res.dtype != dst.dtype or (res.H, res.W) != (Ho, Wo)):
+            raise PlanError(f"{tag}: residual view does not match the conv output")
+        self.add(Node("fce_conv2d", d, [x, wp, bp, res, dst], reads=[x] + ([res] if res is not None else []),
+                      writes=[dst], tag=tag, flops=2.0 * x.B * Ho * Wo * Cout * Cin * k * k))
+        return dst
+
+    def dwconv(self, m, x: View, dst: View | None = None, add: View | None = None, tag="") -> View:
+        w, b, k, s, g, a = self.conv_params(m)
+        if k != 3 or s != 1 or g != x.C or w.shape[0] != x.C or w.shape[1] != 1:
+            raise PlanError(f"{tag}: only depthwise 3x3 stride-1 convs are on the path")
+        if dst is None:
+            dst = self.new_buf(x.H, x.W, x.C)
+        wp = self._w(w.view(x.C, 9).t())  # [9][C]
+        bp = self._w(b)
+        d = L.DwconvDesc(B=x.B, H=x.H, W=x.W, C=x.C, in_pitch=x.pitch, in_off=0, out_pitch=dst.pitch, out_off=0,
+                         add_pitch=add.pitch if add is not None else 0, add_off=0, act=a, dtype=x.dtype)
+        esz = DT_SIZE[x.dtype]
+        self.add(Node("fce_dwconv3x3", d, [x, wp, bp, add, dst], reads=[x] + ([add] if add is not None else []),
+                      writes=[dst], tag=tag, bytes=(2 + (add is not None)) * x.B * x.H * x.W * x.C * esz))
+        return dst
+
+    # ------------------------------------------------------------------ blocks
+    def bottleneck(self, m, x: View, dst=None, tag="") -> View:
+        t = self.conv(m.cv1, x, tag=tag + ".cv1")
+        return self.conv(m.cv2, t, dst=dst, res=x if m.add else None, tag=tag + ".cv2")
+
+    def c3k(self, m, x: View, dst=None, tag="") -> View:
+        c_ = m.cv1.conv.out_channels
+        cat = self.new_buf(x.H, x.W, 2 * c_)
+        a = self.conv(m.cv1, x, tag=tag + ".cv1")
+        blocks = list(m.m)
+        for j, blk in enumerate(blocks):
+            a = self.bottleneck(blk, a, dst=cat.ch(0, c_) if j == len(blocks) - 1 else None, tag=f"{tag}.m.{j}")
+        if not blocks:
+            raise PlanError("C3k without bottlenecks")
+        self.conv(m.cv2, x, dst=cat.ch(c_, 2 * c_), tag=tag + ".cv2")
+        return self.conv(m.cv3, cat, dst=dst, tag=tag + ".cv3")
+
+    def c3k2(self, m, x: View, dst=None, tag="") -> View:
+        c, n = m.c, len(m.m)
+        cat = self.new_buf(x.H, x.W, (2 + n) * c)
+        self.conv(m.cv1, x, dst=cat.ch(0, 2 * c), tag=tag + ".cv1")
+        prev = cat.ch(c, 2 * c)
+        for j, blk in enumerate(m.m):
+            out = cat.ch((2 + j) * c, (3 + j) * c)
+            if type(blk).__name__ == "C3k":
+                self.c3k(blk, prev, dst=out, tag=f"{tag}.m.{j}")
+            else:
+                self.bottleneck(blk, prev, dst=out, tag=f"{tag}.m.{j}")
+            prev = out
+        return self.conv(m.cv2, cat, dst=dst, tag=tag + ".cv2")
+
+    def sppf(self, m, x: View, dst=None, tag="") -> View:
+        k = m.m.kernel_size if isinstance(m.m.kernel_size, int) else m.m.kernel_size[0]
+        if k != 5:
+            raise PlanError("SPPF kernel must be 5")
+        c_ = m.cv1.conv.out_channels
+        cat = self.new_buf(x.H, x.W, 4 * c_)
+        self.conv(m.cv1, x, dst=cat.ch(0, c_), tag=tag + ".cv1")
+        d = L.SppfDesc(B=x.B, H=x.H, W=x.W, C=c_, pitch=cat.pitch, off=0, dtype=cat.dtype)
+        self.add(Node("fce_sppf_pool", d, [cat], reads=[cat], writes=[cat], tag=tag + ".pool",
+                      bytes=4.0 * x.B * x.H * x.W * c_ * DT_SIZE[cat.dtype]))
+        return self.conv(m.cv2, cat, dst=dst, tag=tag + ".cv2")
+
+    def psa_block(self, blk, b: View, tag=""):
+        at = blk.attn
+        nh, kd, hd = at.num_heads, at.key_dim, at.head_dim
+        c = b.C
+        # qkv output channels re-ordered from per-head [q|k|v] (block.py:1296-1298) to [Q | K | V]
+        w, bias, *_ = self.conv_params(at.qkv)
+        per = 2 * kd + hd
+        idx_q = [h * per + j for h in range(nh) for j in range(kd)]
+        idx_k = [h * per + kd + j for h in range(nh) for j in range(kd)]
+        idx_v = [h * per + 2 * kd + j for h in range(nh) for j in range(hd)]
+        perm = torch.tensor(idx_q + idx_k + idx_v, device=w.device)
+        qkv = self.conv(at.qkv, b, w_override=w[perm], b_override=bias[perm], tag=tag + ".attn.qkv")
+        att = self.new_buf(b.H, b.W, c)
+        d = L.PsaDesc(B=b.B, N=b.H * b.W, heads=nh, kd=kd, hd=hd, qkv_pitch=qkv.pitch, q_off=0, k_off=nh * kd,
+                      v_off=2 * nh * kd, out_pitch=att.pitch, out_off=0, dtype=qkv.dtype, scale=float(at.scale))
+        self.add(Node("fce_psa_attention", d, [qkv, att], reads=[qkv], writes=[att], tag=tag + ".attn.core",
+                      flops=2.0 * b.B * nh * (b.H * b.W) ** 2 * (kd + hd)))
+        self.dwconv(at.pe, qkv.ch(2 * nh * kd, 2 * nh * kd + c), dst=att, add=att, tag=tag + ".attn.pe")
+        self.conv(at.proj, att, dst=b, res=b if blk.add else None, tag=tag + ".attn.proj")
+        f = self.conv(blk.ffn[0], b, tag=tag + ".ffn.0")
+        self.conv(blk.ffn[1], f, dst=b, res=b if blk.add else None, tag=tag + ".ffn.1")
+
+    def c2psa(self, m, x: View, dst=None, tag="") -> View:
+        c = m.c
+        ab = self.new_buf(x.H, x.W, 2 * c)
+        self.conv(m.cv1, x, dst=ab, tag=tag + ".cv1")
+        for j, blk in enumerate(m.m):
+            self.psa_block(blk, ab.ch(c, 2 * c), tag=f"{tag}.m.{j}")
+        return self.conv(m.cv2, ab, dst=dst, tag=tag + ".cv2")
+
+    # ------------------------------------------------------------------ resampling / fusion
+    def materialize(self, x, dst: View | None = None) -> View:
+        if isinstance(x, View):
+            if dst is None:
+                return x
+            d = L.CopyDesc(B=x.B, H=x.H, W=x.W, C=x.C, in_pitch=x.pitch, in_off=0, out_pitch=dst.pitch, out_off=0,
+                           dtype=x.dtype)
+            self.add(Node("fce_copy_view", d, [x, dst], reads=[x], writes=[dst], tag="copy",
+                          bytes=2.0 * x.B * x.H * x.W * x.C * DT_SIZE[x.dtype]))
+            return dst
+        if x.mat is not None and dst is None:
+            return x.mat
+        s = x.src
+        out = dst if dst is not None else self.new_buf(2 * s.H, 2 * s.W, s.C, dtype=s.dtype)
+        d = L.UpsampleDesc(B=s.B, H=s.H, W=s.W, C=s.C, in_pitch=s.pitch, in_off=0, out_pitch=out.pitch, out_off=0,
+                           dtype=s.dtype)
+        self.add(Node("fce_upsample2x", d, [s, out], reads=[s], writes=[out], tag="upsample",
+                      bytes=5.0 * s.B * s.H * s.W * s.C * DT_SIZE[s.dtype]))
+        if dst is None:
+            x.mat = out
+        return out
+
+    def concat(self, m, xs, tag="") -> View:
+        if getattr(m, "d", 1) != 1:
+            raise PlanError("Concat is only supported along channels")
+        shapes = [(2 * x.src.H, 2 * x.src.W, x.src.C) if isinstance(x, LazyUp) else (x.H, x.W, x.C) for x in xs]
+        H, W = shapes[0][:2]
+        out = self.new_buf(H, W, sum(s[2] for s in shapes))
+        c0 = 0
+        for x, s in zip(xs, shapes):
+            if s[:2] != (H, W):
+                raise PlanError(f"{tag}: Concat inputs differ in size")
+            self.materialize(x, dst=out.ch(c0, c0 + s[2]))
+            c0 += s[2]
+        return out
+
+    def bifpn(self, m, xs, dst=None, tag="") -> View:
+        if not 2 <= len(xs) <= 3:
+            raise PlanError("BiFPN_Concat fuses 2 or 3 inputs")
+        w = torch.relu(m.w.detach().float().cpu())
+        wn = (w / (w.sum() + m.epsilon)).tolist()  # fce_block.py:55-56
+        views, ups = [], []
+        for i, x in enumerate(xs):
+            r = m.realign_convs[i]
+            up = isinstance(x, LazyUp)
+            v = x.src if up else x
+            if not isinstance(r, nn.Identity):
+                v = self.conv(r, v, tag=f"{tag}.realign.{i}")  # at low resolution when upsampled
+            views.append(v)
+            ups.append(1 if up else 0)
+        H, W = (views[0].H * 2, views[0].W * 2) if ups[0] else (views[0].H, views[0].W)
+        C = views[0].C
+        for v, u in zip(views, ups):
+            if (v.H * (2 if u else 1), v.W * (2 if u else 1), v.C) != (H, W, C):
+                raise PlanError(f"{tag}: BiFPN inputs disagree after realignment")
+        if dst is None:
+            dst = self.new_buf(H, W, C)
+        d = L.BifpnDesc(B=self.B, H=H, W=W, C=C, n=len(xs), out_pitch=dst.pitch, out_off=0, dtype=dst.dtype)
+        for i, (v, u) in enumerate(zip(views, ups)):
+            d.pitch[i], d.off[i], d.up[i], d.wn[i] = v.pitch, 0, u, wn[i]
+        ptrs = views + [None] * (3 - len(views)) + [dst]
+        esz = DT_SIZE[dst.dtype]
+        alg = sum(v.B * v.H * v.W * v.C for v in views) * esz + self.B * H * W * C * esz
+        self.add(Node("fce_bifpn_fuse", d, ptrs, reads=views, writes=[dst], tag=tag + ".fuse", bytes=alg))
+        return dst
+
+    # ------------------------------------------------------------------ coordinate attention family
+    def _pool(self, x: View, tag) -> View:
+        strip = self.strip_buf(x.B * (x.H + x.W), x.C)
+        d = L.PoolDesc(B=x.B, H=x.H, W=x.W, C=x.C, pitch=x.pitch, off=0, dtype=x.dtype)
+        self.add(Node("fce_coord_pool", d, [x, strip, None, 0], reads=[x], writes=[strip], tag=tag + ".pool",
+                      bytes=x.B * x.H * x.W * x.C * DT_SIZE[x.dtype]))
+        return strip
+
+    def _strip_attn(self, q: View, k: View, v: View, B, Lq, Lk, heads, scale, tag) -> View:
+        out = self.strip_buf(B * Lq, q.C)
+        dh = q.C // heads
+        d = L.StripAttnDesc(B=B, heads=heads, dh=dh, Lq=Lq, Lk=Lk, scale=scale,
+                            q_bstride=Lq * q.pitch, q_rstride=q.pitch, k_bstride=Lk * k.pitch, k_rstride=k.pitch,
+                            v_bstride=Lk * v.pitch, v_rstride=v.pitch, o_bstride=Lq * out.pitch, o_rstride=out.pitch)
+        self.add(Node("fce_strip_attn", d, [q, k, v, out], reads=[q, k, v], writes=[out], tag=tag))
+        return out
+
+    def _gate(self, x: View, gh: View, gw: View | None, mode, dst, tag) -> View:
+        if dst is None:
+            dst = self.new_buf(x.H, x.W, x.C)
+        d = L.GateDesc(B=x.B, H=x.H, W=x.W, C=x.C, mode=mode, in_pitch=x.pitch, in_off=0, out_pitch=dst.pitch,
+                       out_off=0, dtype=x.dtype, gh_bstride=x.H * gh.pitch, gh_rstride=gh.pitch,
+                       gw_bstride=x.W * gw.pitch if gw is not None else 0, gw_rstride=gw.pitch if gw is not None else 0)
+        self.add(Node("fce_gate_apply", d, [x, gh, gw, dst], reads=[x, gh] + ([gw] if gw is not None else []),
+                      writes=[dst], tag=tag + ".gate", bytes=2.0 * x.B * x.H * x.W * x.C * DT_SIZE[x.dtype]))
+        return dst
+
+    def _identity(self, m, x: View, tag) -> View:
+        idt = getattr(m, "identity", None)
+        if idt is None or isinstance(idt, nn.Identity):
+            return x
+        return self.conv(idt, x, tag=tag + ".identity")
+
+    def coord_att(self, m, x: View, dst=None, tag="") -> View:
+        BH = x.B * x.H
+        s = self._pool(x, tag)
+        y = self.conv(m.cv1, s, tag=tag + ".cv1")
+        a_h = self.conv(m.cv_h, y.rows(0, BH), act=L.ACT_SIGMOID, tag=tag + ".cv_h")
+        a_w = self.conv(m.cv_w, y.rows(BH, y.H), act=L.ACT_SIGMOID, tag=tag + ".cv_w")
+        return self._gate(self._identity(m, x, tag), a_h, a_w, 0, dst, tag)
+
+    def coord_cross_att(self, m, x: View, dst=None, tag="") -> View:
+        BH = x.B * x.H
+        mip, heads = m.mip, m.num_heads
+        if mip % heads:
+            raise PlanError(f"CoordCrossAtt: mip={mip} is not divisible by num_heads={heads} "
+                            "(the reference fails in view(), fce_block.py:166)")
+        if m.proj.out_channels != x.C:
+            raise PlanError("CoordCrossAtt multiplies the raw input: needs oup == inp (fce_block.py:180)")
+        s = self._pool(x, tag)
+        y = self.conv(m.cv1, s, tag=tag + ".cv1")
+        q = self.conv(m.q_conv, y.rows(0, BH), tag=tag + ".q")
+        wk, bk, *_ = self.conv_params(m.k_conv)
+        wv, bv, *_ = self.conv_params(m.v_conv)
+        kv = self.conv(None, y.rows(BH, y.H), w_override=torch.cat([wk, wv]), b_override=torch.cat([bk, bv]),
+                       tag=tag + ".kv")
+        z = self._strip_attn(q, kv.ch(0, mip), kv.ch(mip, 2 * mip), x.B, x.H, x.W, heads, float(m.scale), tag + ".attn")
+        g = self.conv(m.proj, z, act=L.ACT_SIGMOID, tag=tag + ".proj")
+        return self._gate(x, g, None, 1, dst, tag)
+
+    def bi_coord_cross_att(self, m, x: View, dst=None, tag="") -> View:
+        BH = x.B * x.H
+        mid, heads = m.mid_dim, m.num_heads
+        s = self._pool(x, tag)
+
+        def stacked(names):
+            ws, bs = zip(*[self.conv_params(getattr(m, n))[:2] for n in names])
+            return torch.cat(ws), torch.cat(bs)
+
+        # rows from x_h feed q_h, k_w, v_w ; rows from x_w feed q_w, k_h, v_h (fce_block.py:246-268)
+        w_h, b_h = stacked(["proj_q_h", "proj_k_w", "proj_v_w"])
+        w_w, b_w = stacked(["proj_q_w", "proj_k_h", "proj_v_h"])
+        ph = self.conv(None, s.rows(0, BH), w_override=w_h, b_override=b_h, tag=tag + ".proj_xh")
+        pw = self.conv(None, s.rows(BH, s.H), w_override=w_w, b_override=b_w, tag=tag + ".proj_xw")
+        zh = self._strip_attn(ph.ch(0, mid), pw.ch(mid, 2 * mid), pw.ch(2 * mid, 3 * mid), x.B, x.H, x.W, heads,
+                              float(m.scale), tag + ".attn_h")
+        zw = self._strip_attn(pw.ch(0, mid), ph.ch(mid, 2 * mid), ph.ch(2 * mid, 3 * mid), x.B, x.W, x.H, heads,
+                              float(m.scale), tag + ".attn_w")
+        gh = self.conv(m.out_h, zh, tag=tag + ".out_h")
+        gw = self.conv(m.out_w, zw, tag=tag + ".out_w")
+        return self._gate(self._identity(m, x, tag), gh, gw, 2, dst, tag)
+
+    # ------------------------------------------------------------------ head
+    def detect(self, m, xs, tag=""):
+        if getattr(m, "end2end", False):
+            raise PlanError("end2end heads are outside the path")
+        nl, nc, R = m.nl, m.nc, m.reg_max
+        if nl > 4:
+            raise PlanError("at most 4 detection levels")
+        raws = []
+        for i, x in enumerate(xs):
+            x = self.materialize(x)
+            raw = self.new_buf(x.H, x.W, 4 * R + nc, dtype=L.F32, persistent=True)
+            t = self.conv(m.cv2[i][0], x, tag=f"{tag}.cv2.{i}.0")
+            t = self.conv(m.cv2[i][1], t, tag=f"{tag}.cv2.{i}.1")
+            self.conv(m.cv2[i][2], t, dst=raw.ch(0, 4 * R), tag=f"{tag}.cv2.{i}.2")
+            c = x
+            for j in (0, 1):
+                blk = m.cv3[i][j]
+                if len(blk) != 2:
+                    raise PlanError("legacy Detect heads (dense 3x3 class branch) are outside the path")
+                c = self.dwconv(blk[0], c, tag=f"{tag}.cv3.{i}.{j}.0")
+                c = self.conv(blk[1], c, tag=f"{tag}.cv3.{i}.{j}.1")
+            self.conv(m.cv3[i][2], c, dst=raw.ch(4 * R, 4 * R + nc), tag=f"{tag}.cv3.{i}.2")
+            raws.append(raw)
+        A = sum(r.H * r.W for r in raws)
+        y = self.new_buf(1, 4 + nc, A, dtype=L.F32, persistent=True)  # logical [B, 4+nc, A]
+        d = L.DecodeDesc(B=self.B, nl=nl, nc=nc, reg_max=R)
+        strides = [float(s) for s in m.stride.tolist()]
+        for i, r in enumerate(raws):
+            d.H[i], d.W[i], d.stride[i], d.raw_pitch[i] = r.H, r.W, strides[i], r.pitch
+        ptrs = raws + [None] * (4 - nl) + [y]
+        self.add(Node("fce_detect_decode", d, ptrs, reads=raws, writes=[y], tag=tag + ".decode",
+                      bytes=self.B * A * ((4 * R + nc) + (4 + nc)) * 4.0))
+        return y, raws
+
+    # ------------------------------------------------------------------ dispatch
+    def emit(self, m, x, tag=""):
+        """x: View | LazyUp | list of those.  Returns View | LazyUp | (y, raws) for Detect."""
+        name = type(m).__name__
+        if name == "Upsample":
+            sf = m.scale_factor
+            if m.mode != "nearest" or float(sf if not isinstance(sf, tuple) else sf[0]) != 2.0:
+                raise PlanError("only nearest 2x upsampling is on the path")
+            return LazyUp(self.materialize(x))
+        if name == "BiFPN_Concat":
+            return self.bifpn(m, list(x), tag=tag)
+        if name == "Concat":
+            return self.concat(m, list(x), tag=tag)
+        if name == "Detect":
+            return self.detect(m, list(x), tag=tag)
+        x = self.materialize(x)
+        if name in ("Conv", "Conv2d"):
+            if name == "Conv" and m.conv.groups != 1:
+                return self.dwconv(m, x, tag=tag)
+            return self.conv(m, x, tag=tag)
+        if name == "DWConv":
+            return self.dwconv(m, x, tag=tag)
+        fn = {"Bottleneck": self.bottleneck, "C3k": self.c3k, "C3k2": self.c3k2, "SPPF": self.sppf,
+              "C2PSA": self.c2psa, "CoordAtt": self.coord_att, "CoordCrossAtt": self.coord_cross_att,
+              "BiCoordCrossAtt": self.bi_coord_cross_att}.get(name)
+        if fn is None:
+            raise PlanError(f"module {name} is outside the FCE-YOLO hot path")
+        return fn(m, x, tag=tag)
+
+
+def compile_model(model, batch: int, height: int, width: int, precision: str, device, impl: int = 0,
+                  input_u8: bool = False) -> Plan:
+    """Whole-graph plan of a DetectionModel (mirror or reference): restates the routing of
+    BaseModel._predict_once (tasks.py:172-188) at compile time."""
+    layers = list(model.model)
+    if height % 32 or width % 32:
+        raise PlanError("image height/width must be multiples of 32 (reference loaders.py:603-609)")
+    p = Plan(batch, precision, device, impl)
+    first = layers[0]
+    if type(first).__name__ != "Conv":
+        raise PlanError("the graph must start with a Conv stem")
+    cin = first.conv.in_channels
+    if input_u8:
+        img = p.new_buf(height, width, cin, dtype=L.U8, persistent=True)  # NHWC uint8
+    else:
+        img = p.new_buf(cin, height, width, dtype=L.F32, persistent=True)  # raw NCHW fp32 storage
+    p.inputs = [img]
+    ys = []
+    x = None
+    for i, m in enumerate(layers):
+        f = getattr(m, "f", -1)
+        if i == 0:
+            if input_u8:
+                xin = View(img.buf, 0, cin, batch, height, width)
+                x = p.conv(m, xin, in_scale=1.0 / 255.0, tag="model.0")
+            else:
+                xin = View(img.buf, 0, cin, batch, height, width)  # NCHW: geometry carried by the desc
+                x = p.conv(m, xin, in_layout=L.NCHW, tag="model.0")
+        else:
+            if f != -1:
+                x = ys[f] if isinstance(f, int) else [x if j == -1 else ys[j] for j in f]
+            x = p.emit(m, x, tag=f"model.{i}")
+        ys.append(x)
+        p.layer_out[i] = x
+    last = ys[-1]
+    if isinstance(last, tuple):
+        p.outputs = {"y": last[0], "raw": last[1]}
+    else:
+        p.outputs = {"y": p.materialize(last)}
+    for v in ([p.outputs["y"]] + p.outputs.get("raw", [])):
+        v.buf.persistent = True
+    return p
+
+
+def compile_module(m, in_shapes, precision: str, device, impl: int = 0) -> Plan:
+    """Plan for ONE module (per-module drop-in and teacher-forced parity tests).
+    in_shapes: list of (B, C, H, W)."""
+    B = in_shapes[0][0]
+    p = Plan(B, precision, device, impl)
+    ins = [p.new_buf(h, w, c, persistent=True) for (_, c, h, w) in in_shapes]
+    p.inputs = ins
+    name = type(m).__name__
+    multi = name in ("BiFPN_Concat", "Concat", "Detect")
+    out = p.emit(m, list(ins) if multi else ins[0], tag=name)
+    if isinstance(out, tuple):
+        p.outputs = {"y": out[0], "raw": out[1]}
+    else:
+        p.outputs = {"y": p.materialize(out)}
+    for v in ([p.outputs["y"]] + p.outputs.get("raw", [])):
+        v.buf.persistent = True
+    return p

@@ -1,0 +1,202 @@
+/* fce_yolo_b200 - C ABI of the B200 (sm_100a) FCE-YOLOv11 detection forward path.
+ *
+ * The reference (ShioMisaka/fce-yolo, a fork of Ultralytics 8.3.242) has no native code: every
+ * operator is a torch.nn.Module calling ATen.  Each entry point below replaces the ATen work of
+ * one reference operator (file:line cited per function, relative to the reference root).  The
+ * Python host (fce_yolo_b200/_lib.py) binds them with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  All pointers are DEVICE pointers unless stated; the caller
+ *    (PyTorch caching allocator) owns every buffer, the library allocates nothing.
+ *  - Activations are NHWC ("channels_last"): element (b,h,w,c) of a view lives at
+ *    base + ((b*H + h)*W + w)*pitch + off + c, where `pitch` is the channel count of the
+ *    underlying buffer and `off` the first channel of the view.  Channel-concats and chunk()s of
+ *    the reference (block.py:232,303-307,340,1464; head.py:120) are therefore free: producers
+ *    write, and consumers read, channel slices of one buffer.
+ *  - dtype codes: FCE_BF16 activations/weights with fp32 accumulation ("bf16 mode") or FCE_F32
+ *    end to end ("fp32 mode").  Strips (pooled [B,L,C] vectors), gates, biases, logits and
+ *    detections are always fp32.
+ *  - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous, re-entrant and
+ *    stream-ordered; there is no global mutable state.
+ *  - Return value: 0 on success, negative fce_status otherwise (the Python shim raises).
+ *    There is no CPU fallback anywhere.
+ */
+#ifndef FCE_YOLO_B200_H
+#define FCE_YOLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    FCE_OK = 0,
+    FCE_ERR_BAD_ARG = -1,      /* null pointer, non-positive size */
+    FCE_ERR_UNSUPPORTED = -2,  /* shape / dtype combination outside the path */
+    FCE_ERR_ALIGNMENT = -3,    /* view not aligned for the vector width the kernel needs */
+    FCE_ERR_WORKSPACE = -4,    /* workspace too small */
+    FCE_ERR_CUDA = -5          /* launch / driver error (see fce_last_cuda_error) */
+} fce_status;
+
+typedef enum { FCE_BF16 = 0, FCE_F32 = 1, FCE_U8 = 2 } fce_dtype;
+typedef enum { FCE_ACT_NONE = 0, FCE_ACT_SILU = 1, FCE_ACT_SIGMOID = 2 } fce_act;
+typedef enum { FCE_NHWC = 0, FCE_NCHW = 1 } fce_layout;
+
+int fce_abi_version(void);
+/* last cudaError_t seen by a failing call on this thread, as text */
+const char* fce_last_cuda_error(void);
+/* 1 if the current device is sm_100 (B200) */
+int fce_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense convolution k in {1,3}, stride in {1,2}, pad k/2, groups 1, + bias, + SiLU, + residual.
+ * Replaces Conv.forward_fuse (ultralytics/nn/modules/conv.py:80-89) and every bare nn.Conv2d on
+ * the path (fce_block.py:95,233 identity; head.py:94,103), with the Bottleneck / PSABlock
+ * residual adds (block.py:474-476, 1352-1353) and torch.cat/chunk fused as view offsets.
+ * Weights are OHWI: w[co][kh][kw][ci], dense.  y = act(conv(x*in_scale) + bias) (+ res).
+ * impl: 0 = auto, 1 = force the fp32-accurate SIMT kernel, 2 = force the tcgen05 kernel.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t B, H, W;          /* input spatial size */
+    int32_t Cin, Cout;
+    int32_t in_pitch, in_off;
+    int32_t out_pitch, out_off;
+    int32_t res_pitch, res_off;
+    int32_t k, stride;
+    int32_t act;              /* fce_act */
+    int32_t in_dtype, w_dtype, out_dtype;
+    int32_t in_layout;        /* fce_layout; FCE_NCHW only for the network input image */
+    float in_scale;           /* 1.0, or 1/255 for u8 images */
+    int32_t impl;
+} fce_conv_desc;
+
+int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res,
+               void* y, void* stream);
+
+/* Depthwise 3x3 stride 1 (+bias, +SiLU, + optional add of a second map).  Replaces DWConv
+ * (conv.py:185-199) in Detect.cv3 (head.py:101-102) and Attention.pe with its add
+ * (block.py:1282,1302).  w is fp32 [9][C] (tap-major), bias fp32 [C]. */
+typedef struct {
+    int32_t B, H, W, C;
+    int32_t in_pitch, in_off, out_pitch, out_off, add_pitch, add_off;
+    int32_t act, dtype;
+} fce_dwconv_desc;
+int fce_dwconv3x3(const fce_dwconv_desc* d, const void* x, const float* w, const float* bias, const void* add,
+                  void* y, void* stream);
+
+/* SPPF pyramid: three chained 5x5/s1/p2 max-pools (= 5x5, 9x9, 13x13 windows) of slice 0 of the
+ * concat buffer written to slices 1..3 (block.py:228-232).  buf has 4*C channels. */
+typedef struct {
+    int32_t B, H, W, C;
+    int32_t pitch, off;       /* slice j lives at channel off + j*C */
+    int32_t dtype;
+} fce_sppf_desc;
+int fce_sppf_pool(const fce_sppf_desc* d, void* buf, void* stream);
+
+/* Nearest 2x upsample (nn.Upsample(None, 2, "nearest"), yolo11-fce.yaml:40,44). H,W = input size. */
+typedef struct {
+    int32_t B, H, W, C;
+    int32_t in_pitch, in_off, out_pitch, out_off, dtype;
+} fce_upsample_desc;
+int fce_upsample2x(const fce_upsample_desc* d, const void* x, void* y, void* stream);
+
+/* BiFPN_Concat weighted fusion (fce_block.py:55-61): y = sum_i wn[i] * x_i, n in {2,3}, where wn is
+ * the already normalised relu(w)/(sum relu(w)+1e-4) (host computes it once per weight load) and
+ * input i may be a half-resolution map read through the nearest-2x pattern (up[i] = 1), which
+ * fuses the preceding nn.Upsample.  H,W = output size. */
+typedef struct {
+    int32_t B, H, W, C, n;
+    int32_t pitch[3], off[3], up[3];
+    float wn[3];
+    int32_t out_pitch, out_off, dtype;
+} fce_bifpn_desc;
+int fce_bifpn_fuse(const fce_bifpn_desc* d, const void* x0, const void* x1, const void* x2, void* y, void* stream);
+
+/* Channel concat for the stock Concat module (conv.py:616-641) when it cannot be fused away:
+ * copies a view into a channel slice of another buffer. */
+typedef struct {
+    int32_t B, H, W, C;
+    int32_t in_pitch, in_off, out_pitch, out_off, dtype;
+} fce_copy_desc;
+int fce_copy_view(const fce_copy_desc* d, const void* x, void* y, void* stream);
+
+/* Coordinate pooling (fce_block.py:81-82,101-102,140-141,159-160,212-213,239-240): one pass over x
+ * producing strip[b, 0:H, c] = mean_w x and strip[b, H:H+W, c] = mean_h x, fp32 [B, H+W, C]. */
+typedef struct {
+    int32_t B, H, W, C;
+    int32_t pitch, off, dtype;
+} fce_pool_desc;
+int fce_coord_pool(const fce_pool_desc* d, const void* x, float* strip, void* ws, size_t ws_bytes, void* stream);
+size_t fce_coord_pool_workspace(const fce_pool_desc* d);
+
+/* 1x1 convs on strips - cv1/cv_h/cv_w (fce_block.py:105,112-113), q/k/v/proj (:165-168,178) and the
+ * eight BiCoordCrossAtt projections (:246-249,258,264-268,276) - are fce_conv2d calls on the fp32 strip
+ * seen as a [1, rows, 1, C] map (k = 1, all dtypes FCE_F32, act NONE / SILU / SIGMOID). */
+
+/* Strip cross-attention core (fce_block.py:171-175, 252-256, 271-275):
+ * out[b,l,h*dh+j] = sum_m softmax_m(scale * <q[b,l,h,:], k[b,m,h,:]>) * v[b,m,h*dh+j].
+ * q rows: Lq, k/v rows: Lk; channel c = head*dh + j (the reference's view(n,heads,dh,L)). */
+typedef struct {
+    int32_t B, heads, dh, Lq, Lk;
+    float scale;
+    int64_t q_bstride, q_rstride, k_bstride, k_rstride, v_bstride, v_rstride, o_bstride, o_rstride;
+} fce_strip_attn_desc;
+int fce_strip_attn(const fce_strip_attn_desc* d, const float* q, const float* k, const float* v, float* out,
+                   void* stream);
+
+/* Gate application (fce_block.py:116,180,283-284), one read + one write of x:
+ *  mode 0 (CoordAtt)        y = x * gh[b,h,c] * gw[b,w,c]        (gh, gw already sigmoid-ed)
+ *  mode 1 (CoordCrossAtt)   y = x * gh[b,h,c]
+ *  mode 2 (BiCoordCrossAtt) y = x * sigmoid(gh[b,h,c] + gw[b,w,c])
+ * gh/gw fp32 with row stride g_rstride and batch stride g_bstride (elements). */
+typedef struct {
+    int32_t B, H, W, C, mode;
+    int32_t in_pitch, in_off, out_pitch, out_off, dtype;
+    int64_t gh_bstride, gh_rstride, gw_bstride, gw_rstride;
+} fce_gate_desc;
+int fce_gate_apply(const fce_gate_desc* d, const void* x, const float* gh, const float* gw, void* y, void* stream);
+
+/* C2PSA self-attention core (block.py:1293-1302): per image and head,
+ * out[:, n] = sum_m softmax_m(scale * <q[:,n], k[:,m]>) v[:, m].  qkv is one NHWC buffer whose
+ * channels were re-ordered at weight-pack time to [q(all heads) | k(all heads) | v(all heads)]. */
+typedef struct {
+    int32_t B, N, heads, kd, hd;
+    int32_t qkv_pitch, q_off, k_off, v_off, out_pitch, out_off, dtype;
+    float scale;
+} fce_psa_desc;
+int fce_psa_attention(const fce_psa_desc* d, const void* qkv, void* out, void* stream);
+
+/* Detect decode (head.py:149-167 + block.py:76-79 DFL + tal.py:352-376): raw per-level logits
+ * fp32 NHWC [B,Hi,Wi,4*reg_max+nc] -> y fp32 [B, 4+nc, A] = (cx,cy,w,h in input pixels, sigmoid cls). */
+typedef struct {
+    int32_t B, nl, nc, reg_max;
+    int32_t H[4], W[4];
+    float stride[4];
+    int32_t raw_pitch[4];
+} fce_decode_desc;
+int fce_detect_decode(const fce_decode_desc* d, const float* raw0, const float* raw1, const float* raw2,
+                      const float* raw3, float* y, void* stream);
+
+/* Batched NMS (ultralytics/utils/nms.py:13-166 with torchvision.ops.nms semantics, :151-154).
+ * pred fp32 [B, 4+nc, A].  Outputs: det fp32 [B, max_det, 6] (x1,y1,x2,y2,conf,cls), keep int64
+ * [B, max_det] anchor indices (-1 padded), count int32 [B].  classes: optional device int32 list of
+ * allowed class ids.  Keep indices and class ids are bit-exact w.r.t. the reference. */
+typedef struct {
+    int32_t B, A, nc;
+    float conf_thres;
+    double iou_thres;
+    int32_t max_det, max_nms, multi_label, agnostic;
+    float max_wh;
+    int32_t n_classes;
+} fce_nms_desc;
+size_t fce_nms_workspace(const fce_nms_desc* d);
+int fce_nms(const fce_nms_desc* d, const float* pred, const int32_t* classes, float* det, int64_t* keep,
+            int32_t* count, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCE_YOLO_B200_H */

@@ -1,0 +1,124 @@
+"""TEST-ONLY interpreter of a compiled Plan with torch ops on the CPU.
+
+It executes the *same node list, descriptors, view offsets and packed weights* the CUDA executor would
+launch, so the plan compiler (fusions, concat-by-offset, weight re-ordering, strides) can be validated
+in the GPU-less build container.  It says nothing about the CUDA kernels - those are checked on the
+B200 (tests marked gpu).  Never imported by the product.
+"""
+import torch
+import torch.nn.functional as F
+
+from fce_yolo_b200 import _lib as L
+from fce_yolo_b200.engine import Arena
+from fce_yolo_b200.plan import View
+
+
+def _act(t, a):
+    return F.silu(t) if a == L.ACT_SILU else torch.sigmoid(t) if a == L.ACT_SIGMOID else t
+
+
+class Interp(Arena):
+    def t(self, v):
+        return self.tensor(v)
+
+    def run(self):
+        for n in self.plan.nodes:
+            getattr(self, "_" + n.fn)(n.desc, n.ptrs)
+
+    def _fce_conv2d(self, d, p):
+        x, w, b, res, y = p
+        if d.in_layout == L.NCHW:
+            buf = x.buf
+            xin = self._flat(buf).view(buf.B, buf.H, buf.W, buf.C).float()  # is [B,C,H,W]
+        else:
+            xin = View(x.buf, x.c0, x.C, d.B, d.H, d.W, x.row0)
+            xin = self.t(xin).permute(0, 3, 1, 2).float()
+        xin = xin * d.in_scale
+        wt = w.float().permute(0, 3, 1, 2)  # OHWI -> OIHW
+        o = F.conv2d(xin, wt, b.float(), stride=d.stride, padding=d.k // 2)
+        o = _act(o, d.act)
+        if res is not None:
+            o = o + self.t(res).permute(0, 3, 1, 2).float()
+        self.t(y).copy_(o.permute(0, 2, 3, 1))
+
+    def _fce_dwconv3x3(self, d, p):
+        x, w, b, add, y = p
+        xin = self.t(x).permute(0, 3, 1, 2).float()
+        wt = w.float().t().reshape(d.C, 1, 3, 3)
+        o = _act(F.conv2d(xin, wt, b.float(), padding=1, groups=d.C), d.act)
+        if add is not None:
+            o = o + self.t(add).permute(0, 3, 1, 2).float()
+        self.t(y).copy_(o.permute(0, 2, 3, 1))
+
+    def _fce_sppf_pool(self, d, p):
+        cat = p[0]
+        cur = self.t(cat.ch(0, d.C)).permute(0, 3, 1, 2).float()
+        for j in range(1, 4):
+            cur = F.max_pool2d(cur, 5, 1, 2)
+            self.t(cat.ch(j * d.C, (j + 1) * d.C)).copy_(cur.permute(0, 2, 3, 1))
+
+    def _fce_upsample2x(self, d, p):
+        x, y = p
+        o = F.interpolate(self.t(x).permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest")
+        self.t(y).copy_(o.permute(0, 2, 3, 1))
+
+    def _fce_bifpn_fuse(self, d, p):
+        acc = None
+        for i in range(d.n):
+            t = self.t(p[i]).permute(0, 3, 1, 2).float()
+            if d.up[i]:
+                t = F.interpolate(t, scale_factor=2, mode="nearest")
+            acc = d.wn[i] * t if acc is None else acc + d.wn[i] * t
+        self.t(p[3]).copy_(acc.permute(0, 2, 3, 1))
+
+    def _fce_copy_view(self, d, p):
+        self.t(p[1]).copy_(self.t(p[0]))
+
+    def _fce_coord_pool(self, d, p):
+        x, strip = p[0], p[1]
+        t = self.t(x).float()  # [B,H,W,C]
+        s = self.t(strip).view(-1, d.C)
+        s[: d.B * d.H] = t.mean(2).reshape(-1, d.C)
+        s[d.B * d.H:] = t.mean(1).reshape(-1, d.C)
+
+    def _fce_strip_attn(self, d, p):
+        q, k, v, o = [self.t(z).reshape(-1, z.C) for z in p]
+        B, h, dh = d.B, d.heads, d.dh
+        q = q.view(B, d.Lq, h, dh).permute(0, 2, 1, 3)
+        k = k.view(B, d.Lk, h, dh).permute(0, 2, 3, 1)
+        v = v.view(B, d.Lk, h, dh).permute(0, 2, 1, 3)
+        a = ((q @ k) * d.scale).softmax(-1)
+        z = (a @ v).permute(0, 2, 1, 3).reshape(B * d.Lq, h * dh)
+        self.t(p[3]).reshape(-1, h * dh).copy_(z) if self.t(p[3]).is_contiguous() else self.t(p[3]).copy_(
+            z.view(1, B * d.Lq, 1, h * dh))
+
+    def _fce_gate_apply(self, d, p):
+        x, gh, gw, y = p
+        t = self.t(x).float()
+        a = self.t(gh).reshape(d.B, d.H, 1, d.C)
+        if d.mode == 1:
+            o = t * a
+        else:
+            b = self.t(gw).reshape(d.B, 1, d.W, d.C)
+            o = t * a * b if d.mode == 0 else t * torch.sigmoid(a + b)
+        self.t(y).copy_(o)
+
+    def _fce_psa_attention(self, d, p):
+        qkv, out = p
+        t = self.t(qkv).float().reshape(d.B, d.N, -1)
+        nh, kd, hd = d.heads, d.kd, d.hd
+        q = t[..., d.q_off:d.q_off + nh * kd].view(d.B, d.N, nh, kd).permute(0, 2, 1, 3)
+        k = t[..., d.k_off:d.k_off + nh * kd].view(d.B, d.N, nh, kd).permute(0, 2, 3, 1)
+        v = t[..., d.v_off:d.v_off + nh * hd].view(d.B, d.N, nh, hd).permute(0, 2, 1, 3)
+        a = ((q @ k) * d.scale).softmax(-1)
+        o = (a @ v).permute(0, 2, 1, 3).reshape(d.B, d.N, nh * hd)
+        self.t(out).copy_(o.view(self.t(out).shape))
+
+    def _fce_detect_decode(self, d, p):
+        from oracle.fce_oracle import detect_decode
+
+        raws = [self.t(p[i]).permute(0, 3, 1, 2).float() for i in range(d.nl)]
+        y = detect_decode(raws, [d.stride[i] for i in range(d.nl)], d.reg_max)
+        yv = p[4]
+        b = yv.buf
+        self._flat(b).view(b.B, b.W, b.C).copy_(y)

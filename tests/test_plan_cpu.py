@@ -1,0 +1,91 @@
+"""Plan-compiler logic on CPU: the compiled node list, interpreted with torch ops (tests/plan_interp.py),
+must reproduce the oracle.  Covers fusions done at plan time (concat-by-offset, upsample folding, realign at
+low resolution, stacked q/k/v weights, qkv channel re-ordering) for every graph family of BASELINE.json."""
+import pytest
+import torch
+
+from cases import FORWARD_CASES, MODULE_CASES
+from helpers import golden, load_cfg, rel_max
+from plan_interp import Interp
+from test_oracle_golden import module_case_io
+
+from fce_yolo_b200.plan import compile_model, compile_module
+from fce_yolo_b200.tasks import DetectionModel
+from fce_yolo_b200.weights import load_synthetic, synth_images
+from oracle import fce_oracle as O
+
+
+@pytest.mark.parametrize("name", ["n_fce_64", "s_coordatt_64", "s_cca_bicca8_64", "m_bifpn_64", "x_fce_64",
+                                  "n_stock_64"])
+def test_model_plan_matches_oracle_and_golden(name):
+    case = FORWARD_CASES[name]
+    cfg, scale = load_cfg(case)
+    model = DetectionModel(cfg, scale=scale).fuse().eval()
+    sd = load_synthetic(model, case["seed"])
+    x = synth_images(case["img_seed"], case["batch"], case["size"], case["size"])
+    plan = compile_model(model, case["batch"], case["size"], case["size"], "fp32", torch.device("cpu"))
+    it = Interp(plan, reuse_memory=True)
+    it.input_tensor().copy_(x)
+    it.run()
+    y, raw = it.outputs()
+    (yo, rawo), ys = O.forward(cfg, scale, sd, x, keep_layers=True)
+    assert rel_max(y, yo) < 1e-4
+    for a, b in zip(raw, rawo):
+        assert rel_max(a, b) < 1e-4
+    g = golden("fwd_" + name)
+    assert rel_max(y, g["y"]) < 1e-4
+
+
+def test_memory_reuse_shrinks_arena():
+    case = FORWARD_CASES["n_fce_64"]
+    cfg, scale = load_cfg(case)
+    model = DetectionModel(cfg, scale=scale).fuse().eval()
+    from fce_yolo_b200.engine import assign_offsets
+
+    p1 = compile_model(model, 2, 64, 64, "bf16", torch.device("cpu"))
+    p2 = compile_model(model, 2, 64, 64, "bf16", torch.device("cpu"))
+    assert assign_offsets(p1, reuse=True) < 0.6 * assign_offsets(p2, reuse=False)
+
+
+def test_unfused_model_folds_bn_at_plan_time():
+    """A model that still carries BatchNorm (e.g. a freshly loaded checkpoint) compiles to the same plan as
+    its fused twin: BN is folded when weights are packed (reference torch_utils.py:237-267)."""
+    cfg, scale = load_cfg(FORWARD_CASES["n_fce_64"])
+    m = DetectionModel(cfg, scale=scale).eval()
+    g = torch.Generator().manual_seed(3)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+            mod.weight.data.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+            mod.bias.data.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+    x = synth_images(5, 1, 64, 64)
+    outs = []
+    for fused in (False, True):
+        if fused:
+            m.fuse()
+        it = Interp(compile_model(m, 1, 64, 64, "fp32", torch.device("cpu")))
+        it.input_tensor().copy_(x)
+        it.run()
+        outs.append(it.outputs()[0].clone())
+    assert rel_max(outs[0], outs[1]) < 1e-5
+
+
+@pytest.mark.parametrize("name", list(MODULE_CASES))
+def test_module_plan_matches_golden(name):
+    case = MODULE_CASES[name]
+    mod, sd, xs = module_case_io(case)
+    plan = compile_module(mod.eval(), [tuple(t.shape) for t in xs], "fp32", torch.device("cpu"))
+    it = Interp(plan, reuse_memory=False)
+    for i, t in enumerate(xs):
+        it.nchw(plan.inputs[i]).copy_(t)
+    it.run()
+    y = it.outputs()
+    assert rel_max(y, golden("mod_" + name)["y"]) < 1e-5
+
+
+def test_cca_bad_heads_fails_at_build():
+    from fce_yolo_b200 import modules as M
+
+    with pytest.raises(RuntimeError):
+        M.CoordCrossAtt(512, 512, 22, 2)  # mip = 23, heads = 2: the reference dies in forward (fce_block.py:166)
