@@ -8,6 +8,8 @@
 //
 // fce_strip_attn: softmax(q k^T * scale) v over strips; the whole per-(image, head) K/V fits in
 // shared memory (L <= 160, dh <= 32 on this path), fp32 CUDA-core math - far too small for tensor cores.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace fce {
@@ -205,9 +207,11 @@ extern "C" int fce_strip_attn(const fce_strip_attn_desc* d, const float* q, cons
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = sizeof(float) * ((size_t)2 * d->Lk * d->dh + (AT / 32) * (size_t)d->Lk + (AT / 32) * (size_t)d->dh);
     if (smem > 200 * 1024) return FCE_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(strip_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static std::atomic<bool> attr_done{false};
+    if (!attr_done.load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(strip_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_cuda_error(e); return FCE_ERR_CUDA; }
+        attr_done.store(true, std::memory_order_release);
     }
     int qblocks = (d->Lq + (AT / 32) - 1) / (AT / 32);
     // enough CTAs to cover the SMs, without re-loading K/V more often than needed

@@ -11,6 +11,8 @@
 // keep indices and class ids are bit-exact against the CPU reference, including the fp32 class offset
 // (cls * max_wh added to the coordinates, nms.py:143,149).
 // Integer/bandwidth work: no tensor cores.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace fce {
@@ -402,8 +404,12 @@ extern "C" int fce_nms(const fce_nms_desc* d, const float* pred, const int32_t* 
     if (ws_bytes < fce_nms_workspace(d)) return FCE_ERR_WORKSPACE;
     const size_t smem = kept_smem(d->max_det);
     if (smem > 96 * 1024) return FCE_ERR_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_cuda_error(e); return FCE_ERR_CUDA; }
+    static std::atomic<bool> attr_done{false};
+    if (!attr_done.load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) { set_cuda_error(e); return FCE_ERR_CUDA; }
+        attr_done.store(true, std::memory_order_release);
+    }
     // torchvision compares the fp32 IoU with a C double threshold: reproduce with an fp32 compare
     const float tf = (float)d->iou_thres;
     const int ge = ((double)tf > d->iou_thres) ? 1 : 0;

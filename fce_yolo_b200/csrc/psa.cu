@@ -2,6 +2,8 @@
 // (image, head), streams 64-key tiles through shared memory with an online softmax, and never
 // materialises the N x N score matrix.  key_dim = 32, head_dim = 64 always hold on this path
 // (heads = c/64, attn_ratio = 0.5).  fp32 CUDA-core math (this is also the fp32-mode kernel).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace fce {
@@ -128,9 +130,13 @@ extern "C" int fce_psa_attention(const fce_psa_desc* d, const void* qkv, void* o
     dim3 grid((d->N + BR - 1) / BR, d->heads, d->B);
     constexpr size_t smem = sizeof(float) * (KD * (BR + 4) + KD * (BC + 4) + BC * (HD + 4) + BR * (BC + 4));
     static_assert(smem <= 100 * 1024, "psa smem");
-    cudaError_t e1 = cudaFuncSetAttribute(psa_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e2 = cudaFuncSetAttribute(psa_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) { set_cuda_error(e1 != cudaSuccess ? e1 : e2); return FCE_ERR_CUDA; }
+    static std::atomic<bool> attr_done{false};  // set once per process (not during graph capture replays)
+    if (!attr_done.load(std::memory_order_acquire)) {
+        cudaError_t e1 = cudaFuncSetAttribute(psa_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e2 = cudaFuncSetAttribute(psa_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_cuda_error(e1 != cudaSuccess ? e1 : e2); return FCE_ERR_CUDA; }
+        attr_done.store(true, std::memory_order_release);
+    }
     if (d->dtype == FCE_BF16)
         psa_kernel<__nv_bfloat16><<<grid, NT, smem, st>>>(*d, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out);
     else if (d->dtype == FCE_F32)
