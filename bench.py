@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py - images/s of the FCE-YOLOv11 predict step (forward + DFL decode + NMS) on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload at every N (weak scaling, one replica per GPU): BASELINE.json configs[1] -
+yolo11s-fce.yaml with CoordAtt at layers 5 and 8, bf16, batch 64 per GPU, 640x640 synthetic images,
+synthetic (seeded) weights.  A step is one pass of the hot path over one batch.
+
+ value      : whole-job images/s with the batch resident in HBM (CUDA-event timing, max over ranks).
+ e2e        : same metric through the public Predictor API with HOST buffers: pinned uint8 NHWC images
+              copied H2D, detections copied D2H, every step, inside the timed region.
+ roofline   : dominant kernel class, from per-launch CUDA-event timing of one more eager pass.
+ cpu_baseline / --impl reference : the oracle port of the reference forward + NMS on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(yaml="yolo11s-fce.yaml", variant={5: ("CoordAtt", []), 8: ("CoordAtt", [])}, batch=64, size=640,
+                precision="bf16", conf=0.25, iou=0.7, max_det=300, seed=1)
+WORKLOAD_NAME = "yolo11s-fce (CoordAtt@L5,L8) predict: forward+DFL decode+NMS, bf16, batch 64/GPU, 640x640"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def build_model(w):
+    from fce_yolo_b200.tasks import DetectionModel, variant_cfg, yaml_model_load
+    from fce_yolo_b200.weights import load_synthetic
+
+    cfg = variant_cfg(yaml_model_load(w["yaml"]), w.get("variant"))
+    model = DetectionModel(cfg).fuse().eval()
+    sd = load_synthetic(model, w["seed"])
+    return cfg, model, sd
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(w, cfg, sd, n_images, steps, warmup, threads):
+    """The oracle port of the reference predict path on the host: forward (torch fp32 CPU) + NMS.
+    Returns (images/s, ms per step)."""
+    from fce_yolo_b200.weights import synth_images
+    from oracle import fce_oracle as O
+    from oracle import nms_oracle
+
+    torch.set_num_threads(threads)
+    x = synth_images(1234, n_images, w["size"], w["size"])
+    scale = cfg["scale"]
+
+    def step():
+        y, _ = O.forward(cfg, scale, sd, x)
+        nms_oracle.non_max_suppression(y.numpy(), w["conf"], w["iou"], max_det=w["max_det"])
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return n_images * steps / dt, dt / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=None, help="override batch per GPU (exploration only)")
+    ap.add_argument("--yaml", default=None)
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--kernel-times", default=None, help="write the per-node timing table to this file")
+    a = ap.parse_args()
+
+    w = dict(WORKLOAD)
+    name = WORKLOAD_NAME
+    if a.batch or a.yaml or a.size:
+        w.update({k: v for k, v in (("batch", a.batch), ("yaml", a.yaml), ("size", a.size)) if v})
+        if a.yaml:
+            w["variant"] = None
+        name = f"{w['yaml']} predict bf16 batch {w['batch']}/GPU {w['size']}x{w['size']} (exploration)"
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    warm = max(a.warmup, 3)
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cfg, model, sd = build_model(w)
+        cores = os.cpu_count() or 1
+        n = 4
+        ips, ms = cpu_reference_run(w, cfg, sd, n, a.steps, min(a.warmup, 2), cores)
+        line = {"impl": "reference", "metric": "images/sec", "value": round(ips, 3), "unit": "images/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 2), "ms_per_step": round(ms, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": name, "sample": f"{n} images per step"},
+                "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
+                                 "sample": f"oracle port of the reference forward+NMS (torch fp32 CPU, {cores} threads), "
+                                           f"{n} images/step x {a.steps} steps of the same workload"},
+                "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch.distributed as dist
+
+    from fce_yolo_b200 import _lib
+    from fce_yolo_b200.predict import Predictor
+    from fce_yolo_b200.runner import gather_detections
+    from fce_yolo_b200.weights import synth_images
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load(check_device=True)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, model, sd = build_model(w)
+    B, S = w["batch"], w["size"]
+    pred = Predictor(model, B, S, precision=w["precision"], device=dev, conf=w["conf"], iou=w["iou"],
+                     max_det=w["max_det"], input_u8=True, use_graph=not a.no_graph)
+    # synthetic uint8 NHWC batch (same seeded images, quantised), resident in HBM for `value`
+    img = (synth_images(1234 + rank, B, S, S) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    h_img = img.pin_memory()
+    pred.inp.copy_(h_img)
+    torch.cuda.synchronize()
+
+    def step_device():
+        det, keep, count = pred.run_device()
+        if world > 1:
+            gather_detections(det, count)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # e2e: host buffers, H2D + D2H inside the timed region, through the public API
+    for _ in range(warm):
+        pred.infer(h_img)
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(a.steps):
+        pred.infer(h_img)
+    e3.record()
+    barrier()
+    ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3 * 0.0)
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+
+    t = torch.tensor([ms_dev, ms_e2e, wall_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e, wall_e2e = t.tolist()
+    ms_e2e = max(ms_e2e, wall_e2e)  # host-visible completion is what a caller sees
+
+    # ------------------------------------------------------------------ per-kernel times (rank 0, eager, events)
+    roof = None
+    table = []
+    if rank == 0:
+        ex = pred.ex
+        stream = torch.cuda.current_stream()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(ex._calls) + 1)]
+        import ctypes as C
+
+        reps = 3
+        acc = [0.0] * len(ex._calls)
+        for r in range(reps + 1):
+            torch.cuda.synchronize()
+            evs[0].record()
+            for i, (fn, args, n) in enumerate(ex._calls):
+                fn(*args, C.c_void_p(stream.cuda_stream))
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            if r:  # first rep is warm-up
+                for i in range(len(ex._calls)):
+                    acc[i] += evs[i].elapsed_time(evs[i + 1]) / reps
+        classes = {}
+        for (fn, args, n), ms in zip(ex._calls, acc):
+            c = classes.setdefault(n.fn, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            c["ms"] += ms
+            c["flops"] += n.flops
+            c["bytes"] += n.bytes
+            c["launches"] += 1
+            table.append((n.tag, n.fn, ms, n.flops, n.bytes))
+        total = sum(c["ms"] for c in classes.values())
+        pk = peaks()
+        top = max(classes.items(), key=lambda kv: kv[1]["ms"])
+        fn, c = top
+        if c["flops"] > 0:
+            ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
+            roof = {"kernel": fn, "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sustained"],
+                    "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4), "traffic": None,
+                    "peak_source": pk["src"] + " (sustained bf16 GEMM)", "share_of_step": round(c["ms"] / total, 3),
+                    "launches_per_step": c["launches"], "avg_launch_ms": round(c["ms"] / c["launches"], 4)}
+        else:
+            ach = c["bytes"] / (c["ms"] * 1e-3) / 1e9
+            roof = {"kernel": fn, "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": round(ach / pk["hbm"], 4), "traffic": None, "peak_source": pk["src"],
+                    "share_of_step": round(c["ms"] / total, 3), "launches_per_step": c["launches"],
+                    "avg_launch_ms": round(c["ms"] / c["launches"], 4)}
+        roof["classes"] = {
+            k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total, 3), "launches": v["launches"],
+                **({"TFLOP/s": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] else {}),
+                **({"GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                    "hbm_frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"], 3)} if v["bytes"] else {})}
+            for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}
+        if a.kernel_times:
+            with open(a.kernel_times, "w") as f:
+                f.write("tag,fn,ms,gflop,mbytes\n")
+                for tag, fnn, ms, fl, by in table:
+                    f.write(f"{tag},{fnn},{ms:.4f},{fl / 1e9:.3f},{by / 1e6:.3f}\n")
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = 4
+        ips, ms = cpu_reference_run(w, cfg, sd, n, 3, 1, cores)
+        cpu = {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"oracle port (torch fp32 CPU forward + C/numpy NMS), {n} images/step x 3 steps, "
+                         f"{cores} threads, same model/size"}
+
+    if rank == 0:
+        n_img = B * world * a.steps
+        line = {
+            "metric": "images/sec", "value": round(n_img / (ms_dev * 1e-3), 2), "unit": "images/s", "n_gpus": world,
+            "steps": a.steps, "warmup": warm, "ms_per_step": round(ms_dev / a.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": name, "global_batch": B * world, "parallelism": f"dp{world} (replicas, image-sharded)",
+                       "l2": "inputs larger than L2 (75 MB uint8 batch + >1 GB of activations per step)",
+                       "cuda_graph": not a.no_graph, "arena_mb": round(pred.ex.nbytes / 2 ** 20, 1)},
+            "e2e": {"value": round(n_img / (ms_e2e * 1e-3), 2), "unit": "images/s",
+                    "h2d_bytes_per_step": pred.h2d_bytes(), "d2h_bytes_per_step": pred.d2h_bytes(),
+                    "ms_per_step": round(ms_e2e / a.steps, 4),
+                    "api": "Predictor.infer(pinned uint8 NHWC batch) -> pinned (det, count)"},
+            "gpu_launches": pred.launches_per_call * a.steps,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

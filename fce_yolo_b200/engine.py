@@ -117,6 +117,15 @@ class Arena:
         b = self.plan.inputs[i].buf
         return self._flat(b).view(b.B, b.H, b.W, b.C)  # for the NCHW image buffer this *is* [B, C, H, W]
 
+    def detections(self):
+        """(det [B,max_det,6] fp32, keep [B,max_det] int64, count [B] int32) views, if the plan ends in NMS."""
+        o = self.plan.outputs
+        B, md = self.plan.B, o["max_det"]
+        det = self._flat(o["det"].buf).view(torch.float32).view(B, md, 6)
+        keep = self._flat(o["keep"].buf).view(torch.int64).view(B, md)
+        count = self._flat(o["count"].buf).view(torch.int32).view(B)
+        return det, keep, count
+
     def outputs(self):
         o = self.plan.outputs
         yv = o["y"]

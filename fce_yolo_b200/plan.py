@@ -478,6 +478,29 @@ class Plan:
                       bytes=self.B * A * ((4 * R + nc) + (4 + nc)) * 4.0))
         return y, raws
 
+    def raw_buf(self, nbytes: int) -> View:
+        """Untyped persistent byte buffer (NMS outputs / workspace)."""
+        return self.new_buf(1, 1, int(nbytes), dtype=L.U8, B=1, persistent=True)
+
+    def nms(self, y: View, nc: int, conf=0.25, iou=0.45, max_det=300, max_nms=30000, multi_label=False,
+            agnostic=False, max_wh=7680.0, tag="nms"):
+        """Appends the batched NMS (reference nms.py:13-166) so predict = forward + decode + NMS is ONE plan."""
+        A = y.buf.C
+        B = y.buf.B
+        d = L.NmsDesc(B=B, A=A, nc=nc, conf_thres=float(conf), iou_thres=float(iou), max_det=int(max_det),
+                      max_nms=int(max_nms), multi_label=int(bool(multi_label and nc > 1)), agnostic=int(bool(agnostic)),
+                      max_wh=float(max_wh), n_classes=0)
+        cap = A * nc if d.multi_label else A
+        ws_bytes = B * cap * 16
+        det = self.raw_buf(B * max_det * 6 * 4)
+        keep = self.raw_buf(B * max_det * 8)
+        count = self.raw_buf(B * 4)
+        ws = self.raw_buf(ws_bytes)
+        self.add(Node("fce_nms", d, [y, None, det, keep, count, ws, ws_bytes], reads=[y],
+                      writes=[det, keep, count, ws], tag=tag, bytes=B * ((4.0 + nc) * A * 4 + max_det * 6 * 4)))
+        self.outputs.update({"det": det, "keep": keep, "count": count, "max_det": max_det})
+        return det, keep, count
+
     # ------------------------------------------------------------------ dispatch
     def emit(self, m, x, tag=""):
         """x: View | LazyUp | list of those.  Returns View | LazyUp | (y, raws) for Detect."""
@@ -509,7 +532,7 @@ class Plan:
 
 
 def compile_model(model, batch: int, height: int, width: int, precision: str, device, impl: int = 0,
-                  input_u8: bool = False) -> Plan:
+                  input_u8: bool = False, nms: dict | None = None) -> Plan:
     """Whole-graph plan of a DetectionModel (mirror or reference): restates the routing of
     BaseModel._predict_once (tasks.py:172-188) at compile time."""
     layers = list(model.model)
@@ -549,6 +572,10 @@ def compile_model(model, batch: int, height: int, width: int, precision: str, de
         p.outputs = {"y": p.materialize(last)}
     for v in ([p.outputs["y"]] + p.outputs.get("raw", [])):
         v.buf.persistent = True
+    if nms is not None:
+        if "raw" not in p.outputs:
+            raise PlanError("NMS needs a Detect head")
+        p.nms(p.outputs["y"], layers[-1].nc, **nms)
     return p
 
 

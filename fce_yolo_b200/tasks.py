@@ -48,6 +48,15 @@ def yaml_model_load(path) -> dict:
     raise FileNotFoundError(f"model config '{path}' not found (looked in {CFG_DIR} too)")
 
 
+def variant_cfg(d: dict, variant) -> dict:
+    """YAML variants as cfg dicts (the reference accepts a dict in DetectionModel, tasks.py:377): replace
+    backbone rows, e.g. {5: ("CoordAtt", []), 8: ("CoordAtt", [])} for BASELINE config 2."""
+    d = copy.deepcopy(d)
+    for row, spec in (variant or {}).items():
+        d["backbone"][int(row)] = [-1, 1, spec[0], list(spec[1])]
+    return d
+
+
 def _fce_defaults(inp: int, args: list, width: float, max_ch: float, with_heads: bool):
     """Argument resolution for CoordAtt / CoordCrossAtt / BiCoordCrossAtt rows (tasks.py:1636-1708):
     oup defaults to inp and is width-scaled only when given; reduction defaults to

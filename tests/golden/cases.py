@@ -1,19 +1,8 @@
 """Case tables shared by make_golden.py (reference side) and the tests (oracle / CUDA side)."""
-import copy
-
-import numpy as np
 import torch
 
+from fce_yolo_b200.tasks import variant_cfg  # noqa: F401  (re-exported for make_golden.py / tests)
 from fce_yolo_b200.weights import synth_predictions
-
-
-def variant_cfg(d: dict, variant):
-    """YAML variants of BASELINE configs 2 and 4: replace backbone rows 5 / 8."""
-    d = copy.deepcopy(d)
-    if variant:
-        for row, spec in variant.items():
-            d["backbone"][int(row)] = [-1, 1, spec[0], list(spec[1])]
-    return d
 
 
 FORWARD_CASES = {
