@@ -1,0 +1,107 @@
+"""tcgen05 implicit-GEMM convolution (fce_conv2d, impl=2) through the C ABI against a torch fp32 reference
+of the same op (F.conv2d on the bf16-rounded operands, fp32 math) - the floating-point kernel keeps a torch
+reference next to the oracle.  Tolerance: the output is rounded to bf16 once (2^-9 relative) on top of fp32
+accumulation-order noise, so max |err| <= 1e-2 * max|ref| and relL2 <= 4e-3 (bf16 out) / 1e-5 (fp32 out)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (B, H, W, Cin, Cout, k, stride, act, res, out_f32, in_pitch_extra, out_pitch_extra)
+CASES = [
+    (1, 16, 16, 64, 64, 1, 1, 1, False, False, 0, 0),
+    (2, 20, 20, 64, 128, 1, 1, 1, False, False, 0, 0),       # M = 800: ragged last tile
+    (2, 12, 12, 32, 64, 1, 1, 1, False, False, 0, 0),        # kc = 32 (64B swizzle)
+    (2, 12, 12, 16, 32, 1, 1, 0, False, False, 0, 0),        # kc = 16 (32B swizzle)
+    (2, 12, 12, 96, 80, 1, 1, 1, False, False, 32, 64),      # kc = 32 x3, Cout = 80, channel-slice views
+    (1, 40, 40, 256, 512, 1, 1, 1, False, False, 0, 0),      # two N tiles
+    (1, 40, 40, 128, 64, 1, 1, 0, False, True, 0, 80),       # fp32 output into a wider buffer (Detect)
+    (2, 16, 16, 128, 128, 1, 1, 1, True, False, 0, 128),     # residual
+    (1, 16, 16, 64, 64, 3, 1, 1, False, False, 0, 0),
+    (2, 20, 20, 64, 64, 3, 1, 1, True, False, 64, 0),        # tiles cross rows and images, residual
+    (2, 24, 24, 32, 16, 3, 1, 1, False, False, 0, 0),        # small channels
+    (2, 24, 24, 16, 32, 3, 1, 1, True, False, 16, 32),
+    (2, 32, 32, 64, 128, 3, 2, 1, False, False, 0, 0),       # stride 2
+    (3, 40, 24, 128, 256, 3, 2, 1, False, False, 0, 0),      # stride 2, H != W
+    (1, 80, 80, 128, 128, 3, 1, 1, False, False, 0, 0),
+    (4, 20, 20, 512, 512, 3, 1, 1, False, False, 0, 0),      # long K, two N tiles
+    (1, 8, 8, 192, 384, 1, 1, 2, False, False, 0, 0),        # sigmoid, bn = 192
+]
+
+
+def run_case(lib, L, case, impl):
+    B, H, W, Cin, Cout, k, s, act, has_res, out_f32, ipx, opx = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(hash(case) & 0xFFFF)
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    in_pitch, in_off = Cin + ipx, ipx // 2
+    out_pitch, out_off = Cout + opx, opx // 2
+    xb = torch.randn(B, H, W, in_pitch, generator=g).to(dev, torch.bfloat16)
+    w = (torch.randn(Cout, k, k, Cin, generator=g) / (k * k * Cin) ** 0.5).to(dev, torch.bfloat16)  # OHWI
+    bias = torch.randn(Cout, generator=g).to(dev)
+    odt = torch.float32 if out_f32 else torch.bfloat16
+    yb = torch.full((B, Ho, Wo, out_pitch), 7.0, dtype=odt, device=dev)
+    rb = torch.randn(B, Ho, Wo, out_pitch, generator=g).to(dev, torch.bfloat16) if has_res else None
+    d = L.ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=Cout, in_pitch=in_pitch, in_off=in_off, out_pitch=out_pitch,
+                   out_off=out_off, res_pitch=out_pitch if has_res else 0, res_off=out_off if has_res else 0, k=k,
+                   stride=s, act=act, in_dtype=L.BF16, w_dtype=L.BF16, out_dtype=L.F32 if out_f32 else L.BF16,
+                   in_layout=L.NHWC, in_scale=1.0, impl=impl)
+    st = lib.fce_conv2d(C.byref(d), C.c_void_p(xb.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(bias.data_ptr()),
+                        C.c_void_p(rb.data_ptr() if has_res else 0), C.c_void_p(yb.data_ptr()),
+                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    L.check(st, f"fce_conv2d {case}")
+    torch.cuda.synchronize()
+    x = xb[..., in_off:in_off + Cin].float().permute(0, 3, 1, 2)
+    ref = F.conv2d(x, w.float().permute(0, 3, 1, 2), bias, stride=s, padding=pad)
+    if act == 1:
+        ref = F.silu(ref)
+    elif act == 2:
+        ref = torch.sigmoid(ref)
+    if has_res:
+        ref = ref + rb[..., out_off:out_off + Cout].float().permute(0, 3, 1, 2)
+    out = yb[..., out_off:out_off + Cout].float().permute(0, 3, 1, 2)
+    err_max = ((out - ref).abs().max() / ref.abs().max()).item()
+    err_l2 = ((out - ref).norm() / ref.norm()).item()
+    # channels outside the destination view must be untouched
+    untouched = True
+    if opx:
+        untouched = bool((yb[..., :out_off] == 7.0).all() and (yb[..., out_off + Cout:] == 7.0).all())
+    return err_max, err_l2, untouched
+
+
+@pytest.fixture(scope="module")
+def lib():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from fce_yolo_b200 import _lib as L
+    return L.load(check_device=True), L
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
+def test_conv_tc_vs_torch(lib, case):
+    l, L = lib
+    err_max, err_l2, untouched = run_case(l, L, case, impl=2)
+    print(case, f"max {err_max:.2e} l2 {err_l2:.2e}")
+    assert untouched
+    assert err_max < 1e-2, case
+    assert err_l2 < (2e-5 if case[9] else 4e-3), case
+
+
+if __name__ == "__main__":  # quick report: python tests/test_gpu_conv_tc.py
+    import sys
+    sys.path.insert(0, ".")
+    from fce_yolo_b200 import _lib as L
+    torch.backends.cudnn.allow_tf32 = False
+    l = L.load(check_device=True)
+    for i, case in enumerate(CASES):
+        try:
+            em, el, ut = run_case(l, L, case, impl=2)
+            es, esl, _ = run_case(l, L, case, impl=1)
+            print(f"c{i} {case}: tc max {em:.3e} l2 {el:.3e} untouched {ut} | simt max {es:.3e} l2 {esl:.3e}", flush=True)
+        except Exception as e:  # noqa
+            print(f"c{i} {case}: EXC {e}", flush=True)
+            break
