@@ -86,6 +86,8 @@ _SIGS = {
     "fce_last_cuda_error": (C.c_char_p, []),
     "fce_device_ok": (C.c_int, []),
     "fce_conv2d": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "fce_conv_tc_set_profile": (None, [C.c_int]),
+    "fce_conv_tc_profile": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "fce_dwconv3x3": (C.c_int, [C.POINTER(DwconvDesc), _P, _P, _P, _P, _P, _P]),
     "fce_sppf_pool": (C.c_int, [C.POINTER(SppfDesc), _P, _P]),
     "fce_upsample2x": (C.c_int, [C.POINTER(UpsampleDesc), _P, _P, _P]),

@@ -9,6 +9,8 @@ void set_cuda_error(cudaError_t e) { g_last_err = e; }
 int conv2d_simt(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
 int conv2d_tc(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
 bool conv2d_tc_supported(const fce_conv_desc*, const void*, const void*, const void*, const void*);
+void conv_tc_set_profile(int on);
+int conv_tc_profile(long long* out, int n);
 
 }  // namespace fce
 
@@ -38,3 +40,6 @@ extern "C" int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, 
     if (d->impl == 0 && tc_ok) return conv2d_tc(d, x, w, bias, res, y, st);
     return conv2d_simt(d, x, w, bias, res, y, st);
 }
+
+extern "C" void fce_conv_tc_set_profile(int on) { conv_tc_set_profile(on); }
+extern "C" int fce_conv_tc_profile(long long* out, int n) { return out ? conv_tc_profile(out, n) : FCE_ERR_BAD_ARG; }

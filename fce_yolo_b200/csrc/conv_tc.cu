@@ -26,21 +26,29 @@
 namespace fce {
 namespace {
 
-constexpr int BM = 128;           // UMMA M (cta_group::1)
-constexpr int NUM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, interleaved over 16-column chunks
-constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+constexpr int BM = 128;  // UMMA M (cta_group::1)
+// warp roles
+constexpr int WARP_PROD_A = 0, WARP_PROD_B = 1, WARP_MMA = 2, WARP_ALLOC = 3, WARP_EPI0 = 4;
+constexpr int NUM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, interleaved over 32-column groups
+constexpr int NUM_THREADS = (WARP_EPI0 + NUM_EPI_WARPS) * 32;
 constexpr int MAX_STAGES = 8;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 188 * 1024;  // A/B tiles + bias; staging slabs and barriers come on top
+constexpr int B_RESIDENT_MAX = 96 * 1024;
+constexpr int STG_BYTES = 32 * 64;  // one epilogue staging slab: 32 rows x 64 bytes (64B swizzle)
 
 struct TcParams {
     int M, Cout, Cin;
     int taps, ksz, stride, pad;
     int Ho, Wo;
-    int kc, chunks;  // channels per K step, K steps per tap
+    int kc, chunks;   // channels per K step, K steps per tap
+    int S, groups;    // K steps per pipeline stage, stages per tile (= taps*chunks / S)
     int bn, n_tiles, m_tiles;
     int stages;
-    uint32_t a_bytes, b_bytes;    // TMA bytes per stage
-    uint32_t a_stride, b_stride;  // stage strides in shared memory (1024-aligned)
+    int b_resident;   // whole [Cout, K] weight matrix parked in shared memory for the life of the CTA
+    uint32_t a_sub, b_sub;      // bytes of one K-step sub-tile: 128 x kc and bn x kc bf16
+    uint32_t a_stage, b_stage;  // S sub-tiles
+    uint32_t b_total;           // shared-memory bytes of the B region
+    uint32_t bias_bytes;
     uint32_t tmem_cols;
     int out_pitch, res_pitch, act, out_f32;
     uint32_t desc_hi;  // upper 32 bits of the UMMA shared-memory descriptor (SBO, version, swizzle)
@@ -71,12 +79,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must fault the launch (reported through the C ABI), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
@@ -124,6 +134,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// One MUFU per element: silu(v) = h + h*tanh(h), sigmoid(v) = 0.5 + 0.5*tanh(h), h = v/2.  tanh.approx has
+// 2^-11 relative error - below the bf16 rounding applied to the result.
+__device__ __forceinline__ float act_fast(float v, int act) {
+    if (act == FCE_ACT_SILU) {
+        const float h = 0.5f * v;
+        return fmaf(h, tanh_fast(h), h);
+    }
+    if (act == FCE_ACT_SIGMOID) return fmaf(0.5f, tanh_fast(0.5f * v), 0.5f);
+    return v;
+}
+
 struct Ring {
     int stage = 0;
     uint32_t phase = 0;
@@ -135,176 +161,360 @@ struct Ring {
     }
 };
 
-__device__ __forceinline__ float act_fast(float v, int act) {
-    if (act == FCE_ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
-    if (act == FCE_ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-v));
-    return v;
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
 }
 
+// bias + activation (+ residual) of 16 consecutive output channels of one pixel
+__device__ __forceinline__ void epi_math16(const uint32_t* v, const float* sbias, int act, bool has_res, uint4 r0,
+                                           uint4 r1, float* f) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 b = reinterpret_cast<const float4*>(sbias)[q];
+        f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
+        f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
+        f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
+        f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
+    }
+    if (act != FCE_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = act_fast(f[i], act);
+    }
+    if (has_res) {
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            f[2 * i] += __uint_as_float(rr[i] << 16);
+            f[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
+        }
+    }
+}
+__device__ __forceinline__ void pack16(const float* f, uint32_t* o) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        o[i] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+}
+
+// Optional per-role cycle accounting (debug entry points fce_conv_tc_set_profile / fce_conv_tc_profile):
+// [cta][0..1] A producer wait/total, [4..6] MMA wait-full / wait-tmem-empty / total,
+// [7..8] epilogue warp 0 wait-tmem-full / total.
+constexpr int PROF_SLOTS = 16;
+__device__ long long g_prof[kNumSMs * PROF_SLOTS];
+
+#define PROF_T0() long long _t0 = 0; if (PROF) _t0 = clock64()
+#define PROF_ACC(var) if (PROF) (var) += clock64() - _t0
+
 // ------------------------------------------------------------------------------------------------ kernel
+// The single-thread roles (TMA producers, MMA issuer) run their loops WARP-UNIFORMLY - every lane executes the
+// loop control and the barrier waits, and only the TMA / tcgen05 instruction itself is predicated on one
+// elected lane.  This keeps addresses, phases and descriptors in the uniform datapath (the async-proxy
+// instructions take uniform registers) instead of a per-thread dependent chain with R2UR moves.
+template <bool PROF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
-               const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res, void* __restrict__ y) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const TcParams p, const float* __restrict__ bias,
+               const __nv_bfloat16* __restrict__ res) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = base;
-    const uint32_t sB = sA + p.stages * p.a_stride;
-    const uint32_t bars = sB + p.stages * p.b_stride;
+    const uint32_t sB = sA + p.stages * p.a_stage;
+    const uint32_t sC = sB + p.b_total;  // epilogue staging: NUM_EPI_WARPS x 2 x (32 rows x 64 bytes)
+    const uint32_t sBias = sC + NUM_EPI_WARPS * 2 * STG_BYTES;
+    const uint32_t bars = sBias + p.bias_bytes;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES;
     const uint32_t tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
-    const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t bfull = tempty0 + 16;
+    const uint32_t tmem_slot = bfull + 8;
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
-    const int k_iters = p.taps * p.chunks;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == WARP_PROD_A && lane == 0) {
         for (int i = 0; i < p.stages; ++i) {
-            mbar_init(full0 + 8 * i, 1);
+            mbar_init(full0 + 8 * i, p.b_resident ? 1 : 2);
             mbar_init(empty0 + 8 * i, 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
             mbar_init(tempty0 + 8 * a, NUM_EPI_WARPS);
         }
+        mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
     }
-    if (warp == 1) {
+    if (warp == WARP_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < (int)(p.bias_bytes >> 2); i += NUM_THREADS) bias_s[i] = i < p.Cout ? bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            Ring r;
-            const int hw = p.Ho * p.Wo;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.bn;
-                int img = 0, w0 = 0, h0 = 0;
-                if (p.taps > 1) {
-                    img = m0 / hw;
-                    const int rem = m0 - img * hw;
-                    const int ph = rem / p.Wo;
-                    h0 = ph * p.stride - p.pad;
-                    w0 = (rem - ph * p.Wo) * p.stride - p.pad;
+    if (warp == WARP_PROD_A) {
+        // ------------------------------------------------------------------ A producer (activations)
+        Ring r;
+        const int hw = p.Ho * p.Wo, S = p.S, groups = p.groups, kc = p.kc, chunks = p.chunks, ksz = p.ksz;
+        const bool is_1x1 = p.taps == 1;
+        const uint32_t a_sub = p.a_sub, a_stage = p.a_stage, tx = S * p.a_sub;
+        const int n_tiles = p.n_tiles, nstages = p.stages;
+        long long pw = 0, pt0 = PROF ? clock64() : 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m0 = (n_tiles == 1 ? tile : tile / n_tiles) * BM;
+            int img = 0, w0 = 0, h0 = 0;
+            if (!is_1x1) {
+                img = m0 / hw;
+                const int rem = m0 - img * hw;
+                const int ph = rem / p.Wo;
+                h0 = ph * p.stride - p.pad;
+                w0 = (rem - ph * p.Wo) * p.stride - p.pad;
+            }
+            int ch = 0, kw = 0, kh = 0;
+#pragma unroll 1
+            for (int g = 0; g < groups; ++g) {
+                const uint32_t fb = full0 + 8 * r.stage;
+                {
+                    PROF_T0();
+                    mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
+                    PROF_ACC(pw);
                 }
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    const int kh = tap / p.ksz, kw = tap - kh * p.ksz;
-                    for (int ch = 0; ch < p.chunks; ++ch) {
-                        const uint32_t fb = full0 + 8 * r.stage;
-                        mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
-                        mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
-                        if (p.taps == 1)
-                            tma_load_2d(sA + r.stage * p.a_stride, &tmA, fb, ch * p.kc, m0);
+                if (elect_one()) mbar_expect_tx(fb, tx);
+                uint32_t dst = sA + r.stage * a_stage;
+#pragma unroll 1
+                for (int s = 0; s < S; ++s) {
+                    if (elect_one()) {
+                        if (is_1x1)
+                            tma_load_2d(dst, &tmA, fb, ch * kc, m0);
                         else
-                            tma_load_im2col(sA + r.stage * p.a_stride, &tmA, fb, ch * p.kc, w0, h0, img, (uint16_t)kw,
-                                            (uint16_t)kh);
-                        tma_load_2d(sB + r.stage * p.b_stride, &tmB, fb, tap * p.Cin + ch * p.kc, n0);
-                        r.advance(p.stages);
+                            tma_load_im2col(dst, &tmA, fb, ch * kc, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                    }
+                    dst += a_sub;
+                    if (++ch == chunks) {
+                        ch = 0;
+                        if (++kw == ksz) {
+                            kw = 0;
+                            ++kh;
+                        }
                     }
                 }
+                r.advance(nstages);
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (PROF && lane == 0) {
+            g_prof[blockIdx.x * PROF_SLOTS + 0] = pw;
+            g_prof[blockIdx.x * PROF_SLOTS + 1] = clock64() - pt0;
+        }
+    } else if (warp == WARP_PROD_B) {
+        // ------------------------------------------------------------------ B producer (weights)
+        const int k_steps = p.groups * p.S, kc = p.kc;
+        const uint32_t b_sub = p.b_sub;
+        if (p.b_resident) {
+            // weight-stationary: one load of the whole [Cout, K] matrix for all tiles of this CTA
+            if (elect_one()) {
+                mbar_expect_tx(bfull, (uint32_t)k_steps * b_sub);
+                for (int it = 0; it < k_steps; ++it) tma_load_2d(sB + it * b_sub, &tmB, bfull, it * kc, 0);
+            }
+        } else {
             Ring r;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            const uint64_t hi = (uint64_t)p.desc_hi << 32;
-            const int kk = p.kc >> 4;  // UMMA K = 16 bf16 = 32 bytes
+            const int S = p.S, groups = p.groups, n_tiles = p.n_tiles, nstages = p.stages, bn = p.bn;
+            const uint32_t b_stage = p.b_stage, tx = S * b_sub;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * p.bn;
-                for (int it = 0; it < k_iters; ++it) {
-                    mbar_wait(full0 + 8 * r.stage, r.phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = sA + r.stage * p.a_stride, b_addr = sB + r.stage * p.b_stride;
-                    for (int k = 0; k < kk; ++k) {
-                        const uint64_t ad = hi | (uint64_t)(((a_addr + 32 * k) >> 4) & 0x3FFF) | (1ull << 16);
-                        const uint64_t bd = hi | (uint64_t)(((b_addr + 32 * k) >> 4) & 0x3FFF) | (1ull << 16);
-                        umma_bf16(d_tmem, ad, bd, p.idesc, (it | k) != 0);
+                const int n0 = (n_tiles == 1 ? 0 : tile % n_tiles) * bn;
+                int kcol = 0;
+#pragma unroll 1
+                for (int g = 0; g < groups; ++g) {
+                    const uint32_t fb = full0 + 8 * r.stage;
+                    mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
+                    if (elect_one()) mbar_expect_tx(fb, tx);
+                    uint32_t dst = sB + r.stage * b_stage;
+#pragma unroll 1
+                    for (int s = 0; s < S; ++s) {
+                        if (elect_one()) tma_load_2d(dst, &tmB, fb, kcol, n0);
+                        dst += b_sub;
+                        kcol += kc;
                     }
-                    umma_commit(empty0 + 8 * r.stage);  // frees the smem slot when these MMAs retire
-                    r.advance(p.stages);
+                    r.advance(nstages);
                 }
-                umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
             }
         }
-        __syncwarp();
-    } else {
-        // ------------------------------------------------------------------ epilogue
-        const int quarter = warp & 3;         // TMEM lanes [32*quarter, +32) are the only ones this warp may read
-        const int half = (warp - 2) >> 2;     // which interleaved set of 16-column chunks
-        const int row = quarter * 32 + lane;  // accumulator row = output pixel within the tile
-        const int n_chunks = p.bn >> 4;
+    } else if (warp == WARP_MMA) {
+        // ------------------------------------------------------------------ MMA issuer
+        Ring r;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * p.bn;
-            const int m = m0 + row;
-            const bool m_ok = m < p.M;
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
+        const uint32_t dhi = p.desc_hi;
+        const int kk = p.kc >> 4;  // UMMA K = 16 bf16 = 32 bytes
+        const int S = p.S, groups = p.groups, nstages = p.stages, bn = p.bn;
+        const bool resident = p.b_resident != 0;
+        const uint32_t a_sub = p.a_sub, b_sub = p.b_sub, a_stage = p.a_stage, b_stage = p.b_stage, idesc = p.idesc;
+        long long wf = 0, we = 0, mt0 = PROF ? clock64() : 0;
+        if (resident) {
+            mbar_wait(bfull, 0);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * p.bn;
-            for (int j = half; j < n_chunks; j += 2) {
-                const int n = n0 + j * 16;
-                if (n >= p.Cout) break;
-                uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
-                if (res != nullptr && m_ok) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)m * p.res_pitch + n);
+        }
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            {
+                PROF_T0();
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                PROF_ACC(we);
+            }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * bn;
+            uint32_t accum = 0;
+#pragma unroll 1
+            for (int g = 0; g < groups; ++g) {
+                {
+                    PROF_T0();
+                    mbar_wait(full0 + 8 * r.stage, r.phase);
+                    PROF_ACC(wf);
+                }
+                tc_fence_after();
+                // descriptor low words: (addr >> 4) | LBO(=1) << 16 ; a K step of 16 bf16 advances the address by 32 B
+                uint32_t a_lo = (((sA + r.stage * a_stage) >> 4) & 0x3FFF) | (1u << 16);
+                uint32_t b_lo = (((resident ? sB + g * b_stage : sB + r.stage * b_stage) >> 4) & 0x3FFF) | (1u << 16);
+                if (elect_one()) {
+#pragma unroll 1
+                    for (int s = 0; s < S; ++s) {
+                        if (kk == 4) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_bf16(d_tmem, make_desc(dhi, a_lo + 2 * k), make_desc(dhi, b_lo + 2 * k), idesc, accum);
+                                accum = 1;
+                            }
+                        } else {
+                            for (int k = 0; k < kk; ++k) {
+                                umma_bf16(d_tmem, make_desc(dhi, a_lo + 2 * k), make_desc(dhi, b_lo + 2 * k), idesc, accum);
+                                accum = 1;
+                            }
+                        }
+                        a_lo += a_sub >> 4;
+                        b_lo += b_sub >> 4;
+                    }
+                    umma_commit(empty0 + 8 * r.stage);  // frees the smem slot when these MMAs retire
+                }
+                accum = 1;
+                __syncwarp();
+                r.advance(nstages);
+            }
+            if (elect_one()) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
+            __syncwarp();
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (PROF && lane == 0) {
+            g_prof[blockIdx.x * PROF_SLOTS + 4] = wf;
+            g_prof[blockIdx.x * PROF_SLOTS + 5] = we;
+            g_prof[blockIdx.x * PROF_SLOTS + 6] = clock64() - mt0;
+        }
+    } else if (warp >= WARP_EPI0) {
+        // ------------------------------------------------------------------ epilogue
+        // TMEM -> registers -> bias/activation/residual -> swizzled staging slab in smem -> TMA store.
+        // Each warp owns 32 accumulator rows and two private 32-row x 64-byte slabs, so the only
+        // synchronisation is __syncwarp + the bulk-group wait that recycles a slab.
+        const int e = warp - WARP_EPI0;
+        const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may read
+        const int half = e >> 2;       // which interleaved set of slabs
+        const int n_tiles = p.n_tiles, bn = p.bn, Cout = p.Cout, act = p.act;
+        const bool has_res = res != nullptr, out_f32 = p.out_f32 != 0;
+        const int slab_cols = out_f32 ? 16 : 32;  // 64 bytes of output per row
+        const int n_slabs = (bn + slab_cols - 1) / slab_cols;
+        const uint32_t stg0 = sC + e * 2 * STG_BYTES;
+        const uint32_t swz = (uint32_t)((lane >> 1) & 3);  // 64B swizzle: 16-byte unit u of row r lives at u ^ ((r>>1)&3)
+        const uint32_t my_row = stg0 + lane * 64;
+        int buf = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        long long ew = 0, et0 = PROF ? clock64() : 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = n_tiles == 1 ? tile : tile / n_tiles;
+            const int n0 = n_tiles == 1 ? 0 : (tile - mt * n_tiles) * bn;
+            const int m_warp = mt * BM + quarter * 32;
+            const int m = m_warp + lane;
+            const bool m_ok = m < p.M;
+            const __nv_bfloat16* rrow = res + (size_t)m * p.res_pitch;
+            {
+                PROF_T0();
+                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                PROF_ACC(ew);
+            }
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * bn;
+#pragma unroll 1
+            for (int sl = half; sl < n_slabs; sl += 2) {
+                const int c0 = sl * slab_cols;  // first column of the slab within the tile
+                const int n = n0 + c0;
+                if (n >= Cout) break;
+                const bool two = !out_f32 && (c0 + 16 < bn);
+                uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
+                if (has_res && m_ok) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(rrow + n);
                     r0 = __ldg(rp);
                     r1 = __ldg(rp + 1);
+                    if (two && n + 16 < Cout) {
+                        r2 = __ldg(rp + 2);
+                        r3 = __ldg(rp + 3);
+                    }
                 }
-                uint32_t v[16];
-                tmem_ld16(t_row + j * 16, v);
-                const float4* bp = reinterpret_cast<const float4*>(bias + n);
-                float4 b4[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) b4[q] = __ldg(bp + q);
+                uint32_t v0[16], v1[16];
+                tmem_ld16(t_row + c0, v0);
+                if (two) tmem_ld16(t_row + c0 + 16, v1);
+                // the bulk store that read this slab two slabs ago must have drained it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
                 tmem_ld_wait();
-                float f[16];
-                const float* bf = reinterpret_cast<const float*>(b4);
+                const uint32_t rowp = my_row + buf * STG_BYTES;
+                if (out_f32) {
+                    float f[16];
+                    epi_math16(v0, bias_s + n, act, false, r0, r1, f);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = act_fast(__uint_as_float(v[i]) + bf[i], p.act);
-                if (res != nullptr) {
-                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        f[2 * i] += __uint_as_float(rr[i] << 16);
-                        f[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
+                    for (int q = 0; q < 4; ++q)
+                        st_shared_v4(rowp + ((q ^ swz) << 4), __float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
+                                     __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
+                } else {
+                    float f[16];
+                    uint32_t o[8];
+                    epi_math16(v0, bias_s + n, act, has_res, r0, r1, f);
+                    pack16(f, o);
+                    st_shared_v4(rowp + ((0 ^ swz) << 4), o[0], o[1], o[2], o[3]);
+                    st_shared_v4(rowp + ((1 ^ swz) << 4), o[4], o[5], o[6], o[7]);
+                    if (two) {
+                        epi_math16(v1, bias_s + n + 16, act, has_res, r2, r3, f);
+                        pack16(f, o);
+                        st_shared_v4(rowp + ((2 ^ swz) << 4), o[0], o[1], o[2], o[3]);
+                        st_shared_v4(rowp + ((3 ^ swz) << 4), o[4], o[5], o[6], o[7]);
                     }
                 }
-                if (m_ok) {
-                    if (p.out_f32) {
-                        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (size_t)m * p.out_pitch + n);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                    } else {
-                        uint32_t o[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                            o[i] = *reinterpret_cast<uint32_t*>(&h2);
-                        }
-                        uint4* op =
-                            reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + (size_t)m * p.out_pitch + n);
-                        op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                        op[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                    }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmC, stg0 + buf * STG_BYTES, n, m_warp);  // rows >= M / cols >= Cout are clipped
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+                buf ^= 1;
             }
             tc_fence_before();
             __syncwarp();
@@ -312,12 +522,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+        if (PROF && warp == WARP_EPI0 && lane == 0) {
+            g_prof[blockIdx.x * PROF_SLOTS + 7] = ew;
+            g_prof[blockIdx.x * PROF_SLOTS + 8] = clock64() - et0;
+        }
     }
 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 1) {
+    if (warp == WARP_ALLOC) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
@@ -352,6 +567,8 @@ const DriverApi& driver() {
     static DriverApi api;
     return api;
 }
+
+bool g_profile_on = false;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -394,19 +611,35 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     p.chunks = d->Cin / p.kc;
     p.m_tiles = ceil_div(M, BM);
     p.n_tiles = ceil_div(d->Cout, 256);
-    p.bn = ceil_div(ceil_div(d->Cout, p.n_tiles), 16) * 16;
+    // N tiles that do not end the channel range must end on a 32-column staging-slab boundary
+    p.bn = p.n_tiles == 1 ? d->Cout : ceil_div(ceil_div(d->Cout, p.n_tiles), 32) * 32;
     // small problems: narrower N tiles give the persistent grid more tiles to balance over 148 SMs
-    while ((long long)p.m_tiles * p.n_tiles < 2 * kNumSMs && p.bn >= 128 && (p.bn / 2) % 16 == 0) {
+    while ((long long)p.m_tiles * p.n_tiles < 2 * kNumSMs && p.bn >= 128 && (p.bn / 2) % 32 == 0) {
         p.bn /= 2;
         p.n_tiles = ceil_div(d->Cout, p.bn);
     }
-    p.a_bytes = BM * p.kc * 2;
-    p.b_bytes = p.bn * p.kc * 2;
-    p.a_stride = (p.a_bytes + 1023u) & ~1023u;
-    p.b_stride = (p.b_bytes + 1023u) & ~1023u;
-    p.stages = SMEM_BUDGET / (int)(p.a_stride + p.b_stride);
+    const int k_steps = p.taps * p.chunks;
+    // narrow K chunks: put three K steps behind one barrier round trip (one kernel row of a 3x3 / a 96-wide 1x1)
+    p.S = (p.kc < 64 && k_steps % 3 == 0) ? 3 : 1;
+    p.groups = k_steps / p.S;
+    p.a_sub = BM * p.kc * 2;
+    p.b_sub = p.bn * p.kc * 2;
+    p.a_stage = p.S * p.a_sub;
+    p.b_stage = p.S * p.b_sub;
+    const uint32_t w_bytes = (uint32_t)k_steps * p.b_sub;
+    p.b_resident = (p.n_tiles == 1 && w_bytes <= (uint32_t)B_RESIDENT_MAX) ? 1 : 0;
+    p.bias_bytes = (uint32_t)(p.n_tiles * p.bn * 4 + 1023) & ~1023u;
+    int room = SMEM_BUDGET - (int)p.bias_bytes;
+    if (p.b_resident) {
+        p.b_total = (w_bytes + 1023u) & ~1023u;
+        p.stages = (room - (int)p.b_total) / (int)p.a_stage;
+    } else {
+        p.stages = room / (int)(p.a_stage + p.b_stage);
+        p.b_total = 0;  // set below once the stage count is known
+    }
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     if (p.stages < 2) return FCE_ERR_UNSUPPORTED;
+    if (!p.b_resident) p.b_total = p.stages * p.b_stage;
     p.tmem_cols = 32;
     while (p.tmem_cols < 2u * p.bn) p.tmem_cols <<= 1;
     p.out_pitch = d->out_pitch;
@@ -462,10 +695,26 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
         if (cr != CUDA_SUCCESS) return FCE_ERR_UNSUPPORTED;
     }
 
-    const size_t smem = (size_t)p.stages * (p.a_stride + p.b_stride) + 1024 + 256;
+    alignas(64) CUtensorMap tmC;
+    {
+        const bool f32 = d->out_dtype == FCE_F32;
+        const cuuint64_t gdim[2] = {(cuuint64_t)d->Cout, (cuuint64_t)M};
+        const cuuint64_t gstr[1] = {(cuuint64_t)d->out_pitch * (f32 ? 4 : 2)};
+        const cuuint32_t box[2] = {(cuuint32_t)(f32 ? 16 : 32), 32};
+        const cuuint32_t est[2] = {1, 1};
+        void* yp = f32 ? (void*)(reinterpret_cast<float*>(y) + d->out_off)
+                       : (void*)(reinterpret_cast<__nv_bfloat16*>(y) + d->out_off);
+        cr = api.tiled(&tmC, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, yp, gdim, gstr,
+                       box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return FCE_ERR_UNSUPPORTED;
+    }
+    const size_t smem = (size_t)p.stages * p.a_stage + p.b_total + NUM_EPI_WARPS * 2 * STG_BYTES + p.bias_bytes + 1024 + 256;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_cuda_error(e);
             return FCE_ERR_CUDA;
@@ -475,10 +724,23 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < kNumSMs ? total : kNumSMs;
     const __nv_bfloat16* rp = res ? reinterpret_cast<const __nv_bfloat16*>(res) + d->res_off : nullptr;
-    void* yp = d->out_dtype == FCE_F32 ? (void*)(reinterpret_cast<float*>(y) + d->out_off)
-                                       : (void*)(reinterpret_cast<__nv_bfloat16*>(y) + d->out_off);
-    conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p, bias, rp, yp);
+    if (g_profile_on)
+        conv_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, p, bias, rp);
+    else
+        conv_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, p, bias, rp);
     return check_launch();
+}
+
+void conv_tc_set_profile(int on) { g_profile_on = on != 0; }
+
+int conv_tc_profile(long long* out, int n) {
+    if (n > kNumSMs * PROF_SLOTS) n = kNumSMs * PROF_SLOTS;
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, (size_t)n * sizeof(long long));
+    if (e != cudaSuccess) {
+        set_cuda_error(e);
+        return FCE_ERR_CUDA;
+    }
+    return n;
 }
 
 }  // namespace fce

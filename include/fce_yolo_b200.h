@@ -76,6 +76,12 @@ typedef struct {
 int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res,
                void* y, void* stream);
 
+/* Debug aid for the tcgen05 convolution: when switched on, the next fce_conv2d launches record per-CTA, per-role
+ * cycle counts (16 int64 slots per CTA: A-producer wait/total, -, -, MMA wait-full/wait-tmem/total, epilogue
+ * wait/total); fce_conv_tc_profile copies n slots of the last launch to a HOST buffer and returns n. */
+void fce_conv_tc_set_profile(int on);
+int fce_conv_tc_profile(long long* out, int n);
+
 /* Depthwise 3x3 stride 1 (+bias, +SiLU, + optional add of a second map).  Replaces DWConv
  * (conv.py:185-199) in Detect.cv3 (head.py:101-102) and Attention.pe with its add
  * (block.py:1282,1302).  w is fp32 [9][C] (tap-major), bias fp32 [C]. */
