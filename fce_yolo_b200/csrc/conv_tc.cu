@@ -27,10 +27,11 @@ namespace fce {
 namespace {
 
 constexpr int BM = 128;  // UMMA M (cta_group::1)
-// warp roles
-constexpr int WARP_PROD_A = 0, WARP_PROD_B = 1, WARP_MMA = 2, WARP_ALLOC = 3, WARP_EPI0 = 4;
-constexpr int NUM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, interleaved over 32-column groups
-constexpr int NUM_THREADS = (WARP_EPI0 + NUM_EPI_WARPS) * 32;
+// Warp roles: 8 epilogue warps (two per TMEM lane quarter), then the single-lane roles.
+constexpr int WARP_EPI0 = 0;
+constexpr int NUM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, interleaved over 32-column slabs
+constexpr int WARP_PROD_A = 8, WARP_PROD_B = 9, WARP_MMA = 10, WARP_ALLOC = 11;
+constexpr int NUM_THREADS = 12 * 32;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 188 * 1024;  // A/B tiles + bias; staging slabs and barriers come on top
 constexpr int B_RESIDENT_MAX = 96 * 1024;
@@ -53,6 +54,7 @@ struct TcParams {
     int out_pitch, res_pitch, act, out_f32;
     uint32_t desc_hi;  // upper 32 bits of the UMMA shared-memory descriptor (SBO, version, swizzle)
     uint32_t idesc;    // UMMA instruction descriptor
+    int dbg;           // debug: bit 0 = producers skip the TMA loads (times the MMA + epilogue pipeline alone)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -302,11 +304,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
                     PROF_ACC(pw);
                 }
-                if (elect_one()) mbar_expect_tx(fb, tx);
+                if (elect_one()) {
+                    if (p.dbg & 1) mbar_arrive(fb); else mbar_expect_tx(fb, tx);
+                }
                 uint32_t dst = sA + r.stage * a_stage;
 #pragma unroll 1
                 for (int s = 0; s < S; ++s) {
-                    if (elect_one()) {
+                    if (!(p.dbg & 1) && elect_one()) {
                         if (is_1x1)
                             tma_load_2d(dst, &tmA, fb, ch * kc, m0);
                         else
@@ -349,11 +353,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int g = 0; g < groups; ++g) {
                     const uint32_t fb = full0 + 8 * r.stage;
                     mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
-                    if (elect_one()) mbar_expect_tx(fb, tx);
+                    if (elect_one()) {
+                        if (p.dbg & 1) mbar_arrive(fb); else mbar_expect_tx(fb, tx);
+                    }
                     uint32_t dst = sB + r.stage * b_stage;
 #pragma unroll 1
                     for (int s = 0; s < S; ++s) {
-                        if (elect_one()) tma_load_2d(dst, &tmB, fb, kcol, n0);
+                        if (!(p.dbg & 1) && elect_one()) tma_load_2d(dst, &tmB, fb, kcol, n0);
                         dst += b_sub;
                         kcol += kc;
                     }
@@ -430,7 +436,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             g_prof[blockIdx.x * PROF_SLOTS + 5] = we;
             g_prof[blockIdx.x * PROF_SLOTS + 6] = clock64() - mt0;
         }
-    } else if (warp >= WARP_EPI0) {
+    } else if (warp < WARP_EPI0 + NUM_EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue
         // TMEM -> registers -> bias/activation/residual -> swizzled staging slab in smem -> TMA store.
         // Each warp owns 32 accumulator rows and two private 32-row x 64-byte slabs, so the only
@@ -569,6 +575,7 @@ const DriverApi& driver() {
 }
 
 bool g_profile_on = false;
+int g_debug_flags = 0;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -646,6 +653,7 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     p.res_pitch = d->res_pitch;
     p.act = d->act;
     p.out_f32 = d->out_dtype == FCE_F32;
+    p.dbg = g_debug_flags;
     const uint32_t row_bytes = p.kc * 2;                                        // swizzle span = K-chunk row
     const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);  // UMMA LayoutType
     const uint32_t sbo = 8 * row_bytes;                                         // 8-row core-matrix group pitch
@@ -731,7 +739,10 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     return check_launch();
 }
 
-void conv_tc_set_profile(int on) { g_profile_on = on != 0; }
+void conv_tc_set_profile(int on) {
+    g_profile_on = (on & 1) != 0;
+    g_debug_flags = on >> 1;  // bit 1 of `on`: skip TMA loads (debug timing only - results are garbage)
+}
 
 int conv_tc_profile(long long* out, int n) {
     if (n > kNumSMs * PROF_SLOTS) n = kNumSMs * PROF_SLOTS;

@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--noflush", action="store_true")
     ap.add_argument("--prof", action="store_true", help="per-role cycle accounting of one launch per shape")
+    ap.add_argument("--skip-tma", action="store_true", help="debug: producers skip the loads (MMA+epilogue rate)")
     a = ap.parse_args()
     lib = L.load(check_device=True)
     dev = torch.device("cuda:0")
@@ -86,7 +87,7 @@ def main():
             L.check(lib.fce_conv2d(*args), name)
             torch.cuda.synchronize()
             flush.zero_()
-            lib.fce_conv_tc_set_profile(1)
+            lib.fce_conv_tc_set_profile(3 if a.skip_tma else 1)
             L.check(lib.fce_conv2d(*args), name)
             torch.cuda.synchronize()
             lib.fce_conv_tc_set_profile(0)
@@ -120,7 +121,7 @@ def main():
         tot_roof += roof_ms
         print(f"{name:34s} {t*1e3:8.1f} us  {flops/t/1e9:7.1f} TF/s  {byts/t/1e6:7.0f} GB/s  roofline {roof_ms*1e3:7.1f} us "
               f"({roof_ms/t*100:5.1f}%)", flush=True)
-    if not a.once:
+    if not a.once and tot_ms:
         print(f"TOTAL {tot_ms*1e3:.1f} us, roofline {tot_roof*1e3:.1f} us ({tot_roof/tot_ms*100:.1f}%)")
 
 
