@@ -87,8 +87,8 @@ __device__ __forceinline__ void Vec16<__nv_bfloat16>::pack(const float* f) {
     raw = make_uint4(r[0], r[1], r[2], r[3]);
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
-__device__ __forceinline__ float sigmoid_f(float v) { return 1.f / (1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+__device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 // accurate versions for fp32 mode (expf is ~1 ulp; __expf has ~2^-21 relative error near 0)
 __device__ __forceinline__ float silu_acc(float v) { return v / (1.f + expf(-v)); }
 __device__ __forceinline__ float sigmoid_acc(float v) { return 1.f / (1.f + expf(-v)); }

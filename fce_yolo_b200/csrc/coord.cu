@@ -1,10 +1,10 @@
 // Coordinate pooling and the strip cross-attention core of CoordAtt / CoordCrossAtt / BiCoordCrossAtt.
 //
 // fce_coord_pool: ONE pass over x producing both strips (mean over W per row, mean over H per
-// column), fp32 accumulation, deterministic (no atomics).  A CTA owns (image, 64-channel chunk)
-// [32 channels in fp32 mode]; a warp reads 4 pixels x 128 contiguous bytes per request.  Column sums
-// live in registers for the whole image, row sums are reduced once per 8-row block.
-// HBM-bound: algorithmic bytes = C*H*W*e read (+ (H+W)*C*4 written).
+// column), fp32 accumulation, deterministic (no atomics).  A CTA owns (image, 8-row band, 64-channel
+// chunk) [32 channels in fp32 mode]; a warp reads 4 pixels x 128 contiguous bytes per request.
+// HBM-bound: algorithmic bytes = C*H*W*e read (+ (H+W)*C*4 written; + the band partials, 1/8 of x in fp32... 
+// i.e. 2*W*C*4 bytes per 8 rows, which is why the band is not made smaller).
 //
 // fce_strip_attn: softmax(q k^T * scale) v over strips; the whole per-(image, head) K/V fits in
 // shared memory (L <= 160, dh <= 32 on this path), fp32 CUDA-core math - far too small for tensor cores.
@@ -18,12 +18,16 @@ namespace {
 constexpr int PT = 256;       // threads
 constexpr int CVT = 8;        // channel-vector lanes per CTA
 constexpr int SLOTS = 32;     // pixel slots along W
-constexpr int RB = 8;         // rows per block
-constexpr int BAND = 5;       // column groups held in registers -> band of 160 columns
+constexpr int RB = 8;         // rows per CTA (one band)
+constexpr int BAND = 5;       // column groups held in registers -> 160 columns per sweep
 
+// A CTA owns (image, band of RB rows, 64-channel chunk [32 in fp32 mode]).  Row means are complete inside the
+// CTA; column sums of the band go to the workspace ([B][bands][W][C] fp32) and a second, tiny kernel adds the
+// bands in a fixed order (deterministic, no atomics).  Grid = B * bands * chunks CTAs - thousands of CTAs with
+// 40 independent 16-byte loads in flight per thread, instead of one CTA per image.
 template <typename T>
 __global__ void __launch_bounds__(PT) coord_pool_kernel(const fce_pool_desc d, const T* __restrict__ x,
-                                                        float* __restrict__ strip) {
+                                                        float* __restrict__ strip, float* __restrict__ ws, int bands) {
     constexpr int N = Vec16<T>::N;
     constexpr int CC = CVT * N;  // channels per CTA
     __shared__ float red[PT / 32][RB][CC];
@@ -31,77 +35,92 @@ __global__ void __launch_bounds__(PT) coord_pool_kernel(const fce_pool_desc d, c
     const int cvt = tid & (CVT - 1);
     const int slot = tid / CVT;  // 0..31 ; a warp holds 4 consecutive slots
     const int chunks = (d.C + CC - 1) / CC;
-    const int b = blockIdx.x / chunks;
-    const int c0 = (blockIdx.x % chunks) * CC + cvt * N;
+    const int chunk = blockIdx.x % chunks;
+    const int band = (blockIdx.x / chunks) % bands;
+    const int b = blockIdx.x / (chunks * bands);
+    const int c0 = chunk * CC + cvt * N;
     const bool c_ok = c0 < d.C;  // C is a multiple of N (checked on host)
-    const T* xb = x + (size_t)b * d.H * d.W * d.pitch + d.off + c0;
-    float* xh = strip + ((size_t)b * d.H) * d.C;                      // rows [b*H, b*H+H)
-    float* xw = strip + ((size_t)d.B * d.H + (size_t)b * d.W) * d.C;  // rows B*H + b*W + w
-    const float inv_w = 1.f / (float)d.W, inv_h = 1.f / (float)d.H;
+    const int h_base = band * RB;
+    const T* xb_safe = x + (size_t)b * d.H * d.W * d.pitch + d.off + (c_ok ? c0 : 0);
+    float* xh = strip + ((size_t)b * d.H) * d.C;  // rows [b*H, b*H+H)
+    // column partial sums of this band: straight into the strip when there is a single band
+    float* colp = bands == 1 ? strip + ((size_t)d.B * d.H + (size_t)b * d.W) * d.C
+                             : ws + ((size_t)(b * bands + band) * d.W) * d.C;
+    const float col_scale = bands == 1 ? 1.f / (float)d.H : 1.f;
+    const float inv_w = 1.f / (float)d.W;
 
     for (int w_base = 0; w_base < d.W; w_base += SLOTS * BAND) {
-        float col[BAND][N];
+        float col[BAND][N], row[RB][N];
 #pragma unroll
         for (int g = 0; g < BAND; ++g)
 #pragma unroll
             for (int j = 0; j < N; ++j) col[g][j] = 0.f;
-
-        for (int h_base = 0; h_base < d.H; h_base += RB) {
-            float row[RB][N];
 #pragma unroll
-            for (int r = 0; r < RB; ++r)
+        for (int r = 0; r < RB; ++r)
 #pragma unroll
-                for (int j = 0; j < N; ++j) row[r][j] = 0.f;
+            for (int j = 0; j < N; ++j) row[r][j] = 0.f;
+        // all loads of two rows (2 x BAND 16-byte vectors) are issued before any is consumed; out-of-range
+        // pixels read a clamped (valid) address and are masked to zero afterwards
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                const int h = h_base + r;
+        for (int r = 0; r < RB; r += 2) {
+            Vec16<T> v[2][BAND];
+            bool ok[2][BAND];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int h = h_base + r + rr;
+                const int hc = h < d.H ? h : d.H - 1;
 #pragma unroll
                 for (int g = 0; g < BAND; ++g) {
                     const int w = w_base + g * SLOTS + slot;
-                    if (c_ok && h < d.H && w < d.W) {
-                        Vec16<T> v;
-                        v.load_nc(xb + ((size_t)h * d.W + w) * d.pitch);
-                        float f[N];
-                        v.unpack(f);
-#pragma unroll
-                        for (int j = 0; j < N; ++j) {
-                            row[r][j] += f[j];
-                            col[g][j] += f[j];
-                        }
-                    }
+                    const int wc = w < d.W ? w : d.W - 1;
+                    ok[rr][g] = c_ok && h < d.H && w < d.W;
+                    v[rr][g].load_nc(xb_safe + ((size_t)hc * d.W + wc) * d.pitch);
                 }
             }
-            // reduce row sums over the 32 slots: 4 slots inside the warp (lanes differ by 8, 16), 8 warps via smem
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int g = 0; g < BAND; ++g) {
+                    float f[N];
+                    v[rr][g].unpack(f);
+                    const float mk = ok[rr][g] ? 1.f : 0.f;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        row[r + rr][j] = fmaf(mk, f[j], row[r + rr][j]);
+                        col[g][j] = fmaf(mk, f[j], col[g][j]);
+                    }
+                }
+        }
+        // reduce row sums over the 32 slots: 4 slots inside the warp (lanes differ by 8, 16), 8 warps via smem
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                float v = row[r][j];
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                row[r][j] = v;
+            }
+        __syncthreads();  // previous sweep's readers are done with red[]
+        if (lane < CVT) {
 #pragma unroll
             for (int r = 0; r < RB; ++r)
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    float v = row[r][j];
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    row[r][j] = v;
-                }
-            __syncthreads();  // previous block's readers are done with red[]
-            if (lane < CVT) {
+                for (int j = 0; j < N; ++j) red[warp][r][cvt * N + j] = row[r][j];
+        }
+        __syncthreads();
+        for (int o = tid; o < RB * CC; o += PT) {
+            const int r = o / CC, c = o % CC;
+            const int h = h_base + r;
+            const int cg = chunk * CC + c;
+            if (h < d.H && cg < d.C) {
+                float s = 0.f;
 #pragma unroll
-                for (int r = 0; r < RB; ++r)
-#pragma unroll
-                    for (int j = 0; j < N; ++j) red[warp][r][cvt * N + j] = row[r][j];
-            }
-            __syncthreads();
-            for (int o = tid; o < RB * CC; o += PT) {
-                const int r = o / CC, c = o % CC;
-                const int h = h_base + r;
-                const int cg = (blockIdx.x % chunks) * CC + c;
-                if (h < d.H && cg < d.C) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int wq = 0; wq < PT / 32; ++wq) s += red[wq][r][c];
-                    float* dst = xh + (size_t)h * d.C + cg;
-                    if (w_base > 0) s += *dst;  // later bands of very wide maps accumulate (same CTA, ordered)
-                    if (w_base + SLOTS * BAND >= d.W) s *= inv_w;
-                    *dst = s;
-                }
+                for (int wq = 0; wq < PT / 32; ++wq) s += red[wq][r][c];
+                float* dst = xh + (size_t)h * d.C + cg;
+                if (w_base > 0) s += *dst;  // later sweeps of very wide maps accumulate (same CTA, ordered)
+                if (w_base + SLOTS * BAND >= d.W) s *= inv_w;
+                *dst = s;
             }
         }
         // column sums: every (slot, group) column is owned by exactly one thread
@@ -110,12 +129,27 @@ __global__ void __launch_bounds__(PT) coord_pool_kernel(const fce_pool_desc d, c
             for (int g = 0; g < BAND; ++g) {
                 const int w = w_base + g * SLOTS + slot;
                 if (w < d.W) {
-                    float* dst = xw + (size_t)w * d.C + c0;
+                    float* dst = colp + (size_t)w * d.C + c0;
 #pragma unroll
-                    for (int j = 0; j < N; ++j) dst[j] = col[g][j] * inv_h;
+                    for (int j = 0; j < N; ++j) dst[j] = col[g][j] * col_scale;
                 }
             }
         }
+    }
+}
+
+// strip[B*H + b*W + w][c] = (sum over bands of ws[b][band][w][c]) / H
+__global__ void __launch_bounds__(PT) coord_pool_finish(const fce_pool_desc d, const float* __restrict__ ws,
+                                                        float* __restrict__ strip, int bands) {
+    const size_t n = (size_t)d.B * d.W * d.C;
+    const float inv_h = 1.f / (float)d.H;
+    const size_t wc = (size_t)d.W * d.C;
+    for (size_t i = blockIdx.x * (size_t)PT + threadIdx.x; i < n; i += (size_t)gridDim.x * PT) {
+        const size_t b = i / wc, r = i - b * wc;
+        const float* p = ws + (b * bands) * wc + r;
+        float s = 0.f;
+        for (int k = 0; k < bands; ++k) s += p[(size_t)k * wc];
+        strip[(size_t)d.B * d.H * d.C + i] = s * inv_h;
     }
 }
 
@@ -180,23 +214,34 @@ __global__ void __launch_bounds__(AT) strip_attn_kernel(const fce_strip_attn_des
 
 using namespace fce;
 
-extern "C" size_t fce_coord_pool_workspace(const fce_pool_desc*) { return 0; }
+extern "C" size_t fce_coord_pool_workspace(const fce_pool_desc* d) {
+    if (!d || d->H <= RB) return 0;
+    const size_t bands = (size_t)(d->H + RB - 1) / RB;
+    return (size_t)d->B * bands * d->W * d->C * sizeof(float);
+}
 
 extern "C" int fce_coord_pool(const fce_pool_desc* d, const void* x, float* strip, void* ws, size_t ws_bytes,
                               void* stream) {
-    (void)ws; (void)ws_bytes;
     if (!d || !x || !strip || d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0) return FCE_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int n = d->dtype == FCE_BF16 ? 8 : 4;
     if (d->dtype != FCE_BF16 && d->dtype != FCE_F32) return FCE_ERR_UNSUPPORTED;
     if ((d->C % n) || (d->pitch % n) || (d->off % n) || (((uintptr_t)x) & 15)) return FCE_ERR_ALIGNMENT;
+    const int bands = (d->H + RB - 1) / RB;
+    if (bands > 1 && (!ws || ws_bytes < fce_coord_pool_workspace(d))) return FCE_ERR_WORKSPACE;
     const int cc = CVT * n;
     const int chunks = (d->C + cc - 1) / cc;
-    const int grid = d->B * chunks;
+    const int grid = d->B * bands * chunks;
     if (d->dtype == FCE_BF16)
-        coord_pool_kernel<__nv_bfloat16><<<grid, PT, 0, st>>>(*d, (const __nv_bfloat16*)x, strip);
+        coord_pool_kernel<__nv_bfloat16><<<grid, PT, 0, st>>>(*d, (const __nv_bfloat16*)x, strip, (float*)ws, bands);
     else
-        coord_pool_kernel<float><<<grid, PT, 0, st>>>(*d, (const float*)x, strip);
+        coord_pool_kernel<float><<<grid, PT, 0, st>>>(*d, (const float*)x, strip, (float*)ws, bands);
+    int rc = check_launch();
+    if (rc != FCE_OK || bands == 1) return rc;
+    const size_t nitems = (size_t)d->B * d->W * d->C;
+    int fgrid = (int)((nitems + PT - 1) / PT);
+    if (fgrid > kNumSMs * 8) fgrid = kNumSMs * 8;
+    coord_pool_finish<<<fgrid, PT, 0, st>>>(*d, (const float*)ws, strip, bands);
     return check_launch();
 }
 

@@ -1,7 +1,7 @@
 // Bandwidth-bound NHWC kernels: depthwise 3x3, SPPF max-pool pyramid, nearest 2x upsample,
 // BiFPN weighted fusion, gate application, view copy.  No tensor cores: every thread owns one
 // 16-byte channel vector (8 bf16 / 4 fp32) of one pixel, so a warp touches whole 128-byte lines;
-// grids are sized in multiples of the SM count and walk the tensor with a grid-stride loop.
+// one CTA per image row, no integer division on the device.
 #include "common.cuh"
 
 namespace fce {
@@ -9,12 +9,19 @@ namespace {
 
 constexpr int NT = 256;
 
-inline int grid_for(long long items) {
-    long long blocks = (items + NT - 1) / NT;
-    long long cap = (long long)kNumSMs * 16;  // up to 16 resident 256-thread CTAs' worth of work per SM
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return (int)blocks;
+// Thread-block shape shared by the pointwise kernels: blockDim.x walks the 16-byte channel vectors of one
+// pixel (coalesced 128-byte lines), blockDim.y walks pixels of one image row; blockIdx.x is the image row
+// (b*H + h).  No integer division anywhere on the device.
+struct RowGrid {
+    dim3 grid, block;
+};
+inline RowGrid row_grid(int rows, int cv) {
+    int cx = 1;
+    while (cx < cv && cx < 32) cx <<= 1;
+    RowGrid g;
+    g.block = dim3(cx, NT / cx);
+    g.grid = dim3(rows);
+    return g;
 }
 
 template <typename T, bool VEC>
@@ -40,100 +47,228 @@ struct CV {  // channel-vector accessor: VEC -> 16-byte vectors, else single ele
     }
 };
 
+template <typename T>
+__device__ __forceinline__ float silu_for(float v) {
+    if constexpr (sizeof(T) == 2) return silu_f(v);  // bf16 storage: fast exp is far below the output rounding
+    else return silu_acc(v);
+}
+
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(NT) dwconv3x3_kernel(const fce_dwconv_desc d, const T* __restrict__ x,
-                                                       const float* __restrict__ w, const float* __restrict__ bias,
-                                                       const T* add, T* y) {
-    constexpr int N = CV<T, VEC>::N;
-    const int cv = d.C / N;
-    const long long total = (long long)d.B * d.H * d.W * cv;
-    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        const int c = (int)(i % cv) * N;
-        long long p = i / cv;
-        const int pw = (int)(p % d.W);
-        const int ph = (int)((p / d.W) % d.H);
-        const int pb = (int)(p / ((long long)d.W * d.H));
-        float acc[N];
+// Depthwise 3x3, sliding window.  A warp owns one image row and 32 lanes x 4 bytes of channels (64 bf16 / 32
+// fp32): every load and store is one fully coalesced 128-byte line.  The warp walks the row left to right in
+// chunks of 4 pixels keeping the 3 x 6 input window in registers, so each input element is loaded ONCE per
+// output row (3 loads per output instead of 9) and unpacked once; the 12 loads of the next chunk are issued
+// before the current chunk is computed.  Padding: out-of-range rows get zero weights, out-of-range columns
+// zero values; addresses are clamped so that every load is in bounds.
+template <typename T>
+struct Lane4;  // 4 bytes of channels per lane
+template <>
+struct Lane4<__nv_bfloat16> {
+    static constexpr int E = 2;
+    static __device__ __forceinline__ void unpack(uint32_t r, float* f) {
+        f[0] = __uint_as_float(r << 16);
+        f[1] = __uint_as_float(r & 0xffff0000u);
+    }
+    static __device__ __forceinline__ uint32_t pack(const float* f) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[0], f[1]);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+};
+template <>
+struct Lane4<float> {
+    static constexpr int E = 1;
+    static __device__ __forceinline__ void unpack(uint32_t r, float* f) { f[0] = __uint_as_float(r); }
+    static __device__ __forceinline__ uint32_t pack(const float* f) { return __float_as_uint(f[0]); }
+};
+
+constexpr int DW_WARPS = 4;  // warps per CTA, each an independent (row, channel group)
+constexpr int DW_CHUNK = 4;  // pixels per register chunk
+
+template <typename T>
+__global__ void __launch_bounds__(DW_WARPS * 32) dwconv3x3_kernel(const fce_dwconv_desc d, const T* __restrict__ x,
+                                                                  const float* __restrict__ w,
+                                                                  const float* __restrict__ bias,
+                                                                  const T* __restrict__ add, T* __restrict__ y,
+                                                                  int groups, int total_units) {
+    constexpr int E = Lane4<T>::E;
+    const int lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * DW_WARPS + (threadIdx.x >> 5);  // (row, channel group)
+    if (unit >= total_units) return;
+    const int row = unit / groups, cg = unit - row * groups;  // row = b*H + h
+    const int ph = row % d.H;
+    int c = (cg * 32 + lane) * E;
+    const bool c_ok = c < d.C;
+    if (!c_ok) c = 0;  // idle lanes shadow channel 0 (loads stay in bounds), stores are predicated
+    const bool up_ok = ph > 0, dn_ok = ph < d.H - 1;
+    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(x + (size_t)row * d.W * d.in_pitch + d.in_off + c);
+    const size_t pitch4 = (size_t)d.in_pitch * sizeof(T) / 4;  // pixel pitch in 4-byte units
+    const uint32_t* r0 = up_ok ? r1 - (size_t)d.W * pitch4 : r1;
+    const uint32_t* r2 = dn_ok ? r1 + (size_t)d.W * pitch4 : r1;
+    float wt[9][E], bs[E];
 #pragma unroll
-        for (int j = 0; j < N; ++j) acc[j] = bias[c + j];
+    for (int t = 0; t < 9; ++t) {
+        const bool rok = t < 3 ? up_ok : (t < 6 ? true : dn_ok);
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int hi = ph + kh - 1;
-            if (hi < 0 || hi >= d.H) continue;
+        for (int j = 0; j < E; ++j) wt[t][j] = rok ? w[t * d.C + c + j] : 0.f;
+    }
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int wi = pw + kw - 1;
-                if (wi < 0 || wi >= d.W) continue;
-                float v[N];
-                CV<T, VEC>::load(x + ((size_t)(pb * d.H + hi) * d.W + wi) * d.in_pitch + d.in_off + c, v);
-                const float* wp = w + (kh * 3 + kw) * d.C + c;
+    for (int j = 0; j < E; ++j) bs[j] = bias[c + j];
+    const uint32_t* ap = add ? reinterpret_cast<const uint32_t*>(add + (size_t)row * d.W * d.add_pitch + d.add_off + c) : nullptr;
+    const size_t apitch4 = (size_t)d.add_pitch * sizeof(T) / 4;
+    uint32_t* yp = reinterpret_cast<uint32_t*>(y + (size_t)row * d.W * d.out_pitch + d.out_off + c);
+    const size_t opitch4 = (size_t)d.out_pitch * sizeof(T) / 4;
+    const int W = d.W;
+
+    // window columns: win[k][col] for col = chunk_start-1 .. chunk_start+CHUNK  (CHUNK + 2 columns)
+    float win[3][DW_CHUNK + 2][E];
+    uint32_t nxt[3][DW_CHUNK], nadd[DW_CHUNK];
+    auto load_cols = [&](int w0) {  // raw loads of columns w0 .. w0+CHUNK-1 (clamped), + the add operand of the
+#pragma unroll                     // chunk starting at w0 - 1
+        for (int q = 0; q < DW_CHUNK; ++q) {
+            const int wc = w0 + q < W ? w0 + q : W - 1;
+            nxt[0][q] = __ldg(r0 + (size_t)wc * pitch4);
+            nxt[1][q] = __ldg(r1 + (size_t)wc * pitch4);
+            nxt[2][q] = __ldg(r2 + (size_t)wc * pitch4);
+        }
+    };
+    // prologue: window = [pad, col0 .. col CHUNK]: load columns 0..CHUNK-1 into win[.][1..CHUNK], then column
+    // CHUNK .. 2*CHUNK-1 into nxt (its first column completes the window)
+    load_cols(0);
 #pragma unroll
-                for (int j = 0; j < N; ++j) acc[j] = fmaf(v[j], wp[j], acc[j]);
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) win[k][0][j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < DW_CHUNK; ++q) {
+            Lane4<T>::unpack(nxt[k][q], win[k][q + 1]);
+            if (q >= W) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) win[k][q + 1][j] = 0.f;
             }
         }
-        if (d.act == FCE_ACT_SILU) {
+    }
+    for (int w0 = 0; w0 < W; w0 += DW_CHUNK) {
+        load_cols(w0 + DW_CHUNK);  // columns of the NEXT chunk; in flight while this chunk is computed
+        if (ap) {
 #pragma unroll
-            for (int j = 0; j < N; ++j) acc[j] = silu_acc(acc[j]);
+            for (int q = 0; q < DW_CHUNK; ++q) {
+                const int wc = w0 + q < W ? w0 + q : W - 1;
+                nadd[q] = __ldg(ap + (size_t)wc * apitch4);
+            }
         }
-        if (add) {
-            float v[N];
-            CV<T, VEC>::load(add + (size_t)p * d.add_pitch + d.add_off + c, v);
+        // the window's last column is the first column of the next chunk
 #pragma unroll
-            for (int j = 0; j < N; ++j) acc[j] += v[j];
+        for (int k = 0; k < 3; ++k) {
+            Lane4<T>::unpack(nxt[k][0], win[k][DW_CHUNK + 1]);
+            if (w0 + DW_CHUNK >= W) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) win[k][DW_CHUNK + 1][j] = 0.f;
+            }
         }
-        CV<T, VEC>::store(y + (size_t)p * d.out_pitch + d.out_off + c, acc);
+#pragma unroll
+        for (int q = 0; q < DW_CHUNK; ++q) {
+            if (w0 + q >= W) break;
+            float acc[E];
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                float a = bs[j];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    a = fmaf(win[k][q][j], wt[k * 3 + 0][j], a);
+                    a = fmaf(win[k][q + 1][j], wt[k * 3 + 1][j], a);
+                    a = fmaf(win[k][q + 2][j], wt[k * 3 + 2][j], a);
+                }
+                acc[j] = a;
+            }
+            if (d.act == FCE_ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) acc[j] = silu_for<T>(acc[j]);
+            }
+            if (ap) {
+                float av[E];
+                Lane4<T>::unpack(nadd[q], av);
+#pragma unroll
+                for (int j = 0; j < E; ++j) acc[j] += av[j];
+            }
+            if (c_ok) yp[(size_t)(w0 + q) * opitch4] = Lane4<T>::pack(acc);
+        }
+        // slide: the last two columns of this window open the next one, the rest comes from nxt
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                win[k][0][j] = win[k][DW_CHUNK][j];
+                win[k][1][j] = win[k][DW_CHUNK + 1][j];
+            }
+#pragma unroll
+            for (int q = 1; q < DW_CHUNK; ++q) {
+                Lane4<T>::unpack(nxt[k][q], win[k][q + 1]);
+                if (w0 + DW_CHUNK + q >= W) {
+#pragma unroll
+                    for (int j = 0; j < E; ++j) win[k][q + 1][j] = 0.f;
+                }
+            }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// SPPF: windows 5/9/13 around each pixel, computed from one sweep over the 13x13 neighbourhood
-// (nested row maxima), identical to three chained 5x5/s1/p2 pools with -inf padding.
-template <typename T, bool VEC>
+// SPPF pyramid: three chained 5x5/s1/p2 max-pools (block.py:228-232).  A CTA owns one image and 32 channels
+// (lane = channel): the H x W plane is staged in shared memory once and each pool runs as a separable 5-tap row
+// pass + 5-tap column pass (10 shared-memory reads per output instead of the 169 global reads of the naive
+// window); every pool's result is the next pool's input and is written to its concat slice.  Warps walk the
+// pixels incrementally (no integer division).  max() is exact in any precision.
+constexpr int SPPF_CH = 32;
+template <typename T>
 __global__ void __launch_bounds__(NT) sppf_kernel(const fce_sppf_desc d, T* buf) {
-    constexpr int N = CV<T, VEC>::N;
-    const int cv = d.C / N;
-    const long long total = (long long)d.B * d.H * d.W * cv;
-    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        const int c = (int)(i % cv) * N;
-        long long p = i / cv;
-        const int pw = (int)(p % d.W);
-        const int ph = (int)((p / d.W) % d.H);
-        const int pb = (int)(p / ((long long)d.W * d.H));
-        float m5[N], m9[N], m13[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) m5[j] = m9[j] = m13[j] = -INFINITY;
-        for (int dy = -6; dy <= 6; ++dy) {
-            const int hi = ph + dy;
-            if (hi < 0 || hi >= d.H) continue;
-            float r5[N], r9[N], r13[N];
-#pragma unroll
-            for (int j = 0; j < N; ++j) r5[j] = r9[j] = r13[j] = -INFINITY;
-            for (int dx = -6; dx <= 6; ++dx) {
-                const int wi = pw + dx;
-                if (wi < 0 || wi >= d.W) continue;
-                float v[N];
-                CV<T, VEC>::load(buf + ((size_t)(pb * d.H + hi) * d.W + wi) * d.pitch + d.off + c, v);
-                const int ax = dx < 0 ? -dx : dx;
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    r13[j] = fmaxf(r13[j], v[j]);
-                    if (ax <= 4) r9[j] = fmaxf(r9[j], v[j]);
-                    if (ax <= 2) r5[j] = fmaxf(r5[j], v[j]);
-                }
-            }
-            const int ay = dy < 0 ? -dy : dy;
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                m13[j] = fmaxf(m13[j], r13[j]);
-                if (ay <= 4) m9[j] = fmaxf(m9[j], r9[j]);
-                if (ay <= 2) m5[j] = fmaxf(m5[j], r5[j]);
+    extern __shared__ float sp[];  // [2][H*W][32]
+    const int HW = d.H * d.W, W = d.W, H = d.H;
+    float* A = sp;
+    float* Bm = sp + (size_t)HW * SPPF_CH;
+    const int chunks = (d.C + SPPF_CH - 1) / SPPF_CH;
+    const int b = blockIdx.x / chunks, c0 = (blockIdx.x % chunks) * SPPF_CH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = NT / 32;
+    const bool c_ok = c0 + lane < d.C;
+    T* base = buf + (size_t)b * HW * d.pitch + d.off + c0 + lane;
+    for (int p = warp; p < HW; p += NW) A[p * SPPF_CH + lane] = c_ok ? Elem<T>::to_f(base[(size_t)p * d.pitch]) : 0.f;
+    __syncthreads();
+    const int h_step = NW / W, w_step = NW % W;  // pixel index advances by NW per iteration
+    for (int level = 1; level <= 3; ++level) {
+        int h = warp / W, w0 = warp % W;
+        for (int p = warp; p < HW; p += NW) {  // row pass A -> Bm
+            float m = A[p * SPPF_CH + lane];
+            if (w0 >= 1) m = fmaxf(m, A[(p - 1) * SPPF_CH + lane]);
+            if (w0 >= 2) m = fmaxf(m, A[(p - 2) * SPPF_CH + lane]);
+            if (w0 + 1 < W) m = fmaxf(m, A[(p + 1) * SPPF_CH + lane]);
+            if (w0 + 2 < W) m = fmaxf(m, A[(p + 2) * SPPF_CH + lane]);
+            Bm[p * SPPF_CH + lane] = m;
+            w0 += w_step;
+            h += h_step;
+            if (w0 >= W) {
+                w0 -= W;
+                ++h;
             }
         }
-        T* o = buf + (size_t)p * d.pitch + d.off + c;
-        CV<T, VEC>::store(o + d.C, m5);
-        CV<T, VEC>::store(o + 2 * d.C, m9);
-        CV<T, VEC>::store(o + 3 * d.C, m13);
+        __syncthreads();
+        h = warp / W;
+        w0 = warp % W;
+        for (int p = warp; p < HW; p += NW) {  // column pass Bm -> A (+ global slice `level`)
+            float m = Bm[p * SPPF_CH + lane];
+            if (h >= 1) m = fmaxf(m, Bm[(p - W) * SPPF_CH + lane]);
+            if (h >= 2) m = fmaxf(m, Bm[(p - 2 * W) * SPPF_CH + lane]);
+            if (h + 1 < H) m = fmaxf(m, Bm[(p + W) * SPPF_CH + lane]);
+            if (h + 2 < H) m = fmaxf(m, Bm[(p + 2 * W) * SPPF_CH + lane]);
+            A[p * SPPF_CH + lane] = m;
+            if (c_ok) base[(size_t)p * d.pitch + level * d.C] = Elem<T>::from_f(m);
+            w0 += w_step;
+            h += h_step;
+            if (w0 >= W) {
+                w0 -= W;
+                ++h;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -142,18 +277,18 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(NT) upsample_kernel(const fce_upsample_desc d, const T* __restrict__ x, T* y) {
     constexpr int N = CV<T, VEC>::N;
     const int cv = d.C / N;
-    const int Ho = d.H * 2, Wo = d.W * 2;
-    const long long total = (long long)d.B * Ho * Wo * cv;
-    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        const int c = (int)(i % cv) * N;
-        long long p = i / cv;
-        const int pw = (int)(p % Wo);
-        const int ph = (int)((p / Wo) % Ho);
-        const int pb = (int)(p / ((long long)Wo * Ho));
-        float v[N];
-        CV<T, VEC>::load(x + ((size_t)(pb * d.H + (ph >> 1)) * d.W + (pw >> 1)) * d.in_pitch + d.in_off + c, v);
-        CV<T, VEC>::store(y + (size_t)p * d.out_pitch + d.out_off + c, v);
-    }
+    const int Wo = d.W * 2;
+    const int row = blockIdx.x;  // b*Ho + ho
+    const int Ho = d.H * 2;
+    const int b = row / Ho, ho = row - b * Ho;
+    const T* xr = x + ((size_t)(b * d.H + (ho >> 1)) * d.W) * d.in_pitch + d.in_off;
+    T* yr = y + (size_t)row * Wo * d.out_pitch + d.out_off;
+    for (int cb = threadIdx.x; cb < cv; cb += blockDim.x)
+        for (int pw = threadIdx.y; pw < Wo; pw += blockDim.y) {
+            float v[N];
+            CV<T, VEC>::load(xr + (size_t)(pw >> 1) * d.in_pitch + cb * N, v);
+            CV<T, VEC>::store(yr + (size_t)pw * d.out_pitch + cb * N, v);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -162,28 +297,34 @@ __global__ void __launch_bounds__(NT) bifpn_kernel(const fce_bifpn_desc d, const
                                                    const T* __restrict__ x1, const T* __restrict__ x2, T* y) {
     constexpr int N = CV<T, VEC>::N;
     const int cv = d.C / N;
-    const long long total = (long long)d.B * d.H * d.W * cv;
+    const int row = blockIdx.x;  // b*H + h
+    const int b = row / d.H, h = row - b * d.H;
     const T* xs[3] = {x0, x1, x2};
-    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        const int c = (int)(i % cv) * N;
-        long long p = i / cv;
-        const int pw = (int)(p % d.W);
-        const int ph = (int)((p / d.W) % d.H);
-        const int pb = (int)(p / ((long long)d.W * d.H));
-        float acc[N];
+    const T* xr[3];
 #pragma unroll
-        for (int j = 0; j < N; ++j) acc[j] = 0.f;
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            if (s >= d.n) break;
-            size_t pix = d.up[s] ? ((size_t)(pb * (d.H >> 1) + (ph >> 1)) * (d.W >> 1) + (pw >> 1)) : (size_t)p;
-            float v[N];
-            CV<T, VEC>::load(xs[s] + pix * d.pitch[s] + d.off[s] + c, v);
-#pragma unroll
-            for (int j = 0; j < N; ++j) acc[j] = fmaf(d.wn[s], v[j], acc[j]);
-        }
-        CV<T, VEC>::store(y + (size_t)p * d.out_pitch + d.out_off + c, acc);
+    for (int s = 0; s < 3; ++s) {
+        if (s < d.n)
+            xr[s] = d.up[s] ? xs[s] + ((size_t)(b * (d.H >> 1) + (h >> 1)) * (d.W >> 1)) * d.pitch[s] + d.off[s]
+                            : xs[s] + (size_t)row * d.W * d.pitch[s] + d.off[s];
+        else
+            xr[s] = nullptr;
     }
+    T* yr = y + (size_t)row * d.W * d.out_pitch + d.out_off;
+    for (int cb = threadIdx.x; cb < cv; cb += blockDim.x)
+        for (int pw = threadIdx.y; pw < d.W; pw += blockDim.y) {
+            float acc[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                if (s >= d.n) break;
+                float v[N];
+                CV<T, VEC>::load(xr[s] + (size_t)(d.up[s] ? (pw >> 1) : pw) * d.pitch[s] + cb * N, v);
+#pragma unroll
+                for (int j = 0; j < N; ++j) acc[j] = fmaf(d.wn[s], v[j], acc[j]);
+            }
+            CV<T, VEC>::store(yr + (size_t)pw * d.out_pitch + cb * N, acc);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -191,14 +332,15 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(NT) copy_kernel(const fce_copy_desc d, const T* __restrict__ x, T* y) {
     constexpr int N = CV<T, VEC>::N;
     const int cv = d.C / N;
-    const long long total = (long long)d.B * d.H * d.W * cv;
-    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        const int c = (int)(i % cv) * N;
-        const long long p = i / cv;
-        float v[N];
-        CV<T, VEC>::load(x + (size_t)p * d.in_pitch + d.in_off + c, v);
-        CV<T, VEC>::store(y + (size_t)p * d.out_pitch + d.out_off + c, v);
-    }
+    const size_t row = blockIdx.x;
+    const T* xr = x + row * d.W * d.in_pitch + d.in_off;
+    T* yr = y + row * d.W * d.out_pitch + d.out_off;
+    for (int cb = threadIdx.x; cb < cv; cb += blockDim.x)
+        for (int pw = threadIdx.y; pw < d.W; pw += blockDim.y) {
+            float v[N];
+            CV<T, VEC>::load(xr + (size_t)pw * d.in_pitch + cb * N, v);
+            CV<T, VEC>::store(yr + (size_t)pw * d.out_pitch + cb * N, v);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,30 +349,47 @@ __global__ void __launch_bounds__(NT) gate_kernel(const fce_gate_desc d, const T
                                                   const float* __restrict__ gh, const float* __restrict__ gw, T* y) {
     constexpr int N = CV<T, VEC>::N;
     const int cv = d.C / N;
-    const long long total = (long long)d.B * d.H * d.W * cv;
-    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        const int c = (int)(i % cv) * N;
-        long long p = i / cv;
-        const int pw = (int)(p % d.W);
-        const int ph = (int)((p / d.W) % d.H);
-        const int pb = (int)(p / ((long long)d.W * d.H));
-        float v[N];
-        CV<T, VEC>::load(x + (size_t)p * d.in_pitch + d.in_off + c, v);
-        const float* a = gh + pb * d.gh_bstride + ph * d.gh_rstride + c;
-        if (d.mode == 1) {
+    const int row = blockIdx.x;  // b*H + h
+    const int b = row / d.H, h = row - b * d.H;
+    const T* xr = x + (size_t)row * d.W * d.in_pitch + d.in_off;
+    T* yr = y + (size_t)row * d.W * d.out_pitch + d.out_off;
+    const float* ar = gh + b * d.gh_bstride + h * d.gh_rstride;
+    const float* br = d.mode == 1 ? nullptr : gw + b * d.gw_bstride;
+    for (int cb = threadIdx.x; cb < cv; cb += blockDim.x) {
+        const int c = cb * N;
+        float a[N];
 #pragma unroll
-            for (int j = 0; j < N; ++j) v[j] *= a[j];
-        } else {
-            const float* b = gw + pb * d.gw_bstride + pw * d.gw_rstride + c;
-            if (d.mode == 0) {
+        for (int j = 0; j < N; ++j) a[j] = ar[c + j];
+        for (int pw0 = threadIdx.y; pw0 < d.W; pw0 += 2 * blockDim.y) {
+            const int pw1 = pw0 + blockDim.y;
+            const bool two = pw1 < d.W;
+            float v0[N], v1[N], b0[N], b1[N];
+            CV<T, VEC>::load(xr + (size_t)pw0 * d.in_pitch + c, v0);
+            if (two) CV<T, VEC>::load(xr + (size_t)pw1 * d.in_pitch + c, v1);
+            if (d.mode != 1) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) v[j] = v[j] * a[j] * b[j];
-            } else {
+                for (int j = 0; j < N; ++j) b0[j] = br[pw0 * d.gw_rstride + c + j];
+                if (two) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) v[j] *= sigmoid_f(a[j] + b[j]);
+                    for (int j = 0; j < N; ++j) b1[j] = br[pw1 * d.gw_rstride + c + j];
+                }
             }
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                if (d.mode == 1) {
+                    v0[j] *= a[j];
+                    v1[j] *= a[j];
+                } else if (d.mode == 0) {
+                    v0[j] = v0[j] * a[j] * b0[j];
+                    v1[j] = v1[j] * a[j] * b1[j];
+                } else {
+                    v0[j] *= sigmoid_f(a[j] + b0[j]);
+                    v1[j] *= sigmoid_f(a[j] + b1[j]);
+                }
+            }
+            CV<T, VEC>::store(yr + (size_t)pw0 * d.out_pitch + c, v0);
+            if (two) CV<T, VEC>::store(yr + (size_t)pw1 * d.out_pitch + c, v1);
         }
-        CV<T, VEC>::store(y + (size_t)p * d.out_pitch + d.out_off + c, v);
     }
 }
 
@@ -258,17 +417,19 @@ extern "C" int fce_dwconv3x3(const fce_dwconv_desc* d, const void* x, const floa
                              const void* add, void* y, void* stream) {
     if (!d || !x || !w || !bias || !y || d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0) return FCE_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    return by_dtype(d->dtype, [&](auto tag) {
+    return by_dtype(d->dtype, [&](auto tag) -> int {
         using T = decltype(tag);
-        constexpr int N = 16 / (int)sizeof(T);
-        const bool vec = multiple_of(N, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off,
-                                         add ? d->add_pitch : 0, add ? d->add_off : 0}) &&
-                         ptr16(x) && ptr16(y) && ptr16(add) && ptr16(w) && ptr16(bias);
-        const long long items = (long long)d->B * d->H * d->W * (d->C / (vec ? N : 1));
-        if (vec)
-            dwconv3x3_kernel<T, true><<<grid_for(items), NT, 0, st>>>(*d, (const T*)x, w, bias, (const T*)add, (T*)y);
-        else
-            dwconv3x3_kernel<T, false><<<grid_for(items), NT, 0, st>>>(*d, (const T*)x, w, bias, (const T*)add, (T*)y);
+        constexpr int E = 4 / (int)sizeof(T);  // channels per 4-byte lane
+        if (!multiple_of(E, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off, add ? d->add_pitch : 0,
+                             add ? d->add_off : 0}) ||
+            (((uintptr_t)x | (uintptr_t)y | (uintptr_t)add) & 3))
+            return FCE_ERR_ALIGNMENT;
+        const int groups = (d->C + 32 * E - 1) / (32 * E);
+        const long long units = (long long)d->B * d->H * groups;
+        if (units > 0x7fffffffLL) return FCE_ERR_UNSUPPORTED;
+        const int grid = (int)((units + DW_WARPS - 1) / DW_WARPS);
+        dwconv3x3_kernel<T><<<grid, DW_WARPS * 32, 0, st>>>(*d, (const T*)x, w, bias, (const T*)add, (T*)y, groups,
+                                                            (int)units);
         return check_launch();
     });
 }
@@ -277,13 +438,25 @@ extern "C" int fce_sppf_pool(const fce_sppf_desc* d, void* buf, void* stream) {
     if (!d || !buf || d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0) return FCE_ERR_BAD_ARG;
     if (d->off + 4 * d->C > d->pitch) return FCE_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    return by_dtype(d->dtype, [&](auto tag) {
+    return by_dtype(d->dtype, [&](auto tag) -> int {
         using T = decltype(tag);
-        constexpr int N = 16 / (int)sizeof(T);
-        const bool vec = multiple_of(N, {d->C, d->pitch, d->off}) && ptr16(buf);
-        const long long items = (long long)d->B * d->H * d->W * (d->C / (vec ? N : 1));
-        if (vec) sppf_kernel<T, true><<<grid_for(items), NT, 0, st>>>(*d, (T*)buf);
-        else sppf_kernel<T, false><<<grid_for(items), NT, 0, st>>>(*d, (T*)buf);
+        // two fp32 copies of a 32-channel plane in shared memory: up to 29 x 29 ... 880 x 880 pixels of input per
+        // 100 KB; the path's P5 maps are 20 x 20 (640) and 40 x 40 (1280)
+        const int HW = d->H * d->W;
+        const size_t smem = (size_t)2 * HW * SPPF_CH * sizeof(float);
+        if (smem > 200 * 1024) return FCE_ERR_UNSUPPORTED;
+        static bool attr_set[2] = {false, false};
+        constexpr int ti = sizeof(T) == 2 ? 0 : 1;
+        if (!attr_set[ti]) {
+            cudaError_t e = cudaFuncSetAttribute(sppf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) {
+                set_cuda_error(e);
+                return FCE_ERR_CUDA;
+            }
+            attr_set[ti] = true;
+        }
+        const int chunks = (d->C + SPPF_CH - 1) / SPPF_CH;
+        sppf_kernel<T><<<d->B * chunks, NT, smem, st>>>(*d, (T*)buf);
         return check_launch();
     });
 }
@@ -291,13 +464,13 @@ extern "C" int fce_sppf_pool(const fce_sppf_desc* d, void* buf, void* stream) {
 extern "C" int fce_upsample2x(const fce_upsample_desc* d, const void* x, void* y, void* stream) {
     if (!d || !x || !y || d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0) return FCE_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    return by_dtype(d->dtype, [&](auto tag) {
+    return by_dtype(d->dtype, [&](auto tag) -> int {
         using T = decltype(tag);
         constexpr int N = 16 / (int)sizeof(T);
         const bool vec = multiple_of(N, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off}) && ptr16(x) && ptr16(y);
-        const long long items = (long long)d->B * d->H * d->W * 4 * (d->C / (vec ? N : 1));
-        if (vec) upsample_kernel<T, true><<<grid_for(items), NT, 0, st>>>(*d, (const T*)x, (T*)y);
-        else upsample_kernel<T, false><<<grid_for(items), NT, 0, st>>>(*d, (const T*)x, (T*)y);
+        const RowGrid g = row_grid(d->B * d->H * 2, d->C / (vec ? N : 1));
+        if (vec) upsample_kernel<T, true><<<g.grid, g.block, 0, st>>>(*d, (const T*)x, (T*)y);
+        else upsample_kernel<T, false><<<g.grid, g.block, 0, st>>>(*d, (const T*)x, (T*)y);
         return check_launch();
     });
 }
@@ -309,14 +482,14 @@ extern "C" int fce_bifpn_fuse(const fce_bifpn_desc* d, const void* x0, const voi
     for (int i = 0; i < d->n; ++i)
         if (d->up[i] && ((d->H | d->W) & 1)) return FCE_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    return by_dtype(d->dtype, [&](auto tag) {
+    return by_dtype(d->dtype, [&](auto tag) -> int {
         using T = decltype(tag);
         constexpr int N = 16 / (int)sizeof(T);
         bool vec = multiple_of(N, {d->C, d->out_pitch, d->out_off}) && ptr16(x0) && ptr16(x1) && ptr16(x2) && ptr16(y);
         for (int i = 0; i < d->n; ++i) vec = vec && multiple_of(N, {d->pitch[i], d->off[i]});
-        const long long items = (long long)d->B * d->H * d->W * (d->C / (vec ? N : 1));
-        if (vec) bifpn_kernel<T, true><<<grid_for(items), NT, 0, st>>>(*d, (const T*)x0, (const T*)x1, (const T*)x2, (T*)y);
-        else bifpn_kernel<T, false><<<grid_for(items), NT, 0, st>>>(*d, (const T*)x0, (const T*)x1, (const T*)x2, (T*)y);
+        const RowGrid g = row_grid(d->B * d->H, d->C / (vec ? N : 1));
+        if (vec) bifpn_kernel<T, true><<<g.grid, g.block, 0, st>>>(*d, (const T*)x0, (const T*)x1, (const T*)x2, (T*)y);
+        else bifpn_kernel<T, false><<<g.grid, g.block, 0, st>>>(*d, (const T*)x0, (const T*)x1, (const T*)x2, (T*)y);
         return check_launch();
     });
 }
@@ -324,13 +497,13 @@ extern "C" int fce_bifpn_fuse(const fce_bifpn_desc* d, const void* x0, const voi
 extern "C" int fce_copy_view(const fce_copy_desc* d, const void* x, void* y, void* stream) {
     if (!d || !x || !y || d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0) return FCE_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    return by_dtype(d->dtype, [&](auto tag) {
+    return by_dtype(d->dtype, [&](auto tag) -> int {
         using T = decltype(tag);
         constexpr int N = 16 / (int)sizeof(T);
         const bool vec = multiple_of(N, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off}) && ptr16(x) && ptr16(y);
-        const long long items = (long long)d->B * d->H * d->W * (d->C / (vec ? N : 1));
-        if (vec) copy_kernel<T, true><<<grid_for(items), NT, 0, st>>>(*d, (const T*)x, (T*)y);
-        else copy_kernel<T, false><<<grid_for(items), NT, 0, st>>>(*d, (const T*)x, (T*)y);
+        const RowGrid g = row_grid(d->B * d->H, d->C / (vec ? N : 1));
+        if (vec) copy_kernel<T, true><<<g.grid, g.block, 0, st>>>(*d, (const T*)x, (T*)y);
+        else copy_kernel<T, false><<<g.grid, g.block, 0, st>>>(*d, (const T*)x, (T*)y);
         return check_launch();
     });
 }
@@ -340,13 +513,13 @@ extern "C" int fce_gate_apply(const fce_gate_desc* d, const void* x, const float
     if (!d || !x || !gh || !y || d->mode < 0 || d->mode > 2 || (d->mode != 1 && !gw)) return FCE_ERR_BAD_ARG;
     if (d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0) return FCE_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    return by_dtype(d->dtype, [&](auto tag) {
+    return by_dtype(d->dtype, [&](auto tag) -> int {
         using T = decltype(tag);
         constexpr int N = 16 / (int)sizeof(T);
         const bool vec = multiple_of(N, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off}) && ptr16(x) && ptr16(y);
-        const long long items = (long long)d->B * d->H * d->W * (d->C / (vec ? N : 1));
-        if (vec) gate_kernel<T, true><<<grid_for(items), NT, 0, st>>>(*d, (const T*)x, gh, gw, (T*)y);
-        else gate_kernel<T, false><<<grid_for(items), NT, 0, st>>>(*d, (const T*)x, gh, gw, (T*)y);
+        const RowGrid g = row_grid(d->B * d->H, d->C / (vec ? N : 1));
+        if (vec) gate_kernel<T, true><<<g.grid, g.block, 0, st>>>(*d, (const T*)x, gh, gw, (T*)y);
+        else gate_kernel<T, false><<<g.grid, g.block, 0, st>>>(*d, (const T*)x, gh, gw, (T*)y);
         return check_launch();
     });
 }

@@ -366,8 +366,11 @@ class Plan:
     def _pool(self, x: View, tag) -> View:
         strip = self.strip_buf(x.B * (x.H + x.W), x.C)
         d = L.PoolDesc(B=x.B, H=x.H, W=x.W, C=x.C, pitch=x.pitch, off=0, dtype=x.dtype)
-        self.add(Node("fce_coord_pool", d, [x, strip, None, 0], reads=[x], writes=[strip], tag=tag + ".pool",
-                      bytes=x.B * x.H * x.W * x.C * DT_SIZE[x.dtype]))
+        bands = -(-x.H // 8)  # fce_coord_pool_workspace: fp32 column partials per 8-row band
+        ws_bytes = x.B * bands * x.W * x.C * 4 if bands > 1 else 0
+        ws = self.new_buf(1, 1, ws_bytes, dtype=L.U8, B=1) if ws_bytes else None
+        self.add(Node("fce_coord_pool", d, [x, strip, ws, ws_bytes], reads=[x], writes=[strip] + ([ws] if ws else []),
+                      tag=tag + ".pool", bytes=x.B * x.H * x.W * x.C * DT_SIZE[x.dtype]))
         return strip
 
     def _strip_attn(self, q: View, k: View, v: View, B, Lq, Lk, heads, scale, tag) -> View:
