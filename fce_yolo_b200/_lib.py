@@ -27,6 +27,10 @@ class ConvDesc(C.Structure):
                                    "in_layout")] + [("in_scale", f32), ("impl", i32)]
 
 
+class PackDesc(C.Structure):
+    _fields_ = [(n, i32) for n in ("B", "H", "W", "Cin", "k", "stride", "Kpad", "in_dtype", "in_layout")]
+
+
 class DwconvDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "H", "W", "C", "in_pitch", "in_off", "out_pitch", "out_off", "add_pitch",
                                    "add_off", "act", "dtype")]
@@ -86,6 +90,7 @@ _SIGS = {
     "fce_last_cuda_error": (C.c_char_p, []),
     "fce_device_ok": (C.c_int, []),
     "fce_conv2d": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "fce_stem_pack": (C.c_int, [C.POINTER(PackDesc), _P, _P, _P]),
     "fce_conv_tc_set_profile": (None, [C.c_int]),
     "fce_conv_tc_profile": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "fce_dwconv3x3": (C.c_int, [C.POINTER(DwconvDesc), _P, _P, _P, _P, _P, _P]),

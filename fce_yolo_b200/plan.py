@@ -208,6 +208,25 @@ class Plan:
                       writes=[dst], tag=tag, flops=2.0 * x.B * Ho * Wo * Cout * Cin * k * k))
         return dst
 
+    def stem(self, m, img: View, in_layout, in_scale, tag="") -> View:
+        """First Conv of the graph.  bf16 mode, 3x3/s2 on 3 channels: patch packing (fce_stem_pack) into a
+        [M, 32] bf16 matrix followed by a K = 32 1x1 conv on the tensor cores; anything else: the generic conv."""
+        w, b, k, s, g, a = self.conv_params(m)
+        Cout, Cin = w.shape[0], w.shape[1]
+        if not (self.act_dt == L.BF16 and k == 3 and s == 2 and g == 1 and Cin == 3 and Cout % 16 == 0
+                and self.impl != 1):
+            return self.conv(m, img, in_layout=in_layout, in_scale=in_scale, tag=tag)
+        H, W = (img.H, img.W)
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        packed = self.new_buf(Ho, Wo, 32, dtype=L.BF16, B=img.B)
+        d = L.PackDesc(B=img.B, H=H, W=W, Cin=3, k=3, stride=2, Kpad=32, in_dtype=img.dtype, in_layout=in_layout)
+        self.add(Node("fce_stem_pack", d, [img, packed], reads=[img], writes=[packed], tag=tag + ".pack",
+                      bytes=img.B * (H * W * 3 * DT_SIZE[img.dtype] + Ho * Wo * 64.0)))
+        # OHWI weights flattened to [Cout, 27] (+5 zero columns), input scale folded in
+        wk = torch.zeros(Cout, 32, 1, 1, device=w.device)
+        wk[:, :27, 0, 0] = (w.permute(0, 2, 3, 1).reshape(Cout, 27) * in_scale)
+        return self.conv(None, packed, w_override=wk, b_override=b, act=a, tag=tag)
+
     def dwconv(self, m, x: View, dst: View | None = None, add: View | None = None, tag="") -> View:
         w, b, k, s, g, a = self.conv_params(m)
         if k != 3 or s != 1 or g != x.C or w.shape[0] != x.C or w.shape[1] != 1:
@@ -556,12 +575,11 @@ def compile_model(model, batch: int, height: int, width: int, precision: str, de
     for i, m in enumerate(layers):
         f = getattr(m, "f", -1)
         if i == 0:
+            xin = View(img.buf, 0, cin, batch, height, width)  # for NCHW the geometry is carried by the desc
             if input_u8:
-                xin = View(img.buf, 0, cin, batch, height, width)
-                x = p.conv(m, xin, in_scale=1.0 / 255.0, tag="model.0")
+                x = p.stem(m, xin, L.NHWC, 1.0 / 255.0, tag="model.0")
             else:
-                xin = View(img.buf, 0, cin, batch, height, width)  # NCHW: geometry carried by the desc
-                x = p.conv(m, xin, in_layout=L.NCHW, tag="model.0")
+                x = p.stem(m, xin, L.NCHW, 1.0, tag="model.0")
         else:
             if f != -1:
                 x = ys[f] if isinstance(f, int) else [x if j == -1 else ys[j] for j in f]

@@ -76,6 +76,18 @@ typedef struct {
 int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res,
                void* y, void* stream);
 
+/* Stem patch packing for the first Conv of the graph (3x3, stride 2, pad 1, Cin = 3; conv.py:80-89 applied to the
+ * network input, yolo11-fce.yaml:20): gathers every output pixel's 3x3x3 patch into one row of a bf16 matrix
+ * a[B*Ho*Wo][Kpad = 32] (K index (kh*3+kw)*3+ci as in the OHWI weights, columns 27..31 zero), so that the stem
+ * runs as a K = 32 1x1 fce_conv2d on the tensor cores.  x: uint8 NHWC (values stored unscaled - fold 1/255 into
+ * the weights), fp32 NCHW (the reference's tensor input, loaders.py:562-632) or fp32 NHWC. */
+typedef struct {
+    int32_t B, H, W, Cin;
+    int32_t k, stride, Kpad;
+    int32_t in_dtype, in_layout;
+} fce_pack_desc;
+int fce_stem_pack(const fce_pack_desc* d, const void* x, void* a, void* stream);
+
 /* Debug aid for the tcgen05 convolution: when switched on, the next fce_conv2d launches record per-CTA, per-role
  * cycle counts (16 int64 slots per CTA: A-producer wait/total, -, -, MMA wait-full/wait-tmem/total, epilogue
  * wait/total); fce_conv_tc_profile copies n slots of the last launch to a HOST buffer and returns n. */

@@ -41,6 +41,21 @@ class Interp(Arena):
             o = o + self.t(res).permute(0, 3, 1, 2).float()
         self.t(y).copy_(o.permute(0, 2, 3, 1))
 
+    def _fce_stem_pack(self, d, p):
+        x, a = p
+        buf = x.buf
+        flat = self._flat(buf)
+        if d.in_layout == L.NCHW:
+            xin = flat.view(d.B, 3, d.H, d.W).float()
+        else:
+            xin = flat.view(d.B, d.H, d.W, 3).permute(0, 3, 1, 2).float()
+        cols = F.unfold(xin, kernel_size=3, padding=1, stride=2)  # [B, ci*9 + kh*3 + kw, L]
+        Bn, _, Ln = cols.shape
+        cols = cols.view(Bn, 3, 9, Ln).permute(0, 3, 2, 1).reshape(Bn, Ln, 27)  # K index (kh*3+kw)*3+ci
+        out = torch.zeros(Bn, Ln, 32)
+        out[..., :27] = cols
+        self.t(a).copy_(out.view(self.t(a).shape))
+
     def _fce_dwconv3x3(self, d, p):
         x, w, b, add, y = p
         xin = self.t(x).permute(0, 3, 1, 2).float()
