@@ -1,12 +1,18 @@
 // Batched GPU NMS with the exact semantics of the reference's non_max_suppression
-// (ultralytics/utils/nms.py:13-166) + torchvision.ops.nms (:151-154): one CTA per image runs
-//   1. candidate generation in anchor order (best class, or multi-label (anchor, class) pairs in
-//      torch.where's row-major order), optional class filter;
-//   2. if more than max_nms candidates: exact radix-select of the max_nms best (ties -> lowest index);
-//   3. stable LSD radix sort by descending score (ties -> ascending index, = torchvision's stable sort);
-//   4. greedy suppression against the kept list, 256 sorted candidates at a time, stopping at max_det
-//      (the reference truncates after NMS, nms.py:157 - identical result, bounded work);
-//   5. emission of [max_det, 6] rows, int64 anchor indices and the count.
+// (ultralytics/utils/nms.py:13-166) + torchvision.ops.nms (:151-154).
+//
+// Kernel 1 (fully parallel, HBM-bound: one coalesced pass over pred): every candidate gets a 32-bit sort key
+// (descending score); non-candidates (score <= conf, class filtered out) get the sentinel 0xFFFFFFFF.
+//   predict mode : one key per anchor (best class, nms.py:120-122) + the class id;
+//   multi-label  : one key per (class, anchor) score (nms.py:115-116), same [nc, A] layout as pred.
+// Kernel 2 (one CTA per image) works on 64-bit composites  key << 32 | (anchor * nc + class), which are UNIQUE
+// and whose ascending order is exactly the reference's order: descending score, ties by ascending
+// (anchor, class) = torch.where's row-major order / torchvision's stable sort.  In rounds of 1024 candidates:
+//   a. exact radix select of the 1024 smallest unprocessed composites (8-bit digits, shared-memory histograms);
+//   b. unordered compaction into shared memory + bitonic sort (uniqueness makes stability moot);
+//   c. greedy suppression against the kept list, 256 sorted candidates at a time, stopping at max_det
+//      (the reference truncates after NMS, nms.py:157 - identical result, bounded work) or after max_nms
+//      candidates (nms.py:136-140 keeps only the max_nms best).
 // All box arithmetic uses explicit round-to-nearest fp32 intrinsics so nothing is contracted into FMAs:
 // keep indices and class ids are bit-exact against the CPU reference, including the fp32 class offset
 // (cls * max_wh added to the coordinates, nms.py:143,149).
@@ -18,9 +24,10 @@
 namespace fce {
 namespace {
 
-constexpr int NT = 512;
-constexpr int NW = NT / 32;
-constexpr int CH = 256;  // candidates resolved per suppression round
+constexpr int NT = 1024;
+constexpr int TSEL = 1024;  // candidates selected + sorted per round
+constexpr int CH = 256;     // candidates resolved per suppression step
+constexpr uint32_t INVALID_KEY = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t desc_key(float s) {
     // ascending order of the returned key == descending order of the score
@@ -29,34 +36,48 @@ __device__ __forceinline__ uint32_t desc_key(float s) {
     return ~u;
 }
 
-// exclusive block scan of one int per thread; returns the thread's offset, total through *total
-__device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    __syncthreads();  // warp_sums reuse
-    if (lane == 31) warp_sums[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        int w = lane < NW ? warp_sums[lane] : 0;
-        int winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        if (lane < NW) warp_sums[lane] = winc - w;
-        if (lane == NW - 1) warp_sums[NW] = winc;
-    }
-    __syncthreads();
-    *total = warp_sums[NW];
-    return warp_sums[warp] + inc - v;
+__device__ __forceinline__ bool class_allowed(const int32_t* classes, int n_classes, int c) {
+    if (n_classes <= 0) return true;
+    bool ok = false;
+    for (int q = 0; q < n_classes; ++q) ok |= (classes[q] == c);
+    return ok;
 }
 
+// ---------------------------------------------------------------- kernel 1: keys
+__global__ void __launch_bounds__(256) nms_keys_single(const fce_nms_desc d, const float* __restrict__ pred,
+                                                       const int32_t* __restrict__ classes,
+                                                       uint32_t* __restrict__ keys, uint32_t* __restrict__ cls) {
+    const int b = blockIdx.y;
+    const int a = blockIdx.x * 256 + threadIdx.x;
+    if (a >= d.A) return;
+    const float* ps = pred + ((size_t)b * (4 + d.nc) + 4) * d.A + a;
+    float best = -INFINITY;
+    int bestc = 0;
+#pragma unroll 8
+    for (int j = 0; j < d.nc; ++j) {
+        const float s = __ldg(ps + (size_t)j * d.A);
+        if (s > best) {  // first maximum wins, like torch.max (nms.py:120)
+            best = s;
+            bestc = j;
+        }
+    }
+    const bool ok = best > d.conf_thres && class_allowed(classes, d.n_classes, bestc);
+    keys[(size_t)b * d.A + a] = ok ? desc_key(best) : INVALID_KEY;
+    cls[(size_t)b * d.A + a] = (uint32_t)bestc;
+}
+
+__global__ void __launch_bounds__(256) nms_keys_multi(const fce_nms_desc d, const float* __restrict__ pred,
+                                                      const int32_t* __restrict__ classes,
+                                                      uint32_t* __restrict__ keys) {
+    const int b = blockIdx.z, j = blockIdx.y;
+    const int a = blockIdx.x * 256 + threadIdx.x;
+    if (a >= d.A) return;
+    const float s = __ldg(pred + ((size_t)b * (4 + d.nc) + 4 + j) * d.A + a);
+    const bool ok = s > d.conf_thres && class_allowed(classes, d.n_classes, j);
+    keys[((size_t)b * d.nc + j) * d.A + a] = ok ? desc_key(s) : INVALID_KEY;
+}
+
+// ---------------------------------------------------------------- kernel 2: select / sort / suppress
 struct Box {
     float x1, y1, x2, y2;
 };
@@ -82,296 +103,225 @@ __device__ __forceinline__ bool suppresses(const Box& a, float area_a, const Box
     return ge ? (ovr >= thr) : (ovr > thr);
 }
 
+// Visits every VALID composite of image b: f(composite).  Loop shapes avoid integer division.
+template <typename F>
+__device__ __forceinline__ void for_each_candidate(const fce_nms_desc& d, const uint32_t* __restrict__ keys,
+                                                   const uint32_t* __restrict__ cls, F&& f) {
+    const int A = d.A, nc = d.nc;
+    if (d.multi_label) {
+        for (int j = 0; j < nc; ++j) {
+            const uint32_t* kj = keys + (size_t)j * A;
+            for (int a = threadIdx.x; a < A; a += NT) {
+                const uint32_t k = kj[a];
+                if (k != INVALID_KEY) f(((unsigned long long)k << 32) | (uint32_t)(a * nc + j));
+            }
+        }
+    } else {
+        for (int a = threadIdx.x; a < A; a += NT) {
+            const uint32_t k = keys[a];
+            if (k != INVALID_KEY) f(((unsigned long long)k << 32) | (uint32_t)(a * nc + (int)cls[a]));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(NT) nms_kernel(const fce_nms_desc d, const float* __restrict__ pred,
-                                                 const int32_t* __restrict__ classes, float* __restrict__ det,
-                                                 int64_t* __restrict__ keep, int32_t* __restrict__ count,
-                                                 uint32_t* __restrict__ ws, int cap, float thr_f, int thr_ge) {
+                                                 const uint32_t* __restrict__ keys_all,
+                                                 const uint32_t* __restrict__ cls_all, float* __restrict__ det,
+                                                 int64_t* __restrict__ keep, int32_t* __restrict__ count, float thr_f,
+                                                 int thr_ge) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int warp_sums[NW + 1];
+    __shared__ unsigned long long scomp[TSEL];
     __shared__ int hist[256];
-    __shared__ int digit_base[256];
-    __shared__ int s_n, s_kept, s_prefix_digit, s_need;
+    __shared__ int s_digit, s_need, s_cnt, s_kept, s_valid;
     __shared__ uint32_t alive[CH / 32];
     __shared__ uint32_t sup[CH][CH / 32];
     __shared__ Box cbox[CH];
     __shared__ float carea[CH];
-    __shared__ int warp_hist[NW][256];
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = d.A, nc = d.nc;
     const float* pb = pred + (size_t)b * (4 + nc) * A;
     const float* ps = pb + (size_t)4 * A;
-    uint32_t* keyA = ws + (size_t)b * cap * 4;
-    uint32_t* idxA = keyA + cap;
-    uint32_t* keyB = idxA + cap;
-    uint32_t* idxB = keyB + cap;
-    const float conf = d.conf_thres;
+    const size_t n_keys = d.multi_label ? (size_t)A * nc : (size_t)A;
+    const uint32_t* keys = keys_all + (size_t)b * n_keys;
+    const uint32_t* cls = d.multi_label ? nullptr : cls_all + (size_t)b * A;
 
     // kept boxes live in dynamic smem: [max_det] Box + area + idx
     Box* kbox = reinterpret_cast<Box*>(smem_raw);
     float* karea = reinterpret_cast<float*>(kbox + d.max_det);
     uint32_t* kidx = reinterpret_cast<uint32_t*>(karea + d.max_det);
-    float* kscore = reinterpret_cast<float*>(kidx + d.max_det);
 
-    // ---------------- 1. candidates, in (anchor, class) order ----------------
-    int n = 0;
-    for (int a0 = 0; a0 < A; a0 += NT) {
-        const int a = a0 + tid;
-        int cnt = 0;
-        float best = -INFINITY;
-        int bestc = 0;
-        if (a < A) {
-            if (d.multi_label) {
-                for (int j = 0; j < nc; ++j) {
-                    const float s = ps[(size_t)j * A + a];
-                    if (s > conf) {
-                        bool ok = true;
-                        if (d.n_classes > 0) {
-                            ok = false;
-                            for (int q = 0; q < d.n_classes; ++q) ok |= (classes[q] == j);
-                        }
-                        cnt += ok;
-                    }
-                }
-            } else {
-                for (int j = 0; j < nc; ++j) {
-                    const float s = ps[(size_t)j * A + a];
-                    if (s > best) { best = s; bestc = j; }
-                }
-                bool ok = best > conf;
-                if (ok && d.n_classes > 0) {
-                    ok = false;
-                    for (int q = 0; q < d.n_classes; ++q) ok |= (classes[q] == bestc);
-                }
-                cnt = ok;
-            }
-        }
-        int total;
-        int off = n + block_excl_scan(cnt, warp_sums, &total);
-        if (cnt) {
-            if (d.multi_label) {
-                for (int j = 0; j < nc; ++j) {
-                    const float s = ps[(size_t)j * A + a];
-                    if (s > conf) {
-                        bool ok = true;
-                        if (d.n_classes > 0) {
-                            ok = false;
-                            for (int q = 0; q < d.n_classes; ++q) ok |= (classes[q] == j);
-                        }
-                        if (ok) {
-                            keyA[off] = desc_key(s);
-                            idxA[off] = (uint32_t)a * nc + j;
-                            ++off;
-                        }
-                    }
-                }
-            } else {
-                keyA[off] = desc_key(best);
-                idxA[off] = (uint32_t)a * nc + bestc;
-            }
-        }
-        n += total;
+    // number of candidates
+    if (tid == 0) { s_valid = 0; s_kept = 0; }
+    __syncthreads();
+    {
+        int local = 0;
+        for_each_candidate(d, keys, cls, [&](unsigned long long) { ++local; });
+        local = __reduce_add_sync(0xffffffffu, local);
+        if (lane == 0 && local) atomicAdd(&s_valid, local);
     }
     __syncthreads();
-    uint32_t *kin = keyA, *iin = idxA, *kout = keyB, *iout = idxB;
+    const int limit = min(s_valid, d.max_nms);  // nms.py:136-140: only the max_nms best take part
+    const float offs_scale = d.agnostic ? 0.f : d.max_wh;
 
-    // ---------------- 2. exact top-max_nms selection (nms.py:136-140) ----------------
-    if (n > d.max_nms) {
-        uint32_t prefix = 0, mask = 0;
-        int need = d.max_nms;  // rank (1-based) of the last key to keep, among keys matching the prefix
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            for (int i = tid; i < 256; i += NT) hist[i] = 0;
+    unsigned long long bnd = 0;  // composites <= bnd have been processed (valid once processed > 0)
+    int processed = 0;
+    while (processed < limit && s_kept < d.max_det) {
+        const int target = min(TSEL, limit - processed);
+        const bool have_bnd = processed > 0;
+        // ---- a. exact radix select: the composite of rank `target` among the unprocessed ones
+        unsigned long long prefix = 0, mask = 0;
+        int need = target;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            if (tid < 256) hist[tid] = 0;
             __syncthreads();
-            for (int i = tid; i < n; i += NT) {
-                const uint32_t k = kin[i];
-                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1);
-            }
+            for_each_candidate(d, keys, cls, [&](unsigned long long c) {
+                if ((!have_bnd || c > bnd) && (c & mask) == prefix) atomicAdd(&hist[(int)((c >> shift) & 255)], 1);
+            });
             __syncthreads();
-            if (tid == 0) {
-                int acc = 0, dg = 0;
-                for (; dg < 256; ++dg) {
-                    if (acc + hist[dg] >= need) break;
-                    acc += hist[dg];
+            if (warp == 0) {  // first digit whose cumulative count reaches `need` (8 bins per lane)
+                int loc[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; sum += loc[j]; }
+                int inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
                 }
-                s_prefix_digit = dg;
-                s_need = need - acc;
+                int before = inc - sum;  // candidates in lower digits
+                const bool mine = before < need && inc >= need;
+                if (mine) {
+                    int dg = 0;
+                    for (; dg < 8; ++dg) {
+                        if (before + loc[dg] >= need) break;
+                        before += loc[dg];
+                    }
+                    s_digit = lane * 8 + dg;
+                    s_need = need - before;
+                }
             }
             __syncthreads();
-            prefix |= ((uint32_t)s_prefix_digit) << shift;
-            mask |= 255u << shift;
+            prefix |= (unsigned long long)s_digit << shift;
+            mask |= 255ull << shift;
             need = s_need;
             __syncthreads();
         }
-        // prefix == threshold key T; keep all keys < T and the first `need` keys == T (index order)
-        const uint32_t T = prefix;
-        int out_n = 0, eq_seen = 0;
-        for (int i0 = 0; i0 < n; i0 += NT) {
-            const int i = i0 + tid;
-            uint32_t k = 0;
-            int is_lt = 0, is_eq = 0;
-            if (i < n) {
-                k = kin[i];
-                is_lt = k < T;
-                is_eq = k == T;
-            }
-            int tot_eq;
-            const int eq_rank = eq_seen + block_excl_scan(is_eq, warp_sums, &tot_eq);
-            const int take = is_lt | (is_eq && eq_rank < need);
-            int tot;
-            const int off = out_n + block_excl_scan(take, warp_sums, &tot);
-            if (take) {
-                kout[off] = k;
-                iout[off] = iin[i];
-            }
-            out_n += tot;
-            eq_seen += tot_eq;
-        }
+        const unsigned long long thr = prefix;
+        // ---- b. compaction (any order) + bitonic sort
+        if (tid == 0) s_cnt = 0;
+        for (int i = tid; i < TSEL; i += NT) scomp[i] = ~0ull;
         __syncthreads();
-        n = out_n;
-        uint32_t* t;
-        t = kin; kin = kout; kout = t;
-        t = iin; iin = iout; iout = t;
-    }
-
-    // ---------------- 3. stable LSD radix sort, 4 x 8 bits ----------------
-    if (n > 1) {
-        for (int shift = 0; shift < 32; shift += 8) {
-            for (int i = tid; i < 256; i += NT) hist[i] = 0;
-            __syncthreads();
-            for (int i = tid; i < n; i += NT) atomicAdd(&hist[(kin[i] >> shift) & 255], 1);
-            __syncthreads();
-            if (warp == 0) {  // exclusive scan of 256 bins by one warp (8 bins per lane)
-                int loc[8], s = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; s += loc[j]; }
-                int inc = s;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += t;
-                }
-                int base = inc - s;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { digit_base[lane * 8 + j] = base; base += loc[j]; }
+        for_each_candidate(d, keys, cls, [&](unsigned long long c) {
+            if ((!have_bnd || c > bnd) && c <= thr) {
+                const int pos = atomicAdd(&s_cnt, 1);
+                if (pos < TSEL) scomp[pos] = c;
             }
-            __syncthreads();
-            const bool skip = false;
-            (void)skip;
-            for (int i0 = 0; i0 < n; i0 += NT) {
-                const int i = i0 + tid;
-                const bool valid = i < n;
-                uint32_t k = 0, id = 0;
-                int dg = 256 + 0;  // invalid lanes use a private pseudo digit
-                if (valid) { k = kin[i]; id = iin[i]; dg = (k >> shift) & 255; }
-                for (int j = lane; j < 256; j += 32) warp_hist[warp][j] = 0;
-                __syncwarp();
-                const uint32_t peers = __match_any_sync(0xffffffffu, dg);
-                const int rank_in_warp = __popc(peers & ((1u << lane) - 1));
-                if (valid && rank_in_warp == 0) warp_hist[warp][dg] = __popc(peers);
-                __syncthreads();
-                // per digit: exclusive prefix over warps, then advance the running base
-                if (tid < 256) {
-                    int run = digit_base[tid];
-#pragma unroll
-                    for (int wq = 0; wq < NW; ++wq) {
-                        const int c = warp_hist[wq][tid];
-                        warp_hist[wq][tid] = run;
-                        run += c;
+        });
+        __syncthreads();
+        for (int k = 2; k <= TSEL; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < TSEL; i += NT) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long x = scomp[i], y = scomp[ixj];
+                        const bool asc = (i & k) == 0;
+                        if ((x > y) == asc) {
+                            scomp[i] = y;
+                            scomp[ixj] = x;
+                        }
                     }
-                    digit_base[tid] = run;
-                }
-                __syncthreads();
-                if (valid) {
-                    const int pos = warp_hist[warp][dg] + rank_in_warp;
-                    kout[pos] = k;
-                    iout[pos] = id;
                 }
                 __syncthreads();
             }
-            uint32_t* t;
-            t = kin; kin = kout; kout = t;
-            t = iin; iin = iout; iout = t;
         }
-    }
-    __syncthreads();
-
-    // ---------------- 4. greedy suppression against the kept list ----------------
-    if (tid == 0) s_kept = 0;
-    __syncthreads();
-    const float offs_scale = d.agnostic ? 0.f : d.max_wh;
-    for (int c0 = 0; c0 < n; c0 += CH) {
-        const int kept0 = s_kept;
-        if (kept0 >= d.max_det) break;
-        const int m = min(CH, n - c0);
-        bool dead = true;
-        Box mine = {0, 0, 0, 0};
-        float marea = 0.f;
-        if (tid < m) {
-            const uint32_t id = iin[c0 + tid];
-            const int a = id / nc, cls = id - a * nc;
-            Box r = load_box(pb, A, a);
-            const float off = __fmul_rn((float)cls, offs_scale);  // nms.py:143
-            mine.x1 = __fadd_rn(r.x1, off); mine.y1 = __fadd_rn(r.y1, off);  // nms.py:149
-            mine.x2 = __fadd_rn(r.x2, off); mine.y2 = __fadd_rn(r.y2, off);
-            marea = __fmul_rn(__fsub_rn(mine.x2, mine.x1), __fsub_rn(mine.y2, mine.y1));
-            cbox[tid] = mine;
-            carea[tid] = marea;
-            dead = false;
-            for (int q = 0; q < kept0; ++q)
-                if (suppresses(kbox[q], karea[q], mine, marea, thr_f, thr_ge)) { dead = true; break; }
-        }
-        if (tid < CH / 32) alive[tid] = 0;
-        __syncthreads();
-        if (tid < m && !dead) atomicOr(&alive[tid >> 5], 1u << (tid & 31));
-        // sup[i] = bitmask of later chunk members j > i that candidate i would suppress
-        for (int e = tid; e < CH * (CH / 32); e += NT) {
-            const int i = e / (CH / 32), wq = e % (CH / 32);
-            uint32_t bits = 0;
-            if (i < m) {
-                const Box bi = cbox[i];
-                const float ai = carea[i];
-                for (int t = 0; t < 32; ++t) {
-                    const int j = wq * 32 + t;
-                    if (j > i && j < m && suppresses(bi, ai, cbox[j], carea[j], thr_f, thr_ge)) bits |= 1u << t;
-                }
+        // ---- c. greedy suppression against the kept list
+        for (int c0 = 0; c0 < target; c0 += CH) {
+            const int kept0 = s_kept;
+            if (kept0 >= d.max_det) break;
+            const int m = min(CH, target - c0);
+            bool dead = true;
+            if (tid < m) {
+                const uint32_t id = (uint32_t)scomp[c0 + tid];
+                const int a = id / nc, cl = id - a * nc;
+                const Box r = load_box(pb, A, a);
+                const float off = __fmul_rn((float)cl, offs_scale);  // nms.py:143
+                Box mine;
+                mine.x1 = __fadd_rn(r.x1, off); mine.y1 = __fadd_rn(r.y1, off);  // nms.py:149
+                mine.x2 = __fadd_rn(r.x2, off); mine.y2 = __fadd_rn(r.y2, off);
+                const float marea = __fmul_rn(__fsub_rn(mine.x2, mine.x1), __fsub_rn(mine.y2, mine.y1));
+                cbox[tid] = mine;
+                carea[tid] = marea;
             }
-            sup[i][wq] = bits;
-        }
-        __syncthreads();
-        if (warp == 0) {  // sequential resolve, 8 words handled by lanes 0..7
-            uint32_t al = lane < CH / 32 ? alive[lane] : 0;
-            int kept = kept0;
-            for (int i = 0; i < m && kept < d.max_det; ++i) {
-                const uint32_t wbits = __shfl_sync(0xffffffffu, al, i >> 5);
-                if ((wbits >> (i & 31)) & 1u) {
-                    if (lane == 0) {
-                        kbox[kept] = cbox[i];
-                        karea[kept] = carea[i];
-                        kidx[kept] = iin[c0 + i];
-                        kscore[kept] = 0.f;
+            if (tid < CH / 32) alive[tid] = 0;
+            __syncthreads();
+            // candidate i (0..m) against the kept list: 4 threads per candidate split the list
+            {
+                const int i = tid >> 2, part = tid & 3;
+                bool hit = false;
+                if (i < m) {
+                    const Box mine = cbox[i];
+                    const float marea = carea[i];
+                    for (int q = part; q < kept0; q += 4)
+                        if (suppresses(kbox[q], karea[q], mine, marea, thr_f, thr_ge)) { hit = true; break; }
+                }
+                hit |= __shfl_xor_sync(0xffffffffu, hit, 1);
+                hit |= __shfl_xor_sync(0xffffffffu, hit, 2);
+                dead = hit;
+                if (i < m && part == 0 && !dead) atomicOr(&alive[i >> 5], 1u << (i & 31));
+            }
+            // sup[i] = bitmask of later chunk members j > i that candidate i would suppress
+            for (int e = tid; e < CH * (CH / 32); e += NT) {
+                const int i = e / (CH / 32), wq = e % (CH / 32);
+                uint32_t bits = 0;
+                if (i < m && wq * 32 + 31 > i) {
+                    const Box bi = cbox[i];
+                    const float ai = carea[i];
+                    for (int t = 0; t < 32; ++t) {
+                        const int j = wq * 32 + t;
+                        if (j > i && j < m && suppresses(bi, ai, cbox[j], carea[j], thr_f, thr_ge)) bits |= 1u << t;
                     }
-                    ++kept;
-                    if (lane < CH / 32) al &= ~sup[i][lane];
                 }
+                sup[i][wq] = bits;
             }
-            if (lane == 0) s_kept = kept;
+            __syncthreads();
+            if (warp == 0) {  // sequential resolve, 8 words handled by lanes 0..7
+                uint32_t al = lane < CH / 32 ? alive[lane] : 0;
+                int kept = kept0;
+                for (int i = 0; i < m && kept < d.max_det; ++i) {
+                    const uint32_t wbits = __shfl_sync(0xffffffffu, al, i >> 5);
+                    if ((wbits >> (i & 31)) & 1u) {
+                        if (lane == 0) {
+                            kbox[kept] = cbox[i];
+                            karea[kept] = carea[i];
+                            kidx[kept] = (uint32_t)scomp[c0 + i];
+                        }
+                        ++kept;
+                        if (lane < CH / 32) al &= ~sup[i][lane];
+                    }
+                }
+                if (lane == 0) s_kept = kept;
+            }
+            __syncthreads();
         }
+        processed += target;
+        bnd = thr;
         __syncthreads();
     }
     __syncthreads();
 
-    // ---------------- 5. emit ----------------
+    // ---------------- emit ----------------
     const int kept = s_kept;
     if (tid == 0) count[b] = kept;
     for (int q = tid; q < d.max_det; q += NT) {
         float* o = det + ((size_t)b * d.max_det + q) * 6;
         if (q < kept) {
             const uint32_t id = kidx[q];
-            const int a = id / nc, cls = id - a * nc;
+            const int a = id / nc, cl = id - a * nc;
             const Box r = load_box(pb, A, a);
             o[0] = r.x1; o[1] = r.y1; o[2] = r.x2; o[3] = r.y2;
-            o[4] = ps[(size_t)cls * A + a];
-            o[5] = (float)cls;
+            o[4] = ps[(size_t)cl * A + a];
+            o[5] = (float)cl;
             keep[(size_t)b * d.max_det + q] = a;
         } else {
             o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.f;
@@ -380,7 +330,7 @@ __global__ void __launch_bounds__(NT) nms_kernel(const fce_nms_desc d, const flo
     }
 }
 
-inline size_t kept_smem(int max_det) { return (size_t)max_det * (sizeof(Box) + 3 * sizeof(float)); }
+inline size_t kept_smem(int max_det) { return (size_t)max_det * (sizeof(Box) + 2 * sizeof(float)); }
 
 }  // namespace
 }  // namespace fce
@@ -389,8 +339,9 @@ using namespace fce;
 
 extern "C" size_t fce_nms_workspace(const fce_nms_desc* d) {
     if (!d) return 0;
-    const size_t cap = d->multi_label ? (size_t)d->A * d->nc : (size_t)d->A;
-    return (size_t)d->B * cap * 4 * sizeof(uint32_t);
+    // keys: one uint32 per anchor (predict) or per (class, anchor) (multi-label); + class ids in predict mode
+    const size_t n_keys = d->multi_label ? (size_t)d->A * d->nc : (size_t)d->A;
+    return (size_t)d->B * (n_keys + (d->multi_label ? 0 : (size_t)d->A)) * sizeof(uint32_t);
 }
 
 extern "C" int fce_nms(const fce_nms_desc* d, const float* pred, const int32_t* classes, float* det, int64_t* keep,
@@ -401,6 +352,7 @@ extern "C" int fce_nms(const fce_nms_desc* d, const float* pred, const int32_t* 
     if (!(d->conf_thres >= 0.f && d->conf_thres <= 1.f) || !(d->iou_thres >= 0.0 && d->iou_thres <= 1.0))
         return FCE_ERR_BAD_ARG;  // nms.py:59-60 asserts
     if ((long long)d->A * d->nc >= (1ll << 31)) return FCE_ERR_UNSUPPORTED;
+    if (d->nc > 65535 || d->B > 65535) return FCE_ERR_UNSUPPORTED;
     if (ws_bytes < fce_nms_workspace(d)) return FCE_ERR_WORKSPACE;
     const size_t smem = kept_smem(d->max_det);
     if (smem > 96 * 1024) return FCE_ERR_UNSUPPORTED;
@@ -410,10 +362,20 @@ extern "C" int fce_nms(const fce_nms_desc* d, const float* pred, const int32_t* 
         if (e != cudaSuccess) { set_cuda_error(e); return FCE_ERR_CUDA; }
         attr_done.store(true, std::memory_order_release);
     }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* keys = (uint32_t*)ws;
+    const size_t n_keys = d->multi_label ? (size_t)d->A * d->nc : (size_t)d->A;
+    uint32_t* cls = keys + (size_t)d->B * n_keys;
+    const int ablocks = (d->A + 255) / 256;
+    if (d->multi_label)
+        nms_keys_multi<<<dim3(ablocks, d->nc, d->B), 256, 0, st>>>(*d, pred, classes, keys);
+    else
+        nms_keys_single<<<dim3(ablocks, d->B), 256, 0, st>>>(*d, pred, classes, keys, cls);
+    int rc = check_launch();
+    if (rc != FCE_OK) return rc;
     // torchvision compares the fp32 IoU with a C double threshold: reproduce with an fp32 compare
     const float tf = (float)d->iou_thres;
     const int ge = ((double)tf > d->iou_thres) ? 1 : 0;
-    const int cap = d->multi_label ? d->A * d->nc : d->A;
-    nms_kernel<<<d->B, NT, smem, (cudaStream_t)stream>>>(*d, pred, classes, det, keep, count, (uint32_t*)ws, cap, tf, ge);
+    nms_kernel<<<d->B, NT, smem, st>>>(*d, pred, keys, cls, det, keep, count, tf, ge);
     return check_launch();
 }
