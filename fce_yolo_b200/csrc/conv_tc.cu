@@ -229,7 +229,9 @@ __device__ long long g_prof[kNumSMs * PROF_SLOTS];
 // loop control and the barrier waits, and only the TMA / tcgen05 instruction itself is predicated on one
 // elected lane.  This keeps addresses, phases and descriptors in the uniform datapath (the async-proxy
 // instructions take uniform registers) instead of a per-thread dependent chain with R2UR moves.
-template <bool PROF>
+// KK = K chunk / 16 (UMMA instructions per K step), S = K steps per pipeline stage: compile-time so that the
+// issue loops are straight-line code (descriptor = base + constant).
+template <int KK, int S, bool PROF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcParams p, const float* __restrict__ bias,
@@ -280,9 +282,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == WARP_PROD_A) {
         // ------------------------------------------------------------------ A producer (activations)
         Ring r;
-        const int hw = p.Ho * p.Wo, S = p.S, groups = p.groups, kc = p.kc, chunks = p.chunks, ksz = p.ksz;
-        const bool is_1x1 = p.taps == 1;
-        const uint32_t a_sub = p.a_sub, a_stage = p.a_stage, tx = S * p.a_sub;
+        constexpr int kc = KK * 16;
+        constexpr uint32_t a_sub = BM * kc * 2, a_stage = S * a_sub;
+        const int hw = p.Ho * p.Wo, groups = p.groups, chunks = p.chunks, ksz = p.ksz;
+        const bool is_1x1 = p.taps == 1, skip = (p.dbg & 1) != 0;
         const int n_tiles = p.n_tiles, nstages = p.stages;
         long long pw = 0, pt0 = PROF ? clock64() : 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -304,19 +307,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
                     PROF_ACC(pw);
                 }
+                const uint32_t dst = sA + r.stage * a_stage;
                 if (elect_one()) {
-                    if (p.dbg & 1) mbar_arrive(fb); else mbar_expect_tx(fb, tx);
-                }
-                uint32_t dst = sA + r.stage * a_stage;
-#pragma unroll 1
-                for (int s = 0; s < S; ++s) {
-                    if (!(p.dbg & 1) && elect_one()) {
-                        if (is_1x1)
-                            tma_load_2d(dst, &tmA, fb, ch * kc, m0);
-                        else
-                            tma_load_im2col(dst, &tmA, fb, ch * kc, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                    if (skip) {
+                        mbar_arrive(fb);
+                    } else {
+                        mbar_expect_tx(fb, a_stage);
+                        int c_ = ch, kw_ = kw, kh_ = kh;
+#pragma unroll
+                        for (int q = 0; q < S; ++q) {
+                            if (is_1x1)
+                                tma_load_2d(dst + q * a_sub, &tmA, fb, c_ * kc, m0);
+                            else
+                                tma_load_im2col(dst + q * a_sub, &tmA, fb, c_ * kc, w0, h0, img, (uint16_t)kw_,
+                                                (uint16_t)kh_);
+                            if (++c_ == chunks) {
+                                c_ = 0;
+                                if (++kw_ == ksz) {
+                                    kw_ = 0;
+                                    ++kh_;
+                                }
+                            }
+                        }
                     }
-                    dst += a_sub;
+                }
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
                     if (++ch == chunks) {
                         ch = 0;
                         if (++kw == ksz) {
@@ -334,8 +350,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == WARP_PROD_B) {
         // ------------------------------------------------------------------ B producer (weights)
-        const int k_steps = p.groups * p.S, kc = p.kc;
+        constexpr int kc = KK * 16;
+        const int k_steps = p.groups * S;
         const uint32_t b_sub = p.b_sub;
+        const bool skip = (p.dbg & 1) != 0;
         if (p.b_resident) {
             // weight-stationary: one load of the whole [Cout, K] matrix for all tiles of this CTA
             if (elect_one()) {
@@ -344,8 +362,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         } else {
             Ring r;
-            const int S = p.S, groups = p.groups, n_tiles = p.n_tiles, nstages = p.stages, bn = p.bn;
-            const uint32_t b_stage = p.b_stage, tx = S * b_sub;
+            const int groups = p.groups, n_tiles = p.n_tiles, nstages = p.stages, bn = p.bn;
+            const uint32_t b_stage = p.b_stage;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n0 = (n_tiles == 1 ? 0 : tile % n_tiles) * bn;
                 int kcol = 0;
@@ -353,16 +371,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int g = 0; g < groups; ++g) {
                     const uint32_t fb = full0 + 8 * r.stage;
                     mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
+                    const uint32_t dst = sB + r.stage * b_stage;
                     if (elect_one()) {
-                        if (p.dbg & 1) mbar_arrive(fb); else mbar_expect_tx(fb, tx);
+                        if (skip) {
+                            mbar_arrive(fb);
+                        } else {
+                            mbar_expect_tx(fb, b_stage);
+#pragma unroll
+                            for (int q = 0; q < S; ++q) tma_load_2d(dst + q * b_sub, &tmB, fb, kcol + q * kc, n0);
+                        }
                     }
-                    uint32_t dst = sB + r.stage * b_stage;
-#pragma unroll 1
-                    for (int s = 0; s < S; ++s) {
-                        if (!(p.dbg & 1) && elect_one()) tma_load_2d(dst, &tmB, fb, kcol, n0);
-                        dst += b_sub;
-                        kcol += kc;
-                    }
+                    kcol += S * kc;
                     r.advance(nstages);
                 }
             }
@@ -373,10 +392,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0;
         uint32_t acc_phase = 0;
         const uint32_t dhi = p.desc_hi;
-        const int kk = p.kc >> 4;  // UMMA K = 16 bf16 = 32 bytes
-        const int S = p.S, groups = p.groups, nstages = p.stages, bn = p.bn;
+        constexpr int kc = KK * 16;
+        constexpr uint32_t a_sub = BM * kc * 2, a_stage = S * a_sub;
+        const int groups = p.groups, nstages = p.stages, bn = p.bn;
         const bool resident = p.b_resident != 0;
-        const uint32_t a_sub = p.a_sub, b_sub = p.b_sub, a_stage = p.a_stage, b_stage = p.b_stage, idesc = p.idesc;
+        const uint32_t b_sub16 = p.b_sub >> 4, b_stage = p.b_stage, idesc = p.idesc;
         long long wf = 0, we = 0, mt0 = PROF ? clock64() : 0;
         if (resident) {
             mbar_wait(bfull, 0);
@@ -390,7 +410,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * bn;
-            uint32_t accum = 0;
 #pragma unroll 1
             for (int g = 0; g < groups; ++g) {
                 {
@@ -400,34 +419,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_fence_after();
                 // descriptor low words: (addr >> 4) | LBO(=1) << 16 ; a K step of 16 bf16 advances the address by 32 B
-                uint32_t a_lo = (((sA + r.stage * a_stage) >> 4) & 0x3FFF) | (1u << 16);
-                uint32_t b_lo = (((resident ? sB + g * b_stage : sB + r.stage * b_stage) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t a_lo = (((sA + r.stage * a_stage) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t b_lo = (((resident ? sB + g * b_stage : sB + r.stage * b_stage) >> 4) & 0x3FFF) | (1u << 16);
                 if (elect_one()) {
-#pragma unroll 1
-                    for (int s = 0; s < S; ++s) {
-                        if (kk == 4) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                umma_bf16(d_tmem, make_desc(dhi, a_lo + 2 * k), make_desc(dhi, b_lo + 2 * k), idesc, accum);
-                                accum = 1;
-                            }
-                        } else {
-                            for (int k = 0; k < kk; ++k) {
-                                umma_bf16(d_tmem, make_desc(dhi, a_lo + 2 * k), make_desc(dhi, b_lo + 2 * k), idesc, accum);
-                                accum = 1;
-                            }
+                    for (int q = 0; q < S; ++q) {
+#pragma unroll
+                        for (int k = 0; k < KK; ++k) {
+                            umma_bf16(d_tmem, make_desc(dhi, a_lo + q * (a_sub >> 4) + 2 * k),
+                                      make_desc(dhi, b_lo + q * b_sub16 + 2 * k), idesc, (g | q | k) != 0);
                         }
-                        a_lo += a_sub >> 4;
-                        b_lo += b_sub >> 4;
                     }
                     umma_commit(empty0 + 8 * r.stage);  // frees the smem slot when these MMAs retire
+                    if (g == groups - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
                 }
-                accum = 1;
                 __syncwarp();
                 r.advance(nstages);
             }
-            if (elect_one()) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
-            __syncwarp();
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -718,24 +726,32 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
         if (cr != CUDA_SUCCESS) return FCE_ERR_UNSUPPORTED;
     }
     const size_t smem = (size_t)p.stages * p.a_stage + p.b_total + NUM_EPI_WARPS * 2 * STG_BYTES + p.bias_bytes + 1024 + 256;
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*,
+                             const __nv_bfloat16*);
+    // (KK, S) variants: S = 3 only with narrow K chunks
+    static const KernelFn table[2][5] = {
+        {conv_tc_kernel<1, 1, false>, conv_tc_kernel<2, 1, false>, conv_tc_kernel<4, 1, false>,
+         conv_tc_kernel<1, 3, false>, conv_tc_kernel<2, 3, false>},
+        {conv_tc_kernel<1, 1, true>, conv_tc_kernel<2, 1, true>, conv_tc_kernel<4, 1, true>,
+         conv_tc_kernel<1, 3, true>, conv_tc_kernel<2, 3, true>}};
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) {
-            set_cuda_error(e);
-            return FCE_ERR_CUDA;
-        }
+        for (int a = 0; a < 2; ++a)
+            for (int v = 0; v < 5; ++v) {
+                cudaError_t e = cudaFuncSetAttribute(table[a][v], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                if (e != cudaSuccess) {
+                    set_cuda_error(e);
+                    return FCE_ERR_CUDA;
+                }
+            }
         attr_set = true;
     }
+    const int kk = p.kc >> 4;
+    const int variant = p.S == 1 ? (kk == 1 ? 0 : (kk == 2 ? 1 : 2)) : (kk == 1 ? 3 : 4);
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < kNumSMs ? total : kNumSMs;
     const __nv_bfloat16* rp = res ? reinterpret_cast<const __nv_bfloat16*>(res) + d->res_off : nullptr;
-    if (g_profile_on)
-        conv_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, p, bias, rp);
-    else
-        conv_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, p, bias, rp);
+    table[g_profile_on ? 1 : 0][variant]<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, p, bias, rp);
     return check_launch();
 }
 
