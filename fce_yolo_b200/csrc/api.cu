@@ -10,6 +10,7 @@ int conv2d_simt(const fce_conv_desc*, const void*, const void*, const float*, co
 int conv2d_tc(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
 bool conv2d_tc_supported(const fce_conv_desc*, const void*, const void*, const void*, const void*);
 void conv_tc_set_profile(int on);
+void conv_halo_set_mode(int mode);
 int conv_tc_profile(long long* out, int n);
 
 }  // namespace fce
@@ -41,5 +42,9 @@ extern "C" int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, 
     return conv2d_simt(d, x, w, bias, res, y, st);
 }
 
-extern "C" void fce_conv_tc_set_profile(int on) { conv_tc_set_profile(on); }
+extern "C" void fce_conv_tc_set_profile(int on) {
+    conv_tc_set_profile(on & 3);
+    // bit 4: disable the 3x3 strip kernel (everything goes through the TMA-im2col kernel)
+    conv_halo_set_mode(((on >> 4) & 1) ? 0 : 1);
+}
 extern "C" int fce_conv_tc_profile(long long* out, int n) { return out ? conv_tc_profile(out, n) : FCE_ERR_BAD_ARG; }

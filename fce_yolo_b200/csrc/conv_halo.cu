@@ -1,0 +1,389 @@
+// 3x3 stride-1 convolution with the INPUT STRIP RESIDENT IN SHARED MEMORY ("halo" kernel), tcgen05 + TMEM + TMA.
+//
+// The TMA-im2col kernel (conv_tc.cu) fetches every input pixel nine times (once per tap) through L2 and pays the
+// TMA unit's per-pixel request cost nine times; for the thin 3x3 convs of the C3k2 / C3k bottlenecks and the Detect
+// box branch (conv.py:80-89 inside block.py:474-476, head.py:92-94) that cost, not HBM or the tensor pipe, set
+// the pace.  Here a CTA owns a band of R output rows of one image:
+//
+//   * ONE tiled-mode TMA box {kc channels, W+2 columns, R+2 rows} per K chunk lands the zero-padded input strip in
+//     shared memory as a "padded-flat" pixel list  j = row * (W+2) + col  (the TMA unit's out-of-bounds zero fill
+//     produces the padding columns and rows for free);
+//   * output pixel o = ro * (W+2) + co reads tap (kh, kw) at strip row  o + kh*(W+2) + kw, so the A operand of
+//     every tap is the SAME strip seen through a shifted shared-memory descriptor: 9 * kc/16 tcgen05.mma per
+//     128-row block and K chunk, no data movement between taps;
+//   * the two padding columns of every row produce garbage accumulator rows that are simply never stored;
+//   * the whole [Cout, 9*Cin] weight matrix is parked in shared memory for the life of the CTA.
+//
+// Each input element crosses L2 -> SM (R+2)/R times instead of 9, and the producer issues one TMA per
+// (band, chunk) instead of nine per 128 pixels.  Warp roles as in conv_tc.cu.
+#include "tc_common.cuh"
+
+namespace fce {
+using namespace tc;
+namespace {
+
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int WARP_PROD_A = 8, WARP_PROD_B = 9, WARP_MMA = 10, WARP_ALLOC = 11;
+constexpr int NUM_THREADS = 12 * 32;
+constexpr int A_STAGES = 2;
+constexpr int SMEM_LIMIT = 222 * 1024;
+
+struct HaloParams {
+    int B, H, W, Wp;  // Wp = W + 2
+    int Cin, Cout;
+    int R, bands, nb;  // rows per band, bands per image, 128-row MMA blocks per band
+    int chunks;        // K chunks (kc channels each)
+    int units;         // B * bands
+    int acc_sets;      // 1 or 2 accumulator sets of nb * Cout TMEM columns
+    uint32_t strip_bytes, strip_tx;  // shared-memory bytes of one strip stage / bytes one TMA box delivers
+    uint32_t b_sub;                  // bytes of one (tap, chunk) weight tile: Cout x kc bf16
+    uint32_t b_total, bias_bytes;
+    uint32_t tmem_cols;
+    int out_pitch, res_pitch, act, out_f32;
+    uint32_t desc_hi, idesc;
+};
+
+template <int KK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p,
+                 const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res, void* __restrict__ y) {
+    constexpr int kc = KK * 16;
+    constexpr uint32_t row_b = kc * 2;  // bytes of one strip row (= swizzle span)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base;
+    const uint32_t sB = sA + A_STAGES * p.strip_bytes;
+    const uint32_t sBias = sB + p.b_total;
+    const uint32_t bars = sBias + p.bias_bytes;
+    const uint32_t full0 = bars, empty0 = bars + 16, tfull0 = bars + 32, tempty0 = bars + 48, bfull = bars + 64;
+    const uint32_t tmem_slot = bars + 72;
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == WARP_PROD_A && lane == 0) {
+        for (int i = 0; i < A_STAGES; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull0 + 8 * a, 1);
+            mbar_init(tempty0 + 8 * a, NUM_EPI_WARPS);
+        }
+        mbar_init(bfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == WARP_ALLOC) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < (int)(p.bias_bytes >> 2); i += NUM_THREADS) bias_s[i] = i < p.Cout ? bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int units = p.units, chunks = p.chunks, nb = p.nb, bn = p.Cout;
+
+    if (warp == WARP_PROD_A) {
+        // ------------------------------------------------------------------ strip producer
+        Ring r;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int b = u / p.bands, band = u - b * p.bands;
+            const int h0 = band * p.R;
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = full0 + 8 * r.stage;
+                    mbar_expect_tx(fb, p.strip_tx);
+                    tma_load_4d(sA + r.stage * p.strip_bytes, &tmA, fb, c * kc, -1, h0 - 1, b);
+                }
+                r.advance(A_STAGES);
+            }
+        }
+    } else if (warp == WARP_PROD_B) {
+        // ------------------------------------------------------------------ weights: parked once
+        if (elect_one()) {
+            const int tiles = 9 * chunks;
+            mbar_expect_tx(bfull, (uint32_t)tiles * p.b_sub);
+            // tile index = chunk * 9 + tap ; K column of the OHWI matrix = tap * Cin + chunk * kc
+            for (int c = 0; c < chunks; ++c)
+                for (int t = 0; t < 9; ++t)
+                    tma_load_2d(sB + (c * 9 + t) * p.b_sub, &tmB, bfull, t * p.Cin + c * kc, 0);
+        }
+    } else if (warp == WARP_MMA) {
+        // ------------------------------------------------------------------ MMA issuer
+        Ring r;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const uint32_t dhi = p.desc_hi, idesc = p.idesc, b_sub16 = p.b_sub >> 4;
+        // strip-row offset of every tap, in 16-byte units
+        uint32_t tap16[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) tap16[t] = (uint32_t)((t / 3) * p.Wp + (t % 3)) * (row_b >> 4);
+        mbar_wait(bfull, 0);
+        tc_fence_after();
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + acc * nb * bn;
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(full0 + 8 * r.stage, r.phase);
+                tc_fence_after();
+                const uint32_t a16 = (sA + r.stage * p.strip_bytes) >> 4;
+                const uint32_t b16 = (sB + c * 9 * p.b_sub) >> 4;
+                if (elect_one()) {
+#pragma unroll 1
+                    for (int blk = 0; blk < nb; ++blk) {
+                        const uint32_t d_tmem = d0 + blk * bn;
+                        const uint32_t blk16 = a16 + (uint32_t)blk * (128u * (row_b >> 4));
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            // Start address >> 4 of this tap's A operand: the strip shifted by whole pixel rows.  The
+                            // operand fetch applies the swizzle XOR to the final shared-memory address (as the TMA
+                            // write did), so a start that is only row-aligned needs no descriptor base offset
+                            // (verified on B200: setting the base-offset field from address bits 7..9 breaks it).
+                            const uint32_t as = blk16 + tap16[t];
+                            const uint32_t hi = dhi;
+                            const uint32_t bs = b16 + t * b_sub16;
+#pragma unroll
+                            for (int k = 0; k < KK; ++k) {
+                                umma_bf16(d_tmem, make_desc(hi, ((as + 2 * k) & 0x3FFF) | (1u << 16)),
+                                          make_desc(dhi, ((bs + 2 * k) & 0x3FFF) | (1u << 16)), idesc, (c | t | k) != 0);
+                            }
+                        }
+                    }
+                    umma_commit(empty0 + 8 * r.stage);
+                    if (c == chunks - 1) umma_commit(tfull0 + 8 * acc);
+                }
+                __syncwarp();
+                r.advance(A_STAGES);
+            }
+            if (p.acc_sets == 2) {
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            } else {
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp < NUM_EPI_WARPS) {
+        // ------------------------------------------------------------------ epilogue (direct NHWC stores)
+        const int quarter = warp & 3, half = warp >> 2;
+        const int n_chunks = bn >> 4, act = p.act, Wp = p.Wp, W = p.W, R = p.R, H = p.H;
+        const bool has_res = res != nullptr, out_f32 = p.out_f32 != 0;
+        const int osz = out_f32 ? 4 : 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int b = u / p.bands, band = u - b * p.bands;
+            const int h0 = band * R;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            for (int blk = 0; blk < nb; ++blk) {
+                const int o = blk * 128 + quarter * 32 + lane;  // padded-flat output index inside the band
+                const int ro = o / Wp, co = o - ro * Wp;
+                const bool ok = co < W && ro < R && h0 + ro < H;
+                const size_t m = ((size_t)(b * H + h0 + ro) * W + co);
+                char* yrow = reinterpret_cast<char*>(y) + m * p.out_pitch * osz;
+                const __nv_bfloat16* rrow = res + m * p.res_pitch;
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * nb + blk) * bn;
+#pragma unroll 1
+                for (int j = half * 2; j < n_chunks; j += 4) {
+                    const int n = j * 16;
+                    const bool two = j + 1 < n_chunks;
+                    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
+                    if (has_res && ok) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(rrow + n);
+                        r0 = rp[0];
+                        r1 = rp[1];
+                        if (two) {
+                            r2 = rp[2];
+                            r3 = rp[3];
+                        }
+                    }
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(t_row + n, v0);
+                    if (two) tmem_ld16(t_row + n + 16, v1);
+                    tmem_ld_wait();
+                    float f[16];
+                    epi_math16(v0, bias_s + n, act, has_res, r0, r1, f);
+                    if (ok) {
+                        if (out_f32) {
+                            float4* op = reinterpret_cast<float4*>(yrow + (size_t)n * 4);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                        } else {
+                            uint32_t ov[8];
+                            pack16(f, ov);
+                            uint4* op = reinterpret_cast<uint4*>(yrow + (size_t)n * 2);
+                            op[0] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                            op[1] = make_uint4(ov[4], ov[5], ov[6], ov[7]);
+                        }
+                    }
+                    if (two) {
+                        epi_math16(v1, bias_s + n + 16, act, has_res, r2, r3, f);
+                        if (ok) {
+                            if (out_f32) {
+                                float4* op = reinterpret_cast<float4*>(yrow + (size_t)(n + 16) * 4);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                            } else {
+                                uint32_t ov[8];
+                                pack16(f, ov);
+                                uint4* op = reinterpret_cast<uint4*>(yrow + (size_t)(n + 16) * 2);
+                                op[0] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                                op[1] = make_uint4(ov[4], ov[5], ov[6], ov[7]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (p.acc_sets == 2) {
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            } else {
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == WARP_ALLOC) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+int g_halo_mode = 1;  // 0 = kernel disabled (debug: everything through the TMA-im2col kernel), 1 = on
+
+}  // namespace
+
+void conv_halo_set_mode(int mode) { g_halo_mode = mode; }
+
+// Picks the band height; returns false when the shape does not fit this kernel.
+static bool halo_plan(const fce_conv_desc* d, HaloParams& p) {
+    if (g_halo_mode == 0) return false;
+    if (d->k != 3 || d->stride != 1) return false;
+    if (d->Cout > 256 || d->W + 2 > 256) return false;
+    const int kc = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
+    const int chunks = d->Cin / kc;
+    const uint32_t row_b = kc * 2;
+    const uint32_t b_sub = (uint32_t)d->Cout * row_b;
+    const uint32_t b_total = (9u * chunks * b_sub + 1023u) & ~1023u;
+    const uint32_t bias_bytes = ((uint32_t)d->Cout * 4 + 1023u) & ~1023u;
+    const int Wp = d->W + 2;
+    int best_R = 0;
+    double best_eff = 0.0;
+    for (int R = 1; R <= d->H && R + 2 <= 256; ++R) {
+        const int nb = (R * Wp + 127) / 128;
+        if (nb * d->Cout > 512) break;
+        const uint32_t rows = 128u * nb + 2u * Wp + 2u;
+        const uint32_t strip = (rows * row_b + 1023u) & ~1023u;
+        if ((size_t)A_STAGES * strip + b_total + bias_bytes + 2048 > (size_t)SMEM_LIMIT) break;
+        // useful fraction of the issued MMA rows, discounted by the halo re-read
+        const int bands = (d->H + R - 1) / R;
+        const double eff = (double)d->H * d->W / ((double)bands * nb * 128) * (0.75 + 0.25 * R / (R + 2.0));
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best_R = R;
+        }
+    }
+    if (best_R == 0 || best_eff < 0.55) return false;
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Wp = Wp;
+    p.Cin = d->Cin; p.Cout = d->Cout;
+    p.R = best_R;
+    p.bands = (d->H + best_R - 1) / best_R;
+    p.nb = (best_R * Wp + 127) / 128;
+    p.chunks = chunks;
+    p.units = d->B * p.bands;
+    p.acc_sets = 2 * p.nb * d->Cout <= 512 ? 2 : 1;
+    p.strip_bytes = ((128u * p.nb + 2u * Wp + 2u) * row_b + 1023u) & ~1023u;
+    p.strip_tx = row_b * (uint32_t)Wp * (uint32_t)(best_R + 2);
+    p.b_sub = b_sub;
+    p.b_total = b_total;
+    p.bias_bytes = bias_bytes;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < (uint32_t)(p.acc_sets * p.nb * d->Cout)) p.tmem_cols <<= 1;
+    return true;
+}
+
+bool conv2d_halo_supported(const fce_conv_desc* d) {
+    HaloParams p{};
+    return halo_plan(d, p);
+}
+
+int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res, void* y,
+                cudaStream_t st) {
+    const DriverApi& api = driver();
+    HaloParams p{};
+    if (!api.ok || !halo_plan(d, p)) return FCE_ERR_UNSUPPORTED;
+    const int kc = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
+    const uint32_t row_b = kc * 2;
+    p.out_pitch = d->out_pitch;
+    p.res_pitch = d->res_pitch;
+    p.act = d->act;
+    p.out_f32 = d->out_dtype == FCE_F32;
+    const uint32_t layout = row_b == 128 ? 2u : (row_b == 64 ? 4u : 6u);
+    const uint32_t sbo = 8 * row_b;
+    p.desc_hi = (sbo >> 4) | (1u << 14) | (layout << 29);
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const CUtensorMapSwizzle swz = row_b == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : row_b == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+    alignas(64) CUtensorMap tmA, tmB;
+    const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(x) + d->in_off;
+    {
+        const cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->W * d->in_pitch * 2,
+                                    (cuuint64_t)d->H * d->W * d->in_pitch * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)p.Wp, (cuuint32_t)(p.R + 2), 1};
+        const cuuint32_t est[4] = {1, 1, 1, 1};
+        if (api.tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)xin, gdim, gstr, box, est,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FCE_ERR_UNSUPPORTED;
+    }
+    {
+        const cuuint64_t K = 9ull * d->Cin;
+        const cuuint64_t gdim[2] = {K, (cuuint64_t)d->Cout};
+        const cuuint64_t gstr[1] = {K * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)d->Cout};
+        const cuuint32_t est[2] = {1, 1};
+        if (api.tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, est,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FCE_ERR_UNSUPPORTED;
+    }
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const HaloParams, const float*, const __nv_bfloat16*,
+                             void*);
+    static const KernelFn table[3] = {conv_halo_kernel<1>, conv_halo_kernel<2>, conv_halo_kernel<4>};
+    static bool attr_set = false;
+    if (!attr_set) {
+        for (int v = 0; v < 3; ++v) {
+            cudaError_t e = cudaFuncSetAttribute(table[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) {
+                set_cuda_error(e);
+                return FCE_ERR_CUDA;
+            }
+        }
+        attr_set = true;
+    }
+    const size_t smem = (size_t)A_STAGES * p.strip_bytes + p.b_total + p.bias_bytes + 1024 + 256;
+    const int grid = p.units < kNumSMs ? p.units : kNumSMs;
+    const __nv_bfloat16* rp = res ? reinterpret_cast<const __nv_bfloat16*>(res) + d->res_off : nullptr;
+    void* yp = d->out_dtype == FCE_F32 ? (void*)(reinterpret_cast<float*>(y) + d->out_off)
+                                       : (void*)(reinterpret_cast<__nv_bfloat16*>(y) + d->out_off);
+    table[kc == 16 ? 0 : (kc == 32 ? 1 : 2)]<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p, bias, rp, yp);
+    return check_launch();
+}
+
+}  // namespace fce

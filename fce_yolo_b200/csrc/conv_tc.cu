@@ -19,11 +19,10 @@
 //                   channel offset of the destination view (concat fusion)
 //   * Shared-memory tiles use the hardware swizzle that matches the K chunk (128B / 64B / 32B for
 //     kc = 64 / 32 / 16 channels), identical in the TMA descriptor and the UMMA shared-memory descriptor.
-#include <cuda.h>  // CUtensorMap types only - the two driver entry points are resolved at run time via cudart
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace fce {
+using namespace tc;
 namespace {
 
 constexpr int BM = 128;  // UMMA M (cta_group::1)
@@ -56,164 +55,6 @@ struct TcParams {
     uint32_t idesc;    // UMMA instruction descriptor
     int dbg;           // debug: bit 0 = producers skip the TMA loads (times the MMA + epilogue pipeline alone)
 };
-
-// ------------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must fault the launch (reported through the C ABI), never hang the GPU.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h,
-                                                int n, uint16_t off_w, uint16_t off_h) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
-        "l"(tm), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulation, issued by ONE thread for the CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Arrives on the mbarrier once every MMA issued so far by this thread has completed.
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// One MUFU per element: silu(v) = h + h*tanh(h), sigmoid(v) = 0.5 + 0.5*tanh(h), h = v/2.  tanh.approx has
-// 2^-11 relative error - below the bf16 rounding applied to the result.
-__device__ __forceinline__ float act_fast(float v, int act) {
-    if (act == FCE_ACT_SILU) {
-        const float h = 0.5f * v;
-        return fmaf(h, tanh_fast(h), h);
-    }
-    if (act == FCE_ACT_SIGMOID) return fmaf(0.5f, tanh_fast(0.5f * v), 0.5f);
-    return v;
-}
-
-struct Ring {
-    int stage = 0;
-    uint32_t phase = 0;
-    __device__ __forceinline__ void advance(int n) {
-        if (++stage == n) {
-            stage = 0;
-            phase ^= 1;
-        }
-    }
-};
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
-
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src),
-                 "r"(c0), "r"(c1)
-                 : "memory");
-}
-
-// bias + activation (+ residual) of 16 consecutive output channels of one pixel
-__device__ __forceinline__ void epi_math16(const uint32_t* v, const float* sbias, int act, bool has_res, uint4 r0,
-                                           uint4 r1, float* f) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 b = reinterpret_cast<const float4*>(sbias)[q];
-        f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
-        f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
-        f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
-        f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
-    }
-    if (act != FCE_ACT_NONE) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = act_fast(f[i], act);
-    }
-    if (has_res) {
-        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            f[2 * i] += __uint_as_float(rr[i] << 16);
-            f[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
-        }
-    }
-}
-__device__ __forceinline__ void pack16(const float* f, uint32_t* o) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-        o[i] = *reinterpret_cast<uint32_t*>(&h2);
-    }
-}
 
 // Optional per-role cycle accounting (debug entry points fce_conv_tc_set_profile / fce_conv_tc_profile):
 // [cta][0..1] A producer wait/total, [4..6] MMA wait-full / wait-tmem-empty / total,
@@ -552,40 +393,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
-                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                   CUtensorMapFloatOOBfill);
-
-struct DriverApi {
-    EncodeTiledFn tiled = nullptr;
-    EncodeIm2colFn im2col = nullptr;
-    int driver_version = 0;
-    bool ok = false;
-    DriverApi() {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return;
-        tiled = (EncodeTiledFn)f;
-        f = nullptr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return;
-        im2col = (EncodeIm2colFn)f;
-        cudaDriverGetVersion(&driver_version);
-        ok = true;
-    }
-};
-const DriverApi& driver() {
-    static DriverApi api;
-    return api;
-}
-
 bool g_profile_on = false;
 int g_debug_flags = 0;
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
 
@@ -604,9 +414,14 @@ bool conv2d_tc_supported(const fce_conv_desc* d, const void* x, const void* w, c
     return driver().ok;
 }
 
+bool conv2d_halo_supported(const fce_conv_desc* d);
+int conv2d_halo(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+
 int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res, void* y,
               cudaStream_t st) {
     if (!bias) return FCE_ERR_BAD_ARG;
+    // thin 3x3 stride-1 convs: input strip resident in shared memory (conv_halo.cu)
+    if (conv2d_halo_supported(d)) return conv2d_halo(d, x, w, bias, res, y, st);
     const DriverApi& api = driver();
     if (!api.ok) return FCE_ERR_CUDA;
     const int pad = d->k / 2;

@@ -29,6 +29,13 @@ CASES = [
     (1, 80, 80, 128, 128, 3, 1, 1, False, False, 0, 0),
     (4, 20, 20, 512, 512, 3, 1, 1, False, False, 0, 0),      # long K, two N tiles
     (1, 8, 8, 192, 384, 1, 1, 2, False, False, 0, 0),        # sigmoid, bn = 192
+    # 3x3 stride-1 strip ("halo") kernel shapes: weights resident, odd widths, bands that do not divide H
+    (2, 40, 40, 64, 64, 3, 1, 1, True, False, 0, 64),
+    (2, 80, 80, 64, 32, 3, 1, 1, False, False, 0, 0),
+    (1, 160, 160, 32, 16, 3, 1, 1, False, False, 0, 0),
+    (1, 160, 160, 16, 32, 3, 1, 1, True, False, 16, 0),
+    (3, 20, 20, 128, 32, 3, 1, 1, False, False, 0, 0),       # two K chunks
+    (2, 13, 27, 64, 48, 3, 1, 0, False, True, 0, 16),        # odd sizes, fp32 out
 ]
 
 
@@ -97,6 +104,8 @@ if __name__ == "__main__":  # quick report: python tests/test_gpu_conv_tc.py
     from fce_yolo_b200 import _lib as L
     torch.backends.cudnn.allow_tf32 = False
     l = L.load(check_device=True)
+    if len(sys.argv) > 1:
+        l.fce_conv_tc_set_profile(int(sys.argv[1]) << 4)  # 1 = strip kernel off
     for i, case in enumerate(CASES):
         try:
             em, el, ut = run_case(l, L, case, impl=2)
