@@ -16,6 +16,8 @@
 //
 // Each input element crosses L2 -> SM (R+2)/R times instead of 9, and the producer issues one TMA per
 // (band, chunk) instead of nine per 128 pixels.  Warp roles as in conv_tc.cu.
+#include <cstdio>
+
 #include "tc_common.cuh"
 
 namespace fce {
@@ -38,25 +40,38 @@ struct HaloParams {
     uint32_t strip_bytes, strip_tx;  // shared-memory bytes of one strip stage / bytes one TMA box delivers
     uint32_t b_sub;                  // bytes of one (tap, chunk) weight tile: Cout x kc bf16
     uint32_t b_total, bias_bytes;
+    uint32_t slab_bytes;  // one staged output slab: R*W rows x slab_cols*2 bytes (1024-aligned)
+    int n_slabs, slab_cols, n_stg, has_res;  // slab_cols: 64 (128-byte rows, 128B swizzle) or 32 (64-byte rows, 64B swizzle)
     uint32_t tmem_cols;
-    int out_pitch, res_pitch, act, out_f32;
+    int act;
     uint32_t desc_hi, idesc;
 };
 
-template <int KK>
+// debug cycle accounting, same slot layout as conv_tc.cu: [4] MMA wait-full [5] MMA wait-tmem [6] MMA total
+// [7] epilogue wait-tmem-full [8] epilogue total [9] epilogue wait-staging [10] DMA wait-written [11] DMA total
+constexpr int PROF_SLOTS = 16;
+__device__ long long g_hprof[kNumSMs * PROF_SLOTS];
+#define HP_T0() long long _t0 = 0; if (PROF) _t0 = clock64()
+#define HP_ACC(var) if (PROF) (var) += clock64() - _t0
+
+template <int KK, bool PROF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p,
-                 const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res, void* __restrict__ y) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const HaloParams p,
+                 const float* __restrict__ bias) {
     constexpr int kc = KK * 16;
     constexpr uint32_t row_b = kc * 2;  // bytes of one strip row (= swizzle span)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = base;
     const uint32_t sB = sA + A_STAGES * p.strip_bytes;
-    const uint32_t sBias = sB + p.b_total;
+    const uint32_t sStg = sB + p.b_total;  // output staging: n_stg x n_slabs x [R*W rows][slab row], swizzled
+    const uint32_t stg_bytes = p.n_slabs * p.slab_bytes;
+    const uint32_t sBias = sStg + p.n_stg * stg_bytes;
     const uint32_t bars = sBias + p.bias_bytes;
     const uint32_t full0 = bars, empty0 = bars + 16, tfull0 = bars + 32, tempty0 = bars + 48, bfull = bars + 64;
-    const uint32_t tmem_slot = bars + 72;
+    const uint32_t stg_ready0 = bars + 72, stg_written0 = bars + 88;
+    const uint32_t tmem_slot = bars + 104;
     float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -71,9 +86,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(tempty0 + 8 * a, NUM_EPI_WARPS);
         }
         mbar_init(bfull, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(stg_ready0 + 8 * a, 1);
+            mbar_init(stg_written0 + 8 * a, NUM_EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        if (p.has_res) tma_prefetch_desc(&tmR);
     }
     if (warp == WARP_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
@@ -127,12 +148,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int t = 0; t < 9; ++t) tap16[t] = (uint32_t)((t / 3) * p.Wp + (t % 3)) * (row_b >> 4);
         mbar_wait(bfull, 0);
         tc_fence_after();
+        long long wf = 0, we = 0, mt0 = PROF ? clock64() : 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+            {
+                HP_T0();
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                HP_ACC(we);
+            }
             tc_fence_after();
             const uint32_t d0 = tmem_base + acc * nb * bn;
             for (int c = 0; c < chunks; ++c) {
-                mbar_wait(full0 + 8 * r.stage, r.phase);
+                {
+                    HP_T0();
+                    mbar_wait(full0 + 8 * r.stage, r.phase);
+                    HP_ACC(wf);
+                }
                 tc_fence_after();
                 const uint32_t a16 = (sA + r.stage * p.strip_bytes) >> 4;
                 const uint32_t b16 = (sB + c * 9 * p.b_sub) >> 4;
@@ -170,88 +200,161 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 acc_phase ^= 1;
             }
         }
+        if (PROF && lane == 0) {
+            g_hprof[blockIdx.x * PROF_SLOTS + 4] = wf;
+            g_hprof[blockIdx.x * PROF_SLOTS + 5] = we;
+            g_hprof[blockIdx.x * PROF_SLOTS + 6] = clock64() - mt0;
+        }
+    } else if (warp == WARP_ALLOC) {
+        // ------------------------------------------------------------------ staging DMA: residual in, result out
+        // Per band i (staging buffer i % n_stg): the residual tile arrives by TMA (or the buffer is simply declared
+        // free) -> stg_ready; the eight epilogue warps fill it -> stg_written; one bulk store per slab.  With two
+        // staging buffers the residual of band i+1 is fetched while band i is still in the epilogue.
+        const int n_stg = p.n_stg, n_slabs = p.n_slabs, slab_cols = p.slab_cols;
+        const uint32_t res_tx = (uint32_t)n_slabs * (uint32_t)(slab_cols * 2) * (uint32_t)p.W * (uint32_t)p.R;
+        auto make_ready = [&](int u, int buf) {  // executed by one elected lane
+            if (p.has_res) {
+                const int b = u / p.bands, band = u - b * p.bands;
+                mbar_expect_tx(stg_ready0 + 8 * buf, res_tx);
+                for (int sl = 0; sl < n_slabs; ++sl)
+                    tma_load_4d(sStg + buf * stg_bytes + sl * p.slab_bytes, &tmR, stg_ready0 + 8 * buf, sl * slab_cols, 0,
+                                band * p.R, b);
+            } else {
+                mbar_arrive(stg_ready0 + 8 * buf);
+            }
+        };
+        uint32_t ph[2] = {0, 0};
+        int i = 0;
+        long long dw = 0, dt0 = PROF ? clock64() : 0;
+        if (blockIdx.x < units && elect_one()) make_ready(blockIdx.x, 0);
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++i) {
+            const int buf = n_stg == 2 ? (i & 1) : 0;
+            if (n_stg == 2) {
+                // the other buffer's last store (band i-1) must have drained it before band i+1 may load into it
+                const int un = u + gridDim.x;
+                if (elect_one()) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (un < units) make_ready(un, buf ^ 1);
+                }
+            }
+            {
+                HP_T0();
+                mbar_wait(stg_written0 + 8 * buf, ph[buf]);
+                HP_ACC(dw);
+            }
+            ph[buf] ^= 1;
+            if (elect_one()) {
+                const int b = u / p.bands, band = u - b * p.bands;
+                for (int sl = 0; sl < n_slabs; ++sl)
+                    tma_store_4d(&tmC, sStg + buf * stg_bytes + sl * p.slab_bytes, sl * slab_cols, 0, band * p.R, b);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (n_stg == 1) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    const int un = u + gridDim.x;
+                    if (un < units) make_ready(un, 0);
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (PROF && lane == 0) {
+            g_hprof[blockIdx.x * PROF_SLOTS + 10] = dw;
+            g_hprof[blockIdx.x * PROF_SLOTS + 11] = clock64() - dt0;
+        }
     } else if (warp < NUM_EPI_WARPS) {
-        // ------------------------------------------------------------------ epilogue (direct NHWC stores)
+        // ------------------------------------------------------------------ epilogue
+        // TMEM -> registers -> bias / activation (+ residual, read from the staged tile) -> staging, compacted from the
+        // padded-flat accumulator rows to [R][W] so that ONE 4-D bulk store per 32-column slab writes the band.
         const int quarter = warp & 3, half = warp >> 2;
         const int n_chunks = bn >> 4, act = p.act, Wp = p.Wp, W = p.W, R = p.R, H = p.H;
-        const bool has_res = res != nullptr, out_f32 = p.out_f32 != 0;
-        const int osz = out_f32 ? 4 : 2;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int b = u / p.bands, band = u - b * p.bands;
+        const bool has_res = p.has_res != 0;
+        const bool split_cols = n_chunks >= 4;  // wide outputs: the two halves split columns, else they split blocks
+        const bool wide = p.slab_cols == 64;    // 128-byte staging rows (128B swizzle) vs 64-byte rows (64B swizzle)
+        const uint32_t row_bytes = wide ? 128u : 64u, swz_mask = wide ? 7u : 3u;
+        int acc = 0, i = 0;
+        uint32_t acc_phase = 0, sph[2] = {0, 0};
+        long long ew = 0, es = 0, et0 = PROF ? clock64() : 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++i) {
+            const int band = u % p.bands;
             const int h0 = band * R;
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            const int buf = p.n_stg == 2 ? (i & 1) : 0;
+            const uint32_t stg = sStg + buf * stg_bytes;
+            {
+                HP_T0();
+                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                HP_ACC(ew);
+            }
+            {
+                HP_T0();
+                mbar_wait(stg_ready0 + 8 * buf, sph[buf]);
+                HP_ACC(es);
+            }
+            sph[buf] ^= 1;
             tc_fence_after();
-            for (int blk = 0; blk < nb; ++blk) {
+            for (int blk = split_cols ? 0 : half; blk < nb; blk += split_cols ? 1 : 2) {
                 const int o = blk * 128 + quarter * 32 + lane;  // padded-flat output index inside the band
                 const int ro = o / Wp, co = o - ro * Wp;
                 const bool ok = co < W && ro < R && h0 + ro < H;
-                const size_t m = ((size_t)(b * H + h0 + ro) * W + co);
-                char* yrow = reinterpret_cast<char*>(y) + m * p.out_pitch * osz;
-                const __nv_bfloat16* rrow = res + m * p.res_pitch;
+                const uint32_t lin = (uint32_t)(ro * W + co) * row_bytes;  // byte offset of this pixel's row in a slab
+                const uint32_t swz = ((lin >> 7) & swz_mask) << 4;           // swizzle: address bits 7.. -> bits 4..
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * nb + blk) * bn;
 #pragma unroll 1
-                for (int j = half * 2; j < n_chunks; j += 4) {
+                for (int j = split_cols ? half * 2 : 0; j < n_chunks; j += split_cols ? 4 : 2) {
                     const int n = j * 16;
                     const bool two = j + 1 < n_chunks;
-                    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
-                    if (has_res && ok) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(rrow + n);
-                        r0 = rp[0];
-                        r1 = rp[1];
-                        if (two) {
-                            r2 = rp[2];
-                            r3 = rp[3];
-                        }
-                    }
+                    // 16-column chunk j lives in slab j / (slab_cols / 16), at byte (j % ...) * 32 of the row
+                    const uint32_t rowp = stg + (uint32_t)(wide ? (j >> 2) : (j >> 1)) * p.slab_bytes + lin;
+                    const uint32_t cb = wide ? (uint32_t)(j & 2) * 32u : 0u;  // j is even: chunk pair offset 0 or 64
                     uint32_t v0[16], v1[16];
                     tmem_ld16(t_row + n, v0);
                     if (two) tmem_ld16(t_row + n + 16, v1);
+                    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
+                    if (has_res && ok) {
+                        r0 = ld_shared_v4(rowp + ((cb + 0u) ^ swz));
+                        r1 = ld_shared_v4(rowp + ((cb + 16u) ^ swz));
+                        if (two) {
+                            r2 = ld_shared_v4(rowp + ((cb + 32u) ^ swz));
+                            r3 = ld_shared_v4(rowp + ((cb + 48u) ^ swz));
+                        }
+                    }
                     tmem_ld_wait();
                     float f[16];
+                    uint32_t ov[8];
                     epi_math16(v0, bias_s + n, act, has_res, r0, r1, f);
+                    pack16(f, ov);
                     if (ok) {
-                        if (out_f32) {
-                            float4* op = reinterpret_cast<float4*>(yrow + (size_t)n * 4);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                        } else {
-                            uint32_t ov[8];
-                            pack16(f, ov);
-                            uint4* op = reinterpret_cast<uint4*>(yrow + (size_t)n * 2);
-                            op[0] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-                            op[1] = make_uint4(ov[4], ov[5], ov[6], ov[7]);
-                        }
+                        st_shared_v4(rowp + ((cb + 0u) ^ swz), ov[0], ov[1], ov[2], ov[3]);
+                        st_shared_v4(rowp + ((cb + 16u) ^ swz), ov[4], ov[5], ov[6], ov[7]);
                     }
                     if (two) {
                         epi_math16(v1, bias_s + n + 16, act, has_res, r2, r3, f);
+                        pack16(f, ov);
                         if (ok) {
-                            if (out_f32) {
-                                float4* op = reinterpret_cast<float4*>(yrow + (size_t)(n + 16) * 4);
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                            } else {
-                                uint32_t ov[8];
-                                pack16(f, ov);
-                                uint4* op = reinterpret_cast<uint4*>(yrow + (size_t)(n + 16) * 2);
-                                op[0] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-                                op[1] = make_uint4(ov[4], ov[5], ov[6], ov[7]);
-                            }
+                            st_shared_v4(rowp + ((cb + 32u) ^ swz), ov[0], ov[1], ov[2], ov[3]);
+                            st_shared_v4(rowp + ((cb + 48u) ^ swz), ov[4], ov[5], ov[6], ov[7]);
                         }
                     }
                 }
             }
             tc_fence_before();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (lane == 0) {
+                mbar_arrive(tempty0 + 8 * acc);
+                mbar_arrive(stg_written0 + 8 * buf);
+            }
             if (p.acc_sets == 2) {
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             } else {
                 acc_phase ^= 1;
             }
+        }
+        if (PROF && warp == 0 && lane == 0) {
+            g_hprof[blockIdx.x * PROF_SLOTS + 7] = ew;
+            g_hprof[blockIdx.x * PROF_SLOTS + 8] = clock64() - et0;
+            g_hprof[blockIdx.x * PROF_SLOTS + 9] = es;
         }
     }
 
@@ -263,17 +366,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+bool g_halo_prof = false, g_halo_last = false;
 int g_halo_mode = 1;  // 0 = kernel disabled (debug: everything through the TMA-im2col kernel), 1 = on
 
 }  // namespace
 
 void conv_halo_set_mode(int mode) { g_halo_mode = mode; }
+void conv_halo_set_profile(bool on) { g_halo_prof = on; }
+bool conv_halo_ran_last() { return g_halo_last; }
+void conv_halo_clear_last() { g_halo_last = false; }
+int conv_halo_profile(long long* out, int n) {
+    if (n > kNumSMs * PROF_SLOTS) n = kNumSMs * PROF_SLOTS;
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_hprof, (size_t)n * sizeof(long long));
+    if (e != cudaSuccess) {
+        set_cuda_error(e);
+        return FCE_ERR_CUDA;
+    }
+    return n;
+}
 
 // Picks the band height; returns false when the shape does not fit this kernel.
-static bool halo_plan(const fce_conv_desc* d, HaloParams& p) {
+static bool halo_plan(const fce_conv_desc* d, bool has_res, HaloParams& p) {
     if (g_halo_mode == 0) return false;
     if (d->k != 3 || d->stride != 1) return false;
-    if (d->Cout > 256 || d->W + 2 > 256) return false;
+    if (d->Cout > 256 || d->W + 2 > 256 || d->out_dtype != FCE_BF16) return false;
     const int kc = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
     const int chunks = d->Cin / kc;
     const uint32_t row_b = kc * 2;
@@ -285,10 +401,15 @@ static bool halo_plan(const fce_conv_desc* d, HaloParams& p) {
     double best_eff = 0.0;
     for (int R = 1; R <= d->H && R + 2 <= 256; ++R) {
         const int nb = (R * Wp + 127) / 128;
-        if (nb * d->Cout > 512) break;
+        if (2 * nb * d->Cout > 512) break;  // two accumulator sets: the epilogue of a band overlaps the next band's MMAs
         const uint32_t rows = 128u * nb + 2u * Wp + 2u;
         const uint32_t strip = (rows * row_b + 1023u) & ~1023u;
-        if ((size_t)A_STAGES * strip + b_total + bias_bytes + 2048 > (size_t)SMEM_LIMIT) break;
+        const uint32_t slab_cols = d->Cout % 64 == 0 ? 64u : 32u;
+        const uint32_t slab = ((uint32_t)R * d->W * slab_cols * 2u + 1023u) & ~1023u;
+        const uint32_t n_slabs = ((uint32_t)d->Cout + slab_cols - 1) / slab_cols;
+        // with a residual the staging is double buffered (the next band's residual streams in during the epilogue)
+        const uint32_t n_stg = has_res ? 2u : 1u;
+        if ((size_t)A_STAGES * strip + b_total + n_stg * n_slabs * slab + bias_bytes + 2048 > (size_t)SMEM_LIMIT) break;
         // useful fraction of the issued MMA rows, discounted by the halo re-read
         const int bands = (d->H + R - 1) / R;
         const double eff = (double)d->H * d->W / ((double)bands * nb * 128) * (0.75 + 0.25 * R / (R + 2.0));
@@ -311,27 +432,31 @@ static bool halo_plan(const fce_conv_desc* d, HaloParams& p) {
     p.b_sub = b_sub;
     p.b_total = b_total;
     p.bias_bytes = bias_bytes;
+    p.slab_cols = d->Cout % 64 == 0 ? 64 : 32;
+    p.slab_bytes = ((uint32_t)best_R * d->W * (uint32_t)p.slab_cols * 2u + 1023u) & ~1023u;
+    p.n_slabs = (d->Cout + p.slab_cols - 1) / p.slab_cols;
+    // a second staging buffer (residual prefetch / store overlap) when shared memory allows
+    p.n_stg = ((size_t)A_STAGES * p.strip_bytes + b_total + 2ull * p.n_slabs * p.slab_bytes + bias_bytes + 2048 <=
+               (size_t)SMEM_LIMIT) ? 2 : 1;
     p.tmem_cols = 32;
     while (p.tmem_cols < (uint32_t)(p.acc_sets * p.nb * d->Cout)) p.tmem_cols <<= 1;
     return true;
 }
 
-bool conv2d_halo_supported(const fce_conv_desc* d) {
+bool conv2d_halo_supported(const fce_conv_desc* d, bool has_res) {
     HaloParams p{};
-    return halo_plan(d, p);
+    return halo_plan(d, has_res, p);
 }
 
 int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res, void* y,
                 cudaStream_t st) {
     const DriverApi& api = driver();
     HaloParams p{};
-    if (!api.ok || !halo_plan(d, p)) return FCE_ERR_UNSUPPORTED;
+    if (!api.ok || !halo_plan(d, res != nullptr, p)) return FCE_ERR_UNSUPPORTED;
     const int kc = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
     const uint32_t row_b = kc * 2;
-    p.out_pitch = d->out_pitch;
-    p.res_pitch = d->res_pitch;
     p.act = d->act;
-    p.out_f32 = d->out_dtype == FCE_F32;
+    p.has_res = res != nullptr;
     const uint32_t layout = row_b == 128 ? 2u : (row_b == 64 ? 4u : 6u);
     const uint32_t sbo = 8 * row_b;
     p.desc_hi = (sbo >> 4) | (1u << 14) | (layout << 29);
@@ -339,8 +464,29 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
     const CUtensorMapSwizzle swz = row_b == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                    : row_b == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
-    alignas(64) CUtensorMap tmA, tmB;
+    alignas(64) CUtensorMap tmA, tmB, tmC, tmR;
     const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(x) + d->in_off;
+    // output / residual bands: box {32 channels, W, R rows, 1 image} of the NHWC view, 64B-swizzled staging
+    for (int which = 0; which < 2; ++which) {
+        const bool is_res = which == 1;
+        if (is_res && !res) {
+            tmR = tmC;
+            break;
+        }
+        const int pitch = is_res ? d->res_pitch : d->out_pitch;
+        void* ptr = is_res ? (void*)(reinterpret_cast<const __nv_bfloat16*>(res) + d->res_off)
+                           : (void*)(reinterpret_cast<__nv_bfloat16*>(y) + d->out_off);
+        const cuuint64_t gdim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)d->W * pitch * 2, (cuuint64_t)d->H * d->W * pitch * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)p.slab_cols, (cuuint32_t)d->W, (cuuint32_t)p.R, 1};
+        const cuuint32_t est[4] = {1, 1, 1, 1};
+        if (api.tiled(is_res ? &tmR : &tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, gdim, gstr, box, est,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      p.slab_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FCE_ERR_UNSUPPORTED;
+    }
     {
         const cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
         const cuuint64_t gstr[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->W * d->in_pitch * 2,
@@ -363,12 +509,13 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return FCE_ERR_UNSUPPORTED;
     }
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const HaloParams, const float*, const __nv_bfloat16*,
-                             void*);
-    static const KernelFn table[3] = {conv_halo_kernel<1>, conv_halo_kernel<2>, conv_halo_kernel<4>};
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const HaloParams,
+                             const float*);
+    static const KernelFn table[6] = {conv_halo_kernel<1, false>, conv_halo_kernel<2, false>, conv_halo_kernel<4, false>,
+                                      conv_halo_kernel<1, true>,  conv_halo_kernel<2, true>,  conv_halo_kernel<4, true>};
     static bool attr_set = false;
     if (!attr_set) {
-        for (int v = 0; v < 3; ++v) {
+        for (int v = 0; v < 6; ++v) {
             cudaError_t e = cudaFuncSetAttribute(table[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) {
                 set_cuda_error(e);
@@ -377,12 +524,15 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
         }
         attr_set = true;
     }
-    const size_t smem = (size_t)A_STAGES * p.strip_bytes + p.b_total + p.bias_bytes + 1024 + 256;
+    const size_t smem = (size_t)A_STAGES * p.strip_bytes + p.b_total + (size_t)p.n_stg * p.n_slabs * p.slab_bytes +
+                        p.bias_bytes + 1024 + 256;
     const int grid = p.units < kNumSMs ? p.units : kNumSMs;
-    const __nv_bfloat16* rp = res ? reinterpret_cast<const __nv_bfloat16*>(res) + d->res_off : nullptr;
-    void* yp = d->out_dtype == FCE_F32 ? (void*)(reinterpret_cast<float*>(y) + d->out_off)
-                                       : (void*)(reinterpret_cast<__nv_bfloat16*>(y) + d->out_off);
-    table[kc == 16 ? 0 : (kc == 32 ? 1 : 2)]<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p, bias, rp, yp);
+    g_halo_last = true;
+    if (g_halo_prof)
+        fprintf(stderr, "[halo] R=%d bands=%d nb=%d units=%d acc_sets=%d n_stg=%d slab_cols=%d smem=%zu\n", p.R, p.bands, p.nb,
+                p.units, p.acc_sets, p.n_stg, p.slab_cols, smem);
+    table[(kc == 16 ? 0 : (kc == 32 ? 1 : 2)) + (g_halo_prof ? 3 : 0)]<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p,
+                                                                                                       bias);
     return check_launch();
 }
 

@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--impl", type=int, default=2)
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--noflush", action="store_true")
+    ap.add_argument("--act", type=int, default=1)
     ap.add_argument("--prof", action="store_true", help="per-role cycle accounting of one launch per shape")
     ap.add_argument("--skip-tma", action="store_true", help="debug: producers skip the loads (MMA+epilogue rate)")
     a = ap.parse_args()
@@ -75,7 +76,7 @@ def main():
         y = torch.empty(B, Ho, Wo, Cout, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
         r = torch.randn(B, Ho, Wo, Cout, device=dev).to(torch.bfloat16) if has_res else None
         d = L.ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=Cout, in_pitch=Cin, in_off=0, out_pitch=Cout, out_off=0,
-                       res_pitch=Cout if has_res else 0, res_off=0, k=k, stride=s, act=1, in_dtype=L.BF16,
+                       res_pitch=Cout if has_res else 0, res_off=0, k=k, stride=s, act=a.act, in_dtype=L.BF16,
                        w_dtype=L.BF16, out_dtype=L.F32 if f32 else L.BF16, in_layout=L.NHWC, in_scale=1.0, impl=a.impl)
         args = (C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(bias.data_ptr()),
                 C.c_void_p(r.data_ptr() if has_res else 0), C.c_void_p(y.data_ptr()), C.c_void_p(st))
@@ -98,7 +99,7 @@ def main():
             tiles = -(-(B * Ho * Wo) // 128)
             m = pr.mean(0)
             print(f"{name:34s} tiles/CTA {tiles/148:6.1f} | A-prod wait {m[0]:9.0f} / {m[1]:9.0f} | MMA wait-full {m[4]:9.0f} "
-                  f"wait-tmem {m[5]:9.0f} / {m[6]:9.0f} | epi wait {m[7]:9.0f} / {m[8]:9.0f}  (cycles, mean over CTAs)", flush=True)
+                  f"wait-tmem {m[5]:9.0f} / {m[6]:9.0f} | epi wait {m[7]:9.0f} / {m[8]:9.0f} stg-wait {m[9]:9.0f} | dma wait {m[10]:9.0f} / {m[11]:9.0f}", flush=True)
             continue
         for _ in range(2):
             L.check(lib.fce_conv2d(*args), name)
