@@ -31,6 +31,7 @@ class Predictor:
                                           multi_label=multi_label))
             self.ex = Executor(plan, use_graph=use_graph)
             self.stream = torch.cuda.Stream(self.device)
+            self.stream_ = self.stream
             self.inp = self.ex.input_tensor()
             self.det, self.keep, self.count = self.ex.detections()
             self.h_det = torch.empty(self.det.shape, dtype=torch.float32).pin_memory()
@@ -58,6 +59,64 @@ class Predictor:
             self.h_count.copy_(self.count, non_blocking=True)
         self.stream.synchronize()
         return self.h_det, self.h_count
+
+    def pipeline(self, batches):
+        """Pipelined inference over an iterable of host batches (each shaped like ``input_shape``, ideally pinned):
+        the host->device copy of batch i+1 runs on a copy stream while batch i is in the graph, and the padded
+        detections of batch i come back device->host on the compute stream.  Yields, per batch and in order, pinned
+        host tensors (det [B,max_det,6], count [B]) - valid until the next-but-one ``next()`` (two result slots).
+        Every batch still crosses PCIe inside the call: this is the end-to-end path, only overlapped."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            if not hasattr(self, "_pipe"):
+                self._pipe = dict(
+                    copy_stream=torch.cuda.Stream(dev),
+                    stage=[torch.empty_like(self.inp) for _ in range(2)],
+                    h_det=[torch.empty(self.det.shape, dtype=torch.float32).pin_memory() for _ in range(2)],
+                    h_cnt=[torch.empty(self.count.shape, dtype=torch.int32).pin_memory() for _ in range(2)],
+                    copied=[torch.cuda.Event() for _ in range(2)],
+                    consumed=[torch.cuda.Event() for _ in range(2)],
+                    done=[torch.cuda.Event() for _ in range(2)])
+            P = self._pipe
+            cs, ms = P["copy_stream"], self.stream_
+            it = iter(batches)
+
+            def upload(i, images):
+                if tuple(images.shape) != tuple(self.inp.shape):
+                    raise ValueError(f"expected input of shape {tuple(self.inp.shape)}, got {tuple(images.shape)}")
+                with torch.cuda.stream(cs):
+                    cs.wait_event(P["consumed"][i % 2])  # the staging slot was drained by compute two batches ago
+                    P["stage"][i % 2].copy_(images, non_blocking=True)
+                    P["copied"][i % 2].record(cs)
+
+            for ev in P["consumed"]:
+                ev.record(ms)
+            nxt = next(it, None)
+            i = 0
+            if nxt is not None:
+                upload(0, nxt)
+            pending = None
+            while nxt is not None:
+                cur_i = i
+                nxt = next(it, None)
+                with torch.cuda.stream(ms):
+                    ms.wait_event(P["copied"][cur_i % 2])
+                    self.inp.copy_(P["stage"][cur_i % 2], non_blocking=True)  # device-to-device, ~30 us
+                    P["consumed"][cur_i % 2].record(ms)
+                    self.ex.run()
+                    P["h_det"][cur_i % 2].copy_(self.det, non_blocking=True)
+                    P["h_cnt"][cur_i % 2].copy_(self.count, non_blocking=True)
+                    P["done"][cur_i % 2].record(ms)
+                if nxt is not None:
+                    upload(cur_i + 1, nxt)  # overlaps the graph that was just launched
+                if pending is not None:
+                    P["done"][pending % 2].synchronize()
+                    yield P["h_det"][pending % 2], P["h_cnt"][pending % 2]
+                pending = cur_i
+                i += 1
+            if pending is not None:
+                P["done"][pending % 2].synchronize()
+                yield P["h_det"][pending % 2], P["h_cnt"][pending % 2]
 
     def __call__(self, images: torch.Tensor):
         det, count = self.infer(images)
