@@ -61,6 +61,153 @@ __global__ void __launch_bounds__(NT) stem_pack_kernel(const fce_pack_desc d, co
     for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused stem
+// fce_stem_conv: the whole first layer in ONE pass - image tile -> shared memory (bf16) -> per-warp
+// mma.sync m16n8k16 (M = 16 output pixels, K = 27 padded to 32, N = Cout) -> bias + SiLU -> bf16 NHWC, staged
+// through shared memory so that every global store is a full 16-byte chunk of a contiguous pixel run.
+// Algorithmic HBM bytes per output pixel: 12 * e_in read (each input byte lands in ~2.25 patches but is fetched
+// once per CTA tile) + 2 * Cout written; the [M, 32] patch matrix of the two-kernel route (64 B written + 64 B
+// read per pixel) never exists.  A tcgen05 pipeline has nothing to offer at K = 32, N <= 96: the layer is
+// bound by the output write.
+constexpr int ST_ROWS = 8, ST_COLS = 64;             // output tile of one CTA
+constexpr int ST_IR = 2 * ST_ROWS + 1, ST_IC = 2 * ST_COLS + 1;  // input tile incl. the left/top halo
+constexpr int ST_THREADS = 128;
+
+template <typename TI, int LAYOUT, int NTILES>
+__global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_desc d, const TI* __restrict__ x,
+                                                                const __nv_bfloat16* __restrict__ w,
+                                                                const float* __restrict__ bias,
+                                                                __nv_bfloat16* __restrict__ y, int Ho, int Wo) {
+    constexpr int COUT = NTILES * 8;
+    constexpr int OPITCH = COUT + 8;  // staged pixel pitch (bf16): +16 B keeps the quad-strided writes conflict-free
+    __shared__ __align__(16) __nv_bfloat16 tile[ST_IR * ST_IC * 3];
+    __shared__ __align__(16) __nv_bfloat16 stage[4][16 * OPITCH];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int b = blockIdx.z, ho0 = blockIdx.y * ST_ROWS, wo0 = blockIdx.x * ST_COLS;
+    const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
+
+    // ---- stage the input tile (zero outside the image = the conv padding)
+    if (LAYOUT == FCE_NHWC) {
+        for (int i = tid; i < ST_IR * ST_IC * 3; i += ST_THREADS) {
+            const int r = i / (ST_IC * 3), rem = i - r * (ST_IC * 3);
+            const int c = rem / 3;
+            const int hi = hi0 + r, wi = wi0 + c;
+            float v = 0.f;
+            if (hi >= 0 && hi < d.H && wi >= 0 && wi < d.W)
+                v = Elem<TI>::to_f(__ldg(x + ((size_t)(b * d.H + hi) * d.W + wi0) * 3 + rem));
+            tile[i] = __float2bfloat16_rn(v);
+        }
+    } else {
+        for (int i = tid; i < 3 * ST_IR * ST_IC; i += ST_THREADS) {
+            const int ci = i / (ST_IR * ST_IC), rem = i - ci * (ST_IR * ST_IC);
+            const int r = rem / ST_IC, c = rem - r * ST_IC;
+            const int hi = hi0 + r, wi = wi0 + c;
+            float v = 0.f;
+            if (hi >= 0 && hi < d.H && wi >= 0 && wi < d.W)
+                v = Elem<TI>::to_f(__ldg(x + ((size_t)(b * 3 + ci) * d.H + hi) * d.W + wi));
+            tile[(r * ST_IC + c) * 3 + ci] = __float2bfloat16_rn(v);
+        }
+    }
+    // ---- B fragments (weights [COUT][32] bf16, K index (kh*3+kw)*3+ci, columns 27..31 zero) and bias
+    uint32_t bf[2][NTILES][2];
+    float bs[NTILES][2];
+#pragma unroll
+    for (int nt = 0; nt < NTILES; ++nt) {
+        const uint32_t* wr = reinterpret_cast<const uint32_t*>(w + (nt * 8 + g) * 32);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            bf[ks][nt][0] = __ldg(wr + ks * 8 + t);
+            bf[ks][nt][1] = __ldg(wr + ks * 8 + 4 + t);
+        }
+        bs[nt][0] = __ldg(bias + nt * 8 + 2 * t);
+        bs[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1);
+    }
+    // ---- this thread's 8 patch offsets: k -> kh * (row pitch) + k % 9 (the 9 values of one kh are contiguous)
+    int koff[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = ks * 16 + 2 * t + (j & 1) + 8 * (j >> 1);
+            koff[ks][j] = k < 27 ? (k / 9) * (ST_IC * 3) + k % 9 : -1;
+        }
+    __syncthreads();
+
+    const unsigned short* tl = reinterpret_cast<const unsigned short*>(tile);
+    __nv_bfloat16* stg = stage[warp];
+    // warp w owns output rows 2w, 2w+1 of the tile: 8 runs of 16 consecutive pixels
+#pragma unroll 1
+    for (int run = 0; run < 8; ++run) {
+        const int ro = warp * 2 + (run >> 2), co = (run & 3) * 16;
+        const int ho = ho0 + ro;
+        if (ho >= Ho || wo0 + co >= Wo) continue;  // warp-uniform
+        const int p0 = (2 * ro) * (ST_IC * 3) + 2 * (co + g) * 3;  // patch origin of pixel g; pixel g+8 is +48
+        uint32_t a[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            unsigned short e[4][2];  // [j][row half]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = koff[ks][j];
+                e[j][0] = o >= 0 ? tl[p0 + o] : (unsigned short)0;
+                e[j][1] = o >= 0 ? tl[p0 + 48 + o] : (unsigned short)0;
+            }
+            a[ks][0] = (uint32_t)e[0][0] | ((uint32_t)e[1][0] << 16);  // row g,   k = 2t, 2t+1
+            a[ks][1] = (uint32_t)e[0][1] | ((uint32_t)e[1][1] << 16);  // row g+8
+            a[ks][2] = (uint32_t)e[2][0] | ((uint32_t)e[3][0] << 16);  // row g,   k = 2t+8, 2t+9
+            a[ks][3] = (uint32_t)e[2][1] | ((uint32_t)e[3][1] << 16);  // row g+8
+        }
+        __syncwarp();  // the previous run's staged pixels have been read
+#pragma unroll
+        for (int nt = 0; nt < NTILES; ++nt) {
+            float c[4] = {bs[nt][0], bs[nt][1], bs[nt][0], bs[nt][1]};
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                         : "r"(a[0][0]), "r"(a[0][1]), "r"(a[0][2]), "r"(a[0][3]), "r"(bf[0][nt][0]), "r"(bf[0][nt][1]));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                         : "r"(a[1][0]), "r"(a[1][1]), "r"(a[1][2]), "r"(a[1][3]), "r"(bf[1][nt][0]), "r"(bf[1][nt][1]));
+            if (d.act == FCE_ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[j] = silu_f(c[j]);
+            }
+            __nv_bfloat162 lo = __floats2bfloat162_rn(c[0], c[1]), hi = __floats2bfloat162_rn(c[2], c[3]);
+            *reinterpret_cast<__nv_bfloat162*>(stg + g * OPITCH + nt * 8 + 2 * t) = lo;
+            *reinterpret_cast<__nv_bfloat162*>(stg + (g + 8) * OPITCH + nt * 8 + 2 * t) = hi;
+        }
+        __syncwarp();
+        // 16 pixels x NTILES 16-byte chunks, contiguous in global memory when out_pitch == COUT
+        const size_t pix0 = ((size_t)(b * Ho + ho) * Wo + wo0 + co);
+#pragma unroll
+        for (int i = lane; i < 16 * NTILES; i += 32) {
+            const int px = i / NTILES, ch = i - px * NTILES;
+            if (wo0 + co + px < Wo) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + px * OPITCH + ch * 8);
+                *reinterpret_cast<uint4*>(y + (pix0 + px) * d.out_pitch + d.out_off + ch * 8) = v;
+            }
+        }
+    }
+}
+
+template <typename TI, int LAYOUT>
+int launch_stem(const fce_stem_desc* d, const void* x, const void* w, const float* bias, void* y, cudaStream_t st) {
+    const int Ho = (d->H - 1) / 2 + 1, Wo = (d->W - 1) / 2 + 1;
+    dim3 grid((Wo + ST_COLS - 1) / ST_COLS, (Ho + ST_ROWS - 1) / ST_ROWS, d->B);
+    const TI* xi = (const TI*)x;
+    const __nv_bfloat16* wi = (const __nv_bfloat16*)w;
+    __nv_bfloat16* yo = (__nv_bfloat16*)y;
+    switch (d->Cout / 8) {
+        case 2: stem_fused_kernel<TI, LAYOUT, 2><<<grid, ST_THREADS, 0, st>>>(*d, xi, wi, bias, yo, Ho, Wo); break;
+        case 4: stem_fused_kernel<TI, LAYOUT, 4><<<grid, ST_THREADS, 0, st>>>(*d, xi, wi, bias, yo, Ho, Wo); break;
+        case 6: stem_fused_kernel<TI, LAYOUT, 6><<<grid, ST_THREADS, 0, st>>>(*d, xi, wi, bias, yo, Ho, Wo); break;
+        case 8: stem_fused_kernel<TI, LAYOUT, 8><<<grid, ST_THREADS, 0, st>>>(*d, xi, wi, bias, yo, Ho, Wo); break;
+        case 12: stem_fused_kernel<TI, LAYOUT, 12><<<grid, ST_THREADS, 0, st>>>(*d, xi, wi, bias, yo, Ho, Wo); break;
+        default: return FCE_ERR_UNSUPPORTED;
+    }
+    return check_launch();
+}
+
 }  // namespace
 }  // namespace fce
 
@@ -84,4 +231,17 @@ extern "C" int fce_stem_pack(const fce_pack_desc* d, const void* x, void* a, voi
     else
         return FCE_ERR_UNSUPPORTED;
     return check_launch();
+}
+
+extern "C" int fce_stem_conv(const fce_stem_desc* d, const void* x, const void* w, const float* bias, void* y,
+                             void* stream) {
+    if (!d || !x || !w || !bias || !y || d->B <= 0 || d->H <= 0 || d->W <= 0) return FCE_ERR_BAD_ARG;
+    if (d->Cout % 8 || d->Cout <= 0 || (d->act != FCE_ACT_SILU && d->act != FCE_ACT_NONE)) return FCE_ERR_UNSUPPORTED;
+    if (d->B > 65535) return FCE_ERR_UNSUPPORTED;
+    if (d->out_pitch % 8 || d->out_off % 8 || ((uintptr_t)y & 15) || ((uintptr_t)w & 3)) return FCE_ERR_ALIGNMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->in_dtype == FCE_U8 && d->in_layout == FCE_NHWC) return launch_stem<uint8_t, FCE_NHWC>(d, x, w, bias, y, st);
+    if (d->in_dtype == FCE_F32 && d->in_layout == FCE_NCHW) return launch_stem<float, FCE_NCHW>(d, x, w, bias, y, st);
+    if (d->in_dtype == FCE_F32 && d->in_layout == FCE_NHWC) return launch_stem<float, FCE_NHWC>(d, x, w, bias, y, st);
+    return FCE_ERR_UNSUPPORTED;
 }

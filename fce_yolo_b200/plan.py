@@ -103,6 +103,8 @@ class PlanError(ValueError):
 
 
 class Plan:
+    FUSED_STEM = True  # False: stem = fce_stem_pack + K=32 tcgen05 conv (kept for A/B timing and as a cross-check)
+
     def __init__(self, batch: int, precision: str, device, impl: int = 0):
         if precision not in ("bf16", "fp32"):
             raise PlanError(f"precision must be 'bf16' or 'fp32', got {precision}")
@@ -209,8 +211,9 @@ class Plan:
         return dst
 
     def stem(self, m, img: View, in_layout, in_scale, tag="") -> View:
-        """First Conv of the graph.  bf16 mode, 3x3/s2 on 3 channels: patch packing (fce_stem_pack) into a
-        [M, 32] bf16 matrix followed by a K = 32 1x1 conv on the tensor cores; anything else: the generic conv."""
+        """First Conv of the graph.  bf16 mode, 3x3/s2 on 3 channels: the fused stem kernel (fce_stem_conv); for
+        channel counts it does not cover (or Plan.FUSED_STEM = False): patch packing (fce_stem_pack) into a [M, 32] bf16 matrix
+        followed by a K = 32 1x1 conv on the tensor cores; anything else: the generic conv."""
         w, b, k, s, g, a = self.conv_params(m)
         Cout, Cin = w.shape[0], w.shape[1]
         if not (self.act_dt == L.BF16 and k == 3 and s == 2 and g == 1 and Cin == 3 and Cout % 16 == 0
@@ -218,13 +221,24 @@ class Plan:
             return self.conv(m, img, in_layout=in_layout, in_scale=in_scale, tag=tag)
         H, W = (img.H, img.W)
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        # OHWI weights flattened to [Cout, 27] (+5 zero columns), input scale folded in
+        wk = torch.zeros(Cout, 32, 1, 1, device=w.device)
+        wk[:, :27, 0, 0] = (w.permute(0, 2, 3, 1).reshape(Cout, 27) * in_scale)
+        if Cout in (16, 32, 48, 64, 96) and a in (L.ACT_SILU, L.ACT_NONE) and self.FUSED_STEM:
+            # one fused pass: image tile -> smem -> mma.sync -> bias + SiLU -> NHWC bf16
+            out = self.new_buf(Ho, Wo, Cout, dtype=L.BF16, B=img.B)
+            wp = self._w(wk.view(Cout, 32), torch.bfloat16)
+            bp = self._w(b)
+            d = L.StemDesc(B=img.B, H=H, W=W, Cout=Cout, out_pitch=out.pitch, out_off=0, act=a, in_dtype=img.dtype,
+                           in_layout=in_layout)
+            self.add(Node("fce_stem_conv", d, [img, wp, bp, out], reads=[img], writes=[out], tag=tag,
+                          flops=2.0 * img.B * Ho * Wo * Cout * 27,
+                          bytes=img.B * (H * W * 3.0 * DT_SIZE[img.dtype] + Ho * Wo * Cout * 2.0)))
+            return out
         packed = self.new_buf(Ho, Wo, 32, dtype=L.BF16, B=img.B)
         d = L.PackDesc(B=img.B, H=H, W=W, Cin=3, k=3, stride=2, Kpad=32, in_dtype=img.dtype, in_layout=in_layout)
         self.add(Node("fce_stem_pack", d, [img, packed], reads=[img], writes=[packed], tag=tag + ".pack",
                       bytes=img.B * (H * W * 3 * DT_SIZE[img.dtype] + Ho * Wo * 64.0)))
-        # OHWI weights flattened to [Cout, 27] (+5 zero columns), input scale folded in
-        wk = torch.zeros(Cout, 32, 1, 1, device=w.device)
-        wk[:, :27, 0, 0] = (w.permute(0, 2, 3, 1).reshape(Cout, 27) * in_scale)
         return self.conv(None, packed, w_override=wk, b_override=b, act=a, tag=tag)
 
     def dwconv(self, m, x: View, dst: View | None = None, add: View | None = None, tag="") -> View:

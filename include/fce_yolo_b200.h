@@ -88,6 +88,19 @@ typedef struct {
 } fce_pack_desc;
 int fce_stem_pack(const fce_pack_desc* d, const void* x, void* a, void* stream);
 
+/* Fused stem: the same first Conv (3x3, stride 2, pad 1, Cin = 3, + bias + SiLU; conv.py:80-89 on the network
+ * input) in one pass, bf16 NHWC output - no patch matrix in HBM.  w: bf16 [Cout][32], K index (kh*3+kw)*3+ci as in
+ * the OHWI weights, columns 27..31 zero, any input scale (1/255 for u8) folded in.  Cout in {16,32,48,64,96}
+ * (the n/s/-/m,l/x stems).  x: uint8 NHWC, fp32 NCHW or fp32 NHWC as for fce_stem_pack. */
+typedef struct {
+    int32_t B, H, W;          /* input size */
+    int32_t Cout;
+    int32_t out_pitch, out_off;
+    int32_t act;
+    int32_t in_dtype, in_layout;
+} fce_stem_desc;
+int fce_stem_conv(const fce_stem_desc* d, const void* x, const void* w, const float* bias, void* y, void* stream);
+
 /* Debug aid for the tcgen05 convolution: when switched on, the next fce_conv2d launches record per-CTA, per-role
  * cycle counts (16 int64 slots per CTA: A-producer wait/total, -, -, MMA wait-full/wait-tmem/total, epilogue
  * wait/total); fce_conv_tc_profile copies n slots of the last launch to a HOST buffer and returns n. */

@@ -56,6 +56,17 @@ class Interp(Arena):
         out[..., :27] = cols
         self.t(a).copy_(out.view(self.t(a).shape))
 
+    def _fce_stem_conv(self, d, p):
+        x, w, b, y = p
+        flat = self._flat(x.buf)
+        if d.in_layout == L.NCHW:
+            xin = flat.view(d.B, 3, d.H, d.W).float()
+        else:
+            xin = flat.view(d.B, d.H, d.W, 3).permute(0, 3, 1, 2).float()
+        wt = w.float()[:, :27].reshape(d.Cout, 3, 3, 3).permute(0, 3, 1, 2)  # [co][kh][kw][ci] -> OIHW
+        o = _act(F.conv2d(xin, wt, b.float(), stride=2, padding=1), d.act)
+        self.t(y).copy_(o.permute(0, 2, 3, 1))
+
     def _fce_dwconv3x3(self, d, p):
         x, w, b, add, y = p
         xin = self.t(x).permute(0, 3, 1, 2).float()

@@ -1,0 +1,109 @@
+"""Stand-alone parity of individual sm_100a kernels through the C ABI against a torch fp32 reference of the same
+op (floating-point kernels keep a torch reference next to the oracle).  Tolerances are written per test."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from fce_yolo_b200 import _lib as L
+    return L.load(check_device=True), L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------ fused stem
+@pytest.mark.parametrize("cout", [16, 32, 48, 64, 96])
+@pytest.mark.parametrize("kind", ["u8_nhwc", "f32_nchw", "f32_nhwc"])
+@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 96, 160), (3, 640, 640), (1, 34, 70)])
+def test_stem_conv_vs_torch(lib, cout, kind, shape):
+    """fce_stem_conv = SiLU(conv3x3/s2/p1(x * scale) + b) with bf16 operands, fp32 accumulate, bf16 output:
+    max |err| <= 1e-2 * max|ref|, relL2 <= 4e-3 (one bf16 rounding of the output + __expf SiLU)."""
+    l, L = lib
+    B, H, W = shape
+    g = torch.Generator().manual_seed(cout * 1000 + H + W)
+    w = (torch.randn(cout, 3, 3, 3, generator=g) * 0.3)
+    bias = torch.randn(cout, generator=g) * 0.2
+    if kind == "u8_nhwc":
+        x = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+        scale, x_ref = 1.0 / 255.0, x.float().permute(0, 3, 1, 2)
+        dt, lay = L.U8, L.NHWC
+    else:
+        xr = torch.rand(B, 3, H, W, generator=g)
+        x = xr if kind == "f32_nchw" else xr.permute(0, 2, 3, 1).contiguous()
+        scale, x_ref = 1.0, xr.bfloat16().float()
+        dt, lay = L.F32, (L.NCHW if kind == "f32_nchw" else L.NHWC)
+    wk = torch.zeros(cout, 32)
+    wk[:, :27] = w.permute(0, 2, 3, 1).reshape(cout, 27) * scale
+    wk = wk.bfloat16().cuda()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    pitch, off = cout + 16, 8  # destination is a channel slice of a wider buffer
+    y = torch.full((B, Ho, Wo, pitch), 7.0, dtype=torch.bfloat16, device="cuda")
+    d = L.StemDesc(B=B, H=H, W=W, Cout=cout, out_pitch=pitch, out_off=off, act=L.ACT_SILU, in_dtype=dt, in_layout=lay)
+    xd, bd = x.cuda(), bias.cuda()
+    st = l.fce_stem_conv(C.byref(d), C.c_void_p(xd.data_ptr()), C.c_void_p(wk.data_ptr()), C.c_void_p(bd.data_ptr()),
+                         C.c_void_p(y.data_ptr() + off * 2), _stream())
+    L.check(st, "fce_stem_conv")
+    torch.cuda.synchronize()
+    w_ref = wk.float().cpu()[:, :27].reshape(cout, 3, 3, 3).permute(0, 3, 1, 2)
+    ref = F.silu(F.conv2d(x_ref, w_ref, bias, stride=2, padding=1))
+    out = y[..., off:off + cout].float().cpu().permute(0, 3, 1, 2)
+    assert ((out - ref).abs().max() / ref.abs().max()).item() < 1e-2
+    assert ((out - ref).norm() / ref.norm()).item() < 4e-3
+    assert bool((y[..., :off] == 7.0).all() and (y[..., off + cout:] == 7.0).all())
+
+
+def test_stem_conv_rejects_bad_args(lib):
+    l, L = lib
+    d = L.StemDesc(B=1, H=64, W=64, Cout=20, out_pitch=20, out_off=0, act=L.ACT_SILU, in_dtype=L.U8, in_layout=L.NHWC)
+    t = torch.zeros(64 * 64 * 32, device="cuda")
+    p = C.c_void_p(t.data_ptr())
+    assert l.fce_stem_conv(C.byref(d), p, p, p, p, _stream()) == -2
+    d.Cout, d.out_pitch = 32, 36
+    assert l.fce_stem_conv(C.byref(d), p, p, p, p, _stream()) == -3
+    assert l.fce_stem_conv(C.byref(d), None, p, p, p, _stream()) == -1
+
+
+# ------------------------------------------------------------------------------------------------ C2PSA attention
+@pytest.mark.parametrize("B,N,heads", [(2, 400, 4), (1, 1600, 2), (3, 4, 2), (2, 100, 1), (1, 81, 6), (64, 400, 4)])
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_psa_attention_vs_torch(lib, B, N, heads, dtype):
+    """out[:, n] = sum_m softmax_m(scale <q_n, k_m>) v_m  (block.py:1293-1302) on [Q|K|V]-ordered NHWC channels.
+    fp32 kernel: relL2 <= 1e-5.  bf16 kernel (mma.sync, probabilities rounded to bf16 before P V): relL2 <= 1e-2
+    against fp32 math on the same bf16 inputs."""
+    l, L = lib
+    kd, hd = 32, 64
+    pitch = heads * (2 * kd + hd) + 8
+    g = torch.Generator().manual_seed(N * 10 + heads)
+    qkv = torch.randn(B, N, pitch, generator=g)
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    qkv_d = qkv.to(tdt).cuda()
+    out_pitch = heads * hd + 8
+    out = torch.full((B, N, out_pitch), 3.0, dtype=tdt, device="cuda")
+    scale = kd ** -0.5
+    d = L.PsaDesc(B=B, N=N, heads=heads, kd=kd, hd=hd, qkv_pitch=pitch, q_off=0, k_off=heads * kd, v_off=2 * heads * kd,
+                  out_pitch=out_pitch, out_off=8, dtype=L.BF16 if dtype == "bf16" else L.F32, scale=scale)
+    st = l.fce_psa_attention(C.byref(d), C.c_void_p(qkv_d.data_ptr()), C.c_void_p(out.data_ptr()), _stream())
+    L.check(st, "fce_psa_attention")
+    torch.cuda.synchronize()
+    x = qkv_d.float()
+    q = x[..., :heads * kd].view(B, N, heads, kd).transpose(1, 2)
+    k = x[..., heads * kd:2 * heads * kd].view(B, N, heads, kd).transpose(1, 2)
+    v = x[..., 2 * heads * kd:2 * heads * kd + heads * hd].view(B, N, heads, hd).transpose(1, 2)
+    att = torch.softmax((q @ k.transpose(-1, -2)) * scale, dim=-1)
+    ref = (att @ v).transpose(1, 2).reshape(B, N, heads * hd)
+    got = out[..., 8:].float()
+    err = ((got - ref).norm() / ref.norm()).item()
+    assert err < (1e-2 if dtype == "bf16" else 1e-5), err
+    assert bool((out[..., :8] == 3.0).all())
+    assert math.isfinite(err)
