@@ -129,6 +129,7 @@ def main():
     ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--kernel-times", default=None, help="write the per-node timing table to this file")
     a = ap.parse_args()
 
@@ -255,15 +256,17 @@ def main():
                 for i in range(len(ex._calls)):
                     acc[i] += evs[i].elapsed_time(evs[i + 1]) / reps
         classes = {}
+        pk = peaks()
         for (fn, args, n), ms in zip(ex._calls, acc):
-            c = classes.setdefault(n.fn, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            c = classes.setdefault(n.fn, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, ideal=0.0))
             c["ms"] += ms
+            # this launch's own roofline: the slower of its tensor time and its HBM time
+            c["ideal"] += max(n.flops / (pk["tf_sustained"] * 1e12), n.bytes / (pk["hbm"] * 1e9)) * 1e3
             c["flops"] += n.flops
             c["bytes"] += n.bytes
             c["launches"] += 1
             table.append((n.tag, n.fn, ms, n.flops, n.bytes))
         total = sum(c["ms"] for c in classes.values())
-        pk = peaks()
         top = max(classes.items(), key=lambda kv: kv[1]["ms"])
         fn, c = top
         if c["flops"] > 0:
@@ -271,7 +274,10 @@ def main():
             roof = {"kernel": fn, "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sustained"],
                     "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4), "traffic": None,
                     "peak_source": pk["src"] + " (sustained bf16 GEMM)", "share_of_step": round(c["ms"] / total, 3),
-                    "launches_per_step": c["launches"], "avg_launch_ms": round(c["ms"] / c["launches"], 4)}
+                    "launches_per_step": c["launches"], "avg_launch_ms": round(c["ms"] / c["launches"], 4),
+                    # most conv launches of this model sit LEFT of the ridge (1x1s with Cin, Cout <= 512): fraction
+                    # of the per-launch roofline min(tensor peak, intensity x HBM peak), summed over the launches
+                    "instance_roofline_frac": round(c["ideal"] / c["ms"], 4)}
         else:
             ach = c["bytes"] / (c["ms"] * 1e-3) / 1e9
             roof = {"kernel": fn, "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
@@ -281,6 +287,7 @@ def main():
         roof["classes"] = {
             k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total, 3), "launches": v["launches"],
                 **({"TFLOP/s": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] else {}),
+                "roofline_frac": round(v["ideal"] / v["ms"], 3),
                 **({"GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
                     "hbm_frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"], 3)} if v["bytes"] else {})}
             for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}
@@ -289,6 +296,31 @@ def main():
                 f.write("tag,fn,ms,gflop,mbytes\n")
                 for tag, fnn, ms, fl, by in table:
                     f.write(f"{tag},{fnn},{ms:.4f},{fl / 1e9:.3f},{by / 1e6:.3f}\n")
+
+    # ------------------------------------------------------------------ batch-1 latency (rank 0; BASELINE's 2nd metric)
+    lat = None
+    if rank == 0 and not a.no_latency:
+        p1 = Predictor(model, 1, S, precision=w["precision"], device=dev, conf=w["conf"], iou=w["iou"],
+                       max_det=w["max_det"], input_u8=True, use_graph=not a.no_graph)
+        p1.inp.copy_(h_img[:1])
+        for _ in range(10):
+            p1.run_device()
+        torch.cuda.synchronize()
+        n1 = 200
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(n1):
+            p1.run_device()
+        l1.record()
+        torch.cuda.synchronize()
+        dev_ms = l0.elapsed_time(l1) / n1
+        t0 = time.perf_counter()
+        for _ in range(n1):
+            p1.infer(h_img[:1])  # H2D + graph + D2H + host sync, every image
+        host_ms = (time.perf_counter() - t0) * 1e3 / n1
+        lat = {"device_ms_per_img": round(dev_ms, 4), "e2e_ms_per_img": round(host_ms, 4), "launches": p1.launches_per_call,
+               "note": "batch 1, same model/size; device = back-to-back graph replays, e2e = Predictor.infer from pinned host"}
+        del p1
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -315,7 +347,7 @@ def main():
                     "api": "Predictor.pipeline(pinned uint8 NHWC batches) -> pinned (det, count); H2D of batch i+1 "
                            "overlaps the graph of batch i"},
             "gpu_launches": pred.launches_per_call * a.steps,
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "latency_b1": lat, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:

@@ -76,6 +76,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel's tail
     if (warp == WARP_PROD_A && lane == 0) {
         for (int i = 0; i < A_STAGES; ++i) {
             mbar_init(full0 + 8 * i, 1);
@@ -113,6 +114,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == WARP_PROD_A) {
         // ------------------------------------------------------------------ strip producer
         Ring r;
+        pdl_wait();  // activations come from the previous kernel (the weights loaded by the B producer do not)
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int b = u / p.bands, band = u - b * p.bands;
             const int h0 = band * p.R;
@@ -226,6 +228,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t ph[2] = {0, 0};
         int i = 0;
         long long dw = 0, dt0 = PROF ? clock64() : 0;
+        pdl_wait();  // residual reads and output stores touch buffers the previous kernel may still be using
         if (blockIdx.x < units && elect_one()) make_ready(blockIdx.x, 0);
         for (int u = blockIdx.x; u < units; u += gridDim.x, ++i) {
             const int buf = n_stg == 2 ? (i & 1) : 0;
@@ -531,9 +534,8 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
     if (g_halo_prof)
         fprintf(stderr, "[halo] R=%d bands=%d nb=%d units=%d acc_sets=%d n_stg=%d slab_cols=%d smem=%zu\n", p.R, p.bands, p.nb,
                 p.units, p.acc_sets, p.n_stg, p.slab_cols, smem);
-    table[(kc == 16 ? 0 : (kc == 32 ? 1 : 2)) + (g_halo_prof ? 3 : 0)]<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p,
-                                                                                                       bias);
-    return check_launch();
+    return launch_pdl(table[(kc == 16 ? 0 : (kc == 32 ? 1 : 2)) + (g_halo_prof ? 3 : 0)], grid, NUM_THREADS, smem, st, tmA,
+                      tmB, tmC, tmR, p, bias);
 }
 
 }  // namespace fce

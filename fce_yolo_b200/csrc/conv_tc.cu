@@ -93,6 +93,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
 
+    pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel's tail
     if (warp == WARP_PROD_A && lane == 0) {
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(full0 + 8 * i, p.b_resident ? 1 : 2);
@@ -129,6 +130,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool is_1x1 = p.taps == 1, skip = (p.dbg & 1) != 0;
         const int n_tiles = p.n_tiles, nstages = p.stages;
         long long pw = 0, pt0 = PROF ? clock64() : 0;
+        pdl_wait();  // activations are produced by the previous kernel (weights / bias above are constants)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m0 = (n_tiles == 1 ? tile : tile / n_tiles) * BM;
             int img = 0, w0 = 0, h0 = 0;
@@ -304,6 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0;
         uint32_t acc_phase = 0;
         long long ew = 0, et0 = PROF ? clock64() : 0;
+        pdl_wait();  // residual reads and output stores touch buffers the previous kernel may still be using
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = n_tiles == 1 ? tile : tile / n_tiles;
             const int n0 = n_tiles == 1 ? 0 : (tile - mt * n_tiles) * bn;
@@ -327,11 +330,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
                 if (has_res && m_ok) {
                     const uint4* rp = reinterpret_cast<const uint4*>(rrow + n);
-                    r0 = __ldg(rp);
-                    r1 = __ldg(rp + 1);
+                    r0 = __ldcg(rp);  // L2 only: with PDL this SM's L1 may still hold the previous grid's lines
+                    r1 = __ldcg(rp + 1);
                     if (two && n + 16 < Cout) {
-                        r2 = __ldg(rp + 2);
-                        r3 = __ldg(rp + 3);
+                        r2 = __ldcg(rp + 2);
+                        r3 = __ldcg(rp + 3);
                     }
                 }
                 uint32_t v0[16], v1[16];
@@ -571,8 +574,7 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < kNumSMs ? total : kNumSMs;
     const __nv_bfloat16* rp = res ? reinterpret_cast<const __nv_bfloat16*>(res) + d->res_off : nullptr;
-    table[g_profile_on ? 1 : 0][variant]<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, p, bias, rp);
-    return check_launch();
+    return launch_pdl(table[g_profile_on ? 1 : 0][variant], grid, NUM_THREADS, smem, st, tmA, tmB, tmC, p, bias, rp);
 }
 
 void conv_tc_set_profile(int on) {

@@ -21,13 +21,16 @@ constexpr int SLOTS = 32;     // pixel slots along W
 constexpr int RB = 8;         // rows per CTA (one band)
 constexpr int BAND = 5;       // column groups held in registers -> 160 columns per sweep
 
-// A CTA owns (image, band of RB rows, 64-channel chunk [32 in fp32 mode]).  Row means are complete inside the
-// CTA; column sums of the band go to the workspace ([B][bands][W][C] fp32) and a second, tiny kernel adds the
-// bands in a fixed order (deterministic, no atomics).  Grid = B * bands * chunks CTAs - thousands of CTAs with
-// 40 independent 16-byte loads in flight per thread, instead of one CTA per image.
+// A CTA owns (image, band of rows, 64-channel chunk [32 in fp32 mode]) and walks its band RB rows at a time.  Row
+// means are complete inside the CTA; the band's column sums stay in registers across the walk and go to the
+// workspace ([B][bands][W][C] fp32), where a second, tiny kernel adds the bands in a fixed order (deterministic,
+// no atomics) - or straight to the strip when one band covers the image.  The host picks the band count so that
+// the grid is about two CTAs per SM: at batch 64 that is ONE band (no workspace traffic at all), at batch 1 the
+// bands supply the parallelism.  10 independent 16-byte loads are in flight per thread.
 template <typename T>
 __global__ void __launch_bounds__(PT) coord_pool_kernel(const fce_pool_desc d, const T* __restrict__ x,
-                                                        float* __restrict__ strip, float* __restrict__ ws, int bands) {
+                                                        float* __restrict__ strip, float* __restrict__ ws, int bands,
+                                                        int band_rows) {
     constexpr int N = Vec16<T>::N;
     constexpr int CC = CVT * N;  // channels per CTA
     __shared__ float red[PT / 32][RB][CC];
@@ -40,7 +43,8 @@ __global__ void __launch_bounds__(PT) coord_pool_kernel(const fce_pool_desc d, c
     const int b = blockIdx.x / (chunks * bands);
     const int c0 = chunk * CC + cvt * N;
     const bool c_ok = c0 < d.C;  // C is a multiple of N (checked on host)
-    const int h_base = band * RB;
+    const int h_begin = band * band_rows;
+    const int h_end = min(d.H, h_begin + band_rows);
     const T* xb_safe = x + (size_t)b * d.H * d.W * d.pitch + d.off + (c_ok ? c0 : 0);
     float* xh = strip + ((size_t)b * d.H) * d.C;  // rows [b*H, b*H+H)
     // column partial sums of this band: straight into the strip when there is a single band
@@ -50,77 +54,76 @@ __global__ void __launch_bounds__(PT) coord_pool_kernel(const fce_pool_desc d, c
     const float inv_w = 1.f / (float)d.W;
 
     for (int w_base = 0; w_base < d.W; w_base += SLOTS * BAND) {
-        float col[BAND][N], row[RB][N];
+        float col[BAND][N];
 #pragma unroll
         for (int g = 0; g < BAND; ++g)
 #pragma unroll
             for (int j = 0; j < N; ++j) col[g][j] = 0.f;
-#pragma unroll
-        for (int r = 0; r < RB; ++r)
-#pragma unroll
-            for (int j = 0; j < N; ++j) row[r][j] = 0.f;
-        // all loads of two rows (2 x BAND 16-byte vectors) are issued before any is consumed; out-of-range
-        // pixels read a clamped (valid) address and are masked to zero afterwards
-#pragma unroll
-        for (int r = 0; r < RB; r += 2) {
-            Vec16<T> v[2][BAND];
-            bool ok[2][BAND];
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int h = h_base + r + rr;
-                const int hc = h < d.H ? h : d.H - 1;
-#pragma unroll
-                for (int g = 0; g < BAND; ++g) {
-                    const int w = w_base + g * SLOTS + slot;
-                    const int wc = w < d.W ? w : d.W - 1;
-                    ok[rr][g] = c_ok && h < d.H && w < d.W;
-                    v[rr][g].load_nc(xb_safe + ((size_t)hc * d.W + wc) * d.pitch);
-                }
-            }
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-                for (int g = 0; g < BAND; ++g) {
-                    float f[N];
-                    v[rr][g].unpack(f);
-                    const float mk = ok[rr][g] ? 1.f : 0.f;
-#pragma unroll
-                    for (int j = 0; j < N; ++j) {
-                        row[r + rr][j] = fmaf(mk, f[j], row[r + rr][j]);
-                        col[g][j] = fmaf(mk, f[j], col[g][j]);
-                    }
-                }
-        }
-        // reduce row sums over the 32 slots: 4 slots inside the warp (lanes differ by 8, 16), 8 warps via smem
-#pragma unroll
-        for (int r = 0; r < RB; ++r)
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                float v = row[r][j];
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                row[r][j] = v;
-            }
-        __syncthreads();  // previous sweep's readers are done with red[]
-        if (lane < CVT) {
+        for (int h_base = h_begin; h_base < h_end; h_base += RB) {
+            float row[RB][N];
 #pragma unroll
             for (int r = 0; r < RB; ++r)
 #pragma unroll
-                for (int j = 0; j < N; ++j) red[warp][r][cvt * N + j] = row[r][j];
-        }
-        __syncthreads();
-        for (int o = tid; o < RB * CC; o += PT) {
-            const int r = o / CC, c = o % CC;
-            const int h = h_base + r;
-            const int cg = chunk * CC + c;
-            if (h < d.H && cg < d.C) {
-                float s = 0.f;
+                for (int j = 0; j < N; ++j) row[r][j] = 0.f;
+            // all loads of two rows (2 x BAND 16-byte vectors) are issued before any is consumed; out-of-range
+            // pixels issue no load at all (W = 80 / 40 maps fill only part of the 160-column sweep)
 #pragma unroll
-                for (int wq = 0; wq < PT / 32; ++wq) s += red[wq][r][c];
-                float* dst = xh + (size_t)h * d.C + cg;
-                if (w_base > 0) s += *dst;  // later sweeps of very wide maps accumulate (same CTA, ordered)
-                if (w_base + SLOTS * BAND >= d.W) s *= inv_w;
-                *dst = s;
+            for (int r = 0; r < RB; r += 2) {
+                Vec16<T> v[2][BAND];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int h = h_base + r + rr;
+#pragma unroll
+                    for (int g = 0; g < BAND; ++g) {
+                        const int w = w_base + g * SLOTS + slot;
+                        v[rr][g].raw = make_uint4(0u, 0u, 0u, 0u);
+                        if (c_ok && h < h_end && w < d.W) v[rr][g].load_nc(xb_safe + ((size_t)h * d.W + w) * d.pitch);
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int g = 0; g < BAND; ++g) {
+                        float f[N];
+                        v[rr][g].unpack(f);
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {  // skipped loads contribute exact zeros
+                            row[r + rr][j] += f[j];
+                            col[g][j] += f[j];
+                        }
+                    }
+            }
+            // reduce row sums over the 32 slots: 4 slots inside the warp (lanes differ by 8, 16), 8 warps via smem
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    float v = row[r][j];
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    row[r][j] = v;
+                }
+            __syncthreads();  // previous group's readers are done with red[]
+            if (lane < CVT) {
+#pragma unroll
+                for (int r = 0; r < RB; ++r)
+#pragma unroll
+                    for (int j = 0; j < N; ++j) red[warp][r][cvt * N + j] = row[r][j];
+            }
+            __syncthreads();
+            for (int o = tid; o < RB * CC; o += PT) {
+                const int r = o / CC, c = o % CC;
+                const int h = h_base + r;
+                const int cg = chunk * CC + c;
+                if (h < h_end && cg < d.C) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int wq = 0; wq < PT / 32; ++wq) s += red[wq][r][c];
+                    float* dst = xh + (size_t)h * d.C + cg;
+                    if (w_base > 0) s += *dst;  // later sweeps of very wide maps accumulate (same CTA, ordered)
+                    if (w_base + SLOTS * BAND >= d.W) s *= inv_w;
+                    *dst = s;
+                }
             }
         }
         // column sums: every (slot, group) column is owned by exactly one thread
@@ -227,15 +230,20 @@ extern "C" int fce_coord_pool(const fce_pool_desc* d, const void* x, float* stri
     const int n = d->dtype == FCE_BF16 ? 8 : 4;
     if (d->dtype != FCE_BF16 && d->dtype != FCE_F32) return FCE_ERR_UNSUPPORTED;
     if ((d->C % n) || (d->pitch % n) || (d->off % n) || (((uintptr_t)x) & 15)) return FCE_ERR_ALIGNMENT;
-    const int bands = (d->H + RB - 1) / RB;
-    if (bands > 1 && (!ws || ws_bytes < fce_coord_pool_workspace(d))) return FCE_ERR_WORKSPACE;
     const int cc = CVT * n;
     const int chunks = (d->C + cc - 1) / cc;
+    // bands: enough CTAs for ~2 per SM, never more than one band per RB rows
+    const int max_bands = (d->H + RB - 1) / RB;
+    int bands = (2 * kNumSMs + d->B * chunks - 1) / (d->B * chunks);
+    bands = bands < 1 ? 1 : (bands > max_bands ? max_bands : bands);
+    int band_rows = ((d->H + bands - 1) / bands + RB - 1) / RB * RB;
+    bands = (d->H + band_rows - 1) / band_rows;
+    if (bands > 1 && (!ws || ws_bytes < (size_t)d->B * bands * d->W * d->C * sizeof(float))) return FCE_ERR_WORKSPACE;
     const int grid = d->B * bands * chunks;
     if (d->dtype == FCE_BF16)
-        coord_pool_kernel<__nv_bfloat16><<<grid, PT, 0, st>>>(*d, (const __nv_bfloat16*)x, strip, (float*)ws, bands);
+        coord_pool_kernel<__nv_bfloat16><<<grid, PT, 0, st>>>(*d, (const __nv_bfloat16*)x, strip, (float*)ws, bands, band_rows);
     else
-        coord_pool_kernel<float><<<grid, PT, 0, st>>>(*d, (const float*)x, strip, (float*)ws, bands);
+        coord_pool_kernel<float><<<grid, PT, 0, st>>>(*d, (const float*)x, strip, (float*)ws, bands, band_rows);
     int rc = check_launch();
     if (rc != FCE_OK || bands == 1) return rc;
     const size_t nitems = (size_t)d->B * d->W * d->C;

@@ -81,6 +81,96 @@ struct Lane4<float> {
     static __device__ __forceinline__ uint32_t pack(const float* f) { return __float_as_uint(f[0]); }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Depthwise 3x3, version 2 (used whenever the views are 16-byte aligned): a thread owns ONE 16-byte channel
+// vector (8 bf16 / 4 fp32) of one image column and walks DOWN a band of rows.  Input row r is loaded once per
+// thread as three vectors (columns w-1, w, w+1: the two neighbours are L1 hits - the adjacent threads of the
+// same CTA load them as their own centre) and scattered into three rolling accumulators (output rows r-1, r,
+// r+1), so each output costs one HBM read of its input element (x (TH+2)/TH for the band halo), 9 FMAs per
+// channel and one 16-byte store.  The next row's vectors are in flight while the current row is computed.
+// CTA = 128 threads = 16 columns x 8 vectors (64 bf16 / 32 fp32 channels: 128 contiguous bytes per pixel).
+constexpr int DW2_COLS = 16, DW2_VECS = 8, DW2_THREADS = DW2_COLS * DW2_VECS;
+
+template <typename T>
+__global__ void __launch_bounds__(DW2_THREADS) dwconv3x3_v2_kernel(const fce_dwconv_desc d, const T* __restrict__ x,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ bias,
+                                                                   const T* __restrict__ add, T* __restrict__ y,
+                                                                   int band_rows, int bands, int cgroups) {
+    constexpr int N = Vec16<T>::N;
+    const int vec = threadIdx.x % DW2_VECS, col = threadIdx.x / DW2_VECS;
+    const int cg = blockIdx.x % cgroups;
+    const int wt_ = blockIdx.x / cgroups;
+    const int band = blockIdx.y % bands, b = blockIdx.y / bands;
+    const int c = (cg * DW2_VECS + vec) * N;
+    const int wc = wt_ * DW2_COLS + col;
+    if (c >= d.C || wc >= d.W) return;
+    const int h0 = band * band_rows, h1 = min(d.H, h0 + band_rows);
+    float wt[9][N], bs[N];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < N; ++j) wt[t][j] = __ldg(w + t * d.C + c + j);
+#pragma unroll
+    for (int j = 0; j < N; ++j) bs[j] = __ldg(bias + c + j);
+    const bool l_ok = wc > 0, r_ok = wc + 1 < d.W;
+    const T* xp = x + ((size_t)b * d.H * d.W + wc) * d.in_pitch + d.in_off + c;  // row 0 of this column
+    const size_t row_stride = (size_t)d.W * d.in_pitch;
+
+    Vec16<T> nl, nm, nr;  // next input row, raw
+    auto load_row = [&](int r) {
+        nl.raw = nm.raw = nr.raw = make_uint4(0u, 0u, 0u, 0u);
+        if (r >= 0 && r < d.H) {
+            const T* p = xp + (size_t)r * row_stride;
+            nm.load(p);
+            if (l_ok) nl.load(p - d.in_pitch);
+            if (r_ok) nr.load(p + d.in_pitch);
+        }
+    };
+    float a0[N], a1[N], a2[N];  // accumulators of output rows r-1, r, r+1 while input row r is processed
+#pragma unroll
+    for (int j = 0; j < N; ++j) a0[j] = a1[j] = a2[j] = bs[j];
+    load_row(h0 - 1);
+    for (int r = h0 - 1; r <= h1; ++r) {
+        float fl[N], fm[N], fr[N];
+        nl.unpack(fl);
+        nm.unpack(fm);
+        nr.unpack(fr);
+        if (r < h1) load_row(r + 1);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            // input row r is tap row kh = 2 of output r-1, kh = 1 of output r, kh = 0 of output r+1
+            a0[j] = fmaf(fl[j], wt[6][j], fmaf(fm[j], wt[7][j], fmaf(fr[j], wt[8][j], a0[j])));
+            a1[j] = fmaf(fl[j], wt[3][j], fmaf(fm[j], wt[4][j], fmaf(fr[j], wt[5][j], a1[j])));
+            a2[j] = fmaf(fl[j], wt[0][j], fmaf(fm[j], wt[1][j], fmaf(fr[j], wt[2][j], a2[j])));
+        }
+        const int o = r - 1;  // complete now
+        if (o >= h0) {
+            float out[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) out[j] = d.act == FCE_ACT_SILU ? silu_for<T>(a0[j]) : a0[j];
+            const size_t pix = ((size_t)b * d.H + o) * d.W + wc;
+            if (add) {
+                Vec16<T> av;
+                float af[N];
+                av.load(add + pix * d.add_pitch + d.add_off + c);
+                av.unpack(af);
+#pragma unroll
+                for (int j = 0; j < N; ++j) out[j] += af[j];
+            }
+            Vec16<T> ov;
+            ov.pack(out);
+            ov.store(y + pix * d.out_pitch + d.out_off + c);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            a0[j] = a1[j];
+            a1[j] = a2[j];
+            a2[j] = bs[j];
+        }
+    }
+}
+
 constexpr int DW_WARPS = 4;  // warps per CTA, each an independent (row, channel group)
 constexpr int DW_CHUNK = 4;  // pixels per register chunk
 
@@ -273,6 +363,80 @@ __global__ void __launch_bounds__(NT) sppf_kernel(const fce_sppf_desc d, T* buf)
 }
 
 // ------------------------------------------------------------------------------------------------
+// SPPF pyramid, version 2 (16-byte aligned views): same chained separable passes, but an item is a 16-byte channel
+// vector (8 bf16 / 4 fp32) kept in its STORAGE type in shared memory - max() is exact in any precision, so bf16
+// planes need half the space - and every global access is a 16-byte vector.  A CTA owns (image, 16 bf16 / 8 fp32
+// channels): 2 x HW x 32 bytes of shared memory (25.6 KB for the 20 x 20 map of a 640^2 image, 102 KB for the
+// 40 x 40 map at 1280^2), so several CTAs share an SM and hide each other's barriers.
+template <typename T>
+__device__ __forceinline__ uint4 vmax16(uint4 a, uint4 b);
+template <>
+__device__ __forceinline__ uint4 vmax16<__nv_bfloat16>(uint4 a, uint4 b) {
+    uint4 r;
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+    return r;
+}
+template <>
+__device__ __forceinline__ uint4 vmax16<float>(uint4 a, uint4 b) {
+    return make_uint4(__float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x))),
+                      __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y))),
+                      __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z))),
+                      __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w))));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) sppf_v2_kernel(const fce_sppf_desc d, T* buf, int vpc) {
+    extern __shared__ uint4 spv[];  // [2][H*W][vpc]
+    constexpr int N = Vec16<T>::N;
+    const int HW = d.H * d.W, W = d.W, H = d.H;
+    const int items = HW * vpc;
+    uint4* A = spv;
+    uint4* Bm = spv + items;
+    const int chunks = (d.C + vpc * N - 1) / (vpc * N);
+    const int b = blockIdx.x / chunks, c0 = (blockIdx.x % chunks) * vpc * N;
+    T* base = buf + (size_t)b * HW * d.pitch + d.off + c0;
+    // per-thread item list is fixed across passes: item i -> pixel p = i / vpc (h, w), vector v = i % vpc
+    for (int i = threadIdx.x; i < items; i += NT) {
+        const int p = i / vpc, v = i - p * vpc;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (c0 + v * N < d.C) val = *reinterpret_cast<const uint4*>(base + (size_t)p * d.pitch + v * N);
+        A[i] = val;
+    }
+    __syncthreads();
+    for (int level = 1; level <= 3; ++level) {
+        for (int i = threadIdx.x; i < items; i += NT) {  // row pass A -> Bm
+            const int p = i / vpc;
+            const int w0 = p % W;
+            uint4 m = A[i];
+            if (w0 >= 1) m = vmax16<T>(m, A[i - vpc]);
+            if (w0 >= 2) m = vmax16<T>(m, A[i - 2 * vpc]);
+            if (w0 + 1 < W) m = vmax16<T>(m, A[i + vpc]);
+            if (w0 + 2 < W) m = vmax16<T>(m, A[i + 2 * vpc]);
+            Bm[i] = m;
+        }
+        __syncthreads();
+        const int rs = W * vpc;
+        for (int i = threadIdx.x; i < items; i += NT) {  // column pass Bm -> A (+ global slice `level`)
+            const int p = i / vpc, v = i - p * vpc;
+            const int h = p / W;
+            uint4 m = Bm[i];
+            if (h >= 1) m = vmax16<T>(m, Bm[i - rs]);
+            if (h >= 2) m = vmax16<T>(m, Bm[i - 2 * rs]);
+            if (h + 1 < H) m = vmax16<T>(m, Bm[i + rs]);
+            if (h + 2 < H) m = vmax16<T>(m, Bm[i + 2 * rs]);
+            A[i] = m;
+            if (c0 + v * N < d.C)
+                *reinterpret_cast<uint4*>(base + (size_t)p * d.pitch + level * d.C + v * N) = m;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(NT) upsample_kernel(const fce_upsample_desc d, const T* __restrict__ x, T* y) {
     constexpr int N = CV<T, VEC>::N;
@@ -424,6 +588,22 @@ extern "C" int fce_dwconv3x3(const fce_dwconv_desc* d, const void* x, const floa
                              add ? d->add_off : 0}) ||
             (((uintptr_t)x | (uintptr_t)y | (uintptr_t)add) & 3))
             return FCE_ERR_ALIGNMENT;
+        constexpr int N = 16 / (int)sizeof(T);
+        if (multiple_of(N, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off, add ? d->add_pitch : 0,
+                            add ? d->add_off : 0}) && ptr16(x) && ptr16(y) && ptr16(add)) {
+            const int cgroups = (d->C + DW2_VECS * N - 1) / (DW2_VECS * N);
+            const int wtiles = (d->W + DW2_COLS - 1) / DW2_COLS;
+            // bands of ~20 rows (halo overhead 10 %), but enough of them to give every SM a few CTAs
+            int bands = (d->H + 19) / 20;
+            while ((long long)d->B * bands * wtiles * cgroups < 4 * kNumSMs && bands * 4 <= d->H) bands *= 2;
+            const int band_rows = (d->H + bands - 1) / bands;
+            bands = (d->H + band_rows - 1) / band_rows;
+            if ((long long)d->B * bands > 65535) return FCE_ERR_UNSUPPORTED;
+            dim3 grid(wtiles * cgroups, d->B * bands);
+            dwconv3x3_v2_kernel<T><<<grid, DW2_THREADS, 0, st>>>(*d, (const T*)x, w, bias, (const T*)add, (T*)y,
+                                                                 band_rows, bands, cgroups);
+            return check_launch();
+        }
         const int groups = (d->C + 32 * E - 1) / (32 * E);
         const long long units = (long long)d->B * d->H * groups;
         if (units > 0x7fffffffLL) return FCE_ERR_UNSUPPORTED;
@@ -440,6 +620,27 @@ extern "C" int fce_sppf_pool(const fce_sppf_desc* d, void* buf, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     return by_dtype(d->dtype, [&](auto tag) -> int {
         using T = decltype(tag);
+        constexpr int N = 16 / (int)sizeof(T);
+        if (multiple_of(N, {d->C, d->pitch, d->off}) && ptr16(buf)) {
+            int vpc = 2;
+            size_t sm2 = (size_t)2 * d->H * d->W * vpc * 16;
+            if (sm2 > 110 * 1024) { vpc = 1; sm2 /= 2; }  // very large maps: one vector per CTA
+            if (sm2 <= 220 * 1024) {
+                static bool attr2[2] = {false, false};
+                constexpr int ti2 = sizeof(T) == 2 ? 0 : 1;
+                if (!attr2[ti2]) {
+                    cudaError_t e = cudaFuncSetAttribute(sppf_v2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                    if (e != cudaSuccess) {
+                        set_cuda_error(e);
+                        return FCE_ERR_CUDA;
+                    }
+                    attr2[ti2] = true;
+                }
+                const int chunks2 = (d->C + vpc * N - 1) / (vpc * N);
+                sppf_v2_kernel<T><<<d->B * chunks2, NT, sm2, st>>>(*d, (T*)buf, vpc);
+                return check_launch();
+            }
+        }
         // two fp32 copies of a 32-channel plane in shared memory: up to 29 x 29 ... 880 x 880 pixels of input per
         // 100 KB; the path's P5 maps are 20 x 20 (640) and 40 x 40 (1280)
         const int HW = d->H * d->W;

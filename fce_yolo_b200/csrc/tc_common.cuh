@@ -2,12 +2,23 @@
 // points of the tensor-core convolution kernels (conv_tc.cu: TMA-im2col implicit GEMM; conv_halo.cu: 3x3 stride-1
 // with the input strip resident in shared memory).  sm_100a only.
 #pragma once
+#include <cstdlib>
 #include <cuda.h>  // CUtensorMap types only - the two driver entry points are resolved at run time via cudart
 
 #include "common.cuh"
 
 namespace fce {
 namespace tc {
+
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still draining: everything it does before pdl_wait() - barrier init,
+// TMEM allocation, tensor-map prefetch, loads of CONSTANT data (weights, bias) - overlaps the predecessor's tail.
+// pdl_wait() returns once the predecessor grid has completed and its writes are visible; every access to
+// activations (reads AND writes - arena buffers are recycled) must come after it.  pdl_launch_dependents() lets
+// the successor's CTAs be scheduled as soon as all CTAs of this grid have issued it (or exited).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -233,6 +244,33 @@ inline const DriverApi& driver() {
 
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+
+// Host: launch with the programmatic-stream-serialization attribute (see pdl_wait above).  Captured into CUDA
+// graphs as a programmatic dependency edge.  FCE_NO_PDL=1 in the environment falls back to plain launches (A/B).
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool no_pdl = [] {
+        const char* e = getenv("FCE_NO_PDL");
+        return e && e[0] == '1';
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) {
+        set_cuda_error(e);
+        return FCE_ERR_CUDA;
+    }
+    return check_launch();
+}
 
 }  // namespace tc
 }  // namespace fce

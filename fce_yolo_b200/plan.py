@@ -207,7 +207,9 @@ class Plan:
         if res is not None and (res.C != Cout or res.dtype != dst.dtype or (res.H, res.W) != (Ho, Wo)):
             raise PlanError(f"{tag}: residual view does not match the conv output")
         self.add(Node("fce_conv2d", d, [x, wp, bp, res, dst], reads=[x] + ([res] if res is not None else []),
-                      writes=[dst], tag=tag, flops=2.0 * x.B * Ho * Wo * Cout * Cin * k * k))
+                      writes=[dst], tag=tag, flops=2.0 * x.B * Ho * Wo * Cout * Cin * k * k,
+                      bytes=(x.B * x.H * x.W * Cin * DT_SIZE[x.dtype] + x.B * Ho * Wo * Cout * DT_SIZE[dst.dtype]
+                             * (2 if res is not None else 1) + Cout * Cin * k * k * DT_SIZE[w_dt])))
         return dst
 
     def stem(self, m, img: View, in_layout, in_scale, tag="") -> View:

@@ -107,3 +107,70 @@ def test_psa_attention_vs_torch(lib, B, N, heads, dtype):
     assert err < (1e-2 if dtype == "bf16" else 1e-5), err
     assert bool((out[..., :8] == 3.0).all())
     assert math.isfinite(err)
+
+
+# ------------------------------------------------------------------------------------------------ depthwise 3x3
+@pytest.mark.parametrize("B,H,W,Cc", [(2, 80, 80, 128), (1, 20, 20, 512), (3, 7, 13, 64), (1, 40, 40, 72), (2, 33, 50, 256)])
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("with_add,act", [(False, 1), (True, 0)])
+def test_dwconv3x3_vs_torch(lib, B, H, W, Cc, dtype, with_add, act):
+    """fce_dwconv3x3 (DWConv conv.py:185-199; Attention.pe + add block.py:1302) reading and writing channel
+    slices of wider buffers; the add operand aliases the destination (as in the C2PSA plan).
+    fp32: relL2 <= 1e-5;  bf16 storage (fp32 math, one output rounding): relL2 <= 4e-3, max <= 1e-2."""
+    l, L = lib
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    g = torch.Generator().manual_seed(H * 100 + W + Cc)
+    ip, io, op, oo = Cc + 16, 8, Cc + 24, 16
+    xb = torch.randn(B, H, W, ip, generator=g).to(tdt).cuda()
+    yb = torch.randn(B, H, W, op, generator=g).to(tdt).cuda()
+    y0 = yb.clone()
+    w = (torch.randn(Cc, 3, 3, generator=g) * 0.3)
+    bias = torch.randn(Cc, generator=g) * 0.1
+    wp = w.view(Cc, 9).t().contiguous().cuda()
+    bp = bias.cuda()
+    esz = xb.element_size()
+    d = L.DwconvDesc(B=B, H=H, W=W, C=Cc, in_pitch=ip, in_off=0, out_pitch=op, out_off=0, add_pitch=op if with_add else 0,
+                     add_off=0, act=act, dtype=L.BF16 if dtype == "bf16" else L.F32)
+    yptr = yb.data_ptr() + oo * esz
+    st = l.fce_dwconv3x3(C.byref(d), C.c_void_p(xb.data_ptr() + io * esz), C.c_void_p(wp.data_ptr()),
+                         C.c_void_p(bp.data_ptr()), C.c_void_p(yptr if with_add else 0), C.c_void_p(yptr), _stream())
+    L.check(st, "fce_dwconv3x3")
+    torch.cuda.synchronize()
+    x = xb[..., io:io + Cc].float().cpu().permute(0, 3, 1, 2)
+    ref = F.conv2d(x, w.view(Cc, 1, 3, 3), bias, padding=1, groups=Cc)
+    if act == 1:
+        ref = F.silu(ref)
+    if with_add:
+        ref = ref + y0[..., oo:oo + Cc].float().cpu().permute(0, 3, 1, 2)
+    out = yb[..., oo:oo + Cc].float().cpu().permute(0, 3, 1, 2)
+    l2 = ((out - ref).norm() / ref.norm()).item()
+    mx = ((out - ref).abs().max() / ref.abs().max()).item()
+    assert l2 < (4e-3 if dtype == "bf16" else 1e-5), l2
+    assert mx < (1e-2 if dtype == "bf16" else 1e-5), mx
+    assert torch.equal(yb[..., :oo], y0[..., :oo]) and torch.equal(yb[..., oo + Cc:], y0[..., oo + Cc:])
+
+
+# ------------------------------------------------------------------------------------------------ SPPF pyramid
+@pytest.mark.parametrize("B,H,W,Cc", [(2, 20, 20, 256), (1, 40, 40, 384), (3, 2, 2, 128), (1, 5, 9, 40), (1, 80, 80, 32)])
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_sppf_pool_bit_exact(lib, B, H, W, Cc, dtype):
+    """fce_sppf_pool: slices 1..3 = three chained 5x5/s1/p2 max-pools of slice 0 (block.py:228-232).  max() is
+    exact in every precision: the result must equal torch's max_pool2d BIT FOR BIT, and slice 0 must be untouched.
+    40 x 40 is the P5 map of a 1280^2 image (BASELINE config 5)."""
+    l, L = lib
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    g = torch.Generator().manual_seed(H * 100 + W + Cc)
+    pitch, off = 4 * Cc + 16, 8
+    buf = torch.randn(B, H, W, pitch, generator=g).to(tdt).cuda()
+    b0 = buf.clone()
+    d = L.SppfDesc(B=B, H=H, W=W, C=Cc, pitch=pitch, off=0, dtype=L.BF16 if dtype == "bf16" else L.F32)
+    st = l.fce_sppf_pool(C.byref(d), C.c_void_p(buf.data_ptr() + off * buf.element_size()), _stream())
+    L.check(st, "fce_sppf_pool")
+    torch.cuda.synchronize()
+    y = b0[..., off:off + Cc].float().permute(0, 3, 1, 2)
+    for level in (1, 2, 3):
+        y = F.max_pool2d(y, 5, 1, 2)
+        got = buf[..., off + level * Cc:off + (level + 1) * Cc].float().permute(0, 3, 1, 2)
+        assert torch.equal(got, y), level
+    assert torch.equal(buf[..., :off + Cc], b0[..., :off + Cc])
+    assert torch.equal(buf[..., off + 4 * Cc:], b0[..., off + 4 * Cc:])

@@ -1,7 +1,31 @@
+#!/bin/bash
+# Round job on the B200 box: tests, bench (both arms), ncu launch list of the bench command, and ncu --set full of
+# one eager step for a SELECTION of kernels, exported to CSV on the box (gpurun_out is capped at 64 MiB).
+# usage: bash tools/gpu_job.sh <tag> [skip-tests]
+TAG=${1:-r1x}
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r1j.log 2>&1; echo "pytest rc=$?"
-python bench.py --kernel-times gpurun_out/ktimes_r1j.csv > gpurun_out/bench_r1j.json 2> gpurun_out/bench_r1j.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_r1j.json 2> gpurun_out/bench_ref_r1j.err; echo "ref rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_r1j.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_l_r1j.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/step_r1j python tools/profile_step.py --nodes gpurun_out/nodes_r1j.csv > gpurun_out/ncu_full_r1j.log 2>&1; echo "ncu full rc=$?"
-ls -la gpurun_out/
+if [ -z "$2" ]; then
+  python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"
+  tail -3 gpurun_out/pytest_$TAG.log
+fi
+python bench.py --kernel-times gpurun_out/ktimes_$TAG.csv > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$TAG.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-latency > gpurun_out/ncu_l_$TAG.log 2>&1; echo "ncu launches rc=$?"
+# full-set capture: first 14 conv launches (stem .. layer 4: halo, im2col s2 and 1x1 kernels) + every non-conv kernel
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
+  -k regex:'conv_tc|conv_halo' -c 14 -f -o /tmp/conv_$TAG python tools/profile_step.py --nodes gpurun_out/nodes_$TAG.csv \
+  > gpurun_out/ncu_conv_$TAG.log 2>&1; echo "ncu conv rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
+  -k regex:'dwconv|psa|nms|coord_pool|gate|bifpn|stem|decode|sppf|upsample|strip_attn|simt' -c 40 -f -o /tmp/bw_$TAG \
+  python tools/profile_step.py > gpurun_out/ncu_bw_$TAG.log 2>&1; echo "ncu bw rc=$?"
+for n in conv bw; do
+  ncu -i /tmp/${n}_$TAG.ncu-rep --page raw --csv > gpurun_out/ncu_${n}_${TAG}_raw.csv 2>/dev/null
+  ls -la /tmp/${n}_$TAG.ncu-rep
+done
+# keep the conv report itself when it is small enough to travel
+sz=$(stat -c %s /tmp/conv_$TAG.ncu-rep 2>/dev/null || echo 0)
+if [ "$sz" -gt 0 ] && [ "$sz" -lt 30000000 ]; then cp /tmp/conv_$TAG.ncu-rep gpurun_out/; fi
+sz=$(stat -c %s /tmp/bw_$TAG.ncu-rep 2>/dev/null || echo 0)
+if [ "$sz" -gt 0 ] && [ "$sz" -lt 20000000 ]; then cp /tmp/bw_$TAG.ncu-rep gpurun_out/; fi
+du -sh gpurun_out
