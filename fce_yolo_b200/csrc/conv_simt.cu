@@ -133,12 +133,123 @@ int launch_simt(const fce_conv_desc* d, const void* x, const void* w, const floa
     return check_launch();
 }
 
+
+// ------------------------------------------------------------------------------------------------ strip GEMM
+// 1x1 convolutions on the pooled strips of the coordinate-attention family (fce_block.py:105,112-113,165-168,178,
+// 246-249,258,264-268,276): y[M, N] = act(x[M, K] w[N, K]^T + b) with M = B*(H+W) or B*H rows, K and N between 8
+// and a few hundred, everything fp32 (strips, gates and their weights are fp32 in both modes).  The generic
+// kernel above spends its time in im2col index arithmetic; this one is a plain tiled SGEMM with 16-byte loads:
+// 32 x 64 CTA tile, BK = 32, 256 threads x (2 x 4) outputs.  HBM-bound on the strip itself (a few MB).
+constexpr int SG_BM = 32, SG_BN = 64, SG_BK = 32;
+
+template <bool VEC>
+__global__ void __launch_bounds__(NT) strip_gemm_kernel(const fce_conv_desc d, const float* __restrict__ x,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        const float* res, float* y, int M) {
+    __shared__ float As[SG_BK][SG_BM + 1];
+    __shared__ float Bs[SG_BK][SG_BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;  // outputs: rows ty*2 .. +1, cols tx*4 .. +3
+    const int K = d.Cin, N = d.Cout;
+    const int m_base = blockIdx.x * SG_BM, n_base = blockIdx.y * SG_BN;
+    const int ar = tid >> 3, ak = (tid & 7) * 4;  // A loader: row ar, 4 consecutive k
+    const float* arow = x + (size_t)(m_base + ar) * d.in_pitch + d.in_off;
+    const bool a_ok = m_base + ar < M;
+    float acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += SG_BK) {
+        {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            const int k = k0 + ak;
+            if (a_ok) {
+                if (VEC && k + 3 < K) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(arow + k));
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (k + j < K) v[j] = __ldg(arow + k + j);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) As[ak + j][ar] = v[j];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // B loader: rows (tid>>3) + 32*h, 4 consecutive k
+            const int br = (tid >> 3) + 32 * h;
+            const int n = n_base + br, k = k0 + ak;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (n < N) {
+                const float* wr = w + (size_t)n * K + k;
+                if (VEC && k + 3 < K) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(wr));
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (k + j < K) v[j] = __ldg(wr + j);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Bs[ak + j][br] = v[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < SG_BK; ++kk) {
+            const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
+            acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+            acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
+            acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m_base + ty * 2 + i;
+        if (m >= M) continue;
+        float* yo = y + (size_t)m * d.out_pitch + d.out_off;
+        const float* ro = res ? res + (size_t)m * d.res_pitch + d.res_off : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n_base + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? bias[n] : 0.f);
+            v = apply_act(v, d.act);
+            if (ro) v += ro[n];
+            yo[n] = v;
+        }
+    }
+}
+
+int launch_strip_gemm(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res, void* y,
+                      cudaStream_t st) {
+    const long long M = (long long)d->B * d->H * d->W;
+    if (M > 0x7fffffffLL) return FCE_ERR_UNSUPPORTED;
+    dim3 grid(ceil_div(M, SG_BM), ceil_div(d->Cout, SG_BN));
+    const bool vec = d->Cin % 4 == 0 && d->in_pitch % 4 == 0 && d->in_off % 4 == 0 && (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
+    if (vec)
+        strip_gemm_kernel<true><<<grid, NT, 0, st>>>(*d, (const float*)x, (const float*)w, bias, (const float*)res,
+                                                     (float*)y, (int)M);
+    else
+        strip_gemm_kernel<false><<<grid, NT, 0, st>>>(*d, (const float*)x, (const float*)w, bias, (const float*)res,
+                                                      (float*)y, (int)M);
+    return check_launch();
+}
+
 }  // namespace
 
 int conv2d_simt(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res, void* y,
                 cudaStream_t st) {
     using bf = __nv_bfloat16;
     const int key = d->in_dtype * 100 + d->w_dtype * 10 + d->out_dtype;
+    if (key == FCE_F32 * 100 + FCE_F32 * 10 + FCE_F32 && d->k == 1 && d->stride == 1 && d->in_layout == FCE_NHWC &&
+        d->in_scale == 1.0f)
+        return launch_strip_gemm(d, x, w, bias, res, y, st);  // strips, and every 1x1 of fp32 mode
     switch (key) {
         case FCE_F32 * 100 + FCE_F32 * 10 + FCE_F32: return launch_simt<float, float, float>(d, x, w, bias, res, y, st);
         case FCE_BF16 * 100 + FCE_BF16 * 10 + FCE_BF16: return launch_simt<bf, bf, bf>(d, x, w, bias, res, y, st);

@@ -18,17 +18,18 @@ namespace {
 constexpr int PT = 256;       // threads
 constexpr int CVT = 8;        // channel-vector lanes per CTA
 constexpr int SLOTS = 32;     // pixel slots along W
-constexpr int RB = 8;         // rows per CTA (one band)
-constexpr int BAND = 5;       // column groups held in registers -> 160 columns per sweep
+constexpr int RB = 4;         // rows per reduction group (register budget: 2 CTAs per SM)
+constexpr int WS_ROWS = 8;    // the workspace contract: at most one band per 8 rows (fce_coord_pool_workspace)
+constexpr int BAND = 3;       // column groups held in registers -> 96 columns per sweep
 
 // A CTA owns (image, band of rows, 64-channel chunk [32 in fp32 mode]) and walks its band RB rows at a time.  Row
 // means are complete inside the CTA; the band's column sums stay in registers across the walk and go to the
 // workspace ([B][bands][W][C] fp32), where a second, tiny kernel adds the bands in a fixed order (deterministic,
 // no atomics) - or straight to the strip when one band covers the image.  The host picks the band count so that
 // the grid is about two CTAs per SM: at batch 64 that is ONE band (no workspace traffic at all), at batch 1 the
-// bands supply the parallelism.  10 independent 16-byte loads are in flight per thread.
+// bands supply the parallelism.  6 independent 16-byte loads are in flight per thread, two CTAs per SM.
 template <typename T>
-__global__ void __launch_bounds__(PT) coord_pool_kernel(const fce_pool_desc d, const T* __restrict__ x,
+__global__ void __launch_bounds__(PT, 2) coord_pool_kernel(const fce_pool_desc d, const T* __restrict__ x,
                                                         float* __restrict__ strip, float* __restrict__ ws, int bands,
                                                         int band_rows) {
     constexpr int N = Vec16<T>::N;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(PT) coord_pool_kernel(const fce_pool_desc d, c
 #pragma unroll
                 for (int j = 0; j < N; ++j) row[r][j] = 0.f;
             // all loads of two rows (2 x BAND 16-byte vectors) are issued before any is consumed; out-of-range
-            // pixels issue no load at all (W = 80 / 40 maps fill only part of the 160-column sweep)
+            // pixels issue no load at all (W = 80 / 40 maps fill only part of the 96-column sweep)
 #pragma unroll
             for (int r = 0; r < RB; r += 2) {
                 Vec16<T> v[2][BAND];
@@ -218,8 +219,8 @@ __global__ void __launch_bounds__(AT) strip_attn_kernel(const fce_strip_attn_des
 using namespace fce;
 
 extern "C" size_t fce_coord_pool_workspace(const fce_pool_desc* d) {
-    if (!d || d->H <= RB) return 0;
-    const size_t bands = (size_t)(d->H + RB - 1) / RB;
+    if (!d || d->H <= WS_ROWS) return 0;
+    const size_t bands = (size_t)(d->H + WS_ROWS - 1) / WS_ROWS;
     return (size_t)d->B * bands * d->W * d->C * sizeof(float);
 }
 
@@ -232,11 +233,11 @@ extern "C" int fce_coord_pool(const fce_pool_desc* d, const void* x, float* stri
     if ((d->C % n) || (d->pitch % n) || (d->off % n) || (((uintptr_t)x) & 15)) return FCE_ERR_ALIGNMENT;
     const int cc = CVT * n;
     const int chunks = (d->C + cc - 1) / cc;
-    // bands: enough CTAs for ~2 per SM, never more than one band per RB rows
-    const int max_bands = (d->H + RB - 1) / RB;
-    int bands = (2 * kNumSMs + d->B * chunks - 1) / (d->B * chunks);
+    // bands: enough CTAs for ~4 per SM, never more than one band per WS_ROWS rows
+    const int max_bands = (d->H + WS_ROWS - 1) / WS_ROWS;
+    int bands = (4 * kNumSMs + d->B * chunks - 1) / (d->B * chunks);
     bands = bands < 1 ? 1 : (bands > max_bands ? max_bands : bands);
-    int band_rows = ((d->H + bands - 1) / bands + RB - 1) / RB * RB;
+    int band_rows = ((d->H + bands - 1) / bands + WS_ROWS - 1) / WS_ROWS * WS_ROWS;
     bands = (d->H + band_rows - 1) / band_rows;
     if (bands > 1 && (!ws || ws_bytes < (size_t)d->B * bands * d->W * d->C * sizeof(float))) return FCE_ERR_WORKSPACE;
     const int grid = d->B * bands * chunks;

@@ -508,6 +508,24 @@ __global__ void __launch_bounds__(NT) copy_kernel(const fce_copy_desc d, const T
 }
 
 // ------------------------------------------------------------------------------------------------
+// N consecutive fp32 gate values: 16-byte loads on the vector path (the host checks the alignment)
+template <int N, bool VEC>
+__device__ __forceinline__ void ldf(const float* __restrict__ p, float* f) {
+    if constexpr (VEC && N % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p) + q);
+            f[4 * q] = v.x;
+            f[4 * q + 1] = v.y;
+            f[4 * q + 2] = v.z;
+            f[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) f[j] = __ldg(p + j);
+    }
+}
+
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(NT) gate_kernel(const fce_gate_desc d, const T* __restrict__ x,
                                                   const float* __restrict__ gh, const float* __restrict__ gw, T* y) {
@@ -522,8 +540,7 @@ __global__ void __launch_bounds__(NT) gate_kernel(const fce_gate_desc d, const T
     for (int cb = threadIdx.x; cb < cv; cb += blockDim.x) {
         const int c = cb * N;
         float a[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) a[j] = ar[c + j];
+        ldf<N, VEC>(ar + c, a);
         for (int pw0 = threadIdx.y; pw0 < d.W; pw0 += 2 * blockDim.y) {
             const int pw1 = pw0 + blockDim.y;
             const bool two = pw1 < d.W;
@@ -531,12 +548,8 @@ __global__ void __launch_bounds__(NT) gate_kernel(const fce_gate_desc d, const T
             CV<T, VEC>::load(xr + (size_t)pw0 * d.in_pitch + c, v0);
             if (two) CV<T, VEC>::load(xr + (size_t)pw1 * d.in_pitch + c, v1);
             if (d.mode != 1) {
-#pragma unroll
-                for (int j = 0; j < N; ++j) b0[j] = br[pw0 * d.gw_rstride + c + j];
-                if (two) {
-#pragma unroll
-                    for (int j = 0; j < N; ++j) b1[j] = br[pw1 * d.gw_rstride + c + j];
-                }
+                ldf<N, VEC>(br + pw0 * d.gw_rstride + c, b0);
+                if (two) ldf<N, VEC>(br + pw1 * d.gw_rstride + c, b1);
             }
 #pragma unroll
             for (int j = 0; j < N; ++j) {
@@ -717,7 +730,8 @@ extern "C" int fce_gate_apply(const fce_gate_desc* d, const void* x, const float
     return by_dtype(d->dtype, [&](auto tag) -> int {
         using T = decltype(tag);
         constexpr int N = 16 / (int)sizeof(T);
-        const bool vec = multiple_of(N, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off}) && ptr16(x) && ptr16(y);
+        const bool vec = multiple_of(N, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off}) && ptr16(x) && ptr16(y) &&
+                         multiple_of(4, {d->gh_bstride, d->gh_rstride, d->gw_bstride, d->gw_rstride}) && ptr16(gh) && ptr16(gw);
         const RowGrid g = row_grid(d->B * d->H, d->C / (vec ? N : 1));
         if (vec) gate_kernel<T, true><<<g.grid, g.block, 0, st>>>(*d, (const T*)x, gh, gw, (T*)y);
         else gate_kernel<T, false><<<g.grid, g.block, 0, st>>>(*d, (const T*)x, gh, gw, (T*)y);

@@ -172,7 +172,11 @@ __global__ void __launch_bounds__(NT) nms_kernel(const fce_nms_desc d, const flo
         // ---- a. exact radix select: the composite of rank `target` among the unprocessed ones
         unsigned long long prefix = 0, mask = 0;
         int need = target;
-        for (int shift = 56; shift >= 0; shift -= 8) {
+        // fast path (the usual predict case: a few hundred candidates): everything still unprocessed fits one
+        // round, so the rank-`target` composite need not be found - take them all
+        const bool take_all = s_valid - processed <= TSEL;
+        if (take_all) prefix = ~0ull;
+        for (int shift = 56; shift >= 0 && !take_all; shift -= 8) {
             if (tid < 256) hist[tid] = 0;
             __syncthreads();
             for_each_candidate(d, keys, cls, [&](unsigned long long c) {
@@ -219,9 +223,11 @@ __global__ void __launch_bounds__(NT) nms_kernel(const fce_nms_desc d, const flo
             }
         });
         __syncthreads();
-        for (int k = 2; k <= TSEL; k <<= 1) {
+        int n_sort = 2;  // bitonic network over the next power of two >= target (the tail is ~0 padding)
+        while (n_sort < target) n_sort <<= 1;
+        for (int k = 2; k <= n_sort; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < TSEL; i += NT) {
+                for (int i = tid; i < n_sort; i += NT) {
                     const int ixj = i ^ j;
                     if (ixj > i) {
                         const unsigned long long x = scomp[i], y = scomp[ixj];

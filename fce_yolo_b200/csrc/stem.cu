@@ -69,10 +69,28 @@ __global__ void __launch_bounds__(NT) stem_pack_kernel(const fce_pack_desc d, co
 // Algorithmic HBM bytes per output pixel: 12 * e_in read (each input byte lands in ~2.25 patches but is fetched
 // once per CTA tile) + 2 * Cout written; the [M, 32] patch matrix of the two-kernel route (64 B written + 64 B
 // read per pixel) never exists.  A tcgen05 pipeline has nothing to offer at K = 32, N <= 96: the layer is
-// bound by the output write.
-constexpr int ST_ROWS = 8, ST_COLS = 64;             // output tile of one CTA
-constexpr int ST_IR = 2 * ST_ROWS + 1, ST_IC = 2 * ST_COLS + 1;  // input tile incl. the left/top halo
+// bound by the output write and by instruction issue, so the kernel is written for few instructions per pixel:
+//   * the tile keeps (w, ci) interleaved exactly like the image, so the 9 values of one patch row kh are 9
+//     CONTIGUOUS bf16 starting at a 4-byte aligned address.  The GEMM K axis is therefore re-ordered to
+//     k' = kh * 10 + j (j = 0..8 = kw*3+ci, j = 9 and k' >= 30 carry zero weights): every A-fragment register
+//     (two consecutive k') is ONE aligned 32-bit shared-memory load, no byte gathering or packing;
+//   * uint8 images are staged four bytes per load (the tile origin is shifted left to a 4-byte boundary, one leading
+//     pad element per row keeps the patch origins even) and converted with the 2^23 magic-number trick;
+//   * SiLU is h + h * tanh(h), h = v/2: one MUFU per value.
+constexpr int ST_ROWS = 8, ST_COLS = 64;               // output tile of one CTA
+constexpr int ST_IR = 2 * ST_ROWS + 1;                 // input rows incl. the top halo
+constexpr int ST_SHIFT = 3;                            // extra left columns so that the u8 tile starts 4-byte aligned
+constexpr int ST_IC = 2 * ST_COLS + 2 + ST_SHIFT;      // 133 input columns (399 values) per tile row
+constexpr int ST_PITCH = 400;                          // bf16 elements per tile row: element 1 + 3*c + ci holds (c, ci);
+                                                       // the leading pad element makes every patch origin EVEN
 constexpr int ST_THREADS = 128;
+
+__device__ __forceinline__ float silu_tanh(float v) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 template <typename TI, int LAYOUT, int NTILES>
 __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_desc d, const TI* __restrict__ x,
@@ -81,21 +99,49 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
                                                                 __nv_bfloat16* __restrict__ y, int Ho, int Wo) {
     constexpr int COUT = NTILES * 8;
     constexpr int OPITCH = COUT + 8;  // staged pixel pitch (bf16): +16 B keeps the quad-strided writes conflict-free
-    __shared__ __align__(16) __nv_bfloat16 tile[ST_IR * ST_IC * 3];
+    __shared__ __align__(16) __nv_bfloat16 tile[ST_IR * ST_PITCH];
     __shared__ __align__(16) __nv_bfloat16 stage[4][16 * OPITCH];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int b = blockIdx.z, ho0 = blockIdx.y * ST_ROWS, wo0 = blockIdx.x * ST_COLS;
-    const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
+    const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1 - ST_SHIFT;  // tile origin in the image
 
-    // ---- stage the input tile (zero outside the image = the conv padding)
-    if (LAYOUT == FCE_NHWC) {
-        for (int i = tid; i < ST_IR * ST_IC * 3; i += ST_THREADS) {
-            const int r = i / (ST_IC * 3), rem = i - r * (ST_IC * 3);
-            const int c = rem / 3;
+    // ---- stage the input tile (zero outside the image = the conv padding).  Tile column c is image column
+    // wi0 + c; value (c, ci) lives at element 1 + 3*c + ci of its row.
+    if (LAYOUT == FCE_NHWC && sizeof(TI) == 1 && (d.W & 3) == 0) {
+        // u8: the tile row starts at byte 3 * wi0 = 6 * wo0 - 12 of an image row of 3 * W bytes - both multiples of
+        // 4.  Elements 4q .. 4q+3 are image bytes 4q-1 .. 4q+2 of the row segment: the top byte of word q-1 and the
+        // low three bytes of word q (one funnel shift).
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
+        uint2* tw = reinterpret_cast<uint2*>(tile);
+        const int row_words = d.W * 3 / 4;
+        const int w_first = wi0 * 3 / 4;  // exact (may be negative)
+        for (int i = tid; i < ST_IR * (ST_PITCH / 4); i += ST_THREADS) {
+            const int r = i / (ST_PITCH / 4), q = i - r * (ST_PITCH / 4);
+            const int hi = hi0 + r, wq = w_first + q;
+            uint32_t w0 = 0u, w1 = 0u;
+            if (hi >= 0 && hi < d.H) {
+                const uint32_t* rowp = xw + (size_t)(b * d.H + hi) * row_words;
+                if (wq - 1 >= 0 && wq - 1 < row_words) w0 = __ldg(rowp + wq - 1);
+                if (wq >= 0 && wq < row_words) w1 = __ldg(rowp + wq);
+            }
+            const uint32_t v = __funnelshift_l(w0, w1, 8);
+            // four bytes -> four bf16: (0x4B000000 | byte) is the float 2^23 + byte; subtracting 2^23 leaves the exact
+            // integer, whose upper 16 bits are its bf16 encoding
+            const float f0 = __uint_as_float(0x4B000000u | (v & 0xffu)) - 8388608.f;
+            const float f1 = __uint_as_float(0x4B000000u | ((v >> 8) & 0xffu)) - 8388608.f;
+            const float f2 = __uint_as_float(0x4B000000u | ((v >> 16) & 0xffu)) - 8388608.f;
+            const float f3 = __uint_as_float(0x4B000000u | (v >> 24)) - 8388608.f;
+            tw[i] = make_uint2(__byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632),
+                               __byte_perm(__float_as_uint(f2), __float_as_uint(f3), 0x7632));
+        }
+    } else if (LAYOUT == FCE_NHWC) {
+        for (int i = tid; i < ST_IR * ST_PITCH; i += ST_THREADS) {
+            const int r = i / ST_PITCH, e = i - r * ST_PITCH - 1;  // e = 3*c + ci
+            const int c = e / 3;
             const int hi = hi0 + r, wi = wi0 + c;
             float v = 0.f;
-            if (hi >= 0 && hi < d.H && wi >= 0 && wi < d.W)
-                v = Elem<TI>::to_f(__ldg(x + ((size_t)(b * d.H + hi) * d.W + wi0) * 3 + rem));
+            if (e >= 0 && hi >= 0 && hi < d.H && wi >= 0 && wi < d.W)
+                v = Elem<TI>::to_f(__ldg(x + ((long long)(b * d.H + hi) * d.W + wi) * 3 + (e - c * 3)));
             tile[i] = __float2bfloat16_rn(v);
         }
     } else {
@@ -106,35 +152,45 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
             float v = 0.f;
             if (hi >= 0 && hi < d.H && wi >= 0 && wi < d.W)
                 v = Elem<TI>::to_f(__ldg(x + ((size_t)(b * 3 + ci) * d.H + hi) * d.W + wi));
-            tile[(r * ST_IC + c) * 3 + ci] = __float2bfloat16_rn(v);
+            tile[r * ST_PITCH + 1 + c * 3 + ci] = __float2bfloat16_rn(v);
         }
     }
-    // ---- B fragments (weights [COUT][32] bf16, K index (kh*3+kw)*3+ci, columns 27..31 zero) and bias
+    // ---- B fragments in the re-ordered K axis: k' = kh*10 + j  <->  k = kh*9 + j of the [COUT][32] weight rows
     uint32_t bf[2][NTILES][2];
     float bs[NTILES][2];
+    const unsigned short* wus = reinterpret_cast<const unsigned short*>(w);
 #pragma unroll
     for (int nt = 0; nt < NTILES; ++nt) {
-        const uint32_t* wr = reinterpret_cast<const uint32_t*>(w + (nt * 8 + g) * 32);
+        const unsigned short* wr = wus + (nt * 8 + g) * 32;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            bf[ks][nt][0] = __ldg(wr + ks * 8 + t);
-            bf[ks][nt][1] = __ldg(wr + ks * 8 + 4 + t);
-        }
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int kp = ks * 16 + hf * 8 + 2 * t + e;
+                    const int kh = kp / 10, j = kp - kh * 10;
+                    if (kp < 30 && j < 9) v |= (uint32_t)__ldg(wr + kh * 9 + j) << (16 * e);
+                }
+                bf[ks][nt][hf] = v;
+            }
         bs[nt][0] = __ldg(bias + nt * 8 + 2 * t);
         bs[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1);
     }
-    // ---- this thread's 8 patch offsets: k -> kh * (row pitch) + k % 9 (the 9 values of one kh are contiguous)
-    int koff[2][4];
+    // ---- this thread's 4 A-fragment word offsets (in 32-bit words, relative to the patch origin)
+    int aoff[2][2];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = ks * 16 + 2 * t + (j & 1) + 8 * (j >> 1);
-            koff[ks][j] = k < 27 ? (k / 9) * (ST_IC * 3) + k % 9 : -1;
+        for (int hf = 0; hf < 2; ++hf) {
+            const int kp = ks * 16 + hf * 8 + 2 * t;
+            const int kh = kp / 10, j = kp - kh * 10;
+            aoff[ks][hf] = kp < 30 ? (kh * ST_PITCH + j) / 2 : -1;
         }
     __syncthreads();
 
-    const unsigned short* tl = reinterpret_cast<const unsigned short*>(tile);
+    const uint32_t* tl = reinterpret_cast<const uint32_t*>(tile);
     __nv_bfloat16* stg = stage[warp];
     // warp w owns output rows 2w, 2w+1 of the tile: 8 runs of 16 consecutive pixels
 #pragma unroll 1
@@ -142,22 +198,18 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
         const int ro = warp * 2 + (run >> 2), co = (run & 3) * 16;
         const int ho = ho0 + ro;
         if (ho >= Ho || wo0 + co >= Wo) continue;  // warp-uniform
-        const int p0 = (2 * ro) * (ST_IC * 3) + 2 * (co + g) * 3;  // patch origin of pixel g; pixel g+8 is +48
+        // patch origin of pixel g: row 2*ro, column 2*(co+g) + ST_SHIFT -> element 1 + 3*(2*(co+g) + 3) = 6*(co+g) + 10
+        // (even), in 32-bit words; pixel g+8 is 48 elements = 24 words further
+        const int p0 = ro * ST_PITCH + 3 * (co + g) + 5;
         uint32_t a[2][4];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            unsigned short e[4][2];  // [j][row half]
+        for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int o = koff[ks][j];
-                e[j][0] = o >= 0 ? tl[p0 + o] : (unsigned short)0;
-                e[j][1] = o >= 0 ? tl[p0 + 48 + o] : (unsigned short)0;
+            for (int hf = 0; hf < 2; ++hf) {
+                const int o = aoff[ks][hf];
+                a[ks][2 * hf] = o >= 0 ? tl[p0 + o] : 0u;           // row g
+                a[ks][2 * hf + 1] = o >= 0 ? tl[p0 + 24 + o] : 0u;  // row g+8
             }
-            a[ks][0] = (uint32_t)e[0][0] | ((uint32_t)e[1][0] << 16);  // row g,   k = 2t, 2t+1
-            a[ks][1] = (uint32_t)e[0][1] | ((uint32_t)e[1][1] << 16);  // row g+8
-            a[ks][2] = (uint32_t)e[2][0] | ((uint32_t)e[3][0] << 16);  // row g,   k = 2t+8, 2t+9
-            a[ks][3] = (uint32_t)e[2][1] | ((uint32_t)e[3][1] << 16);  // row g+8
-        }
         __syncwarp();  // the previous run's staged pixels have been read
 #pragma unroll
         for (int nt = 0; nt < NTILES; ++nt) {
@@ -170,7 +222,7 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
                          : "r"(a[1][0]), "r"(a[1][1]), "r"(a[1][2]), "r"(a[1][3]), "r"(bf[1][nt][0]), "r"(bf[1][nt][1]));
             if (d.act == FCE_ACT_SILU) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) c[j] = silu_f(c[j]);
+                for (int j = 0; j < 4; ++j) c[j] = silu_tanh(c[j]);
             }
             __nv_bfloat162 lo = __floats2bfloat162_rn(c[0], c[1]), hi = __floats2bfloat162_rn(c[2], c[3]);
             *reinterpret_cast<__nv_bfloat162*>(stg + g * OPITCH + nt * 8 + 2 * t) = lo;
@@ -238,7 +290,8 @@ extern "C" int fce_stem_conv(const fce_stem_desc* d, const void* x, const void* 
     if (!d || !x || !w || !bias || !y || d->B <= 0 || d->H <= 0 || d->W <= 0) return FCE_ERR_BAD_ARG;
     if (d->Cout % 8 || d->Cout <= 0 || (d->act != FCE_ACT_SILU && d->act != FCE_ACT_NONE)) return FCE_ERR_UNSUPPORTED;
     if (d->B > 65535) return FCE_ERR_UNSUPPORTED;
-    if (d->out_pitch % 8 || d->out_off % 8 || ((uintptr_t)y & 15) || ((uintptr_t)w & 3)) return FCE_ERR_ALIGNMENT;
+    if (d->out_pitch % 8 || d->out_off % 8 || ((uintptr_t)y & 15) || ((uintptr_t)w & 3) || ((uintptr_t)x & 3))
+        return FCE_ERR_ALIGNMENT;
     cudaStream_t st = (cudaStream_t)stream;
     if (d->in_dtype == FCE_U8 && d->in_layout == FCE_NHWC) return launch_stem<uint8_t, FCE_NHWC>(d, x, w, bias, y, st);
     if (d->in_dtype == FCE_F32 && d->in_layout == FCE_NCHW) return launch_stem<float, FCE_NCHW>(d, x, w, bias, y, st);

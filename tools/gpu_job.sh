@@ -1,14 +1,15 @@
 #!/bin/bash
 # Round job on the B200 box: tests, bench (both arms), ncu launch list of the bench command, and ncu --set full of
 # one eager step for a SELECTION of kernels, exported to CSV on the box (gpurun_out is capped at 64 MiB).
-# usage: bash tools/gpu_job.sh <tag> [skip-tests]
+# usage: bash tools/gpu_job.sh <tag> [quick|notest]     quick = tests + bench only
 TAG=${1:-r1x}
 set -x
-if [ -z "$2" ]; then
+if [ "$2" != "notest" ]; then
   python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"
   tail -3 gpurun_out/pytest_$TAG.log
 fi
 python bench.py --kernel-times gpurun_out/ktimes_$TAG.csv > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+if [ "$2" == "quick" ]; then cat gpurun_out/bench_$TAG.json; exit 0; fi
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$TAG.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-latency > gpurun_out/ncu_l_$TAG.log 2>&1; echo "ncu launches rc=$?"
