@@ -2,6 +2,8 @@
 // BiFPN weighted fusion, gate application, view copy.  No tensor cores: every thread owns one
 // 16-byte channel vector (8 bf16 / 4 fp32) of one pixel, so a warp touches whole 128-byte lines;
 // one CTA per image row, no integer division on the device.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fce {
@@ -588,12 +590,29 @@ int by_dtype(int dtype, F&& f) {
 }  // namespace
 }  // namespace fce
 
+namespace fce {
+int dwconv3x3_tma(const fce_dwconv_desc* d, const void* x, const float* w, const float* bias, const void* add, void* y,
+                  cudaStream_t st);
+// FCE_DW_IMPL=1: column-walk kernel, 2: 4-byte-lane row kernel (A/B timing of the depthwise implementations)
+static const int g_dw_impl = [] {
+    const char* e = getenv("FCE_DW_IMPL");
+    return e ? atoi(e) : 0;
+}();
+}  // namespace fce
+
 using namespace fce;
 
 extern "C" int fce_dwconv3x3(const fce_dwconv_desc* d, const void* x, const float* w, const float* bias,
                              const void* add, void* y, void* stream) {
     if (!d || !x || !w || !bias || !y || d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0) return FCE_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if ((d->dtype == FCE_BF16 || d->dtype == FCE_F32) && g_dw_impl == 0) {  // TMA-pipelined kernel when TMA can describe the views
+        const int esz = d->dtype == FCE_BF16 ? 2 : 4;
+        const int rc = dwconv3x3_tma(d, (const char*)x + (size_t)d->in_off * esz, w, bias,
+                                     add ? (const char*)add + (size_t)d->add_off * esz : nullptr,
+                                     (char*)y + (size_t)d->out_off * esz, st);
+        if (rc != FCE_ERR_UNSUPPORTED) return rc;
+    }
     return by_dtype(d->dtype, [&](auto tag) -> int {
         using T = decltype(tag);
         constexpr int E = 4 / (int)sizeof(T);  // channels per 4-byte lane
@@ -602,7 +621,7 @@ extern "C" int fce_dwconv3x3(const fce_dwconv_desc* d, const void* x, const floa
             (((uintptr_t)x | (uintptr_t)y | (uintptr_t)add) & 3))
             return FCE_ERR_ALIGNMENT;
         constexpr int N = 16 / (int)sizeof(T);
-        if (multiple_of(N, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off, add ? d->add_pitch : 0,
+        if (g_dw_impl <= 1 && multiple_of(N, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off, add ? d->add_pitch : 0,
                             add ? d->add_off : 0}) && ptr16(x) && ptr16(y) && ptr16(add)) {
             const int cgroups = (d->C + DW2_VECS * N - 1) / (DW2_VECS * N);
             const int wtiles = (d->W + DW2_COLS - 1) / DW2_COLS;

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(NT) nms_kernel(const fce_nms_desc d, const flo
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long scomp[TSEL];
     __shared__ int hist[256];
-    __shared__ int s_digit, s_need, s_cnt, s_kept, s_valid;
+    __shared__ int s_digit, s_need, s_cnt, s_kept, s_valid, s_full;
     __shared__ uint32_t alive[CH / 32];
     __shared__ uint32_t sup[CH][CH / 32];
     __shared__ Box cbox[CH];
@@ -203,13 +203,19 @@ __global__ void __launch_bounds__(NT) nms_kernel(const fce_nms_desc d, const flo
                     }
                     s_digit = lane * 8 + dg;
                     s_need = need - before;
+                    s_full = loc[dg] == need - before;  // the whole bin is wanted: no need to look at lower digits
                 }
             }
             __syncthreads();
             prefix |= (unsigned long long)s_digit << shift;
             mask |= 255ull << shift;
             need = s_need;
+            const bool full = s_full != 0;
             __syncthreads();
+            if (full) {  // distinct scores: reached after the four score digits, the four index digits are skipped
+                prefix |= shift ? ((1ull << shift) - 1ull) : 0ull;
+                break;
+            }
         }
         const unsigned long long thr = prefix;
         // ---- b. compaction (any order) + bitonic sort
