@@ -43,7 +43,7 @@ extern "C" int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, 
 }
 
 extern "C" void fce_conv_tc_set_profile(int on) {
-    conv_tc_set_profile(on & 3);
+    conv_tc_set_profile(on & 15);  // bit 0 profile, bit 1 skip TMA loads, bit 2 skip TMA stores, bit 3 skip epilogue math
     // bit 4: disable the 3x3 strip kernel (everything goes through the TMA-im2col kernel)
     conv_halo_set_mode(((on >> 4) & 1) ? 0 : 1);
 }

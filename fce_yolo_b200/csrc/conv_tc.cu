@@ -11,12 +11,14 @@
 //     128 consecutive output pixels (across rows and images), applies the conv stride and the (kw, kh) tap
 //     offset and zero-fills the padding halo.  The input map is read from HBM once; the 9 taps hit L2.
 //   * B (weights) is a 2-D tiled box {kc, bn} of the [Cout, K] matrix.
-//   * One CTA per SM, persistent over (m, n) tiles, warp-specialised:
-//       warp 0    : TMA producer (one elected lane), `stages`-deep full/empty mbarrier ring
-//       warp 1    : TMEM allocator + single-thread tcgen05.mma issuer; the accumulator (128 x bn fp32) lives in
-//                   TMEM and is double buffered so the epilogue of tile i overlaps the main loop of tile i+1
-//       warps 2-9 : epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16/fp32 -> NHWC store at the
-//                   channel offset of the destination view (concat fusion)
+//   * One CTA per SM, persistent over (m, n) tiles, warp-specialised (16 warps):
+//       warps 0-11 : epilogue, three groups of four (one warp per TMEM lane quarter), tile i -> group i % 3:
+//                    tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16/fp32 -> swizzled staging slab -> TMA store
+//                    at the channel offset of the destination view (concat fusion)
+//       warp 12/13 : TMA producers for A and B (one elected lane), `stages`-deep full/empty mbarrier ring
+//       warp 14    : single-thread tcgen05.mma issuer; the accumulator (128 x bn fp32) lives in TMEM with up to three
+//                    stages so the epilogues of tiles i, i+1 overlap the main loop of tile i+2
+//       warp 15    : TMEM allocator
 //   * Shared-memory tiles use the hardware swizzle that matches the K chunk (128B / 64B / 32B for
 //     kc = 64 / 32 / 16 channels), identical in the TMA descriptor and the UMMA shared-memory descriptor.
 #include "tc_common.cuh"
@@ -26,13 +28,16 @@ using namespace tc;
 namespace {
 
 constexpr int BM = 128;  // UMMA M (cta_group::1)
-// Warp roles: 8 epilogue warps (two per TMEM lane quarter), then the single-lane roles.
+// Warp roles: 12 epilogue warps (three groups of four, one warp per TMEM lane quarter; tiles rotate over the
+// groups), then the single-lane roles.
 constexpr int WARP_EPI0 = 0;
-constexpr int NUM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, interleaved over 32-column slabs
-constexpr int WARP_PROD_A = 8, WARP_PROD_B = 9, WARP_MMA = 10, WARP_ALLOC = 11;
-constexpr int NUM_THREADS = 12 * 32;
+constexpr int NUM_EPI_WARPS = 12;  // three groups x four lane quarters
+constexpr int NUM_GROUPS = NUM_EPI_WARPS / 4;
+constexpr int MAX_ACC = 3;         // TMEM accumulator stages (3 x bn <= 512 columns, else 2)
+constexpr int WARP_PROD_A = 12, WARP_PROD_B = 13, WARP_MMA = 14, WARP_ALLOC = 15;
+constexpr int NUM_THREADS = 16 * 32;
 constexpr int MAX_STAGES = 8;
-constexpr int SMEM_BUDGET = 188 * 1024;  // A/B tiles + bias; staging slabs and barriers come on top
+constexpr int SMEM_BUDGET = 172 * 1024;  // A/B tiles + bias; staging slabs and barriers come on top
 constexpr int B_RESIDENT_MAX = 96 * 1024;
 constexpr int STG_BYTES = 32 * 64;  // one epilogue staging slab: 32 rows x 64 bytes (64B swizzle)
 
@@ -50,6 +55,7 @@ struct TcParams {
     uint32_t b_total;           // shared-memory bytes of the B region
     uint32_t bias_bytes;
     uint32_t tmem_cols;
+    int acc_stages;    // TMEM accumulator stages: tile `it` of a CTA accumulates in stage it % acc_stages
     int out_pitch, res_pitch, act, out_f32;
     uint32_t desc_hi;  // upper 32 bits of the UMMA shared-memory descriptor (SBO, version, swizzle)
     uint32_t idesc;    // UMMA instruction descriptor
@@ -85,8 +91,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t sBias = sC + NUM_EPI_WARPS * 2 * STG_BYTES;
     const uint32_t bars = sBias + p.bias_bytes;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES;
-    const uint32_t tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
-    const uint32_t bfull = tempty0 + 16;
+    const uint32_t tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 32;
+    const uint32_t bfull = tempty0 + 32;
     const uint32_t tmem_slot = bfull + 8;
     float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - smem_u32(smem_raw)));
 
@@ -99,9 +105,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(full0 + 8 * i, p.b_resident ? 1 : 2);
             mbar_init(empty0 + 8 * i, 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < MAX_ACC; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, NUM_EPI_WARPS);
+            mbar_init(tempty0 + 8 * a, 4);  // one group of four epilogue warps drains an accumulator
         }
         mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -279,8 +285,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 r.advance(nstages);
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (++acc == p.acc_stages) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
         }
         if (PROF && lane == 0) {
             g_prof[blockIdx.x * PROF_SLOTS + 4] = wf;
@@ -292,22 +300,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // TMEM -> registers -> bias/activation/residual -> swizzled staging slab in smem -> TMA store.
         // Each warp owns 32 accumulator rows and two private 32-row x 64-byte slabs, so the only
         // synchronisation is __syncwarp + the bulk-group wait that recycles a slab.
+        // The twelve warps form THREE groups of four (one warp per TMEM lane quarter); tile `it` of this CTA goes to
+        // accumulator stage it % acc_stages and to the group of the same index.  Measured on the 1x1 layers: with loads, stores and
+        // math switched off in turn, neither HBM nor the TMA stores set the pace - the epilogue warps did (8 warps =
+        // 2 per scheduler, each a dependent chain barrier -> tcgen05.ld -> FFMA/MUFU -> st.shared -> fence -> TMA
+        // store): more warps in flight is what raises the rate, and the tensor pipe has slack to run ahead into
+        // the extra accumulator stage.
         const int e = warp - WARP_EPI0;
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may read
-        const int half = e >> 2;       // which interleaved set of slabs
+        const int group = e >> 2;      // which accumulator stage
         const int n_tiles = p.n_tiles, bn = p.bn, Cout = p.Cout, act = p.act;
         const bool has_res = res != nullptr, out_f32 = p.out_f32 != 0;
+        const bool dbg_nostore = (p.dbg & 2) != 0, dbg_nomath = (p.dbg & 4) != 0;  // debug timing only
         const int slab_cols = out_f32 ? 16 : 32;  // 64 bytes of output per row
         const int n_slabs = (bn + slab_cols - 1) / slab_cols;
         const uint32_t stg0 = sC + e * 2 * STG_BYTES;
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);  // 64B swizzle: 16-byte unit u of row r lives at u ^ ((r>>1)&3)
         const uint32_t my_row = stg0 + lane * 64;
         int buf = 0;
-        int acc = 0;
+        int acc = 0;             // accumulator stage and phase of tile `it` (advanced for every tile, mine or not)
         uint32_t acc_phase = 0;
+        int it = 0;
         long long ew = 0, et0 = PROF ? clock64() : 0;
         pdl_wait();  // residual reads and output stores touch buffers the previous kernel may still be using
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            // group g owns accumulator stage g: every barrier has ONE waiting group that sees its phases in order (a
+            // group waiting two phases ahead of a barrier would be fooled by the parity wrap-around).  With two
+            // stages (bn > 170) the third group idles.
+            const bool mine = acc == group;
+            const int my_acc = acc;
+            const uint32_t my_phase = acc_phase;
+            if (++acc == p.acc_stages) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+            if (!mine) continue;
             const int mt = n_tiles == 1 ? tile : tile / n_tiles;
             const int n0 = n_tiles == 1 ? 0 : (tile - mt * n_tiles) * bn;
             const int m_warp = mt * BM + quarter * 32;
@@ -316,13 +343,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const __nv_bfloat16* rrow = res + (size_t)m * p.res_pitch;
             {
                 PROF_T0();
-                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                mbar_wait(tfull0 + 8 * my_acc, my_phase);
                 PROF_ACC(ew);
             }
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * bn;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + my_acc * bn;
 #pragma unroll 1
-            for (int sl = half; sl < n_slabs; sl += 2) {
+            for (int sl = 0; sl < n_slabs; ++sl) {
                 const int c0 = sl * slab_cols;  // first column of the slab within the tile
                 const int n = n0 + c0;
                 if (n >= Cout) break;
@@ -345,7 +372,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 tmem_ld_wait();
                 const uint32_t rowp = my_row + buf * STG_BYTES;
-                if (out_f32) {
+                if (dbg_nomath) {
+                    st_shared_v4(rowp, v0[0], v0[1], v0[2], v0[3]);
+                } else if (out_f32) {
                     float f[16];
                     epi_math16(v0, bias_s + n, act, false, r0, r1, f);
 #pragma unroll
@@ -368,7 +397,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !dbg_nostore) {
                     tma_store_2d(&tmC, stg0 + buf * STG_BYTES, n, m_warp);  // rows >= M / cols >= Cout are clipped
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
@@ -376,9 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);  // this warp has drained its part of the accumulator
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (lane == 0) mbar_arrive(tempty0 + 8 * my_acc);  // this warp has drained its part of the accumulator
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
         if (PROF && warp == WARP_EPI0 && lane == 0) {
@@ -448,7 +475,12 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     p.kc = pick_kc(d->Cin);
     p.chunks = d->Cin / p.kc;
     p.m_tiles = ceil_div(M, BM);
-    p.n_tiles = ceil_div(d->Cout, 256);
+    static const int bn_cap = [] {  // experiment knob: FCE_BN_MAX=128 forces N tiles of at most 128 columns
+        const char* e = getenv("FCE_BN_MAX");
+        const int v = e ? atoi(e) : 0;
+        return v >= 32 ? v : 256;
+    }();
+    p.n_tiles = ceil_div(d->Cout, bn_cap);
     // N tiles that do not end the channel range must end on a 32-column staging-slab boundary
     p.bn = p.n_tiles == 1 ? d->Cout : ceil_div(ceil_div(d->Cout, p.n_tiles), 32) * 32;
     // small problems: narrower N tiles give the persistent grid more tiles to balance over 148 SMs
@@ -478,8 +510,9 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     if (p.stages < 2) return FCE_ERR_UNSUPPORTED;
     if (!p.b_resident) p.b_total = p.stages * p.b_stage;
+    p.acc_stages = 3 * p.bn <= 512 ? 3 : 2;
     p.tmem_cols = 32;
-    while (p.tmem_cols < 2u * p.bn) p.tmem_cols <<= 1;
+    while (p.tmem_cols < (uint32_t)(p.acc_stages * p.bn)) p.tmem_cols <<= 1;
     p.out_pitch = d->out_pitch;
     p.res_pitch = d->res_pitch;
     p.act = d->act;

@@ -57,6 +57,9 @@ def main():
     ap.add_argument("--act", type=int, default=1)
     ap.add_argument("--prof", action="store_true", help="per-role cycle accounting of one launch per shape")
     ap.add_argument("--skip-tma", action="store_true", help="debug: producers skip the loads (MMA+epilogue rate)")
+    ap.add_argument("--dbg", type=int, default=0, help="debug bits for timed runs: 1 skip TMA loads, 2 skip TMA stores, "
+                                                      "4 skip epilogue math (results are garbage)")
+    ap.add_argument("--nohalo", action="store_true")
     a = ap.parse_args()
     lib = L.load(check_device=True)
     dev = torch.device("cuda:0")
@@ -101,6 +104,7 @@ def main():
             print(f"{name:34s} tiles/CTA {tiles/148:6.1f} | A-prod wait {m[0]:9.0f} / {m[1]:9.0f} | MMA wait-full {m[4]:9.0f} "
                   f"wait-tmem {m[5]:9.0f} / {m[6]:9.0f} | epi wait {m[7]:9.0f} / {m[8]:9.0f} stg-wait {m[9]:9.0f} | dma wait {m[10]:9.0f} / {m[11]:9.0f}", flush=True)
             continue
+        lib.fce_conv_tc_set_profile((a.dbg << 1) | (16 if a.nohalo else 0))
         for _ in range(2):
             L.check(lib.fce_conv2d(*args), name)
         ms = []
@@ -113,6 +117,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms.append(e0.elapsed_time(e1))
+        lib.fce_conv_tc_set_profile(0)
         ms.sort()
         t = ms[len(ms) // 2]
         flops = 2.0 * B * Ho * Wo * Cout * Cin * k * k
