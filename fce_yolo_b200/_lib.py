@@ -35,6 +35,11 @@ class StemDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "H", "W", "Cout", "out_pitch", "out_off", "act", "in_dtype", "in_layout")]
 
 
+class LetterboxItem(C.Structure):
+    _fields_ = [("src", C.c_uint64)] + [(n, i32) for n in ("src_pitch", "H", "W", "new_w", "new_h", "top", "left",
+                                                            "reserved")]
+
+
 class DwconvDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "H", "W", "C", "in_pitch", "in_off", "out_pitch", "out_off", "add_pitch",
                                    "add_off", "act", "dtype")]
@@ -96,6 +101,7 @@ _SIGS = {
     "fce_conv2d": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "fce_stem_pack": (C.c_int, [C.POINTER(PackDesc), _P, _P, _P]),
     "fce_stem_conv": (C.c_int, [C.POINTER(StemDesc), _P, _P, _P, _P, _P]),
+    "fce_letterbox": (C.c_int, [_P, _P, _P, i32, i32, i32, i32, _P, _P]),
     "fce_conv_tc_set_profile": (None, [C.c_int]),
     "fce_conv_tc_profile": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "fce_dwconv3x3": (C.c_int, [C.POINTER(DwconvDesc), _P, _P, _P, _P, _P, _P]),

@@ -101,6 +101,24 @@ typedef struct {
 } fce_stem_desc;
 int fce_stem_conv(const fce_stem_desc* d, const void* x, const void* w, const float* bias, void* y, void* stream);
 
+/* Predict-side preprocessing, the step right before the path (LetterBox, ultralytics/data/augment.py:1589-1631,
+ * + the BGR->RGB flip of BasePredictor.preprocess, ultralytics/engine/predictor.py:163-165): a batch of differently
+ * sized uint8 HWC BGR images -> uint8 NHWC RGB [B, out_h, out_w, 3], resized with cv2.resize(INTER_LINEAR)'s 8-bit
+ * fixed-point arithmetic (bit-exact) and padded with pad_value (114).  items: DEVICE array of B records.
+ * xtab [B][out_w][4], ytab [B][out_h][4] (DEVICE, int32): per resized column / row {tap 0 index, tap 1 index,
+ * weight 0, weight 1} with 11-bit weights, entries [0, new_w) / [0, new_h) used; the host computes them with
+ * OpenCV's coordinate arithmetic (fce_yolo_b200/preprocess.py). */
+typedef struct {
+    uint64_t src;             /* device pointer of the source image (uint8, HWC, BGR) */
+    int32_t src_pitch;        /* bytes per source row */
+    int32_t H, W;             /* source size */
+    int32_t new_w, new_h;     /* resized (un-padded) size */
+    int32_t top, left;        /* where the resized image sits in the output */
+    int32_t reserved;
+} fce_letterbox_item;
+int fce_letterbox(const fce_letterbox_item* items, const int32_t* xtab, const int32_t* ytab, int32_t B, int32_t out_h,
+                  int32_t out_w, int32_t pad_value, uint8_t* out, void* stream);
+
 /* Debug aid for the tcgen05 convolution: when switched on, the next fce_conv2d launches record per-CTA, per-role
  * cycle counts (16 int64 slots per CTA: A-producer wait/total, -, -, MMA wait-full/wait-tmem/total, epilogue
  * wait/total); fce_conv_tc_profile copies n slots of the last launch to a HOST buffer and returns n. */

@@ -81,3 +81,21 @@ NMS_CASES = {
     "a33600": dict(make=lambda: synth_predictions(15, 1, 33600, imgsz=1280, sharp=1.5),
                    kw=dict(conf_thres=0.25, iou_thres=0.7, max_det=300), tie_perm=True),
 }
+
+
+# LetterBox + BGR->RGB: (source h, w), new_shape, LetterBox kwargs.  Small sizes keep the fixtures small.
+LETTERBOX_CASES = {
+    "lb_up_landscape": dict(shape=(45, 70), new_shape=(96, 96), kw={}, seed=41),
+    "lb_down_portrait": dict(shape=(201, 133), new_shape=(96, 96), kw={}, seed=42),
+    "lb_auto_rect": dict(shape=(120, 213), new_shape=(128, 128), kw=dict(auto=True), seed=43),
+    "lb_noscaleup": dict(shape=(40, 52), new_shape=(96, 96), kw=dict(scaleup=False), seed=44),
+    "lb_same_size": dict(shape=(96, 96), new_shape=(96, 96), kw={}, seed=45),
+    "lb_half": dict(shape=(192, 192), new_shape=(96, 96), kw={}, seed=46),
+}
+
+
+def letterbox_image(case):
+    import numpy as np
+
+    rng = np.random.default_rng(case["seed"])
+    return rng.integers(0, 256, (case["shape"][0], case["shape"][1], 3), dtype=np.uint8)

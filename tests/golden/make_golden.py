@@ -25,7 +25,7 @@ from ultralytics.utils import nms as ref_nms  # noqa: E402
 
 from fce_yolo_b200.weights import load_synthetic, synth_images, synth_predictions, synth_tensor  # noqa: E402
 
-from cases import FORWARD_CASES, MODULE_CASES, NMS_CASES, variant_cfg  # noqa: E402
+from cases import FORWARD_CASES, LETTERBOX_CASES, MODULE_CASES, NMS_CASES, letterbox_image, variant_cfg  # noqa: E402
 
 
 def build_ref(case):
@@ -92,9 +92,23 @@ def nms_case(name, case):
     print(name, [v.shape[0] for k, v in blob.items() if k.startswith("idx")])
 
 
+def letterbox_case(name, case):
+    """The reference's own preprocessing: LetterBox (data/augment.py:1589-1631, cv2.resize + copyMakeBorder) followed
+    by the BGR->RGB flip of BasePredictor.preprocess (engine/predictor.py:163-165)."""
+    from ultralytics.data.augment import LetterBox
+
+    img = letterbox_image(case)
+    out = LetterBox(case["new_shape"], stride=32, **case["kw"])(image=img)[..., ::-1]
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), out=np.ascontiguousarray(out))
+    print(name, img.shape, "->", out.shape)
+
+
 if __name__ == "__main__":
     import torchvision  # noqa: F401  (the branch ultralytics takes in practice: nms.py:151-154)
-    which = sys.argv[1:] or ["fwd", "mod", "nms"]
+    which = sys.argv[1:] or ["fwd", "mod", "nms", "lb"]
+    if "lb" in which:
+        for n, c in LETTERBOX_CASES.items():
+            letterbox_case(n, c)
     if "fwd" in which:
         for n, c in FORWARD_CASES.items():
             forward_case(n, c)

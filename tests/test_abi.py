@@ -26,7 +26,7 @@ def test_desc_struct_sizes_match_header():
 
     from fce_yolo_b200 import _lib as L
 
-    names = {"fce_conv_desc": L.ConvDesc, "fce_stem_desc": L.StemDesc, "fce_pack_desc": L.PackDesc, "fce_dwconv_desc": L.DwconvDesc, "fce_sppf_desc": L.SppfDesc,
+    names = {"fce_conv_desc": L.ConvDesc, "fce_stem_desc": L.StemDesc, "fce_letterbox_item": L.LetterboxItem, "fce_pack_desc": L.PackDesc, "fce_dwconv_desc": L.DwconvDesc, "fce_sppf_desc": L.SppfDesc,
              "fce_upsample_desc": L.UpsampleDesc, "fce_bifpn_desc": L.BifpnDesc, "fce_copy_desc": L.CopyDesc,
              "fce_pool_desc": L.PoolDesc, "fce_strip_attn_desc": L.StripAttnDesc, "fce_gate_desc": L.GateDesc,
              "fce_psa_desc": L.PsaDesc, "fce_decode_desc": L.DecodeDesc, "fce_nms_desc": L.NmsDesc}

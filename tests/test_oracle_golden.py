@@ -88,3 +88,41 @@ def test_nms_matches_reference(name):
     for b in range(p.shape[0]):
         # keep indices, class ids and the copied-through boxes/conf: all bit-exact
         assert_nms_equal(idxs[b], dets[b], g[f"idx{b}"], g[f"det{b}"], tie_perm=case.get("tie_perm", False))
+
+
+# ---------------------------------------------------------------------------------------------------
+# preprocessing: LetterBox + BGR->RGB, bit-exact against the reference (cv2) fixtures
+# ---------------------------------------------------------------------------------------------------
+from cases import LETTERBOX_CASES, letterbox_image  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(LETTERBOX_CASES))
+def test_letterbox_oracle_matches_reference(name):
+    import numpy as np
+
+    from oracle import letterbox_oracle as LB
+
+    case = LETTERBOX_CASES[name]
+    got = LB.letterbox(letterbox_image(case), case["new_shape"], stride=32, **case["kw"])
+    ref = golden(name)["out"]
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_letterbox_host_tables_match_oracle():
+    """The product's host-side tap tables / geometry (fce_yolo_b200/preprocess.py) against the oracle's restatement."""
+    import numpy as np
+
+    from fce_yolo_b200 import preprocess as P
+    from oracle import letterbox_oracle as LB
+
+    for src, dst in [(45, 96), (201, 64), (96, 96), (1080, 360), (375, 480), (7, 640), (640, 7)]:
+        for clamp in (True, False):
+            i0, i1, w0, w1 = LB.linear_coeffs(src, dst, clamp)
+            t = P._taps(src, dst, clamp)
+            assert np.array_equal(t[:, 0], i0) and np.array_equal(t[:, 1], i1)
+            assert np.array_equal(t[:, 2], w0) and np.array_equal(t[:, 3], w1)
+    for shape, kw in [((480, 640), {}), ((333, 517), dict(auto=True)), ((50, 70), dict(scaleup=False)),
+                      ((1280, 960), dict(auto=True)), ((100, 80), dict(center=False))]:
+        g = LB.letterbox_geometry(shape, (640, 640), stride=32, **kw)
+        assert P.letterbox_geometry(shape, (640, 640), stride=32, **kw) == \
+            (g["new_w"], g["new_h"], g["top"], g["left"], g["out_h"], g["out_w"])
