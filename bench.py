@@ -33,6 +33,20 @@ WORKLOAD = dict(yaml="yolo11s-fce.yaml", variant={5: ("CoordAtt", []), 8: ("Coor
 WORKLOAD_NAME = "yolo11s-fce (CoordAtt@L5,L8) predict: forward+DFL decode+NMS, bf16, batch 64/GPU, 640x640"
 
 
+OTHER_CONFIGS = {
+    0: dict(name="yolo11n-fce predict, bf16, batch 1, 640x640 (BASELINE configs[0] on the GPU path)",
+            yaml="yolo11n-fce.yaml", variant=None, batch=1, size=640),
+    2: dict(name="yolo11m-bifpn predict, bf16, batch 256/GPU, 640x640 (BASELINE configs[2])",
+            yaml="yolo11m-bifpn.yaml", variant=None, batch=256, size=640),
+    3: dict(name="yolo11s-fce (CoordCrossAtt@L5, BiCoordCrossAtt[8 heads]@L8) predict, bf16, batch 128, 640x640 "
+                 "(BASELINE configs[3])",
+            yaml="yolo11s-fce.yaml", variant={5: ("CoordCrossAtt", [512, 16, 2]), 8: ("BiCoordCrossAtt", [512, 8, 8])},
+            batch=128, size=640),
+    4: dict(name="yolo11x-fce predict, bf16, batch 32/GPU, 1280x1280 (BASELINE configs[4])",
+            yaml="yolo11x-fce.yaml", variant=None, batch=32, size=1280),
+}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -128,6 +142,8 @@ def main():
     ap.add_argument("--yaml", default=None)
     ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=None, choices=[0, 1, 2, 3, 4],
+                    help="BASELINE.json configs[i] (exploration; the judged workload is configs[1], the default)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--kernel-times", default=None, help="write the per-node timing table to this file")
@@ -135,6 +151,9 @@ def main():
 
     w = dict(WORKLOAD)
     name = WORKLOAD_NAME
+    if a.config is not None and a.config != 1:  # the other BASELINE.json configs (parity-test cases, run for the record)
+        w.update(OTHER_CONFIGS[a.config])
+        name = w.pop("name")
     if a.batch or a.yaml or a.size:
         w.update({k: v for k, v in (("batch", a.batch), ("yaml", a.yaml), ("size", a.size)) if v})
         if a.yaml:

@@ -110,6 +110,12 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Programmatic dependent launch, primary side: lets the CTAs of the NEXT kernel in the stream be scheduled (and run
+// their prologue up to their own griddepcontrol.wait) once every CTA of this grid has issued it.  The tcgen05 conv
+// kernels are launched with the programmatic-serialization attribute and wait before touching activations
+// (tc_common.cuh); for a successor launched normally this is a no-op.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace fce

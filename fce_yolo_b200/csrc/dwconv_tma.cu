@@ -36,6 +36,7 @@ template <typename T>
 __global__ void __launch_bounds__(THREADS) dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, const DwParams p,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              const T* add, T* __restrict__ y) {
+    pdl_trigger();
     constexpr int N = Vec16<T>::N;  // channels per thread
     constexpr int CB = VECS * N;    // channels per group
     extern __shared__ uint8_t smem_raw[];

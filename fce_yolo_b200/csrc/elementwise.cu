@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(DW2_THREADS) dwconv3x3_v2_kernel(const fce_dwc
                                                                    const float* __restrict__ bias,
                                                                    const T* __restrict__ add, T* __restrict__ y,
                                                                    int band_rows, int bands, int cgroups) {
+    pdl_trigger();
     constexpr int N = Vec16<T>::N;
     const int vec = threadIdx.x % DW2_VECS, col = threadIdx.x / DW2_VECS;
     const int cg = blockIdx.x % cgroups;
@@ -392,6 +393,7 @@ __device__ __forceinline__ uint4 vmax16<float>(uint4 a, uint4 b) {
 
 template <typename T>
 __global__ void __launch_bounds__(NT) sppf_v2_kernel(const fce_sppf_desc d, T* buf, int vpc) {
+    pdl_trigger();
     extern __shared__ uint4 spv[];  // [2][H*W][vpc]
     constexpr int N = Vec16<T>::N;
     const int HW = d.H * d.W, W = d.W, H = d.H;
@@ -441,6 +443,7 @@ __global__ void __launch_bounds__(NT) sppf_v2_kernel(const fce_sppf_desc d, T* b
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(NT) upsample_kernel(const fce_upsample_desc d, const T* __restrict__ x, T* y) {
+    pdl_trigger();
     constexpr int N = CV<T, VEC>::N;
     const int cv = d.C / N;
     const int Wo = d.W * 2;
@@ -461,6 +464,7 @@ __global__ void __launch_bounds__(NT) upsample_kernel(const fce_upsample_desc d,
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(NT) bifpn_kernel(const fce_bifpn_desc d, const T* __restrict__ x0,
                                                    const T* __restrict__ x1, const T* __restrict__ x2, T* y) {
+    pdl_trigger();
     constexpr int N = CV<T, VEC>::N;
     const int cv = d.C / N;
     const int row = blockIdx.x;  // b*H + h
@@ -496,6 +500,7 @@ __global__ void __launch_bounds__(NT) bifpn_kernel(const fce_bifpn_desc d, const
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(NT) copy_kernel(const fce_copy_desc d, const T* __restrict__ x, T* y) {
+    pdl_trigger();
     constexpr int N = CV<T, VEC>::N;
     const int cv = d.C / N;
     const size_t row = blockIdx.x;
@@ -531,6 +536,7 @@ __device__ __forceinline__ void ldf(const float* __restrict__ p, float* f) {
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(NT) gate_kernel(const fce_gate_desc d, const T* __restrict__ x,
                                                   const float* __restrict__ gh, const float* __restrict__ gw, T* y) {
+    pdl_trigger();
     constexpr int N = CV<T, VEC>::N;
     const int cv = d.C / N;
     const int row = blockIdx.x;  // b*H + h

@@ -157,6 +157,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 __global__ void __launch_bounds__(MNT) psa_mma_kernel(const fce_psa_desc d, const __nv_bfloat16* __restrict__ qkv,
                                                       __nv_bfloat16* __restrict__ out) {
+    pdl_trigger();
     __shared__ __align__(16) __nv_bfloat16 Qs[MQ * QK_PITCH];
     __shared__ __align__(16) __nv_bfloat16 Ks[2][MK * QK_PITCH];
     __shared__ __align__(16) __nv_bfloat16 Vs[2][MK * V_PITCH];

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
                                                                 const __nv_bfloat16* __restrict__ w,
                                                                 const float* __restrict__ bias,
                                                                 __nv_bfloat16* __restrict__ y, int Ho, int Wo) {
+    pdl_trigger();
     constexpr int COUT = NTILES * 8;
     constexpr int OPITCH = COUT + 8;  // staged pixel pitch (bf16): +16 B keeps the quad-strided writes conflict-free
     __shared__ __align__(16) __nv_bfloat16 tile[ST_IR * ST_PITCH];
