@@ -24,9 +24,10 @@ namespace fce {
 using namespace tc;
 namespace {
 
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int WARP_PROD_A = 8, WARP_PROD_B = 9, WARP_MMA = 10, WARP_ALLOC = 11;
-constexpr int NUM_THREADS = 12 * 32;
+constexpr int NUM_EPI_WARPS = 12;  // three groups x four TMEM lane quarters (the epilogue, not HBM, paces these layers)
+constexpr int NUM_GROUPS = NUM_EPI_WARPS / 4;
+constexpr int WARP_PROD_A = 12, WARP_PROD_B = 13, WARP_MMA = 14, WARP_ALLOC = 15;
+constexpr int NUM_THREADS = 16 * 32;
 constexpr int A_STAGES = 2;
 constexpr int SMEM_LIMIT = 222 * 1024;
 
@@ -269,10 +270,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ------------------------------------------------------------------ epilogue
         // TMEM -> registers -> bias / activation (+ residual, read from the staged tile) -> staging, compacted from the
         // padded-flat accumulator rows to [R][W] so that ONE 4-D bulk store per 32-column slab writes the band.
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, grp = warp >> 2;
         const int n_chunks = bn >> 4, act = p.act, Wp = p.Wp, W = p.W, R = p.R, H = p.H;
+        const int pairs = (n_chunks + 1) >> 1;  // work item = (128-row block, pair of 16-column chunks), dealt round-robin
+        const int items = nb * pairs;           // to the three warp groups
         const bool has_res = p.has_res != 0;
-        const bool split_cols = n_chunks >= 4;  // wide outputs: the two halves split columns, else they split blocks
         const bool wide = p.slab_cols == 64;    // 128-byte staging rows (128B swizzle) vs 64-byte rows (64B swizzle)
         const uint32_t row_bytes = wide ? 128u : 64u, swz_mask = wide ? 7u : 3u;
         int acc = 0, i = 0;
@@ -295,15 +297,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             sph[buf] ^= 1;
             tc_fence_after();
-            for (int blk = split_cols ? 0 : half; blk < nb; blk += split_cols ? 1 : 2) {
+#pragma unroll 1
+            for (int item = grp; item < items; item += NUM_GROUPS) {
+                const int blk = item / pairs;
+                const int j = (item - blk * pairs) * 2;
                 const int o = blk * 128 + quarter * 32 + lane;  // padded-flat output index inside the band
                 const int ro = o / Wp, co = o - ro * Wp;
                 const bool ok = co < W && ro < R && h0 + ro < H;
                 const uint32_t lin = (uint32_t)(ro * W + co) * row_bytes;  // byte offset of this pixel's row in a slab
                 const uint32_t swz = ((lin >> 7) & swz_mask) << 4;           // swizzle: address bits 7.. -> bits 4..
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * nb + blk) * bn;
-#pragma unroll 1
-                for (int j = split_cols ? half * 2 : 0; j < n_chunks; j += split_cols ? 4 : 2) {
+                {
                     const int n = j * 16;
                     const bool two = j + 1 < n_chunks;
                     // 16-column chunk j lives in slab j / (slab_cols / 16), at byte (j % ...) * 32 of the row

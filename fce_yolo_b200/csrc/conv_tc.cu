@@ -480,7 +480,9 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
         const int v = e ? atoi(e) : 0;
         return v >= 32 ? v : 256;
     }();
-    p.n_tiles = ceil_div(d->Cout, bn_cap);
+    // 1x1 layers are HBM / epilogue bound: 128-column tiles keep three TMEM stages (and all twelve epilogue warps)
+    // busy; re-reading the [128, Cin] A tile for the second N tile is an L2 hit.  3x3 layers keep 256 columns.
+    p.n_tiles = ceil_div(d->Cout, d->k == 1 && bn_cap > 128 ? 128 : bn_cap);
     // N tiles that do not end the channel range must end on a 32-column staging-slab boundary
     p.bn = p.n_tiles == 1 ? d->Cout : ceil_div(ceil_div(d->Cout, p.n_tiles), 32) * 32;
     // small problems: narrower N tiles give the persistent grid more tiles to balance over 148 SMs
