@@ -71,6 +71,28 @@ __global__ void __launch_bounds__(NT) decode_kernel(const fce_decode_desc d, con
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ scale_boxes
+// ops.scale_boxes + clip_boxes (ultralytics/utils/ops.py:102-134, 152-177) as DetectionPredictor.construct_result
+// applies them (models/yolo/detect/predict.py:109-122): detections of the letterboxed image -> original image
+// coordinates, in place on the padded [B, max_det, 6] buffer.  meta[b] = {gain, pad_x, pad_y, w0, h0} fp32.  Same fp32
+// operations in the same order as the reference's CPU path (subtract pad, IEEE divide by gain, clamp).
+__global__ void __launch_bounds__(NT) scale_boxes_kernel(float* __restrict__ det, const int32_t* __restrict__ count,
+                                                         const float* __restrict__ meta, int max_det) {
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * NT + threadIdx.x;
+    if (q >= max_det || q >= count[b]) return;
+    const float gain = meta[b * 5], px = meta[b * 5 + 1], py = meta[b * 5 + 2], w0 = meta[b * 5 + 3], h0 = meta[b * 5 + 4];
+    float4* p = reinterpret_cast<float4*>(det + ((size_t)b * max_det + q) * 6);  // 24-byte rows: 8-byte aligned only
+    float* f = reinterpret_cast<float*>(p);
+    const float x1 = __fdiv_rn(__fsub_rn(f[0], px), gain), y1 = __fdiv_rn(__fsub_rn(f[1], py), gain);
+    const float x2 = __fdiv_rn(__fsub_rn(f[2], px), gain), y2 = __fdiv_rn(__fsub_rn(f[3], py), gain);
+    f[0] = fminf(fmaxf(x1, 0.f), w0);
+    f[1] = fminf(fmaxf(y1, 0.f), h0);
+    f[2] = fminf(fmaxf(x2, 0.f), w0);
+    f[3] = fminf(fmaxf(y2, 0.f), h0);
+}
+
 }  // namespace
 }  // namespace fce
 
@@ -89,5 +111,14 @@ extern "C" int fce_detect_decode(const fce_decode_desc* d, const float* raw0, co
     }
     dim3 grid((A + NT - 1) / NT, d->B);
     decode_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(*d, raw0, raw1, raw2, raw3, y, A);
+    return check_launch();
+}
+
+extern "C" int fce_scale_boxes(float* det, const int32_t* count, const float* meta, int32_t B, int32_t max_det,
+                               void* stream) {
+    if (!det || !count || !meta || B <= 0 || max_det <= 0) return FCE_ERR_BAD_ARG;
+    if (B > 65535) return FCE_ERR_UNSUPPORTED;
+    dim3 grid((max_det + NT - 1) / NT, B);
+    scale_boxes_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(det, count, meta, max_det);
     return check_launch();
 }

@@ -7,10 +7,25 @@ detections.  ``__call__`` returns the reference's list of ``[n_i, 6]`` (x1,y1,x2
 """
 from __future__ import annotations
 
+import ctypes as C
+
+import numpy as np
 import torch
 
+from . import _lib as L
 from .engine import Executor
 from .plan import compile_model
+
+
+def scale_meta(img1_shape, img0_shapes) -> np.ndarray:
+    """[B, 5] fp32 {gain, pad_x, pad_y, w0, h0} for fce_scale_boxes: the gain / padding arithmetic of ops.scale_boxes
+    (ultralytics/utils/ops.py:118-121) for letterboxed shape ``img1_shape`` = (h, w) and original shapes (h0, w0)."""
+    m = np.empty((len(img0_shapes), 5), dtype=np.float32)
+    for b, s0 in enumerate(img0_shapes):
+        gain = min(img1_shape[0] / s0[0], img1_shape[1] / s0[1])
+        m[b] = (gain, round((img1_shape[1] - s0[1] * gain) / 2 - 0.1), round((img1_shape[0] - s0[0] * gain) / 2 - 0.1),
+                s0[1], s0[0])
+    return m
 
 
 class Predictor:
@@ -117,6 +132,38 @@ class Predictor:
             if pending is not None:
                 P["done"][pending % 2].synchronize()
                 yield P["h_det"][pending % 2], P["h_cnt"][pending % 2]
+
+    def predict(self, images):
+        """The reference's ``YOLO(...).predict(list_of_bgr_frames)`` for raw uint8 HWC BGR images of any size (at most
+        ``batch`` of them): LetterBox + BGR->RGB on the GPU (fce_letterbox) -> forward + decode + NMS (one CUDA graph) ->
+        ops.scale_boxes + clip on the GPU (fce_scale_boxes) -> one D2H of the padded detections.  Returns the
+        reference's list of ``[n_i, 6]`` (x1, y1, x2, y2, conf, cls) tensors in ORIGINAL image coordinates
+        (engine/predictor.py:151-201, models/yolo/detect/predict.py:33-122)."""
+        from .preprocess import LetterBoxGPU
+
+        n = len(images)
+        if not 0 < n <= self.batch:
+            raise ValueError(f"predict() takes 1..{self.batch} images per call, got {n}")
+        if not self.input_u8:
+            raise RuntimeError("predict() on raw frames needs a Predictor built with input_u8=True")
+        if not hasattr(self, "_lb"):
+            self._lb = LetterBoxGPU(self.imgsz, auto=False, device=self.device)
+            self._meta_pin = torch.empty(self.batch, 5, dtype=torch.float32).pin_memory()
+            self._meta_dev = torch.empty(self.batch, 5, dtype=torch.float32, device=self.device)
+        meta = scale_meta(self.imgsz, [im.shape[:2] for im in images])
+        self._meta_pin[:n].copy_(torch.from_numpy(meta))
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self._lb(images, out=self.inp[:n])
+            self._meta_dev[:n].copy_(self._meta_pin[:n], non_blocking=True)
+            self.ex.run()
+            st = L.load().fce_scale_boxes(C.c_void_p(self.det.data_ptr()), C.c_void_p(self.count.data_ptr()),
+                                          C.c_void_p(self._meta_dev.data_ptr()), n, self.det.shape[1],
+                                          C.c_void_p(self.stream.cuda_stream))
+            L.check(st, "fce_scale_boxes")
+            self.h_det.copy_(self.det, non_blocking=True)
+            self.h_count.copy_(self.count, non_blocking=True)
+        self.stream.synchronize()
+        return [self.h_det[b, :c].clone() for b, c in enumerate(self.h_count[:n].tolist())]
 
     def __call__(self, images: torch.Tensor):
         det, count = self.infer(images)

@@ -245,6 +245,12 @@ size_t fce_nms_workspace(const fce_nms_desc* d);
 int fce_nms(const fce_nms_desc* d, const float* pred, const int32_t* classes, float* det, int64_t* keep,
             int32_t* count, void* ws, size_t ws_bytes, void* stream);
 
+/* Back to original-image coordinates, the step right after NMS in predict (ops.scale_boxes + clip_boxes,
+ * ultralytics/utils/ops.py:102-134,152-177, applied by models/yolo/detect/predict.py:109-122): rows [0, count[b]) of
+ * det [B, max_det, 6] are rewritten in place as clamp((xyxy - pad) / gain, 0, (w0, h0)); meta[b] = {gain, pad_x, pad_y,
+ * w0, h0} fp32 (host: fce_yolo_b200.predict.scale_meta).  Same fp32 operations as the reference's CPU path. */
+int fce_scale_boxes(float* det, const int32_t* count, const float* meta, int32_t B, int32_t max_det, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,3 +86,19 @@ def letterbox(img_bgr: np.ndarray, new_shape=(640, 640), auto=False, scaleup=Tru
     out = np.full((g["out_h"], g["out_w"], 3), PAD_VALUE, dtype=np.uint8)
     out[g["top"]:g["top"] + g["new_h"], g["left"]:g["left"] + g["new_w"]] = img
     return out[..., ::-1].copy()
+
+
+def scale_boxes(img1_shape, boxes: np.ndarray, img0_shape) -> np.ndarray:
+    """ops.scale_boxes (ultralytics/utils/ops.py:102-134, ratio_pad=None, padding=True, xyxy) + clip_boxes (:152-177) on
+    fp32 boxes [n, 4] of the letterboxed image (h1, w1) -> original image (h0, w0).  Same fp32 op order as torch on CPU:
+    subtract the (integer) pad, divide by the gain rounded to fp32, clamp."""
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad_x = round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1)
+    pad_y = round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1)
+    b = boxes.astype(np.float32).copy()
+    b[:, [0, 2]] -= np.float32(pad_x)
+    b[:, [1, 3]] -= np.float32(pad_y)
+    b /= np.float32(gain)
+    b[:, [0, 2]] = b[:, [0, 2]].clip(0, img0_shape[1])
+    b[:, [1, 3]] = b[:, [1, 3]].clip(0, img0_shape[0])
+    return b

@@ -99,3 +99,22 @@ def letterbox_image(case):
 
     rng = np.random.default_rng(case["seed"])
     return rng.integers(0, 256, (case["shape"][0], case["shape"][1], 3), dtype=np.uint8)
+
+
+# ops.scale_boxes + clip: letterboxed shape, original shape, seed
+SCALE_BOXES_CASES = {
+    "sb_landscape": dict(img1=(640, 640), img0=(480, 640), seed=51),
+    "sb_hd": dict(img1=(384, 640), img0=(1080, 1920), seed=52),
+    "sb_portrait_up": dict(img1=(640, 640), img0=(333, 217), seed=53),
+    "sb_1280": dict(img1=(1280, 1280), img0=(3000, 4000), seed=54),
+}
+
+
+def scale_boxes_input(case, n=64):
+    import numpy as np
+
+    rng = np.random.default_rng(case["seed"])
+    h, w = case["img1"]
+    xy = rng.uniform(-20, 1, (n, 2)).astype(np.float32) * 0 + rng.uniform(-30, max(h, w) + 30, (n, 2)).astype(np.float32)
+    wh = rng.uniform(1, 300, (n, 2)).astype(np.float32)
+    return np.concatenate([xy, xy + wh], 1).astype(np.float32)

@@ -25,7 +25,8 @@ from ultralytics.utils import nms as ref_nms  # noqa: E402
 
 from fce_yolo_b200.weights import load_synthetic, synth_images, synth_predictions, synth_tensor  # noqa: E402
 
-from cases import FORWARD_CASES, LETTERBOX_CASES, MODULE_CASES, NMS_CASES, letterbox_image, variant_cfg  # noqa: E402
+from cases import (FORWARD_CASES, LETTERBOX_CASES, MODULE_CASES, NMS_CASES, SCALE_BOXES_CASES, letterbox_image,  # noqa: E402
+                   scale_boxes_input, variant_cfg)
 
 
 def build_ref(case):
@@ -103,9 +104,21 @@ def letterbox_case(name, case):
     print(name, img.shape, "->", out.shape)
 
 
+def scale_boxes_case(name, case):
+    from ultralytics.utils import ops
+
+    b = torch.from_numpy(scale_boxes_input(case))
+    out = ops.scale_boxes(case["img1"], b.clone(), case["img0"] + (3,))
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), out=out.numpy())
+    print(name, tuple(out.shape))
+
+
 if __name__ == "__main__":
     import torchvision  # noqa: F401  (the branch ultralytics takes in practice: nms.py:151-154)
     which = sys.argv[1:] or ["fwd", "mod", "nms", "lb"]
+    if "sb" in which or "lb" in which:
+        for n, c in SCALE_BOXES_CASES.items():
+            scale_boxes_case(n, c)
     if "lb" in which:
         for n, c in LETTERBOX_CASES.items():
             letterbox_case(n, c)

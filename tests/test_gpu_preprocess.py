@@ -81,3 +81,58 @@ def test_preprocess_feeds_predictor():
     ref_in = torch.from_numpy(np.stack([LB.letterbox(im, (320, 320)) for im in imgs]))
     h_det, h_count = pred.infer(ref_in.pin_memory())
     assert torch.equal(count.cpu(), h_count) and torch.equal(det.cpu(), h_det)
+
+
+def test_scale_boxes_bit_exact():
+    """fce_scale_boxes vs the reference's ops.scale_boxes output (fixtures): same fp32 bits; rows >= count untouched."""
+    import ctypes as C
+
+    from cases import SCALE_BOXES_CASES, scale_boxes_input
+    from fce_yolo_b200 import _lib as L
+    from fce_yolo_b200.predict import scale_meta
+
+    lib = L.load(check_device=True)
+    names = list(SCALE_BOXES_CASES)
+    B, max_det = len(names), 80
+    det = torch.full((B, max_det, 6), 7.0)
+    for b, n in enumerate(names):
+        det[b, :64, :4] = torch.from_numpy(scale_boxes_input(SCALE_BOXES_CASES[n]))
+    before = det.clone()
+    d = det.cuda()
+    count = torch.tensor([64, 64, 10, 0], dtype=torch.int32, device="cuda")
+    meta = np.concatenate([scale_meta(SCALE_BOXES_CASES[n]["img1"], [SCALE_BOXES_CASES[n]["img0"]]) for n in names])
+    m = torch.from_numpy(meta).cuda()
+    st = lib.fce_scale_boxes(C.c_void_p(d.data_ptr()), C.c_void_p(count.data_ptr()), C.c_void_p(m.data_ptr()), B, max_det,
+                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    L.check(st, "fce_scale_boxes")
+    out = d.cpu()
+    for b, n in enumerate(names):
+        c = int(count[b])
+        assert np.array_equal(out[b, :c, :4].numpy(), golden(n)["out"][:c])
+        assert torch.equal(out[b, c:], before[b, c:]) and torch.equal(out[b, :, 4:], before[b, :, 4:])
+
+
+def test_predict_raw_frames_end_to_end():
+    """Predictor.predict(list of raw BGR frames) == oracle letterbox -> Predictor.infer -> oracle scale_boxes."""
+    from fce_yolo_b200.predict import Predictor
+    from fce_yolo_b200.tasks import DetectionModel
+    from fce_yolo_b200.weights import load_synthetic
+    from oracle import letterbox_oracle as LB
+
+    model = DetectionModel("yolo11n-fce.yaml").fuse().eval()
+    load_synthetic(model, 0)
+    pred = Predictor(model, 3, 320, precision="bf16", conf=0.05)
+    rng = np.random.default_rng(8)
+    imgs = [rng.integers(0, 256, s + (3,), dtype=np.uint8) for s in [(240, 320), (400, 300)]]  # 2 frames, batch 3
+    got = pred.predict(imgs)
+    ref_in = torch.zeros(3, 320, 320, 3, dtype=torch.uint8)
+    for b, im in enumerate(imgs):
+        ref_in[b] = torch.from_numpy(LB.letterbox(im, (320, 320)))
+    h_det, h_count = pred.infer(ref_in.pin_memory())
+    assert len(got) == 2
+    for b, im in enumerate(imgs):
+        c = int(h_count[b])
+        assert got[b].shape == (c, 6)
+        ref = h_det[b, :c].clone().numpy()
+        ref[:, :4] = LB.scale_boxes((320, 320), ref[:, :4], im.shape[:2])
+        assert np.array_equal(got[b].numpy(), ref)

@@ -126,3 +126,22 @@ def test_letterbox_host_tables_match_oracle():
         g = LB.letterbox_geometry(shape, (640, 640), stride=32, **kw)
         assert P.letterbox_geometry(shape, (640, 640), stride=32, **kw) == \
             (g["new_w"], g["new_h"], g["top"], g["left"], g["out_h"], g["out_w"])
+
+
+from cases import SCALE_BOXES_CASES, scale_boxes_input  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(SCALE_BOXES_CASES))
+def test_scale_boxes_oracle_matches_reference(name):
+    """ops.scale_boxes + clip_boxes of the live reference (fixtures) vs the numpy restatement: bit-exact fp32."""
+    import numpy as np
+
+    from fce_yolo_b200.predict import scale_meta
+    from oracle import letterbox_oracle as LB
+
+    case = SCALE_BOXES_CASES[name]
+    got = LB.scale_boxes(case["img1"], scale_boxes_input(case), case["img0"])
+    assert np.array_equal(got, golden(name)["out"])
+    m = scale_meta(case["img1"], [case["img0"]])[0]
+    gain = min(case["img1"][0] / case["img0"][0], case["img1"][1] / case["img0"][1])
+    assert m[0] == np.float32(gain) and m[3] == case["img0"][1] and m[4] == case["img0"][0]
