@@ -269,10 +269,13 @@ __global__ void __launch_bounds__(NT) nms_kernel(const fce_nms_desc d, const flo
             }
         }
         // ---- c. greedy suppression against the kept list
-        for (int c0 = 0; c0 < target; c0 += CH) {
+        for (int c0 = 0, m = 0; c0 < target; c0 += m) {
             const int kept0 = s_kept;
             if (kept0 >= d.max_det) break;
-            const int m = min(CH, target - c0);
+            // chunk length: no longer than needed to fill the remaining max_det slots with ~2x head-room (rounded to
+            // whole 32-candidate words) - the all-pairs work of a chunk grows with its square, and after the first
+            // chunk only a few dozen boxes are usually missing
+            m = min(min(CH, target - c0), (2 * (d.max_det - kept0) + 63) & ~31);
             bool dead = true;
             if (tid < m) {
                 const uint32_t id = (uint32_t)scomp[c0 + tid];
