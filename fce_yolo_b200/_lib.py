@@ -101,6 +101,7 @@ _SIGS = {
     "fce_conv2d": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "fce_stem_pack": (C.c_int, [C.POINTER(PackDesc), _P, _P, _P]),
     "fce_stem_conv": (C.c_int, [C.POINTER(StemDesc), _P, _P, _P, _P, _P]),
+    "fce_match_predictions": (C.c_int, [_P, _P, _P, _P, _P, _P, i32, i32, i32, i32, _P, _P]),
     "fce_scale_boxes": (C.c_int, [_P, _P, _P, i32, i32, _P]),
     "fce_letterbox": (C.c_int, [_P, _P, _P, i32, i32, i32, i32, _P, _P]),
     "fce_conv_tc_set_profile": (None, [C.c_int]),

@@ -251,6 +251,18 @@ int fce_nms(const fce_nms_desc* d, const float* pred, const int32_t* classes, fl
  * w0, h0} fp32 (host: fce_yolo_b200.predict.scale_meta).  Same fp32 operations as the reference's CPU path. */
 int fce_scale_boxes(float* det, const int32_t* count, const float* meta, int32_t B, int32_t max_det, void* stream);
 
+/* Validation matching, the step right after NMS in val (box_iou, ultralytics/utils/metrics.py:57-77, + the non-scipy
+ * BaseValidator.match_predictions, ultralytics/engine/validator.py:266-306, as called per image by
+ * DetectionValidator._process_batch, models/yolo/detect/val.py:274-288).  det [B, max_det, 6] / count [B] are the NMS
+ * outputs (boxes in the same coordinate space as the labels); labels of image b are rows gt_offsets[b] ..
+ * gt_offsets[b+1] of gt_boxes [G, 4] (xyxy) / gt_cls [G]; iouv [n_iou] the IoU thresholds (0.5 .. 0.95).
+ * tp [B, max_det, n_iou] uint8: 1 where detection d is a true positive at threshold t, 0 elsewhere (rows >= count
+ * too).  Bit-exact w.r.t. the reference except for exact fp32 IoU ties between two labels of one detection, which the
+ * reference orders with an unstable sort (here: the higher label index). */
+int fce_match_predictions(const float* det, const int32_t* count, const float* gt_boxes, const float* gt_cls,
+                          const int32_t* gt_offsets, const float* iouv, int32_t B, int32_t max_det, int32_t n_iou,
+                          int32_t max_gt_per_image, uint8_t* tp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,3 +118,39 @@ def scale_boxes_input(case, n=64):
     xy = rng.uniform(-20, 1, (n, 2)).astype(np.float32) * 0 + rng.uniform(-30, max(h, w) + 30, (n, 2)).astype(np.float32)
     wh = rng.uniform(1, 300, (n, 2)).astype(np.float32)
     return np.concatenate([xy, xy + wh], 1).astype(np.float32)
+
+
+# validation matching: n_pred, n_gt, nc, seed.  Ground truth = jittered copies of some predictions so
+# that IoUs spread over [0.5, 1]; several predictions per label exercise the "lowest index wins" rule.
+MATCH_CASES = {
+    "match_dense": dict(n_pred=120, n_gt=40, nc=3, seed=61),
+    "match_sparse": dict(n_pred=300, n_gt=7, nc=80, seed=62),
+    "match_crowd": dict(n_pred=64, n_gt=90, nc=2, seed=63),
+    "match_one": dict(n_pred=1, n_gt=1, nc=1, seed=64),
+    "match_nopred": dict(n_pred=0, n_gt=5, nc=4, seed=65),
+    "match_nogt": dict(n_pred=9, n_gt=0, nc=4, seed=66),
+}
+
+
+def match_inputs(case):
+    import numpy as np
+
+    rng = np.random.default_rng(case["seed"])
+    n, g, nc = case["n_pred"], case["n_gt"], case["nc"]
+    xy = rng.uniform(0, 560, (max(g, 1), 2))
+    wh = rng.uniform(20, 120, (max(g, 1), 2))
+    gt = np.concatenate([xy, xy + wh], 1).astype(np.float32)[:g]
+    gt_cls = rng.integers(0, nc, g).astype(np.float32)
+    pred = np.zeros((n, 4), dtype=np.float32)
+    pred_cls = rng.integers(0, nc, n).astype(np.float32)
+    for d in range(n):
+        if g and rng.random() < 0.8:
+            l = rng.integers(0, g)
+            jit = rng.normal(0, rng.choice([1.0, 4.0, 10.0]), 4)
+            pred[d] = gt[l] + jit
+            if rng.random() < 0.85:
+                pred_cls[d] = gt_cls[l]
+        else:
+            p = rng.uniform(0, 560, 2)
+            pred[d] = np.concatenate([p, p + rng.uniform(20, 120, 2)])
+    return pred.astype(np.float32), pred_cls, gt, gt_cls

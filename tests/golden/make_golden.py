@@ -25,8 +25,8 @@ from ultralytics.utils import nms as ref_nms  # noqa: E402
 
 from fce_yolo_b200.weights import load_synthetic, synth_images, synth_predictions, synth_tensor  # noqa: E402
 
-from cases import (FORWARD_CASES, LETTERBOX_CASES, MODULE_CASES, NMS_CASES, SCALE_BOXES_CASES, letterbox_image,  # noqa: E402
-                   scale_boxes_input, variant_cfg)
+from cases import (FORWARD_CASES, LETTERBOX_CASES, MATCH_CASES, MODULE_CASES, NMS_CASES, SCALE_BOXES_CASES,  # noqa: E402
+                   letterbox_image, match_inputs, scale_boxes_input, variant_cfg)
 
 
 def build_ref(case):
@@ -113,9 +113,26 @@ def scale_boxes_case(name, case):
     print(name, tuple(out.shape))
 
 
+def match_case(name, case):
+    """DetectionValidator._process_batch (models/yolo/detect/val.py:274-288) of the live reference."""
+    from ultralytics.models.yolo.detect.val import DetectionValidator
+
+    v = DetectionValidator.__new__(DetectionValidator)  # only iouv / niou are used by the two methods
+    v.iouv = torch.linspace(0.5, 0.95, 10)
+    v.niou = 10
+    pred, pred_cls, gt, gt_cls = match_inputs(case)
+    out = v._process_batch({"bboxes": torch.from_numpy(pred), "cls": torch.from_numpy(pred_cls)},
+                           {"bboxes": torch.from_numpy(gt), "cls": torch.from_numpy(gt_cls)})["tp"]
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), tp=np.asarray(out, dtype=bool))
+    print(name, out.shape, int(np.asarray(out).sum()))
+
+
 if __name__ == "__main__":
     import torchvision  # noqa: F401  (the branch ultralytics takes in practice: nms.py:151-154)
     which = sys.argv[1:] or ["fwd", "mod", "nms", "lb"]
+    if "match" in which or "lb" in which:
+        for n, c in MATCH_CASES.items():
+            match_case(n, c)
     if "sb" in which or "lb" in which:
         for n, c in SCALE_BOXES_CASES.items():
             scale_boxes_case(n, c)

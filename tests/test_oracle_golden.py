@@ -145,3 +145,19 @@ def test_scale_boxes_oracle_matches_reference(name):
     m = scale_meta(case["img1"], [case["img0"]])[0]
     gain = min(case["img1"][0] / case["img0"][0], case["img1"][1] / case["img0"][1])
     assert m[0] == np.float32(gain) and m[3] == case["img0"][1] and m[4] == case["img0"][0]
+
+
+from cases import MATCH_CASES, match_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(MATCH_CASES))
+def test_match_oracle_matches_reference(name):
+    """DetectionValidator._process_batch of the live reference (fixtures) vs the restatement: identical tp matrices."""
+    import numpy as np
+
+    from oracle import match_oracle as MO
+
+    pred, pred_cls, gt, gt_cls = match_inputs(MATCH_CASES[name])
+    got = MO.match_predictions(pred, pred_cls, gt, gt_cls)
+    ref = golden(name)["tp"].reshape(got.shape)
+    assert np.array_equal(got, ref)
