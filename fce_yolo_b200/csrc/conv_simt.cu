@@ -160,43 +160,50 @@ __global__ void __launch_bounds__(NT) strip_gemm_kernel(const fce_conv_desc d, c
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += SG_BK) {
-        {
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            const int k = k0 + ak;
-            if (a_ok) {
-                if (VEC && k + 3 < K) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(arow + k));
-                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                } else {
+    // register double buffering: the global loads of K chunk k0 + BK are in flight while chunk k0 is multiplied
+    float va[4], vb[2][4];
+    auto fetch = [&](int k0) {
+        const int k = k0 + ak;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (k + j < K) v[j] = __ldg(arow + k + j);
-                }
+        for (int j = 0; j < 4; ++j) va[j] = 0.f;
+        if (a_ok) {
+            if (VEC && k + 3 < K) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(arow + k));
+                va[0] = t.x; va[1] = t.y; va[2] = t.z; va[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (k + j < K) va[j] = __ldg(arow + k + j);
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) As[ak + j][ar] = v[j];
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {  // B loader: rows (tid>>3) + 32*h, 4 consecutive k
-            const int br = (tid >> 3) + 32 * h;
-            const int n = n_base + br, k = k0 + ak;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            const int n = n_base + (tid >> 3) + 32 * h;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vb[h][j] = 0.f;
             if (n < N) {
                 const float* wr = w + (size_t)n * K + k;
                 if (VEC && k + 3 < K) {
                     const float4 t = __ldg(reinterpret_cast<const float4*>(wr));
-                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                    vb[h][0] = t.x; vb[h][1] = t.y; vb[h][2] = t.z; vb[h][3] = t.w;
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (k + j < K) v[j] = __ldg(wr + j);
+                        if (k + j < K) vb[h][j] = __ldg(wr + j);
                 }
             }
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += SG_BK) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) Bs[ak + j][br] = v[j];
+        for (int j = 0; j < 4; ++j) {
+            As[ak + j][ar] = va[j];
+            Bs[ak + j][tid >> 3] = vb[0][j];
+            Bs[ak + j][(tid >> 3) + 32] = vb[1][j];
         }
         __syncthreads();
+        if (k0 + SG_BK < K) fetch(k0 + SG_BK);
 #pragma unroll
         for (int kk = 0; kk < SG_BK; ++kk) {
             const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
