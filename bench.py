@@ -195,6 +195,8 @@ def main():
     dev = torch.device("cuda", local)
     _lib.load(check_device=True)
     if world > 1:
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO) to stdout, where the ONE JSON line goes: send it to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cfg, model, sd = build_model(w)
     B, S = w["batch"], w["size"]
