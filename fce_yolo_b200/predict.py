@@ -31,7 +31,7 @@ def scale_meta(img1_shape, img0_shapes) -> np.ndarray:
 class Predictor:
     def __init__(self, model, batch: int, imgsz=(640, 640), precision: str = "bf16", device=None, conf: float = 0.25,
                  iou: float = 0.7, max_det: int = 300, agnostic_nms: bool = False, multi_label: bool = False,
-                 input_u8: bool = True, use_graph: bool = True):
+                 input_u8: bool = True, use_graph: bool = True, overlap_nms: bool = False):
         if isinstance(imgsz, int):
             imgsz = (imgsz, imgsz)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -51,15 +51,34 @@ class Predictor:
             self.det, self.keep, self.count = self.ex.detections()
             self.h_det = torch.empty(self.det.shape, dtype=torch.float32).pin_memory()
             self.h_count = torch.empty(self.count.shape, dtype=torch.int32).pin_memory()
+            self.overlap = bool(overlap_nms and use_graph)
+            if self.overlap:  # NMS of call i runs on a side stream underneath the forward of call i+1 (engine.py)
+                self.ex.enable_overlap()
         self.launches_per_call = self.ex.launches_per_run
+
+    def _run(self):
+        if self.overlap:
+            self.ex.run_overlapped()
+        else:
+            self.ex.run()
+
+    def _out_stream(self):
+        """Stream on which det / keep / count of the last call are valid in stream order."""
+        return self.ex.tail_stream if self.overlap else torch.cuda.current_stream(self.device)
+
+    def join(self):
+        """Makes the caller's current stream wait for the detections of the last run_device()."""
+        self.ex.join()
 
     @property
     def input_shape(self):
         return tuple(self.inp.shape)
 
     def run_device(self):
-        """Forward + decode + NMS on whatever is in the static input buffer (no host traffic)."""
-        self.ex.run()
+        """Forward + decode + NMS on whatever is in the static input buffer (no host traffic).  In overlap mode the
+        NMS is still in flight on a side stream when this returns: call join() before reading the outputs on the
+        current stream (a device-wide synchronize also does)."""
+        self._run()
         return self.det, self.keep, self.count
 
     def infer(self, images: torch.Tensor):
@@ -69,7 +88,8 @@ class Predictor:
             raise ValueError(f"expected input of shape {tuple(self.inp.shape)}, got {tuple(images.shape)}")
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.inp.copy_(images, non_blocking=True)
-            self.ex.run()
+            self._run()
+            self.join()
             self.h_det.copy_(self.det, non_blocking=True)
             self.h_count.copy_(self.count, non_blocking=True)
         self.stream.synchronize()
@@ -118,10 +138,11 @@ class Predictor:
                     ms.wait_event(P["copied"][cur_i % 2])
                     self.inp.copy_(P["stage"][cur_i % 2], non_blocking=True)  # device-to-device, ~30 us
                     P["consumed"][cur_i % 2].record(ms)
-                    self.ex.run()
-                    P["h_det"][cur_i % 2].copy_(self.det, non_blocking=True)
-                    P["h_cnt"][cur_i % 2].copy_(self.count, non_blocking=True)
-                    P["done"][cur_i % 2].record(ms)
+                    self._run()
+                    with torch.cuda.stream(self._out_stream()):  # in overlap mode: behind the NMS, on its side stream
+                        P["h_det"][cur_i % 2].copy_(self.det, non_blocking=True)
+                        P["h_cnt"][cur_i % 2].copy_(self.count, non_blocking=True)
+                        P["done"][cur_i % 2].record(torch.cuda.current_stream(dev))
                 if nxt is not None:
                     upload(cur_i + 1, nxt)  # overlaps the graph that was just launched
                 if pending is not None:
@@ -155,7 +176,8 @@ class Predictor:
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self._lb(images, out=self.inp[:n])
             self._meta_dev[:n].copy_(self._meta_pin[:n], non_blocking=True)
-            self.ex.run()
+            self._run()
+            self.join()
             st = L.load().fce_scale_boxes(C.c_void_p(self.det.data_ptr()), C.c_void_p(self.count.data_ptr()),
                                           C.c_void_p(self._meta_dev.data_ptr()), n, self.det.shape[1],
                                           C.c_void_p(self.stream.cuda_stream))

@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -x -q -k "nms" 2>&1 | tail -2
-python tools/nms_bench.py 2>&1 | tail -3
-python bench.py --no-cpu-baseline --no-latency --steps 30 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'], d['roofline']['classes']['fce_nms'])"
+python -m pytest tests/test_gpu_overlap.py tests/test_gpu_preprocess.py -x -q 2>&1 | tail -4
+python bench.py --no-cpu-baseline --no-latency --steps 30 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('overlap ', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'])"
+python bench.py --no-cpu-baseline --no-latency --steps 30 --no-overlap | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('inline  ', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'])"
