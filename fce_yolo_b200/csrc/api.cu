@@ -45,6 +45,7 @@ extern "C" int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, 
 extern "C" void fce_conv_tc_set_profile(int on) {
     conv_tc_set_profile(on & 15);  // bit 0 profile, bit 1 skip TMA loads, bit 2 skip TMA stores, bit 3 skip epilogue math
     // bit 4: disable the 3x3 strip kernel (everything goes through the TMA-im2col kernel)
-    conv_halo_set_mode(((on >> 4) & 1) ? 0 : 1);
+    // bit 5: strip kernel only with resident weights (the streamed-weight shapes go back to the TMA-im2col kernel)
+    conv_halo_set_mode(((on >> 4) & 1) ? 0 : (((on >> 5) & 1) ? 2 : 1));
 }
 extern "C" int fce_conv_tc_profile(long long* out, int n) { return out ? conv_tc_profile(out, n) : FCE_ERR_BAD_ARG; }

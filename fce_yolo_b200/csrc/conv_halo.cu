@@ -12,7 +12,11 @@
 //     every tap is the SAME strip seen through a shifted shared-memory descriptor: 9 * kc/16 tcgen05.mma per
 //     128-row block and K chunk, no data movement between taps;
 //   * the two padding columns of every row produce garbage accumulator rows that are simply never stored;
-//   * the whole [Cout, 9*Cin] weight matrix is parked in shared memory for the life of the CTA.
+//   * the whole [Cout, 9*Cin] weight matrix is parked in shared memory for the life of the CTA - or, when it does not
+//     fit (Detect box branch: 3x3 with Cin = 128..512 -> 64), the nine tap tiles of K chunk c are streamed together
+//     with strip chunk c into the same ring stage: weights cross L2->SM once per band instead of once per 128-pixel
+//     tile, and the input (R+2)/R times instead of nine (the TMA-im2col kernel ran these layers at 37 % of their
+//     roofline, bound by the TMA request rate).
 //
 // Each input element crosses L2 -> SM (R+2)/R times instead of 9, and the producer issues one TMA per
 // (band, chunk) instead of nine per 128 pixels.  Warp roles as in conv_tc.cu.
@@ -41,6 +45,8 @@ struct HaloParams {
     uint32_t strip_bytes, strip_tx;  // shared-memory bytes of one strip stage / bytes one TMA box delivers
     uint32_t b_sub;                  // bytes of one (tap, chunk) weight tile: Cout x kc bf16
     uint32_t b_total, bias_bytes;
+    int kc;        // channels per K chunk
+    int b_stream;  // weights too large to park: the 9 tap tiles of chunk c travel with strip chunk c (same ring stage)
     uint32_t slab_bytes;  // one staged output slab: R*W rows x slab_cols*2 bytes (1024-aligned)
     int n_slabs, slab_cols, n_stg, has_res;  // slab_cols: 64 (128-byte rows, 128B swizzle) or 32 (64-byte rows, 64B swizzle)
     uint32_t tmem_cols;
@@ -123,15 +129,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
                 if (elect_one()) {
                     const uint32_t fb = full0 + 8 * r.stage;
-                    mbar_expect_tx(fb, p.strip_tx);
+                    mbar_expect_tx(fb, p.b_stream ? p.strip_tx + 9u * p.b_sub : p.strip_tx);
                     tma_load_4d(sA + r.stage * p.strip_bytes, &tmA, fb, c * kc, -1, h0 - 1, b);
+                    if (p.b_stream) {  // this chunk's nine weight tiles ride in the same stage
+                        const uint32_t bdst = sB + r.stage * 9u * p.b_sub;
+                        for (int t = 0; t < 9; ++t) tma_load_2d(bdst + t * p.b_sub, &tmB, fb, t * p.Cin + c * kc, 0);
+                    }
                 }
                 r.advance(A_STAGES);
             }
         }
     } else if (warp == WARP_PROD_B) {
         // ------------------------------------------------------------------ weights: parked once
-        if (elect_one()) {
+        if (!p.b_stream && elect_one()) {
             const int tiles = 9 * chunks;
             mbar_expect_tx(bfull, (uint32_t)tiles * p.b_sub);
             // tile index = chunk * 9 + tap ; K column of the OHWI matrix = tap * Cin + chunk * kc
@@ -149,8 +159,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t tap16[9];
 #pragma unroll
         for (int t = 0; t < 9; ++t) tap16[t] = (uint32_t)((t / 3) * p.Wp + (t % 3)) * (row_b >> 4);
-        mbar_wait(bfull, 0);
-        tc_fence_after();
+        if (!p.b_stream) {
+            mbar_wait(bfull, 0);
+            tc_fence_after();
+        }
         long long wf = 0, we = 0, mt0 = PROF ? clock64() : 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             {
@@ -168,7 +180,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 tc_fence_after();
                 const uint32_t a16 = (sA + r.stage * p.strip_bytes) >> 4;
-                const uint32_t b16 = (sB + c * 9 * p.b_sub) >> 4;
+                const uint32_t b16 = (sB + (p.b_stream ? r.stage : c) * 9 * p.b_sub) >> 4;
                 if (elect_one()) {
 #pragma unroll 1
                     for (int blk = 0; blk < nb; ++blk) {
@@ -392,16 +404,12 @@ int conv_halo_profile(long long* out, int n) {
     return n;
 }
 
-// Picks the band height; returns false when the shape does not fit this kernel.
-static bool halo_plan(const fce_conv_desc* d, bool has_res, HaloParams& p) {
-    if (g_halo_mode == 0) return false;
-    if (d->k != 3 || d->stride != 1) return false;
-    if (d->Cout > 256 || d->W + 2 > 256 || d->out_dtype != FCE_BF16) return false;
-    const int kc = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
+// Band height for a given K chunk / weight mode; returns the efficiency estimate (0 = does not fit).
+static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool stream, HaloParams& p) {
     const int chunks = d->Cin / kc;
     const uint32_t row_b = kc * 2;
     const uint32_t b_sub = (uint32_t)d->Cout * row_b;
-    const uint32_t b_total = (9u * chunks * b_sub + 1023u) & ~1023u;
+    const uint32_t b_total = ((stream ? (uint32_t)A_STAGES * 9u : 9u * chunks) * b_sub + 1023u) & ~1023u;
     const uint32_t bias_bytes = ((uint32_t)d->Cout * 4 + 1023u) & ~1023u;
     const int Wp = d->W + 2;
     int best_R = 0;
@@ -425,9 +433,11 @@ static bool halo_plan(const fce_conv_desc* d, bool has_res, HaloParams& p) {
             best_R = R;
         }
     }
-    if (best_R == 0 || best_eff < 0.55) return false;
+    if (best_R == 0) return 0.0;
     p.B = d->B; p.H = d->H; p.W = d->W; p.Wp = Wp;
     p.Cin = d->Cin; p.Cout = d->Cout;
+    p.kc = kc;
+    p.b_stream = stream ? 1 : 0;
     p.R = best_R;
     p.bands = (d->H + best_R - 1) / best_R;
     p.nb = (best_R * Wp + 127) / 128;
@@ -447,6 +457,33 @@ static bool halo_plan(const fce_conv_desc* d, bool has_res, HaloParams& p) {
                (size_t)SMEM_LIMIT) ? 2 : 1;
     p.tmem_cols = 32;
     while (p.tmem_cols < (uint32_t)(p.acc_sets * p.nb * d->Cout)) p.tmem_cols <<= 1;
+    return best_eff;
+}
+
+// Picks the weight mode, the K chunk and the band height; returns false when the shape does not fit this kernel.
+static bool halo_plan(const fce_conv_desc* d, bool has_res, HaloParams& p) {
+    if (g_halo_mode == 0) return false;
+    if (d->k != 3 || d->stride != 1) return false;
+    if (d->Cout > 256 || d->W + 2 > 256 || d->out_dtype != FCE_BF16) return false;
+    const int kc0 = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
+    if (halo_plan_one(d, has_res, kc0, false, p) >= 0.55) return true;  // weights parked in shared memory
+    if (g_halo_mode == 2) return false;                                // debug: streaming mode off
+    // weights streamed with the strip: worth it for narrow outputs, where the TMA-im2col kernel's nine reads of the
+    // input per output pixel dominate; wide outputs amortise them over the MMA work and keep the im2col kernel
+    if (d->Cout > 64) return false;
+    HaloParams best{};
+    double best_eff = 0.0;
+    for (int kc = 64; kc >= 32; kc >>= 1) {
+        if (d->Cin % kc) continue;
+        HaloParams q{};
+        const double e = halo_plan_one(d, has_res, kc, true, q);
+        if (e > best_eff + 0.05) {  // prefer the wider chunk unless the narrower one buys a clearly better band
+            best_eff = e;
+            best = q;
+        }
+    }
+    if (best_eff < 0.55) return false;
+    p = best;
     return true;
 }
 
@@ -460,7 +497,7 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
     const DriverApi& api = driver();
     HaloParams p{};
     if (!api.ok || !halo_plan(d, res != nullptr, p)) return FCE_ERR_UNSUPPORTED;
-    const int kc = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
+    const int kc = p.kc;
     const uint32_t row_b = kc * 2;
     p.act = d->act;
     p.has_res = res != nullptr;

@@ -36,6 +36,13 @@ CASES = [
     (1, 160, 160, 16, 32, 3, 1, 1, True, False, 16, 0),
     (3, 20, 20, 128, 32, 3, 1, 1, False, False, 0, 0),       # two K chunks
     (2, 13, 27, 64, 48, 3, 1, 0, False, True, 0, 16),        # odd sizes, fp32 out
+    # strip kernel with STREAMED weights (Detect box branch: 3x3, Cin = 128..512 -> 64; the weights do not fit)
+    (2, 80, 80, 128, 64, 3, 1, 1, False, False, 0, 0),
+    (3, 40, 40, 256, 64, 3, 1, 1, False, False, 0, 0),
+    (5, 20, 20, 512, 64, 3, 1, 1, False, False, 0, 0),       # whole image per band, 8-16 K chunks
+    (2, 33, 47, 384, 64, 3, 1, 1, True, False, 128, 64),     # odd sizes, residual, channel-slice views
+    (1, 24, 40, 320, 32, 3, 1, 0, False, False, 0, 0),       # kc = 64 x5, 32 output channels
+    (2, 40, 40, 160, 64, 3, 1, 1, False, False, 0, 0),       # Cin % 64 != 0: kc = 32 x5
 ]
 
 

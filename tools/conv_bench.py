@@ -37,6 +37,8 @@ SHAPES = [
     ("L11.cv2 1x1 1024->512@20", 64, 20, 20, 1024, 512, 1, 1, 0, 0),
     ("Det.cv2.0.0 3x3 128->64@80", 64, 80, 80, 128, 64, 3, 1, 0, 0),
     ("Det.cv2.0.1 3x3 64->64 @80", 64, 80, 80, 64, 64, 3, 1, 0, 0),
+    ("Det.cv2.1.0 3x3 256->64@40", 64, 40, 40, 256, 64, 3, 1, 0, 0),
+    ("Det.cv2.2.0 3x3 512->64@20", 64, 20, 20, 512, 64, 3, 1, 0, 0),
     ("Det.cv3.0.2 1x1 128->80@80", 64, 80, 80, 128, 80, 1, 1, 0, 1),
     ("Det.cv2.0.2 1x1 64->64 @80 f32", 64, 80, 80, 64, 64, 1, 1, 0, 1),
     # L2-resident probes of the TMA feed rate (run with --noflush): A traffic only, tiny N
@@ -60,6 +62,7 @@ def main():
     ap.add_argument("--dbg", type=int, default=0, help="debug bits for timed runs: 1 skip TMA loads, 2 skip TMA stores, "
                                                       "4 skip epilogue math (results are garbage)")
     ap.add_argument("--nohalo", action="store_true")
+    ap.add_argument("--nostream", action="store_true", help="strip kernel only with resident weights")
     a = ap.parse_args()
     lib = L.load(check_device=True)
     dev = torch.device("cuda:0")
@@ -104,7 +107,7 @@ def main():
             print(f"{name:34s} tiles/CTA {tiles/148:6.1f} | A-prod wait {m[0]:9.0f} / {m[1]:9.0f} | MMA wait-full {m[4]:9.0f} "
                   f"wait-tmem {m[5]:9.0f} / {m[6]:9.0f} | epi wait {m[7]:9.0f} / {m[8]:9.0f} stg-wait {m[9]:9.0f} | dma wait {m[10]:9.0f} / {m[11]:9.0f}", flush=True)
             continue
-        lib.fce_conv_tc_set_profile((a.dbg << 1) | (16 if a.nohalo else 0))
+        lib.fce_conv_tc_set_profile((a.dbg << 1) | (16 if a.nohalo else 0) | (32 if a.nostream else 0))
         for _ in range(2):
             L.check(lib.fce_conv2d(*args), name)
         ms = []
