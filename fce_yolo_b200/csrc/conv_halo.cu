@@ -460,6 +460,11 @@ static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool s
     return best_eff;
 }
 
+static const int g_stream_max_cout = [] {  // widest output the streamed-weight mode takes (FCE_STREAM_MAX_COUT to vary)
+    const char* e = getenv("FCE_STREAM_MAX_COUT");
+    return e ? atoi(e) : 128;
+}();
+
 // Picks the weight mode, the K chunk and the band height; returns false when the shape does not fit this kernel.
 static bool halo_plan(const fce_conv_desc* d, bool has_res, HaloParams& p) {
     if (g_halo_mode == 0) return false;
@@ -468,9 +473,10 @@ static bool halo_plan(const fce_conv_desc* d, bool has_res, HaloParams& p) {
     const int kc0 = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
     if (halo_plan_one(d, has_res, kc0, false, p) >= 0.55) return true;  // weights parked in shared memory
     if (g_halo_mode == 2) return false;                                // debug: streaming mode off
-    // weights streamed with the strip: worth it for narrow outputs, where the TMA-im2col kernel's nine reads of the
-    // input per output pixel dominate; wide outputs amortise them over the MMA work and keep the im2col kernel
-    if (d->Cout > 64) return false;
+    // weights streamed with the strip: worth it for narrow outputs (measured: Cout = 64: 117 -> 82 us, Cout = 128 on a
+    // 20x20 map: 26.6 -> 20.5 us), where the TMA-im2col kernel's nine reads of the input per output pixel dominate;
+    // wider outputs amortise them over the MMA work and keep the im2col kernel
+    if (d->Cout > g_stream_max_cout || (d->Cout > 64 && d->H * d->W > 1600)) return false;  // 65..128 outputs: small maps only
     HaloParams best{};
     double best_eff = 0.0;
     for (int kc = 64; kc >= 32; kc >>= 1) {

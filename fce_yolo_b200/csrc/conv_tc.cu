@@ -480,9 +480,14 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
         const int v = e ? atoi(e) : 0;
         return v >= 32 ? v : 256;
     }();
-    // 1x1 layers are HBM / epilogue bound: 128-column tiles keep three TMEM stages (and all twelve epilogue warps)
-    // busy; re-reading the [128, Cin] A tile for the second N tile is an L2 hit.  3x3 layers keep 256 columns.
-    p.n_tiles = ceil_div(d->Cout, d->k == 1 && bn_cap > 128 ? 128 : bn_cap);
+    // short-K 1x1 layers are HBM / epilogue bound: 128-column tiles keep three TMEM stages (and all twelve epilogue
+    // warps) busy; re-reading the small [128, Cin] A tile for the second N tile is an L2 hit.  Long-K 1x1s and 3x3
+    // layers keep 256 columns (their A tiles are large, and each extra N tile re-reads them).
+    static const int cap1x1_k = [] {  // 1x1 layers with at most this many input channels use 128-column tiles
+        const char* e = getenv("FCE_1X1_CAP_K");
+        return e ? atoi(e) : 256;
+    }();
+    p.n_tiles = ceil_div(d->Cout, d->k == 1 && d->Cin <= cap1x1_k && bn_cap > 128 ? 128 : bn_cap);
     // N tiles that do not end the channel range must end on a 32-column staging-slab boundary
     p.bn = p.n_tiles == 1 ? d->Cout : ceil_div(ceil_div(d->Cout, p.n_tiles), 32) * 32;
     // small problems: narrower N tiles give the persistent grid more tiles to balance over 148 SMs

@@ -43,6 +43,8 @@ CASES = [
     (2, 33, 47, 384, 64, 3, 1, 1, True, False, 128, 64),     # odd sizes, residual, channel-slice views
     (1, 24, 40, 320, 32, 3, 1, 0, False, False, 0, 0),       # kc = 64 x5, 32 output channels
     (2, 40, 40, 160, 64, 3, 1, 1, False, False, 0, 0),       # Cin % 64 != 0: kc = 32 x5
+    (3, 20, 20, 128, 128, 3, 1, 1, True, False, 0, 0),       # C3k bottleneck at P5: 128 outputs, residual
+    (2, 40, 40, 192, 96, 3, 1, 1, False, False, 64, 32),
 ]
 
 
