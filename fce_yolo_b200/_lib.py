@@ -66,6 +66,10 @@ class PoolDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "H", "W", "C", "pitch", "off", "dtype")]
 
 
+class CoordAttMlpDesc(C.Structure):
+    _fields_ = [(n, i32) for n in ("rows_h", "rows_w", "C", "mip", "oup", "s_pitch", "out_pitch", "act1", "act2")]
+
+
 class StripAttnDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "heads", "dh", "Lq", "Lk")] + [("scale", f32)] + \
                [(n, i64) for n in ("q_bstride", "q_rstride", "k_bstride", "k_rstride", "v_bstride", "v_rstride",
@@ -113,6 +117,7 @@ _SIGS = {
     "fce_copy_view": (C.c_int, [C.POINTER(CopyDesc), _P, _P, _P]),
     "fce_coord_pool": (C.c_int, [C.POINTER(PoolDesc), _P, _P, _P, C.c_size_t, _P]),
     "fce_coord_pool_workspace": (C.c_size_t, [C.POINTER(PoolDesc)]),
+    "fce_coordatt_mlp": (C.c_int, [C.POINTER(CoordAttMlpDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fce_strip_attn": (C.c_int, [C.POINTER(StripAttnDesc), _P, _P, _P, _P, _P]),
     "fce_gate_apply": (C.c_int, [C.POINTER(GateDesc), _P, _P, _P, _P, _P]),
     "fce_psa_attention": (C.c_int, [C.POINTER(PsaDesc), _P, _P, _P]),

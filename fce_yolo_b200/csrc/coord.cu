@@ -213,6 +213,75 @@ __global__ void __launch_bounds__(AT) strip_attn_kernel(const fce_strip_attn_des
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CoordAtt gate MLP on the pooled strips (fce_block.py:104-113): per strip row s[C],
+//   y = SiLU(W1 s + b1) [mip],  a = sigmoid(W2 y + b2) [oup],  W2/b2 = (w_h, b_h) for the B*H rows pooled over W and
+//   (w_w, b_w) for the B*W rows pooled over H.
+// One launch instead of three strip GEMMs (cv1, cv_h, cv_w) whose fixed costs dominated their ~2 us of work.  A CTA
+// owns MR consecutive rows of one of the two row ranges: the rows sit in shared memory, (row, m) pairs are dealt to
+// threads for layer 1, then thread o keeps MR accumulators for output channel o in layer 2.  Weights arrive
+// transposed ([C][mip] and [mip][oup]) so that a warp's loads are consecutive; they stay L1/L2 resident.
+constexpr int MT = 256;  // threads
+constexpr int MR = 16;   // strip rows per CTA
+
+__global__ void __launch_bounds__(MT) coordatt_mlp_kernel(const fce_coordatt_mlp_desc d, const float* __restrict__ strip,
+                                                          const float* __restrict__ w1t, const float* __restrict__ b1,
+                                                          const float* __restrict__ wht, const float* __restrict__ bh,
+                                                          const float* __restrict__ wwt, const float* __restrict__ bw,
+                                                          float* __restrict__ out) {
+    extern __shared__ float msm[];
+    const int C = d.C, mip = d.mip, oup = d.oup;
+    const int sp = C + 4;          // padded row pitch (keeps 16-byte alignment, staggers the banks of adjacent rows)
+    float* ss = msm;               // [MR][sp]
+    float* ys = msm + MR * sp;     // [MR][mip]
+    const int nh = (d.rows_h + MR - 1) / MR;
+    const bool is_w = (int)blockIdx.x >= nh;
+    const int r0 = is_w ? d.rows_h + ((int)blockIdx.x - nh) * MR : (int)blockIdx.x * MR;
+    const int r_end = is_w ? d.rows_h + d.rows_w : d.rows_h;
+    const int nr = min(MR, r_end - r0);
+    const int tid = threadIdx.x;
+    pdl_trigger();
+    for (int i = tid; i < MR * (C >> 2); i += MT) {
+        const int r = i / (C >> 2), c4 = i - r * (C >> 2);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nr) v = *reinterpret_cast<const float4*>(strip + (size_t)(r0 + r) * d.s_pitch + 4 * c4);
+        *reinterpret_cast<float4*>(ss + r * sp + 4 * c4) = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < MR * mip; i += MT) {
+        const int r = i / mip, m = i - r * mip;
+        const float* sr = ss + r * sp;
+        const float* wp = w1t + m;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int c = 0; c < C; c += 4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sr + c);
+            a0 = fmaf(s4.x, __ldg(wp + (size_t)c * mip), a0);
+            a1 = fmaf(s4.y, __ldg(wp + (size_t)(c + 1) * mip), a1);
+            a2 = fmaf(s4.z, __ldg(wp + (size_t)(c + 2) * mip), a2);
+            a3 = fmaf(s4.w, __ldg(wp + (size_t)(c + 3) * mip), a3);
+        }
+        ys[i] = apply_act((a0 + a1) + (a2 + a3) + __ldg(b1 + m), d.act1);
+    }
+    __syncthreads();
+    const float* w2t = is_w ? wwt : wht;
+    const float* b2 = is_w ? bw : bh;
+    for (int o = tid; o < oup; o += MT) {
+        float acc[MR];
+        const float bo = __ldg(b2 + o);
+#pragma unroll
+        for (int r = 0; r < MR; ++r) acc[r] = bo;
+        for (int m = 0; m < mip; ++m) {
+            const float wv = __ldg(w2t + (size_t)m * oup + o);
+#pragma unroll
+            for (int r = 0; r < MR; ++r) acc[r] = fmaf(wv, ys[r * mip + m], acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < MR; ++r)
+            if (r < nr) out[(size_t)(r0 + r) * d.out_pitch + o] = apply_act(acc[r], d.act2);
+    }
+}
+
 }  // namespace
 }  // namespace fce
 
@@ -274,5 +343,25 @@ extern "C" int fce_strip_attn(const fce_strip_attn_desc* d, const float* q, cons
     if (qblocks < 1) qblocks = 1;
     dim3 grid(d->B * d->heads, qblocks);
     strip_attn_kernel<<<grid, AT, smem, st>>>(*d, q, k, v, out);
+    return check_launch();
+}
+
+extern "C" int fce_coordatt_mlp(const fce_coordatt_mlp_desc* d, const float* strip, const float* w1t, const float* b1,
+                                const float* wht, const float* bh, const float* wwt, const float* bw, float* out,
+                                void* stream) {
+    if (!d || !strip || !w1t || !b1 || !wht || !bh || !wwt || !bw || !out) return FCE_ERR_BAD_ARG;
+    if (d->rows_h < 0 || d->rows_w < 0 || d->rows_h + d->rows_w <= 0 || d->C <= 0 || d->mip <= 0 || d->oup <= 0)
+        return FCE_ERR_BAD_ARG;
+    if ((d->C & 3) || (d->s_pitch & 3) || (((uintptr_t)strip) & 15)) return FCE_ERR_ALIGNMENT;
+    const size_t smem = sizeof(float) * ((size_t)MR * (d->C + 4) + (size_t)MR * d->mip);
+    if (smem > 160 * 1024) return FCE_ERR_UNSUPPORTED;
+    static std::atomic<bool> attr_done{false};
+    if (!attr_done.load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(coordatt_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) { set_cuda_error(e); return FCE_ERR_CUDA; }
+        attr_done.store(true, std::memory_order_release);
+    }
+    const int grid = (d->rows_h + MR - 1) / MR + (d->rows_w + MR - 1) / MR;
+    coordatt_mlp_kernel<<<grid, MT, smem, (cudaStream_t)stream>>>(*d, strip, w1t, b1, wht, bh, wwt, bw, out);
     return check_launch();
 }

@@ -103,6 +103,7 @@ class PlanError(ValueError):
 
 
 class Plan:
+    FUSED_COORDATT_MLP = True  # False: cv1 / cv_h / cv_w as three strip convs (A/B timing, cross-check)
     FUSED_STEM = True  # False: stem = fce_stem_pack + K=32 tcgen05 conv (kept for A/B timing and as a cross-check)
 
     def __init__(self, batch: int, precision: str, device, impl: int = 0):
@@ -436,9 +437,24 @@ class Plan:
     def coord_att(self, m, x: View, dst=None, tag="") -> View:
         BH = x.B * x.H
         s = self._pool(x, tag)
-        y = self.conv(m.cv1, s, tag=tag + ".cv1")
-        a_h = self.conv(m.cv_h, y.rows(0, BH), act=L.ACT_SIGMOID, tag=tag + ".cv_h")
-        a_w = self.conv(m.cv_w, y.rows(BH, y.H), act=L.ACT_SIGMOID, tag=tag + ".cv_w")
+        w1, b1, k1, _, _, act1 = self.conv_params(m.cv1)
+        wh, bh, kh, *_ = self.conv_params(m.cv_h)
+        ww, bw, kw, *_ = self.conv_params(m.cv_w)
+        mip, oup = w1.shape[0], wh.shape[0]
+        if self.FUSED_COORDATT_MLP and (k1, kh, kw) == (1, 1, 1) and x.C % 4 == 0 and 64 * (x.C + 4 + mip) <= 160 * 1024:
+            # cv1 (+BN, SiLU) -> cv_h / cv_w -> sigmoid on the strips in ONE launch (weights transposed for the kernel)
+            a = self.strip_buf(s.H, oup)
+            d = L.CoordAttMlpDesc(rows_h=BH, rows_w=s.H - BH, C=x.C, mip=mip, oup=oup, s_pitch=s.pitch,
+                                  out_pitch=a.pitch, act1=act1, act2=L.ACT_SIGMOID)
+            ptrs = [s, self._w(w1.view(mip, x.C).t()), self._w(b1), self._w(wh.view(oup, mip).t()), self._w(bh),
+                    self._w(ww.view(oup, mip).t()), self._w(bw), a]
+            self.add(Node("fce_coordatt_mlp", d, ptrs, reads=[s], writes=[a], tag=tag + ".mlp",
+                          flops=2.0 * s.H * mip * (x.C + oup), bytes=4.0 * s.H * (x.C + oup)))
+            a_h, a_w = a.rows(0, BH), a.rows(BH, a.H)
+        else:
+            y = self.conv(m.cv1, s, tag=tag + ".cv1")
+            a_h = self.conv(m.cv_h, y.rows(0, BH), act=L.ACT_SIGMOID, tag=tag + ".cv_h")
+            a_w = self.conv(m.cv_w, y.rows(BH, y.H), act=L.ACT_SIGMOID, tag=tag + ".cv_w")
         return self._gate(self._identity(m, x, tag), a_h, a_w, 0, dst, tag)
 
     def coord_cross_att(self, m, x: View, dst=None, tag="") -> View:

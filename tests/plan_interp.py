@@ -107,6 +107,15 @@ class Interp(Arena):
         s[: d.B * d.H] = t.mean(2).reshape(-1, d.C)
         s[d.B * d.H:] = t.mean(1).reshape(-1, d.C)
 
+    def _fce_coordatt_mlp(self, d, p):
+        s = self.t(p[0]).reshape(-1, d.C)
+        w1t, b1, wht, bh, wwt, bw = [z.float().cpu() for z in p[1:7]]
+        act = {0: lambda v: v, 1: torch.nn.functional.silu, 2: torch.sigmoid}
+        y = act[d.act1](s @ w1t + b1)
+        o = self.t(p[7]).reshape(-1, d.oup)
+        o[: d.rows_h] = act[d.act2](y[: d.rows_h] @ wht + bh)
+        o[d.rows_h:] = act[d.act2](y[d.rows_h:] @ wwt + bw)
+
     def _fce_strip_attn(self, d, p):
         q, k, v, o = [self.t(z).reshape(-1, z.C) for z in p]
         B, h, dh = d.B, d.heads, d.dh
