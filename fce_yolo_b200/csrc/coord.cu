@@ -16,8 +16,9 @@ namespace fce {
 namespace {
 
 constexpr int PT = 256;       // threads
-constexpr int CVT = 8;        // channel-vector lanes per CTA
-constexpr int SLOTS = 32;     // pixel slots along W
+// CVT = channel-vector lanes per CTA (template parameter: 8 / 16 / 32), SLOTS = PT / CVT pixel slots along W: the
+// host picks the widest CVT whose 3 * SLOTS columns per sweep still cover W, so 80 / 40 / 20-pixel maps all keep
+// 83 % of the load slots busy (with CVT fixed at 8 a 40-pixel map used 42 % of them: 1.6 TB/s)
 constexpr int RB = 4;         // rows per reduction group (register budget: 2 CTAs per SM)
 constexpr int WS_ROWS = 8;    // the workspace contract: at most one band per 8 rows (fce_coord_pool_workspace)
 constexpr int BAND = 3;       // column groups held in registers -> 96 columns per sweep
@@ -28,16 +29,17 @@ constexpr int BAND = 3;       // column groups held in registers -> 96 columns p
 // no atomics) - or straight to the strip when one band covers the image.  The host picks the band count so that
 // the grid is about two CTAs per SM: at batch 64 that is ONE band (no workspace traffic at all), at batch 1 the
 // bands supply the parallelism.  6 independent 16-byte loads are in flight per thread, two CTAs per SM.
-template <typename T>
+template <typename T, int CVT>
 __global__ void __launch_bounds__(PT, 2) coord_pool_kernel(const fce_pool_desc d, const T* __restrict__ x,
                                                         float* __restrict__ strip, float* __restrict__ ws, int bands,
                                                         int band_rows) {
     constexpr int N = Vec16<T>::N;
     constexpr int CC = CVT * N;  // channels per CTA
+    constexpr int SLOTS = PT / CVT;
     __shared__ float red[PT / 32][RB][CC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cvt = tid & (CVT - 1);
-    const int slot = tid / CVT;  // 0..31 ; a warp holds 4 consecutive slots
+    const int slot = tid / CVT;  // a warp holds 32 / CVT consecutive slots
     const int chunks = (d.C + CC - 1) / CC;
     const int chunk = blockIdx.x % chunks;
     const int band = (blockIdx.x / chunks) % bands;
@@ -94,14 +96,14 @@ __global__ void __launch_bounds__(PT, 2) coord_pool_kernel(const fce_pool_desc d
                         }
                     }
             }
-            // reduce row sums over the 32 slots: 4 slots inside the warp (lanes differ by 8, 16), 8 warps via smem
+            // reduce row sums over the slots: the 32 / CVT slots inside the warp by shuffles, the 8 warps via smem
 #pragma unroll
             for (int r = 0; r < RB; ++r)
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     float v = row[r][j];
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    if (CVT <= 8) v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    if (CVT <= 16) v += __shfl_xor_sync(0xffffffffu, v, 16);
                     row[r][j] = v;
                 }
             __syncthreads();  // previous group's readers are done with red[]
@@ -218,67 +220,112 @@ __global__ void __launch_bounds__(AT) strip_attn_kernel(const fce_strip_attn_des
 // CoordAtt gate MLP on the pooled strips (fce_block.py:104-113): per strip row s[C],
 //   y = SiLU(W1 s + b1) [mip],  a = sigmoid(W2 y + b2) [oup],  W2/b2 = (w_h, b_h) for the B*H rows pooled over W and
 //   (w_w, b_w) for the B*W rows pooled over H.
-// One launch instead of three strip GEMMs (cv1, cv_h, cv_w) whose fixed costs dominated their ~2 us of work.  A CTA
-// owns MR consecutive rows of one of the two row ranges: the rows sit in shared memory, (row, m) pairs are dealt to
-// threads for layer 1, then thread o keeps MR accumulators for output channel o in layer 2.  Weights arrive
-// transposed ([C][mip] and [mip][oup]) so that a warp's loads are consecutive; they stay L1/L2 resident.
-constexpr int MT = 256;  // threads
-constexpr int MR = 16;   // strip rows per CTA
+// One launch instead of three strip GEMMs (cv1, cv_h, cv_w) whose fixed costs dominated their ~2 us of work.
+// 84 M MACs on 10 K rows: too thin for the tensor cores in fp32, so the kernel is built to issue few instructions
+// per MAC (two earlier versions - weights through L1, then a warp reduction per hidden unit - both took 35 us):
+//   * persistent CTAs, blockIdx.y picks the row range (and with it W2); both weight matrices are parked in shared
+//     memory once per CTA; W1 arrives regrouped as [C/4][mip][4] so that lanes read consecutive hidden units;
+//   * a warp owns a PAIR of rows; layer 1: lane (half, m) computes the whole dot product of row `half` with hidden
+//     unit m - no cross-lane reduction; the row is a shared-memory broadcast, the math packed fp32 pairs (FFMA2);
+//   * layer 2: lane owns float4 groups of output channels for both rows, so every W2^T read feeds eight MACs;
+//     conflict-free shared-memory reads, 16-byte coalesced stores.
+constexpr int MT = 256;    // threads
+constexpr int MIP_MAX = 64;
+
+__device__ __forceinline__ float mlp_act(float v, int act) {  // fast forms: ~1e-6 relative, far inside fp32-mode parity
+    if (act == FCE_ACT_SILU) return silu_f(v);
+    if (act == FCE_ACT_SIGMOID) return sigmoid_f(v);
+    return v;
+}
 
 __global__ void __launch_bounds__(MT) coordatt_mlp_kernel(const fce_coordatt_mlp_desc d, const float* __restrict__ strip,
-                                                          const float* __restrict__ w1t, const float* __restrict__ b1,
+                                                          const float* __restrict__ w1q_g, const float* __restrict__ b1,
                                                           const float* __restrict__ wht, const float* __restrict__ bh,
                                                           const float* __restrict__ wwt, const float* __restrict__ bw,
                                                           float* __restrict__ out) {
-    extern __shared__ float msm[];
-    const int C = d.C, mip = d.mip, oup = d.oup;
-    const int sp = C + 4;          // padded row pitch (keeps 16-byte alignment, staggers the banks of adjacent rows)
-    float* ss = msm;               // [MR][sp]
-    float* ys = msm + MR * sp;     // [MR][mip]
-    const int nh = (d.rows_h + MR - 1) / MR;
-    const bool is_w = (int)blockIdx.x >= nh;
-    const int r0 = is_w ? d.rows_h + ((int)blockIdx.x - nh) * MR : (int)blockIdx.x * MR;
-    const int r_end = is_w ? d.rows_h + d.rows_w : d.rows_h;
-    const int nr = min(MR, r_end - r0);
-    const int tid = threadIdx.x;
+    extern __shared__ float4 msm4[];
+    const int C4 = d.C >> 2, O4 = d.oup >> 2, mip = d.mip;
+    float4* w1q = msm4;                      // [C4][mip]: w1q[c4 * mip + m] = W1[m][4 c4 .. 4 c4 + 3]
+    float4* w2s = w1q + mip * C4;            // [mip][O4]  (W2 transposed)
+    float4* b2s = w2s + mip * O4;            // [O4]
+    float4* srow = b2s + O4;                 // [warps][2][C4]
+    float* b1s = reinterpret_cast<float*>(srow + (MT / 32) * 2 * C4);  // [MIP_MAX]
+    float2* ysm = reinterpret_cast<float2*>(b1s + MIP_MAX);            // [warps][MIP_MAX] (row A, row B)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_w = blockIdx.y == 1;
+    const int seg_rows = is_w ? d.rows_w : d.rows_h;
+    const int row0 = is_w ? d.rows_h : 0;
     pdl_trigger();
-    for (int i = tid; i < MR * (C >> 2); i += MT) {
-        const int r = i / (C >> 2), c4 = i - r * (C >> 2);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nr) v = *reinterpret_cast<const float4*>(strip + (size_t)(r0 + r) * d.s_pitch + 4 * c4);
-        *reinterpret_cast<float4*>(ss + r * sp + 4 * c4) = v;
+    if ((int)blockIdx.x * (MT / 16) >= seg_rows) return;  // this CTA has no rows (uniform)
+    {
+        const float4* g1 = reinterpret_cast<const float4*>(w1q_g);
+        const float4* g2 = reinterpret_cast<const float4*>(is_w ? wwt : wht);
+        const float4* gb = reinterpret_cast<const float4*>(is_w ? bw : bh);
+        for (int i = tid; i < mip * C4; i += MT) w1q[i] = __ldg(g1 + i);  // already regrouped by the caller
+        for (int i = tid; i < mip * O4; i += MT) w2s[i] = __ldg(g2 + i);
+        for (int i = tid; i < O4; i += MT) b2s[i] = __ldg(gb + i);
+        for (int i = tid; i < mip; i += MT) b1s[i] = __ldg(b1 + i);
     }
     __syncthreads();
-    for (int i = tid; i < MR * mip; i += MT) {
-        const int r = i / mip, m = i - r * mip;
-        const float* sr = ss + r * sp;
-        const float* wp = w1t + m;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int c = 0; c < C; c += 4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(sr + c);
-            a0 = fmaf(s4.x, __ldg(wp + (size_t)c * mip), a0);
-            a1 = fmaf(s4.y, __ldg(wp + (size_t)(c + 1) * mip), a1);
-            a2 = fmaf(s4.z, __ldg(wp + (size_t)(c + 2) * mip), a2);
-            a3 = fmaf(s4.w, __ldg(wp + (size_t)(c + 3) * mip), a3);
+    const int half = lane >> 4, ml = lane & 15;
+    float4* sw = srow + (warp * 2 + half) * C4;
+    float2* yw = ysm + warp * MIP_MAX;
+    const int pstep = gridDim.x * (MT / 32);
+    const int pairs = (seg_rows + 1) >> 1;
+    for (int pr = blockIdx.x * (MT / 32) + warp; pr < pairs; pr += pstep) {
+        const int rA = 2 * pr, rB = min(2 * pr + 1, seg_rows - 1);  // an odd tail row is computed twice, stored once
+        const size_t my_row = (size_t)(row0 + (half ? rB : rA));
+        {
+            const float4* sp = reinterpret_cast<const float4*>(strip + my_row * d.s_pitch);
+            for (int i = ml; i < C4; i += 16) sw[i] = sp[i];
         }
-        ys[i] = apply_act((a0 + a1) + (a2 + a3) + __ldg(b1 + m), d.act1);
-    }
-    __syncthreads();
-    const float* w2t = is_w ? wwt : wht;
-    const float* b2 = is_w ? bw : bh;
-    for (int o = tid; o < oup; o += MT) {
-        float acc[MR];
-        const float bo = __ldg(b2 + o);
-#pragma unroll
-        for (int r = 0; r < MR; ++r) acc[r] = bo;
-        for (int m = 0; m < mip; ++m) {
-            const float wv = __ldg(w2t + (size_t)m * oup + o);
-#pragma unroll
-            for (int r = 0; r < MR; ++r) acc[r] = fmaf(wv, ys[r * mip + m], acc[r]);
+        __syncwarp();
+        for (int m = ml; m < mip; m += 16) {
+            const float4* wq = w1q + m;
+            float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+            int c4 = 0;
+            for (; c4 + 2 <= C4; c4 += 2) {
+                const float4 s0 = sw[c4], s1 = sw[c4 + 1];
+                const float4 u0 = wq[c4 * mip], u1 = wq[(c4 + 1) * mip];
+                a0 = __ffma2_rn(make_float2(s0.x, s0.y), make_float2(u0.x, u0.y), a0);
+                a1 = __ffma2_rn(make_float2(s0.z, s0.w), make_float2(u0.z, u0.w), a1);
+                a2 = __ffma2_rn(make_float2(s1.x, s1.y), make_float2(u1.x, u1.y), a2);
+                a3 = __ffma2_rn(make_float2(s1.z, s1.w), make_float2(u1.z, u1.w), a3);
+            }
+            if (c4 < C4) {
+                const float4 s0 = sw[c4];
+                const float4 u0 = wq[c4 * mip];
+                a0 = __ffma2_rn(make_float2(s0.x, s0.y), make_float2(u0.x, u0.y), a0);
+                a1 = __ffma2_rn(make_float2(s0.z, s0.w), make_float2(u0.z, u0.w), a1);
+            }
+            const float2 t = __fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3));
+            const float yv = mlp_act(t.x + t.y + b1s[m], d.act1);
+            if (half) yw[m].y = yv;
+            else yw[m].x = yv;
         }
-#pragma unroll
-        for (int r = 0; r < MR; ++r)
-            if (r < nr) out[(size_t)(r0 + r) * d.out_pitch + o] = apply_act(acc[r], d.act2);
+        __syncwarp();
+        float4* opA = reinterpret_cast<float4*>(out + (size_t)(row0 + rA) * d.out_pitch);
+        float4* opB = reinterpret_cast<float4*>(out + (size_t)(row0 + rB) * d.out_pitch);
+        for (int o4 = lane; o4 < O4; o4 += 32) {
+            const float4 bb = b2s[o4];
+            float2 pA0 = make_float2(bb.x, bb.y), pA1 = make_float2(bb.z, bb.w), pB0 = pA0, pB1 = pA1;
+#pragma unroll 4
+            for (int m = 0; m < mip; ++m) {
+                const float2 yy = yw[m];
+                const float4 w = w2s[m * O4 + o4];
+                const float2 ya = make_float2(yy.x, yy.x), yb = make_float2(yy.y, yy.y);
+                pA0 = __ffma2_rn(ya, make_float2(w.x, w.y), pA0);
+                pA1 = __ffma2_rn(ya, make_float2(w.z, w.w), pA1);
+                pB0 = __ffma2_rn(yb, make_float2(w.x, w.y), pB0);
+                pB1 = __ffma2_rn(yb, make_float2(w.z, w.w), pB1);
+            }
+            opA[o4] = make_float4(mlp_act(pA0.x, d.act2), mlp_act(pA0.y, d.act2), mlp_act(pA1.x, d.act2),
+                                  mlp_act(pA1.y, d.act2));
+            if (rB != rA)
+                opB[o4] = make_float4(mlp_act(pB0.x, d.act2), mlp_act(pB0.y, d.act2), mlp_act(pB1.x, d.act2),
+                                      mlp_act(pB1.y, d.act2));
+        }
+        __syncwarp();  // sw / yw are rewritten by the next pair
     }
 }
 
@@ -300,20 +347,32 @@ extern "C" int fce_coord_pool(const fce_pool_desc* d, const void* x, float* stri
     const int n = d->dtype == FCE_BF16 ? 8 : 4;
     if (d->dtype != FCE_BF16 && d->dtype != FCE_F32) return FCE_ERR_UNSUPPORTED;
     if ((d->C % n) || (d->pitch % n) || (d->off % n) || (((uintptr_t)x) & 15)) return FCE_ERR_ALIGNMENT;
-    const int cc = CVT * n;
+    // widest channel group whose sweep (3 column groups of PT / cvt slots) still covers W
+    const int cvt = (d->W <= 24 && d->C >= 32 * n) ? 32 : ((d->W <= 48 && d->C >= 16 * n) ? 16 : 8);
+    const int cc = cvt * n;
     const int chunks = (d->C + cc - 1) / cc;
-    // bands: enough CTAs for ~4 per SM, never more than one band per WS_ROWS rows
+    // bands: with at least one (image, chunk) pair per SM a single band is best - no workspace traffic, no finish
+    // kernel, and splitting the pairs further only re-slices the same two-CTAs-per-SM rounds; small batches get their
+    // parallelism from the bands (never more than one per WS_ROWS rows)
     const int max_bands = (d->H + WS_ROWS - 1) / WS_ROWS;
-    int bands = (4 * kNumSMs + d->B * chunks - 1) / (d->B * chunks);
+    int bands = d->B * chunks >= kNumSMs ? 1 : (4 * kNumSMs + d->B * chunks - 1) / (d->B * chunks);
     bands = bands < 1 ? 1 : (bands > max_bands ? max_bands : bands);
     int band_rows = ((d->H + bands - 1) / bands + WS_ROWS - 1) / WS_ROWS * WS_ROWS;
     bands = (d->H + band_rows - 1) / band_rows;
     if (bands > 1 && (!ws || ws_bytes < (size_t)d->B * bands * d->W * d->C * sizeof(float))) return FCE_ERR_WORKSPACE;
     const int grid = d->B * bands * chunks;
-    if (d->dtype == FCE_BF16)
-        coord_pool_kernel<__nv_bfloat16><<<grid, PT, 0, st>>>(*d, (const __nv_bfloat16*)x, strip, (float*)ws, bands, band_rows);
-    else
-        coord_pool_kernel<float><<<grid, PT, 0, st>>>(*d, (const float*)x, strip, (float*)ws, bands, band_rows);
+#define FCE_POOL_LAUNCH(T, CV) \
+    coord_pool_kernel<T, CV><<<grid, PT, 0, st>>>(*d, (const T*)x, strip, (float*)ws, bands, band_rows)
+    if (d->dtype == FCE_BF16) {
+        if (cvt == 32) FCE_POOL_LAUNCH(__nv_bfloat16, 32);
+        else if (cvt == 16) FCE_POOL_LAUNCH(__nv_bfloat16, 16);
+        else FCE_POOL_LAUNCH(__nv_bfloat16, 8);
+    } else {
+        if (cvt == 32) FCE_POOL_LAUNCH(float, 32);
+        else if (cvt == 16) FCE_POOL_LAUNCH(float, 16);
+        else FCE_POOL_LAUNCH(float, 8);
+    }
+#undef FCE_POOL_LAUNCH
     int rc = check_launch();
     if (rc != FCE_OK || bands == 1) return rc;
     const size_t nitems = (size_t)d->B * d->W * d->C;
@@ -346,22 +405,30 @@ extern "C" int fce_strip_attn(const fce_strip_attn_desc* d, const float* q, cons
     return check_launch();
 }
 
-extern "C" int fce_coordatt_mlp(const fce_coordatt_mlp_desc* d, const float* strip, const float* w1t, const float* b1,
+extern "C" int fce_coordatt_mlp(const fce_coordatt_mlp_desc* d, const float* strip, const float* w1, const float* b1,
                                 const float* wht, const float* bh, const float* wwt, const float* bw, float* out,
                                 void* stream) {
-    if (!d || !strip || !w1t || !b1 || !wht || !bh || !wwt || !bw || !out) return FCE_ERR_BAD_ARG;
+    if (!d || !strip || !w1 || !b1 || !wht || !bh || !wwt || !bw || !out) return FCE_ERR_BAD_ARG;
     if (d->rows_h < 0 || d->rows_w < 0 || d->rows_h + d->rows_w <= 0 || d->C <= 0 || d->mip <= 0 || d->oup <= 0)
         return FCE_ERR_BAD_ARG;
-    if ((d->C & 3) || (d->s_pitch & 3) || (((uintptr_t)strip) & 15)) return FCE_ERR_ALIGNMENT;
-    const size_t smem = sizeof(float) * ((size_t)MR * (d->C + 4) + (size_t)MR * d->mip);
-    if (smem > 160 * 1024) return FCE_ERR_UNSUPPORTED;
+    if ((d->C & 3) || (d->oup & 3) || (d->s_pitch & 3) || (d->out_pitch & 3)) return FCE_ERR_ALIGNMENT;
+    for (const void* p : {(const void*)strip, (const void*)w1, (const void*)wht, (const void*)bh, (const void*)wwt,
+                          (const void*)bw, (const void*)out})
+        if (((uintptr_t)p) & 15) return FCE_ERR_ALIGNMENT;
+    if (d->mip > MIP_MAX) return FCE_ERR_UNSUPPORTED;
+    const size_t smem = sizeof(float) * ((size_t)d->mip * (d->C + d->oup) + d->oup + (MT / 32) * 2 * (size_t)d->C +
+                                         MIP_MAX + (MT / 32) * 2 * MIP_MAX);
+    if (smem > 200 * 1024) return FCE_ERR_UNSUPPORTED;
     static std::atomic<bool> attr_done{false};
     if (!attr_done.load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(coordatt_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(coordatt_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_cuda_error(e); return FCE_ERR_CUDA; }
         attr_done.store(true, std::memory_order_release);
     }
-    const int grid = (d->rows_h + MR - 1) / MR + (d->rows_w + MR - 1) / MR;
-    coordatt_mlp_kernel<<<grid, MT, smem, (cudaStream_t)stream>>>(*d, strip, w1t, b1, wht, bh, wwt, bw, out);
+    // one CTA per SM and row range: the weights are read once per CTA, row pairs are dealt to warps round-robin
+    const int seg = d->rows_h > d->rows_w ? d->rows_h : d->rows_w;
+    int gx = (seg + MT / 16 - 1) / (MT / 16);
+    if (gx > kNumSMs) gx = kNumSMs;
+    coordatt_mlp_kernel<<<dim3(gx, 2), MT, smem, (cudaStream_t)stream>>>(*d, strip, w1, b1, wht, bh, wwt, bw, out);
     return check_launch();
 }

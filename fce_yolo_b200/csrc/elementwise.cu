@@ -578,6 +578,64 @@ __global__ void __launch_bounds__(NT) gate_kernel(const fce_gate_desc d, const T
     }
 }
 
+// Column-walking variant (vector path): a thread owns one 16-byte channel vector of one pixel COLUMN and walks
+// down a band of image rows, four rows per step (four independent 16-byte loads in flight).  Its W-gate values stay
+// in registers for the whole band, the H-gate row (1 KB per 256 channels) is shared by the CTA's eight pixel columns
+// through L1.  The row-per-CTA kernel above re-read the whole [W, C] fp32 W-gate of the image in every CTA - twice
+// the bytes of x itself through L2 - and kept only two loads in flight per thread (4.2 TB/s).
+constexpr int GC_PX = 8;     // pixel columns per CTA (blockDim.y)
+constexpr int GC_ROWS = 4;   // rows per step
+template <typename T>
+__global__ void __launch_bounds__(32 * GC_PX) gate_cols_kernel(const fce_gate_desc d, const T* __restrict__ x,
+                                                               const float* __restrict__ gh, const float* __restrict__ gw,
+                                                               T* y, int col_groups, int band_rows) {
+    pdl_trigger();
+    constexpr int N = Vec16<T>::N;
+    int u = blockIdx.x;  // (b, band, column group): column group fastest
+    const int cg = u % col_groups;
+    u /= col_groups;
+    const int bands = (d.H + band_rows - 1) / band_rows;
+    const int band = u % bands, b = u / bands;
+    const int c = (blockIdx.y * 32 + threadIdx.x) * N;
+    const int pw = cg * GC_PX + threadIdx.y;
+    if (c >= d.C || pw >= d.W) return;
+    const int h0 = band * band_rows, h1 = min(d.H, h0 + band_rows);
+    float bwv[N];
+    if (d.mode != 1) ldf<N, true>(gw + b * d.gw_bstride + pw * d.gw_rstride + c, bwv);
+    const size_t in_row = (size_t)d.W * d.in_pitch, out_row = (size_t)d.W * d.out_pitch;
+    const T* xp = x + ((size_t)(b * d.H + h0) * d.W + pw) * d.in_pitch + d.in_off + c;
+    T* yp = y + ((size_t)(b * d.H + h0) * d.W + pw) * d.out_pitch + d.out_off + c;
+    const float* ap = gh + b * d.gh_bstride + h0 * d.gh_rstride + c;
+    for (int h = h0; h < h1; h += GC_ROWS) {
+        Vec16<T> v[GC_ROWS];
+        float a[GC_ROWS][N];
+#pragma unroll
+        for (int r = 0; r < GC_ROWS; ++r)
+            if (h + r < h1) {
+                v[r].load_nc(xp + r * in_row);
+                ldf<N, true>(ap + r * d.gh_rstride, a[r]);
+            }
+#pragma unroll
+        for (int r = 0; r < GC_ROWS; ++r)
+            if (h + r < h1) {
+                float f[N];
+                v[r].unpack(f);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    if (d.mode == 1) f[j] *= a[r][j];
+                    else if (d.mode == 0) f[j] = f[j] * a[r][j] * bwv[j];
+                    else f[j] *= sigmoid_f(a[r][j] + bwv[j]);
+                }
+                Vec16<T> o;
+                o.pack(f);
+                o.store(yp + r * out_row);
+            }
+        xp += GC_ROWS * in_row;
+        yp += GC_ROWS * out_row;
+        ap += GC_ROWS * d.gh_rstride;
+    }
+}
+
 inline bool multiple_of(int n, std::initializer_list<long long> vals) {
     for (long long v : vals)
         if (v % n) return false;
@@ -757,6 +815,26 @@ extern "C" int fce_gate_apply(const fce_gate_desc* d, const void* x, const float
         constexpr int N = 16 / (int)sizeof(T);
         const bool vec = multiple_of(N, {d->C, d->in_pitch, d->in_off, d->out_pitch, d->out_off}) && ptr16(x) && ptr16(y) &&
                          multiple_of(4, {d->gh_bstride, d->gh_rstride, d->gw_bstride, d->gw_rstride}) && ptr16(gh) && ptr16(gw);
+        static const bool rows_only = [] {  // FCE_GATE_ROWS=1: the row-per-CTA kernel everywhere (A/B timing)
+            const char* e = getenv("FCE_GATE_ROWS");
+            return e && e[0] == '1';
+        }();
+        if (vec && !rows_only && x != y && d->C / N >= 16) {
+            // column walk: (image, row band, 8-column group) CTAs; bands sized for ~8 CTAs per SM
+            const int col_groups = (d->W + GC_PX - 1) / GC_PX;
+            const int cchunks = (d->C / N + 31) / 32;
+            int bands = (8 * kNumSMs + d->B * col_groups * cchunks - 1) / (d->B * col_groups * cchunks);
+            const int max_bands = (d->H + 2 * GC_ROWS - 1) / (2 * GC_ROWS);
+            bands = bands < 1 ? 1 : (bands > max_bands ? max_bands : bands);
+            const int band_rows = ((d->H + bands - 1) / bands + GC_ROWS - 1) / GC_ROWS * GC_ROWS;
+            bands = (d->H + band_rows - 1) / band_rows;
+            const long long ctas = (long long)d->B * bands * col_groups;
+            if (ctas <= 0x7fffffffLL && cchunks <= 65535) {
+                gate_cols_kernel<T><<<dim3((unsigned)ctas, cchunks), dim3(32, GC_PX), 0, st>>>(*d, (const T*)x, gh, gw, (T*)y,
+                                                                                           col_groups, band_rows);
+                return check_launch();
+            }
+        }
         const RowGrid g = row_grid(d->B * d->H, d->C / (vec ? N : 1));
         if (vec) gate_kernel<T, true><<<g.grid, g.block, 0, st>>>(*d, (const T*)x, gh, gw, (T*)y);
         else gate_kernel<T, false><<<g.grid, g.block, 0, st>>>(*d, (const T*)x, gh, gw, (T*)y);

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(NT) stem_pack_kernel(const fce_pack_desc d, co
 //     (two consecutive k') is ONE aligned 32-bit shared-memory load, no byte gathering or packing;
 //   * uint8 images are staged four bytes per load (the tile origin is shifted left to a 4-byte boundary, one leading
 //     pad element per row keeps the patch origins even) and converted with the 2^23 magic-number trick;
-//   * SiLU is h + h * tanh(h), h = v/2: one MUFU per value.
+//   * SiLU is h + h * tanh(h), h = v/2: one MUFU per value; the weights and the bias are halved when the B fragments
+//     are built (exact in bf16), so the accumulator IS h, and the h + h*t runs on packed fp32 pairs (FFMA2).
 constexpr int ST_ROWS = 8, ST_COLS = 64;               // output tile of one CTA
 constexpr int ST_IR = 2 * ST_ROWS + 1;                 // input rows incl. the top halo
 constexpr int ST_SHIFT = 3;                            // extra left columns so that the u8 tile starts 4-byte aligned
@@ -84,13 +85,6 @@ constexpr int ST_IC = 2 * ST_COLS + 2 + ST_SHIFT;      // 133 input columns (399
 constexpr int ST_PITCH = 400;                          // bf16 elements per tile row: element 1 + 3*c + ci holds (c, ci);
                                                        // the leading pad element makes every patch origin EVEN
 constexpr int ST_THREADS = 128;
-
-__device__ __forceinline__ float silu_tanh(float v) {
-    const float h = 0.5f * v;
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
-}
 
 template <typename TI, int LAYOUT, int NTILES>
 __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_desc d, const TI* __restrict__ x,
@@ -190,10 +184,16 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
                     const int kh = kp / 10, j = kp - kh * 10;
                     if (kp < 30 && j < 9) v |= (uint32_t)__ldg(wr + kh * 9 + j) << (16 * e);
                 }
+                // SiLU epilogue: the MMA produces h = v/2 directly (halving a bf16 is exact), see below
+                if (d.act == FCE_ACT_SILU) {
+                    const float lo = __uint_as_float(v << 16) * 0.5f, hi = __uint_as_float(v & 0xffff0000u) * 0.5f;
+                    v = (__float_as_uint(hi) & 0xffff0000u) | (__float_as_uint(lo) >> 16);
+                }
                 bf[ks][nt][hf] = v;
             }
-        bs[nt][0] = __ldg(bias + nt * 8 + 2 * t);
-        bs[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1);
+        const float bscale = d.act == FCE_ACT_SILU ? 0.5f : 1.f;
+        bs[nt][0] = __ldg(bias + nt * 8 + 2 * t) * bscale;
+        bs[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1) * bscale;
     }
     // ---- this thread's 4 A-fragment word offsets (in 32-bit words, relative to the patch origin)
     int aoff[2][2];
@@ -237,9 +237,17 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
             asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                          : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                          : "r"(a[1][0]), "r"(a[1][1]), "r"(a[1][2]), "r"(a[1][3]), "r"(bf[1][nt][0]), "r"(bf[1][nt][1]));
-            if (d.act == FCE_ACT_SILU) {
+            if (d.act == FCE_ACT_SILU) {  // c holds h = v/2: silu(v) = h + h*tanh(h), on packed pairs
 #pragma unroll
-                for (int j = 0; j < 4; ++j) c[j] = silu_tanh(c[j]);
+                for (int j = 0; j < 4; j += 2) {
+                    const float2 h = make_float2(c[j], c[j + 1]);
+                    float t0, t1;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h.x));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h.y));
+                    const float2 o = __ffma2_rn(h, make_float2(t0, t1), h);
+                    c[j] = o.x;
+                    c[j + 1] = o.y;
+                }
             }
             __nv_bfloat162 lo = __floats2bfloat162_rn(c[0], c[1]), hi = __floats2bfloat162_rn(c[2], c[3]);
             *reinterpret_cast<__nv_bfloat162*>(stg + g * OPITCH + nt * 8 + 2 * t) = lo;

@@ -162,44 +162,53 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
                  : "memory");
 }
 
-// bias + activation (+ residual) of 16 consecutive output channels of one pixel.
-// SiLU as h = 0.5*(acc + bias) (one FFMA), t = tanh.approx(h) (the one MUFU op), out = h + h*t (one FFMA).
+// bias + activation (+ residual) of 16 consecutive output channels of one pixel, on PACKED fp32 pairs (FFMA2 /
+// FADD2: sm_100's two-wide fp32 pipe halves the issue slots of the epilogue, which - not HBM and not the tensor
+// pipe - sets the pace of the short-K layers).  `sbias` holds the bias PRE-SCALED by epi_bias_scale(act):
+// SiLU as h = 0.5*acc + 0.5*bias (one FFMA2 per pair), t = tanh.approx(h) (the one MUFU op per element),
+// out = h + h*t (one FFMA2 per pair).
 // (Measured alternatives: ex2+rcp = two MUFU ops; f16x2 tanh halves the MUFU work but costs more issue slots in
 // conversions and was 5% slower - the epilogue is issue-bound, not MUFU-bound.)
+__host__ __device__ __forceinline__ float epi_bias_scale(int act) { return act == FCE_ACT_SILU ? 0.5f : 1.f; }
 __device__ __forceinline__ void epi_math16(const uint32_t* v, const float* sbias, int act, bool has_res, uint4 r0,
                                            uint4 r1, float* f) {
+    float2 o[8];
     if (act == FCE_ACT_SILU) {
+        const float2 half2 = make_float2(0.5f, 0.5f);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 b = reinterpret_cast<const float4*>(sbias)[q];
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float h = 0.5f * (__uint_as_float(v[4 * q + e]) + bb[e]);
-                f[4 * q + e] = fmaf(h, tanh_fast(h), h);
-            }
+            const float2 h0 = __ffma2_rn(make_float2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), half2,
+                                         make_float2(b.x, b.y));
+            const float2 h1 = __ffma2_rn(make_float2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), half2,
+                                         make_float2(b.z, b.w));
+            o[2 * q] = __ffma2_rn(h0, make_float2(tanh_fast(h0.x), tanh_fast(h0.y)), h0);
+            o[2 * q + 1] = __ffma2_rn(h1, make_float2(tanh_fast(h1.x), tanh_fast(h1.y)), h1);
         }
     } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 b = reinterpret_cast<const float4*>(sbias)[q];
-            f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
-            f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
-            f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
-            f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
+            o[2 * q] = __fadd2_rn(make_float2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
+                                  make_float2(b.x, b.y));
+            o[2 * q + 1] = __fadd2_rn(make_float2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])),
+                                      make_float2(b.z, b.w));
         }
         if (act != FCE_ACT_NONE) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = act_fast(f[i], act);
+            for (int i = 0; i < 8; ++i) o[i] = make_float2(act_fast(o[i].x, act), act_fast(o[i].y, act));
         }
     }
     if (has_res) {
         const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            f[2 * i] += __uint_as_float(rr[i] << 16);
-            f[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
-        }
+        for (int i = 0; i < 8; ++i)
+            o[i] = __fadd2_rn(o[i], make_float2(__uint_as_float(rr[i] << 16), __uint_as_float(rr[i] & 0xffff0000u)));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        f[2 * i] = o[i].x;
+        f[2 * i + 1] = o[i].y;
     }
 }
 __device__ __forceinline__ void pack16(const float* f, uint32_t* o) {

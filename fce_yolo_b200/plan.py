@@ -441,12 +441,13 @@ class Plan:
         wh, bh, kh, *_ = self.conv_params(m.cv_h)
         ww, bw, kw, *_ = self.conv_params(m.cv_w)
         mip, oup = w1.shape[0], wh.shape[0]
-        if self.FUSED_COORDATT_MLP and (k1, kh, kw) == (1, 1, 1) and x.C % 4 == 0 and 64 * (x.C + 4 + mip) <= 160 * 1024:
-            # cv1 (+BN, SiLU) -> cv_h / cv_w -> sigmoid on the strips in ONE launch (weights transposed for the kernel)
+        if (self.FUSED_COORDATT_MLP and (k1, kh, kw) == (1, 1, 1) and x.C % 4 == 0 and oup % 4 == 0 and x.C <= 1024
+                and mip <= 64 and 4 * (mip * (x.C + oup) + oup + 16 * x.C + 1100) <= 200 * 1024):
+            # cv1 (+BN, SiLU) -> cv_h / cv_w -> sigmoid on the strips in ONE launch (second layer transposed for the kernel)
             a = self.strip_buf(s.H, oup)
             d = L.CoordAttMlpDesc(rows_h=BH, rows_w=s.H - BH, C=x.C, mip=mip, oup=oup, s_pitch=s.pitch,
                                   out_pitch=a.pitch, act1=act1, act2=L.ACT_SIGMOID)
-            ptrs = [s, self._w(w1.view(mip, x.C).t()), self._w(b1), self._w(wh.view(oup, mip).t()), self._w(bh),
+            ptrs = [s, self._w(w1.view(mip, x.C // 4, 4).permute(1, 0, 2)), self._w(b1), self._w(wh.view(oup, mip).t()), self._w(bh),
                     self._w(ww.view(oup, mip).t()), self._w(bw), a]
             self.add(Node("fce_coordatt_mlp", d, ptrs, reads=[s], writes=[a], tag=tag + ".mlp",
                           flops=2.0 * s.H * mip * (x.C + oup), bytes=4.0 * s.H * (x.C + oup)))

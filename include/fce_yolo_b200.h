@@ -187,14 +187,15 @@ size_t fce_coord_pool_workspace(const fce_pool_desc* d);
 
 /* CoordAtt gate MLP on the pooled strips, fused (fce_block.py:104-113 - cv1 with its folded BN + SiLU, then cv_h /
  * cv_w + sigmoid): out[r, :] = act2(W2 act1(W1 strip[r, :] + b1) + b2) with (W2, b2) = (w_h, b_h) for rows
- * [0, rows_h) and (w_w, b_w) for rows [rows_h, rows_h + rows_w).  All operands fp32; weights TRANSPOSED:
- * w1t [C][mip], wht / wwt [mip][oup].  Replaces three fce_conv2d calls on the strips. */
+ * [0, rows_h) and (w_w, b_w) for rows [rows_h, rows_h + rows_w).  All operands fp32, 16-byte aligned, C / oup /
+ * pitches multiples of 4, mip <= 64, weights + 16 staged rows within 200 KB of shared memory; w1q is W1 regrouped as [C/4][mip][4] (w1q[c4][m][j] = W1[m][4 c4 + j]), the
+ * second layer TRANSPOSED: wht / wwt [mip][oup].  Replaces three fce_conv2d calls on the strips. */
 typedef struct {
     int32_t rows_h, rows_w, C, mip, oup;
     int32_t s_pitch, out_pitch; /* row pitches of strip / out, elements */
     int32_t act1, act2;
 } fce_coordatt_mlp_desc;
-int fce_coordatt_mlp(const fce_coordatt_mlp_desc* d, const float* strip, const float* w1t, const float* b1,
+int fce_coordatt_mlp(const fce_coordatt_mlp_desc* d, const float* strip, const float* w1q, const float* b1,
                      const float* wht, const float* bh, const float* wwt, const float* bw, float* out, void* stream);
 
 /* Strip cross-attention core (fce_block.py:171-175, 252-256, 271-275):

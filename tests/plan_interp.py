@@ -109,9 +109,10 @@ class Interp(Arena):
 
     def _fce_coordatt_mlp(self, d, p):
         s = self.t(p[0]).reshape(-1, d.C)
-        w1t, b1, wht, bh, wwt, bw = [z.float().cpu() for z in p[1:7]]
+        w1, b1, wht, bh, wwt, bw = [z.float().cpu() for z in p[1:7]]
         act = {0: lambda v: v, 1: torch.nn.functional.silu, 2: torch.sigmoid}
-        y = act[d.act1](s @ w1t + b1)
+        w1 = w1.reshape(d.C // 4, d.mip, 4).permute(1, 0, 2).reshape(d.mip, d.C)  # undo the kernel's regrouping
+        y = act[d.act1](s @ w1.t() + b1)
         o = self.t(p[7]).reshape(-1, d.oup)
         o[: d.rows_h] = act[d.act2](y[: d.rows_h] @ wht + bh)
         o[d.rows_h:] = act[d.act2](y[d.rows_h:] @ wwt + bw)

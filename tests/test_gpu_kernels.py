@@ -174,3 +174,136 @@ def test_sppf_pool_bit_exact(lib, B, H, W, Cc, dtype):
         assert torch.equal(got, y), level
     assert torch.equal(buf[..., :off + Cc], b0[..., :off + Cc])
     assert torch.equal(buf[..., off + 4 * Cc:], b0[..., off + 4 * Cc:])
+
+
+# ------------------------------------------------------------------------------------------------ CoordAtt gate MLP
+@pytest.mark.parametrize("rows_h,rows_w,Cc,mip,oup", [(160, 160, 256, 16, 256), (80, 40, 128, 8, 128), (5, 9, 64, 11, 96), (3, 300, 768, 32, 64),
+                                                      (33, 1, 512, 32, 512), (64 * 80, 64 * 80, 256, 16, 256),
+                                                      (7, 20, 768, 23, 384)])
+def test_coordatt_mlp_vs_torch(lib, rows_h, rows_w, Cc, mip, oup):
+    """fce_coordatt_mlp: a = sigmoid(W2 SiLU(W1 s + b1) + b2) per strip row, (W2, b2) switching from cv_h to cv_w at
+    row rows_h (fce_block.py:104-113).  fp32 throughout: 1e-5 relative to the largest output."""
+    l, L = lib
+    g = torch.Generator().manual_seed(rows_h + 7 * rows_w + Cc + mip)
+    rows = rows_h + rows_w
+    s_pitch, o_pitch = Cc + 8, oup + 4
+    s = torch.randn(rows, s_pitch, generator=g).cuda()
+    w1, b1 = torch.randn(mip, Cc, generator=g).cuda() / math.sqrt(Cc), torch.randn(mip, generator=g).cuda()
+    wh, bh = torch.randn(oup, mip, generator=g).cuda() / math.sqrt(mip), torch.randn(oup, generator=g).cuda()
+    ww, bw = torch.randn(oup, mip, generator=g).cuda() / math.sqrt(mip), torch.randn(oup, generator=g).cuda()
+    out = torch.full((rows, o_pitch), -7.0).cuda()
+    d = L.CoordAttMlpDesc(rows_h=rows_h, rows_w=rows_w, C=Cc, mip=mip, oup=oup, s_pitch=s_pitch, out_pitch=o_pitch,
+                          act1=L.ACT_SILU, act2=L.ACT_SIGMOID)
+    w1t = w1.view(mip, Cc // 4, 4).permute(1, 0, 2).contiguous()  # [C/4][mip][4]
+    wht, wwt = wh.t().contiguous(), ww.t().contiguous()
+    st = l.fce_coordatt_mlp(C.byref(d), *[C.c_void_p(t.data_ptr()) for t in (s, w1t, b1, wht, bh, wwt, bw, out)],
+                            _stream())
+    L.check(st, "fce_coordatt_mlp")
+    torch.cuda.synchronize()
+    y = F.silu(s[:, :Cc].double() @ w1.double().t() + b1.double())
+    ref = torch.cat([torch.sigmoid(y[:rows_h] @ wh.double().t() + bh.double()),
+                     torch.sigmoid(y[rows_h:] @ ww.double().t() + bw.double())]).float()
+    assert (out[:, :oup] - ref).abs().max().item() <= 1e-5
+    assert torch.all(out[:, oup:] == -7.0)  # the pitch padding is not written
+
+
+def test_coordatt_mlp_rejects_bad_args(lib):
+    l, L = lib
+    t = torch.zeros(64, 64).cuda()
+    p = C.c_void_p(t.data_ptr())
+    d = L.CoordAttMlpDesc(rows_h=4, rows_w=4, C=30, mip=8, oup=32, s_pitch=32, out_pitch=32, act1=1, act2=2)
+    assert l.fce_coordatt_mlp(C.byref(d), p, p, p, p, p, p, p, p, _stream()) == -3  # C not a multiple of 4
+    d.C, d.mip = 32, 65
+    assert l.fce_coordatt_mlp(C.byref(d), p, p, p, p, p, p, p, p, _stream()) == -2  # hidden width above the kernel's limit
+    d.mip = 8
+    d.C = 32
+    assert l.fce_coordatt_mlp(C.byref(d), p, p, None, p, p, p, p, p, _stream()) == -1
+
+
+# ------------------------------------------------------------------------------------------------ gate application
+@pytest.mark.parametrize("B,H,W,Cc", [(2, 80, 80, 256), (3, 40, 40, 512), (1, 13, 27, 128), (2, 20, 20, 64),
+                                      (1, 7, 5, 1024), (2, 10, 12, 40)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_gate_apply_vs_torch(lib, B, H, W, Cc, mode, dtype):
+    """fce_gate_apply (fce_block.py:116, 180, 283-284) on both launch shapes (column walk for wide channel counts,
+    row-per-CTA otherwise), pitched views.  fp32: 1e-6 relative; bf16: one output rounding (2^-8) + fast sigmoid."""
+    l, L = lib
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    g = torch.Generator().manual_seed(B + 3 * H + 5 * W + Cc + mode)
+    pitch, off = Cc + 16, 8
+    xb = torch.randn(B, H, W, pitch, generator=g).to(tdt).cuda()
+    yb = torch.full((B, H, W, pitch), 3.0).to(tdt).cuda()
+    gh = torch.rand(B, H, Cc, generator=g).cuda() if mode != 2 else torch.randn(B, H, Cc, generator=g).cuda()
+    gw = torch.rand(B, W, Cc, generator=g).cuda() if mode != 2 else torch.randn(B, W, Cc, generator=g).cuda()
+    d = L.GateDesc(B=B, H=H, W=W, C=Cc, mode=mode, in_pitch=pitch, in_off=off, out_pitch=pitch, out_off=off,
+                   dtype=L.BF16 if dtype == "bf16" else L.F32, gh_bstride=H * Cc, gh_rstride=Cc, gw_bstride=W * Cc,
+                   gw_rstride=Cc)
+    st = l.fce_gate_apply(C.byref(d), C.c_void_p(xb.data_ptr()), C.c_void_p(gh.data_ptr()),
+                          C.c_void_p(gw.data_ptr() if mode != 1 else 0), C.c_void_p(yb.data_ptr()), _stream())
+    L.check(st, "fce_gate_apply")
+    torch.cuda.synchronize()
+    x = xb[..., off:off + Cc].float()
+    a, b = gh[:, :, None, :], gw[:, None, :, :]
+    ref = x * a * b if mode == 0 else (x * a if mode == 1 else x * torch.sigmoid(a + b))
+    got = yb[..., off:off + Cc].float()
+    tol = 1e-6 if dtype == "fp32" and mode != 2 else (2e-6 if dtype == "fp32" else 2 ** -7)
+    assert ((got - ref).abs() <= tol * ref.abs() + 1e-6).all()
+    assert torch.all(yb[..., :off].float() == 3.0) and torch.all(yb[..., off + Cc:].float() == 3.0)
+
+
+# ------------------------------------------------------------------------------------------------ coordinate pooling
+@pytest.mark.parametrize("B,H,W,Cc", [(2, 80, 80, 256), (64, 40, 40, 512), (3, 20, 20, 512), (1, 160, 160, 64),
+                                      (2, 13, 27, 128), (1, 7, 100, 40), (5, 33, 50, 256)])
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_coord_pool_vs_torch(lib, B, H, W, Cc, dtype):
+    """fce_coord_pool: strip[b, 0:H] = mean over W, strip[B*H + b*W ...] = mean over H (fce_block.py:101-102), every
+    channel-group width (8 / 16 / 32 vector lanes) and both band modes (single band, bands + finish kernel).
+    fp32 accumulation in a different order than torch: 2e-6 relative to the largest mean."""
+    l, L = lib
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    g = torch.Generator().manual_seed(B + 3 * H + 5 * W + Cc)
+    pitch, off = Cc + 16, 8
+    xb = (torch.randn(B, H, W, pitch, generator=g) + 0.5).to(tdt).cuda()
+    strip = torch.full((B * (H + W), Cc), -5.0).cuda()
+    d = L.PoolDesc(B=B, H=H, W=W, C=Cc, pitch=pitch, off=0, dtype=L.BF16 if dtype == "bf16" else L.F32)
+    nws = l.fce_coord_pool_workspace(C.byref(d))
+    ws = torch.empty(max(nws, 16), dtype=torch.uint8).cuda()
+    st = l.fce_coord_pool(C.byref(d), C.c_void_p(xb.data_ptr() + off * xb.element_size()), C.c_void_p(strip.data_ptr()),
+                          C.c_void_p(ws.data_ptr()), C.c_size_t(nws), _stream())
+    L.check(st, "fce_coord_pool")
+    torch.cuda.synchronize()
+    x = xb[..., off:off + Cc].double()
+    ref = torch.cat([x.mean(2).reshape(B * H, Cc), x.mean(1).reshape(B * W, Cc)]).float()
+    assert (strip - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------ Detect decode
+@pytest.mark.parametrize("B,shapes,nc,pad", [(3, [(80, 80), (40, 40), (20, 20)], 80, 0), (2, [(8, 8), (4, 4), (2, 2)], 80, 16),
+                                             (1, [(13, 7), (5, 9)], 4, 4), (2, [(20, 20)], 12, 0),
+                                             (1, [(160, 160), (80, 80), (40, 40), (3, 3)], 80, 0)])
+def test_detect_decode_vs_oracle(lib, B, shapes, nc, pad):
+    """fce_detect_decode (head.py:149-167, DFL block.py:76-79, tal.py:352-376) against the CPU oracle on random
+    logits: level boundaries inside a warp's 32-anchor slab, ragged level sizes, padded raw pitch, 1-4 levels.
+    Boxes within 2e-3 pixel (approximate ex2 / rcp forms), class probabilities within 2e-6."""
+    from oracle.fce_oracle import detect_decode
+    l, L = lib
+    g = torch.Generator().manual_seed(B + nc + len(shapes))
+    R = 16
+    no = 4 * R + nc
+    raws = [torch.randn(B, h, w, no + pad, generator=g) * 3.0 for (h, w) in shapes]
+    strides = [8.0, 16.0, 32.0, 64.0][:len(shapes)]
+    A = sum(h * w for h, w in shapes)
+    d = L.DecodeDesc(B=B, nl=len(shapes), nc=nc, reg_max=R)
+    for i, (h, w) in enumerate(shapes):
+        d.H[i], d.W[i], d.stride[i], d.raw_pitch[i] = h, w, strides[i], no + pad
+    dev = [r.cuda() for r in raws]
+    y = torch.full((B, 4 + nc, A), -9.0).cuda()
+    ptrs = [C.c_void_p(t.data_ptr()) for t in dev] + [C.c_void_p(0)] * (4 - len(dev))
+    st = l.fce_detect_decode(C.byref(d), *ptrs, C.c_void_p(y.data_ptr()), _stream())
+    L.check(st, "fce_detect_decode")
+    torch.cuda.synchronize()
+    ref = detect_decode([r[..., :no].permute(0, 3, 1, 2).contiguous() for r in raws], strides, R)
+    got = y.cpu()
+    assert (got[:, :4] - ref[:, :4]).abs().max().item() <= 2e-3
+    assert (got[:, 4:] - ref[:, 4:]).abs().max().item() <= 2e-6

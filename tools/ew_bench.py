@@ -67,6 +67,16 @@ def main():
                        gh_bstride=H * Cc, gh_rstride=Cc, gw_bstride=H * Cc, gw_rstride=Cc)
         ms = timeit(lambda: lib.fce_gate_apply(C.byref(g), P(x), P(gh), P(gw), P(y), st), flush)
         report(f"gate_apply {H}x{H}x{Cc}", ms, 2 * x.numel() * 2)
+    for (H, Cc, mip) in [(80, 256, 16), (40, 512, 16)]:
+        rows = B * H
+        strip = torch.randn(2 * rows, Cc, device=dev)
+        out = torch.empty(2 * rows, Cc, device=dev)
+        w1t, b1 = torch.randn(Cc // 4, mip, 4, device=dev), torch.randn(mip, device=dev)
+        wht, bh = torch.randn(mip, Cc, device=dev), torch.randn(Cc, device=dev)
+        d = L.CoordAttMlpDesc(rows_h=rows, rows_w=rows, C=Cc, mip=mip, oup=Cc, s_pitch=Cc, out_pitch=Cc, act1=1, act2=2)
+        ms = timeit(lambda: lib.fce_coordatt_mlp(C.byref(d), P(strip), P(w1t), P(b1), P(wht), P(bh), P(wht), P(bh), P(out),
+                                                 st), flush)
+        report(f"coordatt_mlp {2 * rows}x{Cc}->{mip}->{Cc}", ms, 2 * strip.numel() * 4)
     for (H, Cc) in [(20, 256)]:
         buf = torch.randn(B, H, H, 4 * Cc, device=dev).to(torch.bfloat16)
         d = L.SppfDesc(B=B, H=H, W=H, C=Cc, pitch=4 * Cc, off=0, dtype=L.BF16)
