@@ -5,6 +5,8 @@
 // 1x1 convolution (K = 32) on the tcgen05 kernel with the reference's OHWI weights laid out the same way.
 // uint8 images are stored unscaled (0..255 are exact in bf16) - the 1/255 is folded into the weights.
 // HBM-bound: algorithmic bytes per output pixel = 27 * e_in / 4 (input, each byte used ~2.25 times) + 64 written.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace fce {
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(NT) stem_pack_kernel(const fce_pack_desc d, co
 
 
 // ------------------------------------------------------------------------------------------------ fused stem
-// fce_stem_conv: the whole first layer in ONE pass - image tile -> shared memory (bf16) -> per-warp
+// fce_stem_conv: the whole first layer in ONE pass - image tile -> shared memory (fp16) -> per-warp
 // mma.sync m16n8k16 (M = 16 output pixels, K = 27 padded to 32, N = Cout) -> bias + SiLU -> bf16 NHWC, staged
 // through shared memory so that every global store is a full 16-byte chunk of a contiguous pixel run.
 // Algorithmic HBM bytes per output pixel: 12 * e_in read (each input byte lands in ~2.25 patches but is fetched
@@ -71,18 +73,20 @@ __global__ void __launch_bounds__(NT) stem_pack_kernel(const fce_pack_desc d, co
 // read per pixel) never exists.  A tcgen05 pipeline has nothing to offer at K = 32, N <= 96: the layer is
 // bound by the output write and by instruction issue, so the kernel is written for few instructions per pixel:
 //   * the tile keeps (w, ci) interleaved exactly like the image, so the 9 values of one patch row kh are 9
-//     CONTIGUOUS bf16 starting at a 4-byte aligned address.  The GEMM K axis is therefore re-ordered to
+//     CONTIGUOUS fp16 starting at a 4-byte aligned address.  The GEMM K axis is therefore re-ordered to
 //     k' = kh * 10 + j (j = 0..8 = kw*3+ci, j = 9 and k' >= 30 carry zero weights): every A-fragment register
 //     (two consecutive k') is ONE aligned 32-bit shared-memory load, no byte gathering or packing;
-//   * uint8 images are staged four bytes per load (the tile origin is shifted left to a 4-byte boundary, one leading
-//     pad element per row keeps the patch origins even) and converted with the 2^23 magic-number trick;
+//   * uint8 images are staged eight values per item from three aligned words (the tile origin is shifted left to a
+//     4-byte boundary, one leading pad element per row keeps the patch origins even) and converted two at a time to
+//     fp16 (magic-number trick in the half domain); the operands are fp16, not bf16: byte/256 is exact in fp16 and the
+//     bf16 weights convert exactly;
 //   * SiLU is h + h * tanh(h), h = v/2: one MUFU per value; the weights and the bias are halved when the B fragments
 //     are built (exact in bf16), so the accumulator IS h, and the h + h*t runs on packed fp32 pairs (FFMA2).
 constexpr int ST_ROWS = 8, ST_COLS = 64;               // output tile of one CTA
 constexpr int ST_IR = 2 * ST_ROWS + 1;                 // input rows incl. the top halo
 constexpr int ST_SHIFT = 3;                            // extra left columns so that the u8 tile starts 4-byte aligned
 constexpr int ST_IC = 2 * ST_COLS + 2 + ST_SHIFT;      // 133 input columns (399 values) per tile row
-constexpr int ST_PITCH = 400;                          // bf16 elements per tile row: element 1 + 3*c + ci holds (c, ci);
+constexpr int ST_PITCH = 400;                          // fp16 elements per tile row: element 1 + 3*c + ci holds (c, ci);
                                                        // the leading pad element makes every patch origin EVEN
 constexpr int ST_THREADS = 128;
 
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
     pdl_trigger();
     constexpr int COUT = NTILES * 8;
     constexpr int OPITCH = COUT + 8;  // staged pixel pitch (bf16): +16 B keeps the quad-strided writes conflict-free
-    __shared__ __align__(16) __nv_bfloat16 tile[ST_IR * ST_PITCH];
+    __shared__ __align__(16) __half tile[ST_IR * ST_PITCH];  // fp16: u8 / 256 and [0, 1] floats are (near-)exact
     __shared__ __align__(16) __nv_bfloat16 stage[4][16 * OPITCH];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int b = blockIdx.z, ho0 = blockIdx.y * ST_ROWS, wo0 = blockIdx.x * ST_COLS;
@@ -107,43 +111,42 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
         // 4.  Elements 4q .. 4q+3 are image bytes 4q-1 .. 4q+2 of the row segment: the top byte of word q-1 and the
         // low three bytes of word q (one funnel shift).
         const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
-        uint2* tw = reinterpret_cast<uint2*>(tile);
+        uint4* tw = reinterpret_cast<uint4*>(tile);
         const int row_words = d.W * 3 / 4;
         const int w_first = wi0 * 3 / 4;  // exact (may be negative)
-        // fully unrolled in two halves so that all global loads of a half are in flight before the first conversion
-        // (measured: with a rolled loop half of the kernel's time was this staging, one exposed load latency per trip)
-        constexpr int ITEMS = ST_IR * (ST_PITCH / 4);                      // 1700 groups of four values
-        constexpr int TRIPS = (ITEMS + ST_THREADS - 1) / ST_THREADS;       // 14
-        constexpr int HALF = (TRIPS + 1) / 2;
+        // A thread converts EIGHT values per item from three consecutive words (the first version loaded two words per
+        // four values and spent half of the kernel's issue slots on this staging); fully unrolled so that all global
+        // loads are in flight before the first conversion.
+        constexpr int ITEMS = ST_IR * (ST_PITCH / 8);                      // 850 groups of eight values
+        constexpr int TRIPS = (ITEMS + ST_THREADS - 1) / ST_THREADS;       // 7
+        uint32_t wa[TRIPS], wb[TRIPS], wc[TRIPS];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t w0[HALF], w1[HALF];
-#pragma unroll
-            for (int t = 0; t < HALF; ++t) {
-                const int i = tid + (h * HALF + t) * ST_THREADS;
-                const int r = i / (ST_PITCH / 4), q = i - r * (ST_PITCH / 4);
-                const int hi = hi0 + r, wq = w_first + q;
-                w0[t] = w1[t] = 0u;
-                if (i < ITEMS && hi >= 0 && hi < d.H) {
-                    const uint32_t* rowp = xw + (size_t)(b * d.H + hi) * row_words;
-                    if (wq - 1 >= 0 && wq - 1 < row_words) w0[t] = __ldg(rowp + wq - 1);
-                    if (wq >= 0 && wq < row_words) w1[t] = __ldg(rowp + wq);
-                }
+        for (int t = 0; t < TRIPS; ++t) {
+            const int i = tid + t * ST_THREADS;
+            const int r = i / (ST_PITCH / 8), q = 2 * (i - r * (ST_PITCH / 8));
+            const int hi = hi0 + r, wq = w_first + q;
+            wa[t] = wb[t] = wc[t] = 0u;
+            if (i < ITEMS && hi >= 0 && hi < d.H) {
+                const uint32_t* rowp = xw + (size_t)(b * d.H + hi) * row_words;
+                if (wq - 1 >= 0 && wq - 1 < row_words) wa[t] = __ldg(rowp + wq - 1);
+                if (wq >= 0 && wq < row_words) wb[t] = __ldg(rowp + wq);
+                if (wq + 1 >= 0 && wq + 1 < row_words) wc[t] = __ldg(rowp + wq + 1);
             }
+        }
+        // two bytes -> two fp16 at once: 0x4400 | byte is the half 4 + byte/256 (ulp 2^-8 in [4, 8)); subtracting 4
+        // leaves byte/256 exactly.  The 256 is folded into the B fragments below.
+        const __half2 four = __float2half2_rn(4.f);
+        auto cvt2 = [&](uint32_t v, uint32_t sel) {
+            const uint32_t m = __byte_perm(v, 0x44444444u, sel);
+            const __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&m), four);
+            return *reinterpret_cast<const uint32_t*>(&h);
+        };
 #pragma unroll
-            for (int t = 0; t < HALF; ++t) {
-                const int i = tid + (h * HALF + t) * ST_THREADS;
-                if (i >= ITEMS) continue;
-                const uint32_t v = __funnelshift_l(w0[t], w1[t], 8);
-                // four bytes -> four bf16: (0x4B000000 | byte) is the float 2^23 + byte; subtracting 2^23 leaves the
-                // exact integer, whose upper 16 bits are its bf16 encoding
-                const float f0 = __uint_as_float(0x4B000000u | (v & 0xffu)) - 8388608.f;
-                const float f1 = __uint_as_float(0x4B000000u | ((v >> 8) & 0xffu)) - 8388608.f;
-                const float f2 = __uint_as_float(0x4B000000u | ((v >> 16) & 0xffu)) - 8388608.f;
-                const float f3 = __uint_as_float(0x4B000000u | (v >> 24)) - 8388608.f;
-                tw[i] = make_uint2(__byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632),
-                                   __byte_perm(__float_as_uint(f2), __float_as_uint(f3), 0x7632));
-            }
+        for (int t = 0; t < TRIPS; ++t) {
+            const int i = tid + t * ST_THREADS;
+            if (i >= ITEMS) continue;
+            const uint32_t v0 = __funnelshift_l(wa[t], wb[t], 8), v1 = __funnelshift_l(wb[t], wc[t], 8);
+            tw[i] = make_uint4(cvt2(v0, 0x4140), cvt2(v0, 0x4342), cvt2(v1, 0x4140), cvt2(v1, 0x4342));
         }
     } else if (LAYOUT == FCE_NHWC) {
         for (int i = tid; i < ST_IR * ST_PITCH; i += ST_THREADS) {
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
             float v = 0.f;
             if (e >= 0 && hi >= 0 && hi < d.H && wi >= 0 && wi < d.W)
                 v = Elem<TI>::to_f(__ldg(x + ((long long)(b * d.H + hi) * d.W + wi) * 3 + (e - c * 3)));
-            tile[i] = __float2bfloat16_rn(v);
+            tile[i] = __float2half_rn(sizeof(TI) == 1 ? v * (1.f / 256.f) : v);  // u8 tiles hold byte/256 on every path
         }
     } else {
         for (int i = tid; i < 3 * ST_IR * ST_IC; i += ST_THREADS) {
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
             float v = 0.f;
             if (hi >= 0 && hi < d.H && wi >= 0 && wi < d.W)
                 v = Elem<TI>::to_f(__ldg(x + ((size_t)(b * 3 + ci) * d.H + hi) * d.W + wi));
-            tile[r * ST_PITCH + 1 + c * 3 + ci] = __float2bfloat16_rn(v);
+            tile[r * ST_PITCH + 1 + c * 3 + ci] = __float2half_rn(v);
         }
     }
     // ---- B fragments in the re-ordered K axis: k' = kh*10 + j  <->  k = kh*9 + j of the [COUT][32] weight rows
@@ -184,10 +187,13 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
                     const int kh = kp / 10, j = kp - kh * 10;
                     if (kp < 30 && j < 9) v |= (uint32_t)__ldg(wr + kh * 9 + j) << (16 * e);
                 }
-                // SiLU epilogue: the MMA produces h = v/2 directly (halving a bf16 is exact), see below
-                if (d.act == FCE_ACT_SILU) {
-                    const float lo = __uint_as_float(v << 16) * 0.5f, hi = __uint_as_float(v & 0xffff0000u) * 0.5f;
-                    v = (__float_as_uint(hi) & 0xffff0000u) | (__float_as_uint(lo) >> 16);
+                // bf16 weights -> fp16 B fragments, scaled by 256 for u8 tiles (which hold byte/256) and by 1/2 for the
+                // SiLU epilogue (the MMA then produces h = v/2 directly, see below); powers of two: exact
+                {
+                    const float sc = (sizeof(TI) == 1 ? 256.f : 1.f) *
+                                     (d.act == FCE_ACT_SILU ? 0.5f : 1.f);
+                    const __half2 h = __floats2half2_rn(__uint_as_float(v << 16) * sc, __uint_as_float(v & 0xffff0000u) * sc);
+                    v = *reinterpret_cast<const uint32_t*>(&h);
                 }
                 bf[ks][nt][hf] = v;
             }
@@ -231,10 +237,10 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_kernel(const fce_stem_d
 #pragma unroll
         for (int nt = 0; nt < NTILES; ++nt) {
             float c[4] = {bs[nt][0], bs[nt][1], bs[nt][0], bs[nt][1]};
-            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                          : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                          : "r"(a[0][0]), "r"(a[0][1]), "r"(a[0][2]), "r"(a[0][3]), "r"(bf[0][nt][0]), "r"(bf[0][nt][1]));
-            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                          : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                          : "r"(a[1][0]), "r"(a[1][1]), "r"(a[1][2]), "r"(a[1][3]), "r"(bf[1][nt][0]), "r"(bf[1][nt][1]));
             if (d.act == FCE_ACT_SILU) {  // c holds h = v/2: silu(v) = h + h*tanh(h), on packed pairs

@@ -1,3 +1,3 @@
 set -x
-python -m pytest tests/test_gpu_kernels.py -x -q -k "decode" 2>&1 | tail -3
-bash tools/gpu_job.sh r2f quick | tail -3 | cut -c1-300
+python -m pytest tests/test_gpu_kernels.py -x -q -k "stem" 2>&1 | tail -3
+bash tools/gpu_job.sh r2g quick | tail -3 | cut -c1-300
