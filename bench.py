@@ -328,6 +328,19 @@ def main():
                     "frac": round(ach / pk["hbm"], 4), "traffic": None, "peak_source": pk["src"],
                     "share_of_step": round(c["ms"] / total, 3), "launches_per_step": c["launches"],
                     "avg_launch_ms": round(c["ms"] / c["launches"], 4)}
+        # measured DRAM traffic of the dominant class (ncu capture of the same step, committed under profiles/):
+        # bytes per launch next to the algorithmic bytes per launch - a ratio well above 1 means wasted re-reads
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                tc = tj.get("classes", {}).get(fn)
+                if tc and tj.get("workload") == name:
+                    roof["traffic"] = round(tc["dram_bytes_per_step"] / c["launches"], 1)
+                    roof["traffic_unit"] = "bytes per launch (ncu dram__bytes_read+write, profiles/traffic.json)"
+                    roof["algorithmic_bytes_per_launch"] = round(c["bytes"] / c["launches"], 1)
+            except (OSError, ValueError, KeyError):
+                pass
         roof["classes"] = {
             k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total, 3), "launches": v["launches"],
                 **({"TFLOP/s": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] else {}),

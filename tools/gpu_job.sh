@@ -20,6 +20,10 @@ timeout 900 ncu --set full --clock-control none --import-source on --profile-fro
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
   -k regex:'dwconv|psa|nms|coord_pool|gate|bifpn|stem|decode|sppf|upsample|strip_attn|simt' -c 40 -f -o /tmp/bw_$TAG \
   python tools/profile_step.py > gpurun_out/ncu_bw_$TAG.log 2>&1; echo "ncu bw rc=$?"
+# DRAM bytes of every launch of one eager step -> profiles/traffic.json (bench.py's roofline.traffic)
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv \
+  --log-file gpurun_out/traffic_$TAG.csv python tools/profile_step.py > gpurun_out/ncu_t_$TAG.log 2>&1; echo "ncu traffic rc=$?"
+python tools/ncu_traffic.py gpurun_out/traffic_$TAG.csv gpurun_out/traffic_$TAG.json "$(python -c 'import bench; print(bench.WORKLOAD_NAME)')" > /dev/null
 for n in conv bw; do
   ncu -i /tmp/${n}_$TAG.ncu-rep --page raw --csv > gpurun_out/ncu_${n}_${TAG}_raw.csv 2>/dev/null
   ls -la /tmp/${n}_$TAG.ncu-rep
