@@ -302,7 +302,9 @@ def main():
         classes = {}
         pk = peaks()
         for (fn, args, n), ms in zip(ex._calls, acc):
-            c = classes.setdefault(n.fn, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, ideal=0.0))
+            # the fused Detect epilogues are launches of the same tcgen05 conv kernel: one class
+            cls = "fce_conv2d" if n.fn == "fce_conv2d_detect" else n.fn
+            c = classes.setdefault(cls, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, ideal=0.0))
             c["ms"] += ms
             # this launch's own roofline: the slower of its tensor time and its HBM time
             c["ideal"] += max(n.flops / (pk["tf_sustained"] * 1e12), n.bytes / (pk["hbm"] * 1e9)) * 1e3

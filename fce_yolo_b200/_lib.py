@@ -27,6 +27,10 @@ class ConvDesc(C.Structure):
                                    "in_layout")] + [("in_scale", f32), ("impl", i32)]
 
 
+class DetectEpiDesc(C.Structure):
+    _fields_ = [(n, i32) for n in ("mode", "A", "a_base", "rows", "reg_max")] + [("stride", f32)]
+
+
 class PackDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "H", "W", "Cin", "k", "stride", "Kpad", "in_dtype", "in_layout")]
 
@@ -103,6 +107,7 @@ _SIGS = {
     "fce_last_cuda_error": (C.c_char_p, []),
     "fce_device_ok": (C.c_int, []),
     "fce_conv2d": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "fce_conv2d_detect": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(DetectEpiDesc), _P, _P, _P, _P, _P]),
     "fce_stem_pack": (C.c_int, [C.POINTER(PackDesc), _P, _P, _P]),
     "fce_stem_conv": (C.c_int, [C.POINTER(StemDesc), _P, _P, _P, _P, _P]),
     "fce_match_predictions": (C.c_int, [_P, _P, _P, _P, _P, _P, i32, i32, i32, i32, _P, _P]),

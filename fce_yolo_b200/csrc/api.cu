@@ -7,7 +7,8 @@ static thread_local cudaError_t g_last_err = cudaSuccess;
 void set_cuda_error(cudaError_t e) { g_last_err = e; }
 
 int conv2d_simt(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
-int conv2d_tc(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+int conv2d_tc(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t,
+              const fce_detect_epi_desc* epi = nullptr);
 bool conv2d_tc_supported(const fce_conv_desc*, const void*, const void*, const void*, const void*);
 void conv_tc_set_profile(int on);
 void conv_halo_set_mode(int mode);
@@ -40,6 +41,28 @@ extern "C" int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, 
     if (d->impl == 2) return tc_ok ? conv2d_tc(d, x, w, bias, res, y, st) : FCE_ERR_UNSUPPORTED;
     if (d->impl == 0 && tc_ok) return conv2d_tc(d, x, w, bias, res, y, st);
     return conv2d_simt(d, x, w, bias, res, y, st);
+}
+
+// Last conv of a Detect branch with the decode fused into the tcgen05 epilogue (conv_tc.cu): y is the prediction
+// tensor [B, 4 + nc, A] fp32, not a logit map.  tcgen05 path only - there is no SIMT twin (the plan compiler keeps
+// the unfused fce_conv2d + fce_detect_decode route for every shape this entry point rejects).
+extern "C" int fce_conv2d_detect(const fce_conv_desc* d, const fce_detect_epi_desc* e, const void* x, const void* w,
+                                 const float* bias, float* y, void* stream) {
+    if (!d || !e || !x || !w || !bias || !y) return FCE_ERR_BAD_ARG;
+    if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0) return FCE_ERR_BAD_ARG;
+    if (e->mode != 1 && e->mode != 2) return FCE_ERR_BAD_ARG;
+    if (e->A <= 0 || e->a_base < 0 || e->a_base + d->H * d->W > e->A || e->rows < 4) return FCE_ERR_BAD_ARG;
+    if (d->k != 1 || d->stride != 1 || d->act != FCE_ACT_NONE) return FCE_ERR_UNSUPPORTED;
+    if (d->in_dtype != FCE_BF16 || d->w_dtype != FCE_BF16 || d->in_layout != FCE_NHWC || d->in_scale != 1.0f)
+        return FCE_ERR_UNSUPPORTED;
+    if (d->Cin % 16 || d->Cout % 16) return FCE_ERR_UNSUPPORTED;
+    if (e->mode == 1 && e->rows < 4 + d->Cout) return FCE_ERR_BAD_ARG;
+    if (e->mode == 2 && (e->reg_max != 16 || d->Cout != 64)) return FCE_ERR_UNSUPPORTED;
+    if (d->in_pitch % 8 || d->in_off % 8 || (((uintptr_t)x) & 15) || (((uintptr_t)w) & 15) || (((uintptr_t)y) & 3))
+        return FCE_ERR_ALIGNMENT;
+    fce_conv_desc dd = *d;
+    dd.out_dtype = FCE_F32;  // the epilogue writes fp32 straight from the accumulator
+    return conv2d_tc(&dd, x, w, bias, nullptr, y, (cudaStream_t)stream, e);
 }
 
 extern "C" void fce_conv_tc_set_profile(int on) {

@@ -60,6 +60,10 @@ struct TcParams {
     uint32_t desc_hi;  // upper 32 bits of the UMMA shared-memory descriptor (SBO, version, swizzle)
     uint32_t idesc;    // UMMA instruction descriptor
     int dbg;           // debug: bit 0 = producers skip the TMA loads (times the MMA + epilogue pipeline alone)
+    // Detect-head epilogues (fce_conv2d_detect): the accumulator never becomes a logit tensor in HBM
+    int epi_mode;      // 0 = plain; 1 = class scores -> y[b, 4 + n, a] = sigmoid; 2 = DFL boxes -> y[b, 0..3, a]
+    int epi_A, epi_abase, epi_rows;  // anchors per image, first anchor of this level, rows of y per image (4 + nc)
+    float epi_stride;
 };
 
 // Optional per-role cycle accounting (debug entry points fce_conv_tc_set_profile / fce_conv_tc_profile):
@@ -82,7 +86,7 @@ template <int KK, int S, bool PROF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcParams p, const float* __restrict__ bias,
-               const __nv_bfloat16* __restrict__ res) {
+               const __nv_bfloat16* __restrict__ res, float* __restrict__ ydet) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = base;
@@ -348,6 +352,67 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + my_acc * bn;
+            if (p.epi_mode != 0) {
+                // Detect head, last conv of a branch (head.py:94,103 -> :149-167): this thread's accumulator row IS the
+                // logit vector of anchor `rem` of image `bimg`; decode it here and store straight into the prediction
+                // tensor y[B, 4 + nc, A] (anchor-major rows: a warp's 32 pixels are 32 consecutive floats per channel).
+                const int hw = p.Ho * p.Wo;
+                const int mm = m_ok ? m : 0;
+                const int bimg = mm / hw, rem = mm - bimg * hw;
+                float* yb = ydet + (size_t)bimg * p.epi_rows * p.epi_A + p.epi_abase + rem;
+                const size_t A = (size_t)p.epi_A;
+                if (p.epi_mode == 1) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < bn; c0 += 16) {
+                        const int n = n0 + c0;
+                        if (n >= Cout) break;
+                        uint32_t v[16];
+                        tmem_ld16(t_row + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (m_ok && n + j < Cout)
+                                yb[(size_t)(4 + n + j) * A] = sigmoid_f(__uint_as_float(v[j]) + bias_s[n + j]);
+                    }
+                } else {
+                    // DFL (block.py:76-79): softmax over the 16 bins of each side, expectation, then dist2bbox
+                    // (tal.py:367-376) around the anchor centre (tal.py:352-364) and the level's stride
+                    float dist[4];
+#pragma unroll
+                    for (int sd = 0; sd < 4; ++sd) {
+                        uint32_t v[16];
+                        tmem_ld16(t_row + 16 * sd, v);
+                        tmem_ld_wait();
+                        float f[16], mx = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            f[j] = __uint_as_float(v[j]) + bias_s[16 * sd + j];
+                            mx = fmaxf(mx, f[j]);
+                        }
+                        float sum = 0.f, wsum = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float e = __expf(f[j] - mx);
+                            sum += e;
+                            wsum = fmaf(e, (float)j, wsum);
+                        }
+                        dist[sd] = __fdividef(wsum, sum);
+                    }
+                    const int ph = rem / p.Wo, pw = rem - ph * p.Wo;
+                    const float ax = (float)pw + 0.5f, ay = (float)ph + 0.5f;
+                    const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
+                    if (m_ok) {
+                        yb[0] = (x1 + x2) * 0.5f * p.epi_stride;
+                        yb[A] = (y1 + y2) * 0.5f * p.epi_stride;
+                        yb[2 * A] = (x2 - x1) * p.epi_stride;
+                        yb[3 * A] = (y2 - y1) * p.epi_stride;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * my_acc);
+                continue;
+            }
 #pragma unroll 1
             for (int sl = 0; sl < n_slabs; ++sl) {
                 const int c0 = sl * slab_cols;  // first column of the slab within the tile
@@ -452,10 +517,10 @@ int conv_halo_profile(long long* out, int n);
 int conv2d_halo(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
 
 int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res, void* y,
-              cudaStream_t st) {
+              cudaStream_t st, const fce_detect_epi_desc* epi) {
     if (!bias) return FCE_ERR_BAD_ARG;
     // thin 3x3 stride-1 convs: input strip resident in shared memory (conv_halo.cu)
-    if (conv2d_halo_supported(d, res != nullptr)) return conv2d_halo(d, x, w, bias, res, y, st);
+    if (!epi && conv2d_halo_supported(d, res != nullptr)) return conv2d_halo(d, x, w, bias, res, y, st);
     conv_halo_clear_last();
     const DriverApi& api = driver();
     if (!api.ok) return FCE_ERR_CUDA;
@@ -525,6 +590,14 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     p.act = d->act;
     p.out_f32 = d->out_dtype == FCE_F32;
     p.dbg = g_debug_flags;
+    if (epi) {
+        if (p.n_tiles != 1 && epi->mode == 2) return FCE_ERR_UNSUPPORTED;
+        p.epi_mode = epi->mode;
+        p.epi_A = epi->A;
+        p.epi_abase = epi->a_base;
+        p.epi_rows = epi->rows;
+        p.epi_stride = epi->stride;
+    }
     const uint32_t row_bytes = p.kc * 2;                                        // swizzle span = K-chunk row
     const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);  // UMMA LayoutType
     const uint32_t sbo = 8 * row_bytes;                                         // 8-row core-matrix group pitch
@@ -575,7 +648,9 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     }
 
     alignas(64) CUtensorMap tmC;
-    {
+    if (epi) {
+        tmC = tmA;  // never used for a store in the Detect epilogues; only prefetched
+    } else {
         const bool f32 = d->out_dtype == FCE_F32;
         const cuuint64_t gdim[2] = {(cuuint64_t)d->Cout, (cuuint64_t)M};
         const cuuint64_t gstr[1] = {(cuuint64_t)d->out_pitch * (f32 ? 4 : 2)};
@@ -590,7 +665,7 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     }
     const size_t smem = (size_t)p.stages * p.a_stage + p.b_total + NUM_EPI_WARPS * 2 * STG_BYTES + p.bias_bytes + 1024 + 256;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*,
-                             const __nv_bfloat16*);
+                             const __nv_bfloat16*, float*);
     // (KK, S) variants: S = 3 only with narrow K chunks
     static const KernelFn table[2][5] = {
         {conv_tc_kernel<1, 1, false>, conv_tc_kernel<2, 1, false>, conv_tc_kernel<4, 1, false>,
@@ -614,7 +689,8 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < kNumSMs ? total : kNumSMs;
     const __nv_bfloat16* rp = res ? reinterpret_cast<const __nv_bfloat16*>(res) + d->res_off : nullptr;
-    return launch_pdl(table[g_profile_on ? 1 : 0][variant], grid, NUM_THREADS, smem, st, tmA, tmB, tmC, p, bias, rp);
+    float* ydet = epi ? reinterpret_cast<float*>(y) : nullptr;
+    return launch_pdl(table[g_profile_on ? 1 : 0][variant], grid, NUM_THREADS, smem, st, tmA, tmB, tmC, p, bias, rp, ydet);
 }
 
 void conv_tc_set_profile(int on) {

@@ -351,11 +351,11 @@ extern "C" int fce_coord_pool(const fce_pool_desc* d, const void* x, float* stri
     const int cvt = (d->W <= 24 && d->C >= 32 * n) ? 32 : ((d->W <= 48 && d->C >= 16 * n) ? 16 : 8);
     const int cc = cvt * n;
     const int chunks = (d->C + cc - 1) / cc;
-    // bands: with at least one (image, chunk) pair per SM a single band is best - no workspace traffic, no finish
+    // bands: with (image, chunk) pairs for at least three quarters of the SMs a single band is best - no workspace traffic, no finish
     // kernel, and splitting the pairs further only re-slices the same two-CTAs-per-SM rounds; small batches get their
     // parallelism from the bands (never more than one per WS_ROWS rows)
     const int max_bands = (d->H + WS_ROWS - 1) / WS_ROWS;
-    int bands = d->B * chunks >= kNumSMs ? 1 : (4 * kNumSMs + d->B * chunks - 1) / (d->B * chunks);
+    int bands = d->B * chunks >= (kNumSMs * 3) / 4 ? 1 : (4 * kNumSMs + d->B * chunks - 1) / (d->B * chunks);
     bands = bands < 1 ? 1 : (bands > max_bands ? max_bands : bands);
     int band_rows = ((d->H + bands - 1) / bands + WS_ROWS - 1) / WS_ROWS * WS_ROWS;
     bands = (d->H + band_rows - 1) / band_rows;

@@ -44,27 +44,34 @@ __global__ void __launch_bounds__(NT) decode_kernel(const fce_decode_desc d, con
     float4* slab = dsm + warp * 32 * sp4;
     {
         const float4* src = reinterpret_cast<const float4*>(raws[lvl]) + ((size_t)b * hw + rem0) * pitch4;
-        int an = 0, q = lane;
-        while (q >= n4) { q -= n4; ++an; }
         // asynchronous 16-byte copies: all of a lane's ~36 requests are in flight at once (a register-staged loop
-        // serialises on each load's latency - in-order issue stalls at the first dependent shared-memory store)
+        // serialises on each load's latency - in-order issue stalls at the first dependent shared-memory store).
+        // Two commit groups: the DFL columns first, the class columns second, so the box math below runs while the
+        // class logits are still landing.
         const uint32_t slab_s = (uint32_t)__cvta_generic_to_shared(slab);
-        while (an < n_here) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slab_s + (uint32_t)(an * sp4 + q) * 16u),
-                         "l"(src + (size_t)an * pitch4 + q)
-                         : "memory");
-            q += 32;
-            while (q >= n4) { q -= n4; ++an; }
+        const int nbox4 = R;  // 4 * R floats of box logits = R float4
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            const int q0 = part ? nbox4 : 0, qn = part ? n4 - nbox4 : nbox4;  // column range [q0, q0 + qn)
+            int an = 0, q = lane;
+            while (q >= qn && an < n_here) { q -= qn; ++an; }
+            while (an < n_here) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slab_s + (uint32_t)(an * sp4 + q0 + q) * 16u),
+                             "l"(src + (size_t)an * pitch4 + q0 + q)
+                             : "memory");
+                q += 32;
+                while (q >= qn && an < n_here) { q -= qn; ++an; }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
     }
     __syncwarp();
-    if (lane >= n_here) return;
-    const int rem = rem0 + lane;
+    const bool active = lane < n_here;  // idle lanes of a ragged tail stay for the waits below (their copies feed others)
+    const int rem = rem0 + (active ? lane : 0);
     const int a = a_base + rem;
     const int ph = rem / d.W[lvl], pw = rem - ph * d.W[lvl];
-    const float4* p4 = slab + lane * sp4;
+    const float4* p4 = slab + (active ? lane : 0) * sp4;
     const float stride = d.stride[lvl];
 
     float dist[4];
@@ -95,10 +102,15 @@ __global__ void __launch_bounds__(NT) decode_kernel(const fce_decode_desc d, con
     const float ax = (float)pw + 0.5f, ay = (float)ph + 0.5f;
     const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
     const size_t yb = (size_t)b * (4 + d.nc) * A + a;
-    y[yb] = (x1 + x2) * 0.5f * stride;
-    y[yb + (size_t)A] = (y1 + y2) * 0.5f * stride;
-    y[yb + (size_t)2 * A] = (x2 - x1) * stride;
-    y[yb + (size_t)3 * A] = (y2 - y1) * stride;
+    if (active) {
+        y[yb] = (x1 + x2) * 0.5f * stride;
+        y[yb + (size_t)A] = (y1 + y2) * 0.5f * stride;
+        y[yb + (size_t)2 * A] = (x2 - x1) * stride;
+        y[yb + (size_t)3 * A] = (y2 - y1) * stride;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");  // class columns (every lane waits on its own copies ...
+    __syncwarp();                                          // ... and then on everybody else's)
+    if (!active) return;
     const float4* pc = p4 + R;
     for (int c = 0; c < d.nc; c += 4) {
         const float4 t = pc[c >> 2];

@@ -153,6 +153,8 @@ class Executor(Arena):
                     args.append(C.c_void_p(base + p.buf.offset + p.byte_offset()))
                 elif isinstance(p, torch.Tensor):
                     args.append(C.c_void_p(p.data_ptr()))
+                elif isinstance(p, C.Structure):  # a second descriptor (kept alive by the node)
+                    args.append(C.byref(p))
                 elif p is None:
                     args.append(C.c_void_p(0))
                 else:
@@ -194,7 +196,8 @@ class Executor(Arena):
 
     # -- NMS overlapped with the next call's forward -------------------------------------------------
     # The batched NMS is a latency-bound tail (one CTA per image: 64 of 148 SMs at batch 64, ~5 % of the step).  In
-    # overlap mode the plan is replayed as three graphs: [everything before the decode] and [decode] on the caller's
+    # overlap mode the plan is replayed as three graphs: [everything before the first writer of y] and [the writers of y:
+    # the decode, or the six fused Detect epilogues] on the caller's
     # stream, [NMS] on a side stream, so the NMS of call i runs underneath the forward of call i+1.  The only buffer
     # both touch is the decoded prediction tensor y: the decode of call i+1 waits for the NMS of call i (an event that
     # fired ~3 ms earlier in steady state).  NMS reads / writes persistent buffers only (y, its workspace, det, keep,
@@ -202,8 +205,13 @@ class Executor(Arena):
     # themselves after `nms_done` (join(), or work on `tail_stream`).
     def enable_overlap(self):
         fns = [n.fn for n in self.plan.nodes]
-        if len(fns) < 3 or fns[-1] != "fce_nms" or fns[-2] != "fce_detect_decode":
-            raise RuntimeError("NMS overlap needs a plan that ends with fce_detect_decode, fce_nms")
+        ybuf = self.plan.outputs["y"].buf if "y" in self.plan.outputs else None
+        # first node that writes the prediction tensor: fce_detect_decode, or the first fused Detect epilogue
+        k = next((i for i, nd in enumerate(self.plan.nodes) if any(v.buf is ybuf for v in nd.writes)), None)
+        if len(fns) < 3 or fns[-1] != "fce_nms" or k is None or k >= len(fns) - 1:
+            raise RuntimeError("NMS overlap needs a plan that ends with the prediction writers and fce_nms")
+        if any(any(v.buf is ybuf for v in nd.reads) for nd in self.plan.nodes[:k]):
+            raise RuntimeError("NMS overlap: a node before the prediction writers reads the prediction tensor")
         if not self.use_graph:
             raise RuntimeError("NMS overlap needs CUDA graphs")
         with torch.cuda.device(self.device):
@@ -215,7 +223,7 @@ class Executor(Arena):
             self._warm = True
             n = len(self._calls)
             self._segs = []
-            for lo, hi in ((0, n - 2), (n - 2, n - 1), (n - 1, n)):
+            for lo, hi in ((0, k), (k, n - 1), (n - 1, n)):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     sp = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -103,6 +103,7 @@ class PlanError(ValueError):
 
 
 class Plan:
+    fuse_decode = False  # set by compile_model: Detect's last convs decode in their epilogue (fce_conv2d_detect)
     FUSED_COORDATT_MLP = True  # False: cv1 / cv_h / cv_w as three strip convs (A/B timing, cross-check)
     FUSED_STEM = True  # False: stem = fce_stem_pack + K=32 tcgen05 conv (kept for A/B timing and as a cross-check)
 
@@ -506,13 +507,22 @@ class Plan:
         nl, nc, R = m.nl, m.nc, m.reg_max
         if nl > 4:
             raise PlanError("at most 4 detection levels")
-        raws = []
+        xs = [self.materialize(x) for x in xs]
+        strides = [float(s) for s in m.stride.tolist()]
+        A = sum(x.H * x.W for x in xs)
+        # Fused decode: the last 1x1 conv of each branch decodes in its tcgen05 epilogue and writes the prediction
+        # tensor directly - no fp32 logit maps, no decode launch.  bf16 plans whose head fits fce_conv2d_detect.
+        fused = (self.fuse_decode and self.act_dt == L.BF16 and self.impl != 1 and R == 16 and nc % 16 == 0
+                 and all(m.cv2[i][2].in_channels % 16 == 0 and m.cv3[i][2].in_channels % 16 == 0 for i in range(nl)))
+        raws, tails = [], []
         for i, x in enumerate(xs):
-            x = self.materialize(x)
-            raw = self.new_buf(x.H, x.W, 4 * R + nc, dtype=L.F32, persistent=True)
+            raw = None if fused else self.new_buf(x.H, x.W, 4 * R + nc, dtype=L.F32, persistent=True)
             t = self.conv(m.cv2[i][0], x, tag=f"{tag}.cv2.{i}.0")
             t = self.conv(m.cv2[i][1], t, tag=f"{tag}.cv2.{i}.1")
-            self.conv(m.cv2[i][2], t, dst=raw.ch(0, 4 * R), tag=f"{tag}.cv2.{i}.2")
+            if fused:
+                tails.append((m.cv2[i][2], t, 2, i, f"{tag}.cv2.{i}.2"))
+            else:
+                self.conv(m.cv2[i][2], t, dst=raw.ch(0, 4 * R), tag=f"{tag}.cv2.{i}.2")
             c = x
             for j in (0, 1):
                 blk = m.cv3[i][j]
@@ -520,12 +530,32 @@ class Plan:
                     raise PlanError("legacy Detect heads (dense 3x3 class branch) are outside the path")
                 c = self.dwconv(blk[0], c, tag=f"{tag}.cv3.{i}.{j}.0")
                 c = self.conv(blk[1], c, tag=f"{tag}.cv3.{i}.{j}.1")
-            self.conv(m.cv3[i][2], c, dst=raw.ch(4 * R, 4 * R + nc), tag=f"{tag}.cv3.{i}.2")
-            raws.append(raw)
-        A = sum(r.H * r.W for r in raws)
+            if fused:
+                tails.append((m.cv3[i][2], c, 1, i, f"{tag}.cv3.{i}.2"))
+            else:
+                self.conv(m.cv3[i][2], c, dst=raw.ch(4 * R, 4 * R + nc), tag=f"{tag}.cv3.{i}.2")
+                raws.append(raw)
         y = self.new_buf(1, 4 + nc, A, dtype=L.F32, persistent=True)  # logical [B, 4+nc, A]
+        if fused:
+            # the six y-writing convs go LAST: in overlap mode they form the short segment that waits for the previous
+            # call's NMS to be done with y (engine.enable_overlap)
+            a_base = [sum(v.H * v.W for v in xs[:i]) for i in range(nl)]
+            for conv_m, t, mode, i, tg in tails:
+                w, b, k, s_, g, a = self.conv_params(conv_m)
+                if (k, s_, g, a) != (1, 1, 1, L.ACT_NONE):
+                    raise PlanError(f"{tg}: the Detect branch must end in a bare 1x1 conv")
+                Cout, Cin = w.shape[0], w.shape[1]
+                d = L.ConvDesc(B=t.B, H=t.H, W=t.W, Cin=Cin, Cout=Cout, in_pitch=t.pitch, in_off=0, out_pitch=0, out_off=0,
+                               res_pitch=0, res_off=0, k=1, stride=1, act=L.ACT_NONE, in_dtype=t.dtype, w_dtype=L.BF16,
+                               out_dtype=L.F32, in_layout=L.NHWC, in_scale=1.0, impl=self.impl)
+                e = L.DetectEpiDesc(mode=mode, A=A, a_base=a_base[i], rows=4 + nc, reg_max=R, stride=strides[i])
+                wp = self._w(w.permute(0, 2, 3, 1), torch.bfloat16)
+                out_rows = 4 if mode == 2 else nc
+                self.add(Node("fce_conv2d_detect", d, [e, t, wp, self._w(b), y], reads=[t], writes=[y], tag=tg,
+                              flops=2.0 * t.B * t.H * t.W * Cout * Cin,
+                              bytes=t.B * t.H * t.W * (Cin * 2.0 + out_rows * 4.0) + Cout * Cin * 2.0))
+            return y, []
         d = L.DecodeDesc(B=self.B, nl=nl, nc=nc, reg_max=R)
-        strides = [float(s) for s in m.stride.tolist()]
         for i, r in enumerate(raws):
             d.H[i], d.W[i], d.stride[i], d.raw_pitch[i] = r.H, r.W, strides[i], r.pitch
         ptrs = raws + [None] * (4 - nl) + [y]
@@ -587,13 +617,14 @@ class Plan:
 
 
 def compile_model(model, batch: int, height: int, width: int, precision: str, device, impl: int = 0,
-                  input_u8: bool = False, nms: dict | None = None) -> Plan:
+                  input_u8: bool = False, nms: dict | None = None, fuse_decode: bool = False) -> Plan:
     """Whole-graph plan of a DetectionModel (mirror or reference): restates the routing of
     BaseModel._predict_once (tasks.py:172-188) at compile time."""
     layers = list(model.model)
     if height % 32 or width % 32:
         raise PlanError("image height/width must be multiples of 32 (reference loaders.py:603-609)")
     p = Plan(batch, precision, device, impl)
+    p.fuse_decode = bool(fuse_decode)  # predict-only plans: Detect's raw logit maps (x_list, head.py:124) are not kept
     first = layers[0]
     if type(first).__name__ != "Conv":
         raise PlanError("the graph must start with a Conv stem")

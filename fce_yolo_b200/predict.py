@@ -31,7 +31,8 @@ def scale_meta(img1_shape, img0_shapes) -> np.ndarray:
 class Predictor:
     def __init__(self, model, batch: int, imgsz=(640, 640), precision: str = "bf16", device=None, conf: float = 0.25,
                  iou: float = 0.7, max_det: int = 300, agnostic_nms: bool = False, multi_label: bool = False,
-                 input_u8: bool = True, use_graph: bool = True, overlap_nms: bool = False):
+                 input_u8: bool = True, use_graph: bool = True, overlap_nms: bool = False,
+                 fuse_decode: bool = True):
         if isinstance(imgsz, int):
             imgsz = (imgsz, imgsz)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -43,7 +44,8 @@ class Predictor:
         with torch.cuda.device(self.device):
             plan = compile_model(model, batch, imgsz[0], imgsz[1], precision, self.device, input_u8=input_u8,
                                  nms=dict(conf=conf, iou=iou, max_det=max_det, agnostic=agnostic_nms,
-                                          multi_label=multi_label))
+                                          multi_label=multi_label),
+                                 fuse_decode=fuse_decode)  # predict never returns Detect's raw logit maps
             self.ex = Executor(plan, use_graph=use_graph)
             self.stream = torch.cuda.Stream(self.device)
             self.stream_ = self.stream

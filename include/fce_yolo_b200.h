@@ -185,6 +185,21 @@ size_t fce_coord_pool_workspace(const fce_pool_desc* d);
  * eight BiCoordCrossAtt projections (:246-249,258,264-268,276) - are fce_conv2d calls on the fp32 strip
  * seen as a [1, rows, 1, C] map (k = 1, all dtypes FCE_F32, act NONE / SILU / SIGMOID). */
 
+/* Last conv of a Detect branch with the decode fused into the epilogue (head.py:94,103 + :149-167, DFL block.py:76-79,
+ * anchors / dist2bbox tal.py:352-376): the [B, H, W, Cin] feature map goes through the 1x1 conv on the tensor cores and
+ * the accumulator row of each pixel is decoded in registers and stored into the prediction tensor y [B, rows, A] fp32 -
+ * the logit maps never exist in HBM.
+ *   mode 1 (cv3[i][2], Cout = nc):      y[b, 4 + n, a_base + p] = sigmoid(conv + bias)
+ *   mode 2 (cv2[i][2], Cout = 4 * 16):  y[b, 0..3, a_base + p]  = (cx, cy, w, h) * stride from the softmax-integral
+ * p = h * W + w.  bf16 NHWC input, bf16 OHWI weights, k = 1 only; anything else returns FCE_ERR_UNSUPPORTED and the
+ * caller uses fce_conv2d (fp32 logits) + fce_detect_decode. */
+typedef struct {
+    int32_t mode, A, a_base, rows, reg_max;
+    float stride;
+} fce_detect_epi_desc;
+int fce_conv2d_detect(const fce_conv_desc* d, const fce_detect_epi_desc* e, const void* x, const void* w,
+                      const float* bias, float* y, void* stream);
+
 /* CoordAtt gate MLP on the pooled strips, fused (fce_block.py:104-113 - cv1 with its folded BN + SiLU, then cv_h /
  * cv_w + sigmoid): out[r, :] = act2(W2 act1(W1 strip[r, :] + b1) + b2) with (W2, b2) = (w_h, b_h) for rows
  * [0, rows_h) and (w_w, b_w) for rows [rows_h, rows_h + rows_w).  All operands fp32, 16-byte aligned, C / oup /

@@ -150,6 +150,22 @@ class Interp(Arena):
         o = (a @ v).permute(0, 2, 1, 3).reshape(d.B, d.N, nh * hd)
         self.t(out).copy_(o.view(self.t(out).shape))
 
+    def _fce_conv2d_detect(self, d, p):
+        """1x1 conv + the slice of Detect._inference this branch owns, written into y [B, 4+nc, A]."""
+        from oracle.fce_oracle import detect_decode
+
+        e, x, w, b, yv = p
+        xin = self.t(View(x.buf, x.c0, x.C, d.B, d.H, d.W, x.row0)).permute(0, 3, 1, 2).float()
+        o = F.conv2d(xin, w.float().permute(0, 3, 1, 2), b.float())  # [B, Cout, H, W]
+        yb = yv.buf
+        y = self._flat(yb).view(yb.B, yb.W, yb.C)
+        sl = slice(e.a_base, e.a_base + d.H * d.W)
+        if e.mode == 1:
+            y[:, 4:4 + d.Cout, sl] = torch.sigmoid(o.reshape(d.B, d.Cout, -1))
+        else:
+            full = torch.cat([o, torch.zeros(d.B, 1, d.H, d.W)], 1)  # dummy class row for the oracle's splitter
+            y[:, 0:4, sl] = detect_decode([full], [e.stride], e.reg_max)[:, :4]
+
     def _fce_detect_decode(self, d, p):
         from oracle.fce_oracle import detect_decode
 

@@ -307,3 +307,53 @@ def test_detect_decode_vs_oracle(lib, B, shapes, nc, pad):
     got = y.cpu()
     assert (got[:, :4] - ref[:, :4]).abs().max().item() <= 2e-3
     assert (got[:, 4:] - ref[:, 4:]).abs().max().item() <= 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ fused Detect epilogues
+@pytest.mark.parametrize("B,H,W,Cin,nc", [(2, 80, 80, 128, 80), (3, 20, 20, 256, 80), (1, 13, 9, 64, 16), (5, 40, 40, 64, 80)])
+def test_conv2d_detect_vs_torch(lib, B, H, W, Cin, nc):
+    """fce_conv2d_detect: the last 1x1 conv of a Detect branch with the decode in its tcgen05 epilogue (head.py:94,103,
+    149-167).  mode 1 writes sigmoid class scores, mode 2 the DFL boxes, both straight into y[B, 4+nc, A] at the
+    level's anchor offset; the rest of y must stay untouched.  bf16 operands, fp32 accumulation: scores within 2e-3 of
+    a torch fp32 conv on the same bf16 operands (accumulation order), boxes within 2e-2 pixel."""
+    from oracle.fce_oracle import detect_decode
+    l, L = lib
+    g = torch.Generator().manual_seed(B + H + W + Cin + nc)
+    A, a_base, stride = H * W + 37, 21, 16.0
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16).cuda()
+    y = torch.full((B, 4 + nc, A), -3.0).cuda()
+    refs = {}
+    for mode, Cout in ((1, nc), (2, 64)):
+        w = (torch.randn(Cout, 1, 1, Cin, generator=g) / math.sqrt(Cin) * 2).to(torch.bfloat16).cuda()
+        b = torch.randn(Cout, generator=g).cuda()
+        d = L.ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=Cout, in_pitch=Cin, in_off=0, out_pitch=0, out_off=0, res_pitch=0,
+                       res_off=0, k=1, stride=1, act=L.ACT_NONE, in_dtype=L.BF16, w_dtype=L.BF16, out_dtype=L.F32,
+                       in_layout=L.NHWC, in_scale=1.0, impl=0)
+        e = L.DetectEpiDesc(mode=mode, A=A, a_base=a_base, rows=4 + nc, reg_max=16, stride=stride)
+        st = l.fce_conv2d_detect(C.byref(d), C.byref(e), C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()),
+                                 C.c_void_p(b.data_ptr()), C.c_void_p(y.data_ptr()), _stream())
+        L.check(st, "fce_conv2d_detect")
+        refs[mode] = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b)  # [B, Cout, H, W]
+    torch.cuda.synchronize()
+    sl = slice(a_base, a_base + H * W)
+    cls_ref = torch.sigmoid(refs[1].reshape(B, nc, -1))
+    assert (y[:, 4:, sl] - cls_ref).abs().max().item() <= 2e-3
+    full = torch.cat([refs[2], torch.zeros(B, 1, H, W, device=y.device)], 1).cpu()
+    box_ref = detect_decode([full], [stride], 16)[:, :4]
+    assert (y[:, :4, sl].cpu() - box_ref).abs().max().item() <= 2e-2
+    assert torch.all(y[:, :, :a_base] == -3.0) and torch.all(y[:, :, a_base + H * W:] == -3.0)
+
+
+def test_conv2d_detect_rejects_what_it_cannot_fuse(lib):
+    l, L = lib
+    t = torch.zeros(1 << 16, dtype=torch.bfloat16).cuda()
+    p = C.c_void_p(t.data_ptr())
+    d = L.ConvDesc(B=1, H=8, W=8, Cin=64, Cout=64, in_pitch=64, in_off=0, out_pitch=0, out_off=0, res_pitch=0, res_off=0,
+                   k=1, stride=1, act=L.ACT_NONE, in_dtype=L.BF16, w_dtype=L.BF16, out_dtype=L.F32, in_layout=L.NHWC,
+                   in_scale=1.0, impl=0)
+    e = L.DetectEpiDesc(mode=2, A=64, a_base=0, rows=84, reg_max=8, stride=8.0)
+    assert l.fce_conv2d_detect(C.byref(d), C.byref(e), p, p, p, p, _stream()) == -2   # reg_max other than 16
+    e.reg_max, e.a_base = 16, 1
+    assert l.fce_conv2d_detect(C.byref(d), C.byref(e), p, p, p, p, _stream()) == -1   # level does not fit into A
+    e.a_base, d.k = 0, 3
+    assert l.fce_conv2d_detect(C.byref(d), C.byref(e), p, p, p, p, _stream()) == -2   # only the 1x1 tail convs

@@ -53,3 +53,27 @@ def test_overlap_needs_graphs_and_nms_tail():
 
     p = Predictor(_model(), 1, 64, overlap_nms=True, use_graph=False)
     assert not p.overlap  # silently in-line without graphs: same results, no side stream
+
+
+def test_fused_decode_matches_decode_kernel():
+    """Predictor(fuse_decode=True) - Detect's last convs decode in their tcgen05 epilogue, no logit maps, no decode
+    launch - against the unfused plan (fp32 logits + fce_detect_decode) on the same batch: class scores within 2e-6
+    (approximate ex2 / rcp), boxes within 2e-2 pixel, and the same detections after NMS."""
+    from fce_yolo_b200.predict import Predictor
+
+    model = _model()
+    B, S = 4, 640
+    plain = Predictor(model, B, S, precision="bf16", conf=0.05, fuse_decode=False)
+    fused = Predictor(model, B, S, precision="bf16", conf=0.05, fuse_decode=True)
+    fns = [n.fn for n in fused.ex.plan.nodes]
+    assert "fce_detect_decode" not in fns and fns.count("fce_conv2d_detect") == 6
+    assert fused.launches_per_call == plain.launches_per_call - 1
+    g = torch.Generator().manual_seed(11)
+    x = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory()
+    d0, c0 = [t.clone() for t in plain.infer(x)]
+    d1, c1 = [t.clone() for t in fused.infer(x)]
+    y0, y1 = plain.ex.outputs()[0], fused.ex.outputs()[0]
+    assert (y0[:, 4:] - y1[:, 4:]).abs().max().item() <= 2e-6
+    assert (y0[:, :4] - y1[:, :4]).abs().max().item() <= 2e-2
+    assert torch.equal(c0, c1) and int(c0.sum()) > 0
+    assert torch.allclose(d0, d1, atol=2e-2, rtol=0)

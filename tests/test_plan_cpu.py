@@ -89,3 +89,30 @@ def test_cca_bad_heads_fails_at_build():
 
     with pytest.raises(RuntimeError):
         M.CoordCrossAtt(512, 512, 22, 2)  # mip = 23, heads = 2: the reference dies in forward (fce_block.py:166)
+
+
+def test_fused_decode_plan_structure_and_values():
+    """compile_model(fuse_decode=True) in bf16: Detect's last convs become fce_conv2d_detect nodes placed LAST (they
+    are the short tail that waits for the previous call's NMS in overlap mode), there is no decode node and no logit
+    map; the interpreted plan gives the same predictions as the unfused plan."""
+    case = FORWARD_CASES["n_fce_64"]
+    cfg, scale = load_cfg(case)
+    model = DetectionModel(cfg, scale=scale).fuse().eval()
+    load_synthetic(model, case["seed"])
+    x = synth_images(case["img_seed"], case["batch"], case["size"], case["size"])
+    plans = {f: compile_model(model, case["batch"], case["size"], case["size"], "bf16", torch.device("cpu"), fuse_decode=f)
+             for f in (False, True)}
+    fns = [n.fn for n in plans[True].nodes]
+    assert "fce_detect_decode" not in fns and fns[-6:] == ["fce_conv2d_detect"] * 6
+    assert plans[True].outputs["raw"] == [] and len(plans[False].outputs["raw"]) == 3
+    assert [n.fn for n in plans[False].nodes].count("fce_detect_decode") == 1
+    # fp32 plans keep the unfused route (the fused epilogue exists on the tensor-core path only)
+    assert "fce_conv2d_detect" not in [n.fn for n in compile_model(model, 1, 64, 64, "fp32", torch.device("cpu"),
+                                                                    fuse_decode=True).nodes]
+    ys = {}
+    for f, plan in plans.items():
+        it = Interp(plan, reuse_memory=True)
+        it.input_tensor().copy_(x)
+        it.run()
+        ys[f] = it.outputs()[0].float()
+    assert rel_max(ys[True], ys[False]) < 1e-3  # same bf16 activations; only the logits skip their fp32 round trip

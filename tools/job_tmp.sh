@@ -1,4 +1,4 @@
-python tools/conv_bench.py --prof > gpurun_out/cb_prof_r2h.log 2>&1
-python tools/conv_bench.py --dbg 1 > gpurun_out/cb_dbg1_r2h.log 2>&1
-python tools/conv_bench.py --dbg 6 > gpurun_out/cb_dbg6_r2h.log 2>&1
-cat gpurun_out/cb_prof_r2h.log
+set -x
+python -m pytest tests/test_gpu_kernels.py -x -q -k "detect" 2>&1 | tail -5
+python -m pytest tests/test_gpu_overlap.py -x -q 2>&1 | tail -5
+bash tools/gpu_job.sh r3c quick | tail -3 | cut -c1-300
