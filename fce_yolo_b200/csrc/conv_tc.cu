@@ -124,7 +124,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < (int)(p.bias_bytes >> 2); i += NUM_THREADS) bias_s[i] = i < p.Cout ? bias[i] * epi_bias_scale(p.act) : 0.f;  // pre-scaled for epi_math16
+    {   // bias pre-scaled for the epilogue: x 1/2 for SiLU (epi_math16), x -log2(e) for the fused class sigmoid
+        const float bsc = p.epi_mode == 1 ? -1.4426950408889634f : epi_bias_scale(p.act);
+        for (int i = threadIdx.x; i < (int)(p.bias_bytes >> 2); i += NUM_THREADS) bias_s[i] = i < p.Cout ? bias[i] * bsc : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -369,10 +372,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint32_t v[16];
                         tmem_ld16(t_row + c0, v);
                         tmem_ld_wait();
+                        // sigmoid(acc + b) = 1 / (1 + 2^(-(acc + b) log2 e)) on packed pairs; the bias sits in shared
+                        // memory pre-multiplied by -log2 e (see the prologue): FFMA2, 2 x ex2, FADD2, 2 x rcp per pair
+                        float2 o[8];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (m_ok && n + j < Cout)
-                                yb[(size_t)(4 + n + j) * A] = sigmoid_f(__uint_as_float(v[j]) + bias_s[n + j]);
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 bq = reinterpret_cast<const float4*>(bias_s + n)[q];
+                            const float2 nl2e = make_float2(-1.4426950408889634f, -1.4426950408889634f);
+                            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
+                                                         nl2e, make_float2(bq.x, bq.y));
+                            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])),
+                                                         nl2e, make_float2(bq.z, bq.w));
+                            const float2 one = make_float2(1.f, 1.f);
+                            const float2 d0 = __fadd2_rn(make_float2(ex2_fast(t0.x), ex2_fast(t0.y)), one);
+                            const float2 d1 = __fadd2_rn(make_float2(ex2_fast(t1.x), ex2_fast(t1.y)), one);
+                            o[2 * q] = make_float2(rcp_fast(d0.x), rcp_fast(d0.y));
+                            o[2 * q + 1] = make_float2(rcp_fast(d1.x), rcp_fast(d1.y));
+                        }
+                        if (m_ok) {  // Cout is a multiple of 16: every column of the group is a real class
+                            float* yc = yb + (size_t)(4 + n) * A;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                yc[(size_t)(2 * j) * A] = o[j].x;
+                                yc[(size_t)(2 * j + 1) * A] = o[j].y;
+                            }
+                        }
                     }
                 } else {
                     // DFL (block.py:76-79): softmax over the 16 bins of each side, expectation, then dist2bbox

@@ -110,6 +110,16 @@ __device__ __forceinline__ float tanh_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // One MUFU per element: silu(v) = h + h*tanh(h), sigmoid(v) = 0.5 + 0.5*tanh(h), h = v/2.  tanh.approx has
 // 2^-11 relative error - below the bf16 rounding applied to the result.
 __device__ __forceinline__ float act_fast(float v, int act) {
