@@ -24,7 +24,8 @@ i32, f32, f64, i64 = C.c_int32, C.c_float, C.c_double, C.c_int64
 class ConvDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "H", "W", "Cin", "Cout", "in_pitch", "in_off", "out_pitch", "out_off",
                                    "res_pitch", "res_off", "k", "stride", "act", "in_dtype", "w_dtype", "out_dtype",
-                                   "in_layout")] + [("in_scale", f32), ("impl", i32)]
+                                   "in_layout")] + [("in_scale", f32), ("impl", i32), ("weighted", i32), ("out_scale", f32),
+                                                    ("res_scale", f32), ("res_up", i32)]
 
 
 class DetectEpiDesc(C.Structure):

@@ -38,6 +38,12 @@ extern "C" int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, 
     if (d->in_layout == FCE_NCHW && d->in_dtype == FCE_BF16) return FCE_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const bool tc_ok = conv2d_tc_supported(d, x, w, res, y);
+    const bool weighted = d->weighted != 0 || d->res_up != 0;
+    if (weighted) {  // BiFPN-fused epilogue: 1x1 convs on the tcgen05 kernel only
+        if (d->res_up && (!res || (d->H & 1) || (d->W & 1))) return FCE_ERR_BAD_ARG;
+        if (!tc_ok || d->k != 1 || d->impl == 1 || d->out_dtype != FCE_BF16) return FCE_ERR_UNSUPPORTED;
+        return conv2d_tc(d, x, w, bias, res, y, st);
+    }
     if (d->impl == 2) return tc_ok ? conv2d_tc(d, x, w, bias, res, y, st) : FCE_ERR_UNSUPPORTED;
     if (d->impl == 0 && tc_ok) return conv2d_tc(d, x, w, bias, res, y, st);
     return conv2d_simt(d, x, w, bias, res, y, st);

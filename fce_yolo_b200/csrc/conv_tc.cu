@@ -64,6 +64,9 @@ struct TcParams {
     int epi_mode;      // 0 = plain; 1 = class scores -> y[b, 4 + n, a] = sigmoid; 2 = DFL boxes -> y[b, 0..3, a]
     int epi_A, epi_abase, epi_rows;  // anchors per image, first anchor of this level, rows of y per image (4 + nc)
     float epi_stride;
+    // weighted-sum epilogue (BiFPN fused into its realign conv): y = out_scale * act(..) + res_scale * res
+    float out_scale, res_scale;
+    int res_up;        // res is a half-resolution map read through a nearest 2x upsample
 };
 
 // Optional per-role cycle accounting (debug entry points fce_conv_tc_set_profile / fce_conv_tc_profile):
@@ -347,7 +350,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m_warp = mt * BM + quarter * 32;
             const int m = m_warp + lane;
             const bool m_ok = m < p.M;
-            const __nv_bfloat16* rrow = res + (size_t)m * p.res_pitch;
+            size_t ridx = (size_t)m;
+            if (p.res_up && has_res && m_ok) {  // nearest 2x: output pixel (h, w) reads low-resolution pixel (h/2, w/2)
+                const int hw = p.Ho * p.Wo;
+                const int bimg = m / hw, rem = m - bimg * hw;
+                const int ph = rem / p.Wo, pw = rem - ph * p.Wo;
+                ridx = ((size_t)bimg * (p.Ho >> 1) + (ph >> 1)) * (p.Wo >> 1) + (pw >> 1);
+            }
+            const __nv_bfloat16* rrow = res + ridx * p.res_pitch;
             {
                 PROF_T0();
                 mbar_wait(tfull0 + 8 * my_acc, my_phase);
@@ -473,12 +483,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     float f[16];
                     uint32_t o[8];
-                    epi_math16(v0, bias_s + n, act, has_res, r0, r1, f);
+                    epi_math16(v0, bias_s + n, act, has_res, r0, r1, f, p.out_scale, p.res_scale);
                     pack16(f, o);
                     st_shared_v4(rowp + ((0 ^ swz) << 4), o[0], o[1], o[2], o[3]);
                     st_shared_v4(rowp + ((1 ^ swz) << 4), o[4], o[5], o[6], o[7]);
                     if (two) {
-                        epi_math16(v1, bias_s + n + 16, act, has_res, r2, r3, f);
+                        epi_math16(v1, bias_s + n + 16, act, has_res, r2, r3, f, p.out_scale, p.res_scale);
                         pack16(f, o);
                         st_shared_v4(rowp + ((2 ^ swz) << 4), o[0], o[1], o[2], o[3]);
                         st_shared_v4(rowp + ((3 ^ swz) << 4), o[4], o[5], o[6], o[7]);
@@ -614,6 +624,9 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     p.act = d->act;
     p.out_f32 = d->out_dtype == FCE_F32;
     p.dbg = g_debug_flags;
+    p.out_scale = d->weighted ? d->out_scale : 1.f;
+    p.res_scale = d->weighted ? d->res_scale : 1.f;
+    p.res_up = d->res_up;
     if (epi) {
         if (p.n_tiles != 1 && epi->mode == 2) return FCE_ERR_UNSUPPORTED;
         p.epi_mode = epi->mode;

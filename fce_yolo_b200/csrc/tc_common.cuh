@@ -180,8 +180,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
 // (Measured alternatives: ex2+rcp = two MUFU ops; f16x2 tanh halves the MUFU work but costs more issue slots in
 // conversions and was 5% slower - the epilogue is issue-bound, not MUFU-bound.)
 __host__ __device__ __forceinline__ float epi_bias_scale(int act) { return act == FCE_ACT_SILU ? 0.5f : 1.f; }
+// osc / rsc: weighted-sum epilogue y = osc * act(..) + rsc * res (BiFPN fusion); both 1 for the plain conv.
 __device__ __forceinline__ void epi_math16(const uint32_t* v, const float* sbias, int act, bool has_res, uint4 r0,
-                                           uint4 r1, float* f) {
+                                           uint4 r1, float* f, float osc = 1.f, float rsc = 1.f) {
     float2 o[8];
     if (act == FCE_ACT_SILU) {
         const float2 half2 = make_float2(0.5f, 0.5f);
@@ -209,11 +210,24 @@ __device__ __forceinline__ void epi_math16(const uint32_t* v, const float* sbias
             for (int i = 0; i < 8; ++i) o[i] = make_float2(act_fast(o[i].x, act), act_fast(o[i].y, act));
         }
     }
+    const bool scaled = osc != 1.f || rsc != 1.f;  // warp-uniform
     if (has_res) {
         const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        if (!scaled) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            o[i] = __fadd2_rn(o[i], make_float2(__uint_as_float(rr[i] << 16), __uint_as_float(rr[i] & 0xffff0000u)));
+            for (int i = 0; i < 8; ++i)
+                o[i] = __fadd2_rn(o[i], make_float2(__uint_as_float(rr[i] << 16), __uint_as_float(rr[i] & 0xffff0000u)));
+        } else {
+            const float2 o2 = make_float2(osc, osc), r2 = make_float2(rsc, rsc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                o[i] = __ffma2_rn(o[i], o2, __fmul2_rn(make_float2(__uint_as_float(rr[i] << 16),
+                                                                   __uint_as_float(rr[i] & 0xffff0000u)), r2));
+        }
+    } else if (scaled) {
+        const float2 o2 = make_float2(osc, osc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = __fmul2_rn(o[i], o2);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {

@@ -104,6 +104,7 @@ class PlanError(ValueError):
 
 class Plan:
     fuse_decode = False  # set by compile_model: Detect's last convs decode in their epilogue (fce_conv2d_detect)
+    FUSED_BIFPN = True  # False: realign convs + fce_bifpn_fuse as separate launches (A/B timing, cross-check)
     FUSED_COORDATT_MLP = True  # False: cv1 / cv_h / cv_w as three strip convs (A/B timing, cross-check)
     FUSED_STEM = True  # False: stem = fce_stem_pack + K=32 tcgen05 conv (kept for A/B timing and as a cross-check)
 
@@ -176,7 +177,8 @@ class Plan:
         return w, b, k, conv.stride[0], conv.groups, act
 
     def conv(self, m, x: View, dst: View | None = None, res: View | None = None, out_dtype=None, act=None,
-             w_override=None, b_override=None, in_layout=L.NHWC, in_scale=1.0, tag="") -> View:
+             w_override=None, b_override=None, in_layout=L.NHWC, in_scale=1.0, tag="", out_scale=1.0, res_scale=1.0,
+             res_up=False) -> View:
         w, b, k, s, g, a = self.conv_params(m) if m is not None else (w_override, b_override, 1, 1, 1, L.ACT_NONE)
         if w_override is not None:
             w, b = w_override, b_override
@@ -205,8 +207,10 @@ class Plan:
         d = L.ConvDesc(B=x.B, H=x.H, W=x.W, Cin=Cin, Cout=Cout, in_pitch=x.pitch, in_off=0, out_pitch=dst.pitch,
                        out_off=0, res_pitch=res.pitch if res is not None else 0, res_off=0, k=k, stride=s, act=a,
                        in_dtype=x.dtype, w_dtype=w_dt, out_dtype=dst.dtype, in_layout=in_layout, in_scale=in_scale,
-                       impl=self.impl)
-        if res is not None and (res.C != Cout or res.dtype != dst.dtype or (res.H, res.W) != (Ho, Wo)):
+                       impl=self.impl, weighted=1 if (out_scale != 1.0 or res_scale != 1.0) else 0,
+                       out_scale=float(out_scale), res_scale=float(res_scale), res_up=1 if res_up else 0)
+        rs = 2 if res_up else 1
+        if res is not None and (res.C != Cout or res.dtype != dst.dtype or (res.H * rs, res.W * rs) != (Ho, Wo)):
             raise PlanError(f"{tag}: residual view does not match the conv output")
         self.add(Node("fce_conv2d", d, [x, wp, bp, res, dst], reads=[x] + ([res] if res is not None else []),
                       writes=[dst], tag=tag, flops=2.0 * x.B * Ho * Wo * Cout * Cin * k * k,
@@ -375,12 +379,33 @@ class Plan:
         w = torch.relu(m.w.detach().float().cpu())
         wn = (w / (w.sum() + m.epsilon)).tolist()  # fce_block.py:55-56
         views, ups = [], []
+        # Fusable: full-resolution inputs whose realign is a 1x1 Conv on the tensor-core path; at most ONE other operand
+        # (each fused epilogue adds a single residual).  pending = [(index, conv, input view)], others = [(view, w, up)].
+        def fusable(i, x):
+            r = m.realign_convs[i]
+            return (self.FUSED_BIFPN and self.act_dt == L.BF16 and self.impl != 1 and not isinstance(x, LazyUp)
+                    and not isinstance(r, nn.Identity) and self.conv_params(r)[2:5] == (1, 1, 1)
+                    and x.C % 16 == 0 and self.conv_params(r)[0].shape[0] % 16 == 0)
+        n_fus = sum(1 for i, x in enumerate(xs) if fusable(i, x))
+        # Two-input nodes only: measured on the three-input node (two chained fused convs, s scale, batch 64) the epilogue
+        # residual reads cost more than the separate fusion launch saves (67 -> 72 us), while the two-input nodes gain
+        # (108 -> 80 us at 80x80, 31 -> 21 us at 20x20)
+        fuse = len(xs) == 2 and n_fus >= 1
+        pending, others = [], []
         for i, x in enumerate(xs):
             r = m.realign_convs[i]
             up = isinstance(x, LazyUp)
             v = x.src if up else x
+            if fuse and fusable(i, x):
+                pending.append((i, r, v))
+                # geometry checks below see the conv's OUTPUT shape
+                views.append(View(v.buf, 0, self.conv_params(r)[0].shape[0], v.B, v.H, v.W))
+                ups.append(0)
+                continue
             if not isinstance(r, nn.Identity):
                 v = self.conv(r, v, tag=f"{tag}.realign.{i}")  # at low resolution when upsampled
+            if fuse:
+                others.append((v, wn[i], up))
             views.append(v)
             ups.append(1 if up else 0)
         H, W = (views[0].H * 2, views[0].W * 2) if ups[0] else (views[0].H, views[0].W)
@@ -388,6 +413,21 @@ class Plan:
         for v, u in zip(views, ups):
             if (v.H * (2 if u else 1), v.W * (2 if u else 1), v.C) != (H, W, C):
                 raise PlanError(f"{tag}: BiFPN inputs disagree after realignment")
+        if pending:
+            # Weighted sum inside the realign convs' epilogues (bf16 plans): the first pending conv folds in the one
+            # other operand (identity or upsampled view), every later one the running sum; the last writes dst.  The
+            # realigned maps are never stored and re-read, and there is no separate fusion launch.
+            acc, acc_w, acc_up = (others[0][0], others[0][1], others[0][2]) if others else (None, 1.0, False)
+            for j, (i, r, v) in enumerate(pending):
+                last = j == len(pending) - 1
+                out = dst if (last and dst is not None) else self.new_buf(H, W, C)
+                if acc is None:  # first of several convs and nothing to fold yet: plain conv, scaled later
+                    acc, acc_w, acc_up = self.conv(r, v, tag=f"{tag}.realign.{i}"), wn[i], False
+                    continue
+                acc = self.conv(r, v, dst=out, res=acc, out_scale=wn[i], res_scale=acc_w, res_up=acc_up,
+                                tag=f"{tag}.realign.{i}+fuse")
+                acc_w, acc_up = 1.0, False
+            return acc
         if dst is None:
             dst = self.new_buf(H, W, C)
         d = L.BifpnDesc(B=self.B, H=H, W=W, C=C, n=len(xs), out_pitch=dst.pitch, out_off=0, dtype=dst.dtype)

@@ -56,7 +56,8 @@ int fce_device_ok(void);
  * Replaces Conv.forward_fuse (ultralytics/nn/modules/conv.py:80-89) and every bare nn.Conv2d on
  * the path (fce_block.py:95,233 identity; head.py:94,103), with the Bottleneck / PSABlock
  * residual adds (block.py:474-476, 1352-1353) and torch.cat/chunk fused as view offsets.
- * Weights are OHWI: w[co][kh][kw][ci], dense.  y = act(conv(x*in_scale) + bias) (+ res).
+ * Weights are OHWI: w[co][kh][kw][ci], dense.  y = act(conv(x*in_scale) + bias) (+ res), optionally as a weighted sum
+ * (out_scale / res_scale / res_up below).
  * impl: 0 = auto, 1 = force the fp32-accurate SIMT kernel, 2 = force the tcgen05 kernel.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -71,6 +72,14 @@ typedef struct {
     int32_t in_layout;        /* fce_layout; FCE_NCHW only for the network input image */
     float in_scale;           /* 1.0, or 1/255 for u8 images */
     int32_t impl;
+    /* Weighted-sum epilogue (BiFPN_Concat.forward, fce_block.py:55-63, fused into its realign conv), when
+     * weighted != 0:   y = out_scale * act(conv(x) + bias) + res_scale * res     (a scale of 0 is legitimate: relu(w) = 0)
+     * res_up = 1: res is a [B, Ho/2, Wo/2, Cout] map read through a nearest 2x upsample (the Upsample layer in front of
+     * the BiFPN node, yolo11-fce.yaml:40,44).  weighted / res_up: 1x1 convs on the tcgen05 path only
+     * (FCE_ERR_UNSUPPORTED otherwise). */
+    int32_t weighted;
+    float out_scale, res_scale;
+    int32_t res_up;
 } fce_conv_desc;
 
 int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res,

@@ -29,7 +29,8 @@ def test_desc_struct_sizes_match_header():
     names = {"fce_conv_desc": L.ConvDesc, "fce_stem_desc": L.StemDesc, "fce_letterbox_item": L.LetterboxItem, "fce_pack_desc": L.PackDesc, "fce_dwconv_desc": L.DwconvDesc, "fce_sppf_desc": L.SppfDesc,
              "fce_upsample_desc": L.UpsampleDesc, "fce_bifpn_desc": L.BifpnDesc, "fce_copy_desc": L.CopyDesc,
              "fce_pool_desc": L.PoolDesc, "fce_strip_attn_desc": L.StripAttnDesc, "fce_gate_desc": L.GateDesc,
-             "fce_psa_desc": L.PsaDesc, "fce_decode_desc": L.DecodeDesc, "fce_nms_desc": L.NmsDesc}
+             "fce_psa_desc": L.PsaDesc, "fce_decode_desc": L.DecodeDesc, "fce_nms_desc": L.NmsDesc,
+             "fce_coordatt_mlp_desc": L.CoordAttMlpDesc, "fce_detect_epi_desc": L.DetectEpiDesc}
     src = '#include <stdio.h>\n#include "fce_yolo_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:

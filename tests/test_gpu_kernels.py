@@ -357,3 +357,48 @@ def test_conv2d_detect_rejects_what_it_cannot_fuse(lib):
     assert l.fce_conv2d_detect(C.byref(d), C.byref(e), p, p, p, p, _stream()) == -1   # level does not fit into A
     e.a_base, d.k = 0, 3
     assert l.fce_conv2d_detect(C.byref(d), C.byref(e), p, p, p, p, _stream()) == -2   # only the 1x1 tail convs
+
+
+# ------------------------------------------------------------------------------------------------ BiFPN-fused conv epilogue
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 80, 80, 256, 128), (3, 20, 20, 512, 256), (1, 6, 10, 64, 32)])
+@pytest.mark.parametrize("res_up", [0, 1])
+@pytest.mark.parametrize("scales", [(0.705, 0.295), (0.0, 0.43), (0.57, 1.0)])
+def test_conv_weighted_sum_epilogue(lib, B, H, W, Cin, Cout, res_up, scales):
+    """fce_conv2d with weighted / res_up: y = out_scale * SiLU(conv1x1(x) + b) + res_scale * res, res optionally a
+    half-resolution map read through a nearest 2x upsample - BiFPN_Concat's weighted sum (fce_block.py:55-63) inside
+    its realign conv.  A zero weight (relu(w) = 0) is a real case.  bf16 in / out: 2^-7 relative + accumulation noise."""
+    l, L = lib
+    g = torch.Generator().manual_seed(B + H + Cin + Cout + res_up)
+    osc, rsc = scales
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(Cout, 1, 1, Cin, generator=g) / math.sqrt(Cin)).to(torch.bfloat16).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    rh, rw = (H // 2, W // 2) if res_up else (H, W)
+    res = torch.randn(B, rh, rw, Cout, generator=g).to(torch.bfloat16).cuda()
+    y = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16).cuda()
+    d = L.ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=Cout, in_pitch=Cin, in_off=0, out_pitch=Cout, out_off=0, res_pitch=Cout,
+                   res_off=0, k=1, stride=1, act=L.ACT_SILU, in_dtype=L.BF16, w_dtype=L.BF16, out_dtype=L.BF16,
+                   in_layout=L.NHWC, in_scale=1.0, impl=0, weighted=1, out_scale=osc, res_scale=rsc, res_up=res_up)
+    st = l.fce_conv2d(C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
+                      C.c_void_p(res.data_ptr()), C.c_void_p(y.data_ptr()), _stream())
+    L.check(st, "fce_conv2d weighted")
+    torch.cuda.synchronize()
+    conv = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b))
+    r = res.float().permute(0, 3, 1, 2)
+    if res_up:
+        r = F.interpolate(r, scale_factor=2, mode="nearest")
+    ref = (osc * conv + rsc * r).permute(0, 2, 3, 1)
+    err = (y.float() - ref).abs()
+    assert (err <= 2 ** -7 * ref.abs() + 2e-2).all(), err.max().item()
+
+
+def test_conv_weighted_sum_needs_the_tensor_core_1x1(lib):
+    l, L = lib
+    t = torch.zeros(1 << 16, dtype=torch.bfloat16).cuda()
+    p = C.c_void_p(t.data_ptr())
+    d = L.ConvDesc(B=1, H=8, W=8, Cin=32, Cout=32, in_pitch=32, in_off=0, out_pitch=32, out_off=0, res_pitch=32, res_off=0,
+                   k=3, stride=1, act=L.ACT_SILU, in_dtype=L.BF16, w_dtype=L.BF16, out_dtype=L.BF16, in_layout=L.NHWC,
+                   in_scale=1.0, impl=0, weighted=1, out_scale=0.5, res_scale=0.5, res_up=0)
+    assert l.fce_conv2d(C.byref(d), p, p, p, p, p, _stream()) == -2      # 3x3: no weighted epilogue
+    d.k, d.res_up, d.H = 1, 1, 7
+    assert l.fce_conv2d(C.byref(d), p, p, p, p, p, _stream()) == -1      # odd map cannot be a 2x upsample

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from cases import FORWARD_CASES, MODULE_CASES
-from helpers import golden, load_cfg, rel_max
+from helpers import golden, load_cfg, rel_l2, rel_max
 from plan_interp import Interp
 from test_oracle_golden import module_case_io
 
@@ -116,3 +116,38 @@ def test_fused_decode_plan_structure_and_values():
         it.run()
         ys[f] = it.outputs()[0].float()
     assert rel_max(ys[True], ys[False]) < 1e-3  # same bf16 activations; only the logits skip their fp32 round trip
+
+
+@pytest.mark.parametrize("name", ["n_fce_64", "s_coordatt_64", "m_bifpn_64"])
+def test_bifpn_fused_into_realign_convs(name):
+    """bf16 plans fold BiFPN_Concat's weighted sum (fce_block.py:55-63) into the epilogue of its full-resolution
+    realign convs (fce_conv_desc.out_scale / res_scale / res_up).  Same predictions as the separate
+    fce_bifpn_fuse launches up to bf16 rounding of the intermediates; nodes without a fusable conv keep the kernel."""
+    from fce_yolo_b200.plan import Plan
+
+    case = FORWARD_CASES[name]
+    cfg, scale = load_cfg(case)
+    model = DetectionModel(cfg, scale=scale).fuse().eval()
+    load_synthetic(model, case["seed"])
+    x = synth_images(case["img_seed"], case["batch"], case["size"], case["size"])
+    ys, counts = {}, {}
+    for fused in (False, True):
+        Plan.FUSED_BIFPN = fused
+        try:
+            plan = compile_model(model, case["batch"], case["size"], case["size"], "bf16", torch.device("cpu"))
+        finally:
+            Plan.FUSED_BIFPN = True
+        counts[fused] = sum(1 for n in plan.nodes if n.fn == "fce_bifpn_fuse")
+        it = Interp(plan, reuse_memory=False)  # layer outputs are read back after the run
+        it.input_tensor().copy_(x)
+        it.run()
+        bif = [i for i, m in enumerate(model.model) if type(m).__name__ == "BiFPN_Concat"]
+        ys[fused] = (it.outputs()[0].float(), [it.nchw(plan.layer_out[i]).float() for i in bif])
+    assert counts[False] == 4 and counts[True] <= counts[False]
+    if name != "m_bifpn_64":  # m scale: every input but one is an Identity realign (SURVEY A.1-3)
+        assert counts[True] < counts[False]
+    # the first BiFPN node sees identical inputs in both plans: only the rounding of the intermediates differs
+    assert rel_max(ys[True][1][0], ys[False][1][0]) < 1e-2
+    for a, b in zip(ys[True][1], ys[False][1]):
+        assert rel_l2(a, b) < 2e-2
+    assert rel_l2(ys[True][0], ys[False][0]) < 5e-2  # end to end: two bf16 evaluation orders of the same graph
