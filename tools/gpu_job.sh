@@ -18,7 +18,7 @@ timeout 900 ncu --set full --clock-control none --import-source on --profile-fro
   -k regex:'conv_tc|conv_halo' -c 14 -f -o /tmp/conv_$TAG python tools/profile_step.py --nodes gpurun_out/nodes_$TAG.csv \
   > gpurun_out/ncu_conv_$TAG.log 2>&1; echo "ncu conv rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k regex:'dwconv|psa|nms|coord_pool|gate|bifpn|stem|decode|sppf|upsample|strip_attn|simt' -c 40 -f -o /tmp/bw_$TAG \
+  -k regex:'dwconv|psa|nms|coord_pool|coordatt_mlp|gate|bifpn|stem|decode|sppf|upsample|strip_attn|simt' -c 40 -f -o /tmp/bw_$TAG \
   python tools/profile_step.py > gpurun_out/ncu_bw_$TAG.log 2>&1; echo "ncu bw rc=$?"
 # DRAM bytes of every launch of one eager step -> profiles/traffic.json (bench.py's roofline.traffic)
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv \
