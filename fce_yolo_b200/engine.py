@@ -161,6 +161,7 @@ class Executor(Arena):
                     args.append(C.c_size_t(int(p)))
             self._calls.append((fn, args, n))
         self.use_graph = use_graph
+        self._side_streams = {}  # branch id -> torch stream (plans with Node.stream > 0, graph mode only)
         self.graph = None
         self._warm = False
         self.launches_per_run = len(self._calls)
@@ -173,6 +174,44 @@ class Executor(Arena):
             if st != 0:
                 L.check(st, f"{n.fn} [{n.tag}]")
 
+    def _launch_branched(self, lo: int, hi: int):
+        """Launches nodes [lo, hi) with the plan's side branches (Node.stream > 0) on side streams, ordered by events
+        derived from Plan.dependencies().  Called under CUDA-graph capture, where the events become graph edges: e.g.
+        the Detect chains of the fine levels run concurrently with the small-map layers that finish the neck.  Every
+        side stream is joined back into the current stream before returning."""
+        main = torch.cuda.current_stream(self.device)
+        deps = self.plan.dependencies(lo, hi)
+        stream_of = {i: self.plan.nodes[i].stream for i in range(lo, hi)}
+        if not any(stream_of.values()):
+            sp = C.c_void_p(main.cuda_stream)
+            for fn, args, n in self._calls[lo:hi]:
+                st = fn(*args, sp)
+                if st != 0:
+                    L.check(st, f"{n.fn} [{n.tag}]")
+            return
+        needed = {j for i in range(lo, hi) for j in deps[i] if stream_of[j] != stream_of[i]}
+        side, events, used = self._side_streams, {}, set()
+        for i in range(lo, hi):
+            fn, args, n = self._calls[i]
+            k = stream_of[i]
+            st_obj = main if k == 0 else side.setdefault(k, torch.cuda.Stream(self.device))
+            cross = [j for j in deps[i] if stream_of[j] != k]
+            for j in cross:
+                st_obj.wait_event(events[j])
+            if k and k not in used:
+                used.add(k)
+                if not cross:  # a branch must descend from the capturing stream
+                    st_obj.wait_stream(main)
+            rc = fn(*args, C.c_void_p(st_obj.cuda_stream))
+            if rc != 0:
+                L.check(rc, f"{n.fn} [{n.tag}]")
+            if i in needed:
+                ev = torch.cuda.Event()
+                ev.record(st_obj)
+                events[i] = ev
+        for k in used:
+            main.wait_stream(side[k])
+
     def run(self):
         stream = torch.cuda.current_stream(self.device)
         if not self._warm:
@@ -182,7 +221,7 @@ class Executor(Arena):
             if self.use_graph:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._launch_all(torch.cuda.current_stream(self.device).cuda_stream)
+                    self._launch_branched(0, len(self._calls))
                 self.graph = g
                 self.graph.replay()  # outputs of this call come from the replayed graph
             return
@@ -226,11 +265,7 @@ class Executor(Arena):
             for lo, hi in ((0, k), (k, n - 1), (n - 1, n)):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    sp = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-                    for fn, args, node in self._calls[lo:hi]:
-                        st = fn(*args, sp)
-                        if st != 0:
-                            L.check(st, f"{node.fn} [{node.tag}]")
+                    self._launch_branched(lo, hi)
                 self._segs.append(g)
             self.nms_done.record(stream)
         self.overlap = True

@@ -17,6 +17,7 @@ classes in fce_yolo_b200.modules and the reference's own ultralytics instances (
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -96,6 +97,8 @@ class Node:
     tag: str = ""
     flops: float = 0.0      # algorithmic FLOPs (2*MAC) for convs
     bytes: float = 0.0      # algorithmic bytes for bandwidth kernels
+    stream: int = 0         # 0 = the caller's stream; k > 0 = side branch k of the captured graph (engine.Executor)
+    disjoint: str = ""      # nodes sharing a non-empty key write DISJOINT parts of a common buffer (no WAW edge)
 
 
 class PlanError(ValueError):
@@ -104,6 +107,8 @@ class PlanError(ValueError):
 
 class Plan:
     fuse_decode = False  # set by compile_model: Detect's last convs decode in their epilogue (fce_conv2d_detect)
+    # Detect's conv chains as concurrent branches of the captured graph (fused-decode plans); FCE_HEAD_STREAMS=0/1 overrides
+    HEAD_STREAMS = os.environ.get("FCE_HEAD_STREAMS", "0") == "1"
     FUSED_BIFPN = True  # False: realign convs + fce_bifpn_fuse as separate launches (A/B timing, cross-check)
     FUSED_COORDATT_MLP = True  # False: cv1 / cv_h / cv_w as three strip convs (A/B timing, cross-check)
     FUSED_STEM = True  # False: stem = fce_stem_pack + K=32 tcgen05 conv (kept for A/B timing and as a cross-check)
@@ -117,6 +122,7 @@ class Plan:
         self.device = device
         self.impl = impl
         self.bufs: list[Buf] = []
+        self.cur_stream = 0     # stream id stamped on the nodes being added (Detect branches use 1..2*nl)
         self.nodes: list[Node] = []
         self.weights: list[torch.Tensor] = []  # keeps packed device tensors alive
         self.layer_out: dict[int, object] = {}
@@ -140,12 +146,45 @@ class Plan:
 
     def add(self, node: Node):
         idx = len(self.nodes)
+        node.stream = self.cur_stream
         for v in node.reads + node.writes:
             b = v.buf
             if b.first < 0:
                 b.first = idx
             b.last = idx
+            if node.stream:  # touched by a concurrent branch: never recycled by the sequential lifetime packing
+                b.persistent = True
         self.nodes.append(node)
+
+    def dependencies(self, lo: int = 0, hi: int | None = None):
+        """deps[i] = indices j < i (both inside [lo, hi)) that node i must be ordered after: RAW, WAR and WAW on whole
+        buffers, except WAW between nodes that declare the same `disjoint` key.  Used by the executor to turn the side
+        branches into graph edges; conservative (buffer granularity), so a missing edge is impossible."""
+        hi = len(self.nodes) if hi is None else hi
+        writers, readers, deps = {}, {}, {}
+        for i in range(lo, hi):
+            n = self.nodes[i]
+            d = set()
+            for v in n.reads:
+                d.update(writers.get(id(v.buf), ()))
+            for v in n.writes:
+                key = id(v.buf)
+                d.update(readers.get(key, ()))
+                for j in writers.get(key, ()):
+                    if not (n.disjoint and self.nodes[j].disjoint == n.disjoint):
+                        d.add(j)
+            d.discard(i)
+            deps[i] = d
+            for v in n.reads:
+                readers.setdefault(id(v.buf), []).append(i)
+            for v in n.writes:
+                key = id(v.buf)
+                if n.disjoint and all(self.nodes[j].disjoint == n.disjoint for j in writers.get(key, ())):
+                    writers.setdefault(key, []).append(i)   # co-writers of disjoint parts
+                else:
+                    writers[key] = [i]
+                    readers[key] = []
+        return deps
 
     # ------------------------------------------------------------------ conv family
     @staticmethod
@@ -555,8 +594,13 @@ class Plan:
         fused = (self.fuse_decode and self.act_dt == L.BF16 and self.impl != 1 and R == 16 and nc % 16 == 0
                  and all(m.cv2[i][2].in_channels % 16 == 0 and m.cv3[i][2].in_channels % 16 == 0 for i in range(nl)))
         raws, tails = [], []
+        # Concurrent branches: the 2 * nl conv chains of the head are independent of each other and, for the finer
+        # levels, of the rest of the neck - each gets its own branch of the captured graph (HEAD_STREAMS), so the big P3
+        # chains run underneath the latency-bound small-map layers that finish the neck.
+        branch = (lambda i, b: 1 + 2 * i + b) if (self.HEAD_STREAMS and fused) else (lambda i, b: 0)
         for i, x in enumerate(xs):
             raw = None if fused else self.new_buf(x.H, x.W, 4 * R + nc, dtype=L.F32, persistent=True)
+            self.cur_stream = branch(i, 0)
             t = self.conv(m.cv2[i][0], x, tag=f"{tag}.cv2.{i}.0")
             t = self.conv(m.cv2[i][1], t, tag=f"{tag}.cv2.{i}.1")
             if fused:
@@ -564,6 +608,7 @@ class Plan:
             else:
                 self.conv(m.cv2[i][2], t, dst=raw.ch(0, 4 * R), tag=f"{tag}.cv2.{i}.2")
             c = x
+            self.cur_stream = branch(i, 1)
             for j in (0, 1):
                 blk = m.cv3[i][j]
                 if len(blk) != 2:
@@ -575,6 +620,7 @@ class Plan:
             else:
                 self.conv(m.cv3[i][2], c, dst=raw.ch(4 * R, 4 * R + nc), tag=f"{tag}.cv3.{i}.2")
                 raws.append(raw)
+            self.cur_stream = 0
         y = self.new_buf(1, 4 + nc, A, dtype=L.F32, persistent=True)  # logical [B, 4+nc, A]
         if fused:
             # the six y-writing convs go LAST: in overlap mode they form the short segment that waits for the previous
@@ -591,9 +637,12 @@ class Plan:
                 e = L.DetectEpiDesc(mode=mode, A=A, a_base=a_base[i], rows=4 + nc, reg_max=R, stride=strides[i])
                 wp = self._w(w.permute(0, 2, 3, 1), torch.bfloat16)
                 out_rows = 4 if mode == 2 else nc
+                self.cur_stream = branch(i, 0 if mode == 2 else 1)
                 self.add(Node("fce_conv2d_detect", d, [e, t, wp, self._w(b), y], reads=[t], writes=[y], tag=tg,
                               flops=2.0 * t.B * t.H * t.W * Cout * Cin,
-                              bytes=t.B * t.H * t.W * (Cin * 2.0 + out_rows * 4.0) + Cout * Cin * 2.0))
+                              bytes=t.B * t.H * t.W * (Cin * 2.0 + out_rows * 4.0) + Cout * Cin * 2.0,
+                              disjoint="detect-y"))  # each tail owns its rows / anchor range of y
+                self.cur_stream = 0
             return y, []
         d = L.DecodeDesc(B=self.B, nl=nl, nc=nc, reg_max=R)
         for i, r in enumerate(raws):

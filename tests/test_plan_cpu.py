@@ -151,3 +151,47 @@ def test_bifpn_fused_into_realign_convs(name):
     for a, b in zip(ys[True][1], ys[False][1]):
         assert rel_l2(a, b) < 2e-2
     assert rel_l2(ys[True][0], ys[False][0]) < 5e-2  # end to end: two bf16 evaluation orders of the same graph
+
+
+def test_detect_branches_and_dependencies():
+    """Fused-decode plans put the 2 * nl Detect conv chains on side branches (Node.stream 1..6).  Plan.dependencies()
+    must order every chain after the neck node that produces its level (and after nothing later), chain nodes after
+    their predecessor, the six tails only after their own chain (they write disjoint parts of y), and the NMS after all
+    tails; buffers touched by a branch are excluded from the sequential lifetime packing."""
+    from fce_yolo_b200.plan import Plan
+
+    case = FORWARD_CASES["n_fce_64"]
+    cfg, scale = load_cfg(case)
+    model = DetectionModel(cfg, scale=scale).fuse().eval()
+    saved, Plan.HEAD_STREAMS = Plan.HEAD_STREAMS, True
+    try:
+        plan = compile_model(model, 2, 64, 64, "bf16", torch.device("cpu"), fuse_decode=True,
+                             nms=dict(conf=0.25, iou=0.7, max_det=300))
+    finally:
+        Plan.HEAD_STREAMS = saved
+    nodes, deps = plan.nodes, plan.dependencies()
+    by_stream = {}
+    for i, n in enumerate(nodes):
+        by_stream.setdefault(n.stream, []).append(i)
+    assert sorted(by_stream) == [0, 1, 2, 3, 4, 5, 6]
+    level_of = {1: "model.18", 2: "model.18", 3: "model.21", 4: "model.21", 5: "model.24", 6: "model.24"}
+    for k in range(1, 7):
+        chain = by_stream[k]
+        assert nodes[chain[-1]].fn == "fce_conv2d_detect" and len(chain) == (3 if k % 2 else 5)
+        (src,) = deps[chain[0]]
+        assert nodes[src].stream == 0 and nodes[src].tag.startswith(level_of[k])
+        for a, b in zip(chain, chain[1:]):
+            assert deps[b] == {a}
+        for i in chain:
+            for v in nodes[i].reads + nodes[i].writes:
+                assert v.buf.persistent
+    assert nodes[-1].fn == "fce_nms" and {by_stream[k][-1] for k in range(1, 7)} <= deps[len(nodes) - 1]
+    # main-stream nodes never wait for a branch (except the NMS)
+    for i in by_stream[0][:-1]:
+        assert all(nodes[j].stream == 0 for j in deps[i])
+    # a sub-range (the overlap mode's second graph: the six tails) has no internal edges
+    k = min(i for i, n in enumerate(nodes) if n.fn == "fce_conv2d_detect")
+    sub = plan.dependencies(k, len(nodes) - 1)
+    assert all(not d for d in sub.values())
+    # unfused plans stay on one stream
+    assert all(n.stream == 0 for n in compile_model(model, 2, 64, 64, "bf16", torch.device("cpu")).nodes)
