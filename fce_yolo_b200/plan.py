@@ -107,8 +107,12 @@ class PlanError(ValueError):
 
 class Plan:
     fuse_decode = False  # set by compile_model: Detect's last convs decode in their epilogue (fce_conv2d_detect)
-    # Detect's conv chains as concurrent branches of the captured graph (fused-decode plans); FCE_HEAD_STREAMS=0/1 overrides
-    HEAD_STREAMS = os.environ.get("FCE_HEAD_STREAMS", "0") == "1"
+    # Detect's conv chains as concurrent branches of the captured graph (fused-decode plans).  None = automatic: on for
+    # small workloads, where the step is a chain of latency-bound launches (measured, yolo11s-fce 640^2: batch 1
+    # 0.714 -> 0.614 ms), off for large batches, where every kernel already fills the GPU and concurrent persistent
+    # kernels only time-slice (batch 64: 3.157 -> 3.195 ms).  FCE_HEAD_STREAMS=0/1 or Plan.HEAD_STREAMS = bool overrides.
+    HEAD_STREAMS = {"0": False, "1": True}.get(os.environ.get("FCE_HEAD_STREAMS", ""), None)
+    HEAD_STREAMS_MAX_PIXELS = 8 * 640 * 640  # automatic mode: batch * H * W of the network input
     FUSED_BIFPN = True  # False: realign convs + fce_bifpn_fuse as separate launches (A/B timing, cross-check)
     FUSED_COORDATT_MLP = True  # False: cv1 / cv_h / cv_w as three strip convs (A/B timing, cross-check)
     FUSED_STEM = True  # False: stem = fce_stem_pack + K=32 tcgen05 conv (kept for A/B timing and as a cross-check)
@@ -597,7 +601,10 @@ class Plan:
         # Concurrent branches: the 2 * nl conv chains of the head are independent of each other and, for the finer
         # levels, of the rest of the neck - each gets its own branch of the captured graph (HEAD_STREAMS), so the big P3
         # chains run underneath the latency-bound small-map layers that finish the neck.
-        branch = (lambda i, b: 1 + 2 * i + b) if (self.HEAD_STREAMS and fused) else (lambda i, b: 0)
+        hs = self.HEAD_STREAMS
+        if hs is None:
+            hs = self.B * xs[0].H * xs[0].W * int(strides[0]) ** 2 <= self.HEAD_STREAMS_MAX_PIXELS
+        branch = (lambda i, b: 1 + 2 * i + b) if (hs and fused) else (lambda i, b: 0)
         for i, x in enumerate(xs):
             raw = None if fused else self.new_buf(x.H, x.W, 4 * R + nc, dtype=L.F32, persistent=True)
             self.cur_stream = branch(i, 0)

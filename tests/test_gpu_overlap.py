@@ -77,3 +77,34 @@ def test_fused_decode_matches_decode_kernel():
     assert (y0[:, :4] - y1[:, :4]).abs().max().item() <= 2e-2
     assert torch.equal(c0, c1) and int(c0.sum()) > 0
     assert torch.allclose(d0, d1, atol=2e-2, rtol=0)
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_head_branches_match_single_stream(overlap):
+    """Plan.HEAD_STREAMS: the six Detect conv chains captured as concurrent branches of the CUDA graph (event edges from
+    Plan.dependencies()).  Same kernels on the same data in a different schedule: predictions and detections must be
+    BIT-IDENTICAL to the single-stream graph, over a stream of different batches, with and without the NMS overlap."""
+    from fce_yolo_b200.plan import Plan
+    from fce_yolo_b200.predict import Predictor
+
+    model = _model()
+    B, S = 4, 640
+    saved = Plan.HEAD_STREAMS
+    preds = {}
+    try:
+        for hs in (False, True):
+            Plan.HEAD_STREAMS = hs
+            preds[hs] = Predictor(model, B, S, precision="bf16", conf=0.05, overlap_nms=overlap)
+    finally:
+        Plan.HEAD_STREAMS = saved
+    assert max(n.stream for n in preds[True].ex.plan.nodes) == 6 and max(n.stream for n in preds[False].ex.plan.nodes) == 0
+    g = torch.Generator().manual_seed(5)
+    total = 0
+    for it in range(5):
+        x = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory()
+        d0, c0 = [t.clone() for t in preds[False].infer(x)]
+        d1, c1 = [t.clone() for t in preds[True].infer(x)]
+        assert torch.equal(c0, c1) and torch.equal(d0, d1), it
+        assert torch.equal(preds[False].ex.outputs()[0], preds[True].ex.outputs()[0]), it
+        total += int(c0.sum())
+    assert total > 0
