@@ -189,13 +189,23 @@ class Executor(Arena):
                 if st != 0:
                     L.check(st, f"{n.fn} [{n.tag}]")
             return
-        needed = {j for i in range(lo, hi) for j in deps[i] if stream_of[j] != stream_of[i]}
+        # cross-stream edges only (same-stream order is implicit); per foreign stream the LATEST node implies the rest
+        cross_of = {}
+        for i in range(lo, hi):
+            latest = {}
+            for j in deps[i]:
+                if stream_of[j] != stream_of[i]:
+                    latest[stream_of[j]] = max(latest.get(stream_of[j], -1), j)
+            cross_of[i] = sorted(latest.values())
+        needed = {j for i in range(lo, hi) for j in cross_of[i]}
         side, events, used = self._side_streams, {}, set()
         for i in range(lo, hi):
             fn, args, n = self._calls[i]
             k = stream_of[i]
-            st_obj = main if k == 0 else side.setdefault(k, torch.cuda.Stream(self.device))
-            cross = [j for j in deps[i] if stream_of[j] != k]
+            if k and k not in side:
+                side[k] = torch.cuda.Stream(self.device)
+            st_obj = main if k == 0 else side[k]
+            cross = cross_of[i]
             for j in cross:
                 st_obj.wait_event(events[j])
             if k and k not in used:

@@ -126,7 +126,9 @@ class Plan:
         self.device = device
         self.impl = impl
         self.bufs: list[Buf] = []
-        self.cur_stream = 0     # stream id stamped on the nodes being added (Detect branches use 1..2*nl)
+        self.cur_stream = 0     # stream id stamped on the nodes being added (0 = main)
+        self.branching = False  # set by compile_model: independent sub-chains become branches of the captured graph
+        self.n_branches = 0
         self.nodes: list[Node] = []
         self.weights: list[torch.Tensor] = []  # keeps packed device tensors alive
         self.layer_out: dict[int, object] = {}
@@ -160,35 +162,57 @@ class Plan:
                 b.persistent = True
         self.nodes.append(node)
 
+    @staticmethod
+    def _overlap(a: View, b: View) -> bool:
+        """Do two views touch common elements?  Channel slices of one buffer (concat-by-offset) and row ranges of a
+        strip are told apart; anything else on the same buffer counts as overlapping."""
+        if a.buf is not b.buf:
+            return False
+        if a.c0 >= b.c0 + b.C or b.c0 >= a.c0 + a.C:
+            return False
+        if a.buf.B == 1 and a.buf.W == 1 and a.W == 1 and b.W == 1:  # strip rows
+            if a.row0 >= b.row0 + b.H or b.row0 >= a.row0 + a.H:
+                return False
+        return True
+
     def dependencies(self, lo: int = 0, hi: int | None = None):
-        """deps[i] = indices j < i (both inside [lo, hi)) that node i must be ordered after: RAW, WAR and WAW on whole
-        buffers, except WAW between nodes that declare the same `disjoint` key.  Used by the executor to turn the side
-        branches into graph edges; conservative (buffer granularity), so a missing edge is impossible."""
+        """deps[i] = indices j < i (both inside [lo, hi)) that node i must be ordered after: RAW, WAR and WAW between
+        overlapping views, except WAW between nodes that declare the same `disjoint` key.  Used by the executor to turn
+        the side branches into graph edges.  Conservative: views are compared by buffer, channel range and (strips) row
+        range only, so a missing edge is impossible; redundant (transitively implied) edges are kept."""
         hi = len(self.nodes) if hi is None else hi
-        writers, readers, deps = {}, {}, {}
+        deps = {}
         for i in range(lo, hi):
             n = self.nodes[i]
             d = set()
-            for v in n.reads:
-                d.update(writers.get(id(v.buf), ()))
-            for v in n.writes:
-                key = id(v.buf)
-                d.update(readers.get(key, ()))
-                for j in writers.get(key, ()):
-                    if not (n.disjoint and self.nodes[j].disjoint == n.disjoint):
-                        d.add(j)
-            d.discard(i)
+            for j in range(lo, i):
+                m = self.nodes[j]
+                hit = any(self._overlap(r, w) for r in n.reads for w in m.writes) or \
+                    any(self._overlap(w, r) for w in n.writes for r in m.reads)
+                if not hit and not (n.disjoint and m.disjoint == n.disjoint):
+                    hit = any(self._overlap(w, v) for w in n.writes for v in m.writes)
+                if hit:
+                    d.add(j)
             deps[i] = d
-            for v in n.reads:
-                readers.setdefault(id(v.buf), []).append(i)
-            for v in n.writes:
-                key = id(v.buf)
-                if n.disjoint and all(self.nodes[j].disjoint == n.disjoint for j in writers.get(key, ())):
-                    writers.setdefault(key, []).append(i)   # co-writers of disjoint parts
-                else:
-                    writers[key] = [i]
-                    readers[key] = []
         return deps
+
+    def branch(self):
+        """Context manager: nodes added inside go to a fresh side branch when branching is on (small workloads)."""
+        plan = self
+
+        class _B:
+            def __enter__(self_b):
+                self_b.saved = plan.cur_stream
+                if plan.branching and plan.cur_stream == 0:
+                    plan.n_branches += 1
+                    plan.cur_stream = plan.n_branches
+                return self_b
+
+            def __exit__(self_b, *exc):
+                plan.cur_stream = self_b.saved
+                return False
+
+        return _B()
 
     # ------------------------------------------------------------------ conv family
     @staticmethod
@@ -321,7 +345,8 @@ class Plan:
             a = self.bottleneck(blk, a, dst=cat.ch(0, c_) if j == len(blocks) - 1 else None, tag=f"{tag}.m.{j}")
         if not blocks:
             raise PlanError("C3k without bottlenecks")
-        self.conv(m.cv2, x, dst=cat.ch(c_, 2 * c_), tag=tag + ".cv2")
+        with self.branch():  # independent of the bottleneck chain: same input, its own half of the concat buffer
+            self.conv(m.cv2, x, dst=cat.ch(c_, 2 * c_), tag=tag + ".cv2")
         return self.conv(m.cv3, cat, dst=dst, tag=tag + ".cv3")
 
     def c3k2(self, m, x: View, dst=None, tag="") -> View:
@@ -446,7 +471,8 @@ class Plan:
                 ups.append(0)
                 continue
             if not isinstance(r, nn.Identity):
-                v = self.conv(r, v, tag=f"{tag}.realign.{i}")  # at low resolution when upsampled
+                with self.branch():  # realign convs of one node are independent of each other
+                    v = self.conv(r, v, tag=f"{tag}.realign.{i}")  # at low resolution when upsampled
             if fuse:
                 others.append((v, wn[i], up))
             views.append(v)
@@ -601,10 +627,15 @@ class Plan:
         # Concurrent branches: the 2 * nl conv chains of the head are independent of each other and, for the finer
         # levels, of the rest of the neck - each gets its own branch of the captured graph (HEAD_STREAMS), so the big P3
         # chains run underneath the latency-bound small-map layers that finish the neck.
-        hs = self.HEAD_STREAMS
-        if hs is None:
-            hs = self.B * xs[0].H * xs[0].W * int(strides[0]) ** 2 <= self.HEAD_STREAMS_MAX_PIXELS
-        branch = (lambda i, b: 1 + 2 * i + b) if (hs and fused) else (lambda i, b: 0)
+        ids = {}
+
+        def branch(i, b):
+            if not (self.branching and fused):
+                return 0
+            if (i, b) not in ids:
+                self.n_branches += 1
+                ids[(i, b)] = self.n_branches
+            return ids[(i, b)]
         for i, x in enumerate(xs):
             raw = None if fused else self.new_buf(x.H, x.W, 4 * R + nc, dtype=L.F32, persistent=True)
             self.cur_stream = branch(i, 0)
@@ -721,6 +752,8 @@ def compile_model(model, batch: int, height: int, width: int, precision: str, de
         raise PlanError("image height/width must be multiples of 32 (reference loaders.py:603-609)")
     p = Plan(batch, precision, device, impl)
     p.fuse_decode = bool(fuse_decode)  # predict-only plans: Detect's raw logit maps (x_list, head.py:124) are not kept
+    hs = Plan.HEAD_STREAMS
+    p.branching = bool(batch * height * width <= Plan.HEAD_STREAMS_MAX_PIXELS if hs is None else hs) and p.fuse_decode
     first = layers[0]
     if type(first).__name__ != "Conv":
         raise PlanError("the graph must start with a Conv stem")

@@ -154,10 +154,12 @@ def test_bifpn_fused_into_realign_convs(name):
 
 
 def test_detect_branches_and_dependencies():
-    """Fused-decode plans put the 2 * nl Detect conv chains on side branches (Node.stream 1..6).  Plan.dependencies()
-    must order every chain after the neck node that produces its level (and after nothing later), chain nodes after
-    their predecessor, the six tails only after their own chain (they write disjoint parts of y), and the NMS after all
-    tails; buffers touched by a branch are excluded from the sequential lifetime packing."""
+    """Branching plans (small workloads): the 2 * nl Detect conv chains, C3k's cv2 and BiFPN's realign convs go to side
+    branches (Node.stream > 0).  Plan.dependencies() must order every Detect chain after the neck node that produces
+    its level (and after nothing later), chain nodes after their predecessor, the six tails only after their own chain
+    (they write disjoint parts of y), and the NMS after all tails; C3k.cv2 must not be ordered against the bottleneck
+    chain that fills the other half of the concat buffer; buffers touched by a branch are excluded from the
+    sequential lifetime packing."""
     from fce_yolo_b200.plan import Plan
 
     case = FORWARD_CASES["n_fce_64"]
@@ -173,25 +175,41 @@ def test_detect_branches_and_dependencies():
     by_stream = {}
     for i, n in enumerate(nodes):
         by_stream.setdefault(n.stream, []).append(i)
-    assert sorted(by_stream) == [0, 1, 2, 3, 4, 5, 6]
-    level_of = {1: "model.18", 2: "model.18", 3: "model.21", 4: "model.21", 5: "model.24", 6: "model.24"}
-    for k in range(1, 7):
-        chain = by_stream[k]
-        assert nodes[chain[-1]].fn == "fce_conv2d_detect" and len(chain) == (3 if k % 2 else 5)
+    head = {k: v for k, v in by_stream.items() if k and nodes[v[0]].tag.startswith("model.25")}
+    assert len(head) == 6
+    level_of = {"0": "model.18", "1": "model.21", "2": "model.24"}
+    for k, chain in head.items():
+        tag = nodes[chain[0]].tag  # model.25.cv2.<level>.0 or model.25.cv3.<level>.0.0
+        assert nodes[chain[-1]].fn == "fce_conv2d_detect" and len(chain) == (3 if ".cv2." in tag else 5)
         (src,) = deps[chain[0]]
-        assert nodes[src].stream == 0 and nodes[src].tag.startswith(level_of[k])
+        assert nodes[src].stream == 0 and nodes[src].tag.startswith(level_of[tag.split(".")[3]])
         for a, b in zip(chain, chain[1:]):
             assert deps[b] == {a}
         for i in chain:
             for v in nodes[i].reads + nodes[i].writes:
                 assert v.buf.persistent
-    assert nodes[-1].fn == "fce_nms" and {by_stream[k][-1] for k in range(1, 7)} <= deps[len(nodes) - 1]
-    # main-stream nodes never wait for a branch (except the NMS)
+    tails = {chain[-1] for chain in head.values()}
+    assert nodes[-1].fn == "fce_nms" and tails <= deps[len(nodes) - 1]
+    # C3k: cv2 (branch) and the bottleneck chain write different halves of one buffer -> no edge between them; cv3 waits
+    # for both
+    c3k_cv2 = [i for i, n in enumerate(nodes) if n.stream and n.tag.endswith(".m.0.cv2") and "model.25" not in n.tag]
+    assert c3k_cv2
+    for i in c3k_cv2:
+        base = nodes[i].tag[:-len(".cv2")]
+        chain = [j for j, n in enumerate(nodes) if n.tag.startswith(base + ".m.")]
+        cv3 = next(j for j, n in enumerate(nodes) if n.tag == base + ".cv3")
+        assert chain and not (set(chain) & deps[i]) and i in deps[cv3] and chain[-1] in deps[cv3]
+    # main-stream nodes wait for a branch only when they consume its output
     for i in by_stream[0][:-1]:
-        assert all(nodes[j].stream == 0 for j in deps[i])
+        for j in deps[i]:
+            if nodes[j].stream:
+                assert any(Plan._overlap(r, w) for r in nodes[i].reads for w in nodes[j].writes) or \
+                    any(Plan._overlap(a, b) for a in nodes[i].writes for b in nodes[j].reads + nodes[j].writes)
     # a sub-range (the overlap mode's second graph: the six tails) has no internal edges
     k = min(i for i, n in enumerate(nodes) if n.fn == "fce_conv2d_detect")
     sub = plan.dependencies(k, len(nodes) - 1)
     assert all(not d for d in sub.values())
-    # unfused plans stay on one stream
+    # large workloads and unfused plans stay on one stream
     assert all(n.stream == 0 for n in compile_model(model, 2, 64, 64, "bf16", torch.device("cpu")).nodes)
+    big = compile_model(model, 64, 640, 640, "bf16", torch.device("cpu"), fuse_decode=True)
+    assert all(n.stream == 0 for n in big.nodes)
