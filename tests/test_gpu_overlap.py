@@ -97,7 +97,7 @@ def test_head_branches_match_single_stream(overlap):
             preds[hs] = Predictor(model, B, S, precision="bf16", conf=0.05, overlap_nms=overlap)
     finally:
         Plan.HEAD_STREAMS = saved
-    assert max(n.stream for n in preds[True].ex.plan.nodes) == 6 and max(n.stream for n in preds[False].ex.plan.nodes) == 0
+    assert max(n.stream for n in preds[True].ex.plan.nodes) >= 6 and max(n.stream for n in preds[False].ex.plan.nodes) == 0
     g = torch.Generator().manual_seed(5)
     total = 0
     for it in range(5):
