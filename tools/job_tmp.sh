@@ -1,3 +1,6 @@
 set -x
-python -m pytest tests/test_gpu_overlap.py -x -q 2>&1 | tail -3
-bash tools/gpu_job.sh r4d quick | tail -3 | cut -c1-200
+python bench.py --kernel-times gpurun_out/ktimes_r5.csv > gpurun_out/bench_r5.json 2> gpurun_out/bench_r5.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_r5.json 2> gpurun_out/bench_ref_r5.err; echo "ref rc=$?"
+python bench.py --config 0 --no-cpu-baseline > gpurun_out/bench_cfg0_r5.json 2>/dev/null; echo "cfg0 rc=$?"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+cut -c1-250 gpurun_out/bench_r5.json
