@@ -202,7 +202,10 @@ def main():
         saved_fd = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            import datetime
+
+            # a short collective timeout: a rank-asymmetric bug must fail loudly instead of holding the box
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
             dist.barrier()
             torch.cuda.synchronize()
         finally:
@@ -267,9 +270,12 @@ def main():
     ms_e2e = wall_e2e
 
     if rank == 0 and len(sampler.rows) < 3:  # keep the GPU busy until the sampler has something to report
+        # rank-0-only code: LOCAL work only (run_device, no gather) - a collective here would wait for ranks that are
+        # already in the all_reduce below (this hung a 4-GPU run, where nvidia-smi starts more slowly)
         t_end = time.perf_counter() + 1.5
         while time.perf_counter() < t_end and len(sampler.rows) < 3:
-            step_device()
+            pred.run_device()
+            pred.join()
             torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_dev, ms_e2e, wall_e2e], device=dev, dtype=torch.float64)
