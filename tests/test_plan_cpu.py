@@ -213,3 +213,54 @@ def test_detect_branches_and_dependencies():
     assert all(n.stream == 0 for n in compile_model(model, 2, 64, 64, "bf16", torch.device("cpu")).nodes)
     big = compile_model(model, 64, 640, 640, "bf16", torch.device("cpu"), fuse_decode=True)
     assert all(n.stream == 0 for n in big.nodes)
+
+
+@pytest.mark.parametrize("name", ["n_fce_64", "s_coordatt_64"])
+def test_branch_schedules_are_equivalent(name):
+    """The executor orders side branches with events derived from Plan.dependencies(); everything else may run in
+    any interleaving.  Interpret the branching plan in RANDOM legal orders (per-branch order kept, cross-branch edges
+    respected) on the SAME packed arena the executor uses (lifetime-recycled offsets): a missing edge or a buffer
+    recycled under a running branch would change the predictions."""
+    import random
+
+    from fce_yolo_b200.plan import Plan
+
+    case = FORWARD_CASES[name]
+    cfg, scale = load_cfg(case)
+    model = DetectionModel(cfg, scale=scale).fuse().eval()
+    load_synthetic(model, case["seed"])
+    x = synth_images(case["img_seed"], case["batch"], case["size"], case["size"])
+    saved, Plan.HEAD_STREAMS = Plan.HEAD_STREAMS, True
+    try:
+        plan = compile_model(model, case["batch"], case["size"], case["size"], "bf16", torch.device("cpu"),
+                             fuse_decode=True)
+    finally:
+        Plan.HEAD_STREAMS = saved
+    nodes, deps = plan.nodes, plan.dependencies()
+    assert max(n.stream for n in nodes) >= 6
+
+    def run(order):
+        it = Interp(plan, reuse_memory=True)
+        it.input_tensor().copy_(x)
+        for i in order:
+            n = nodes[i]
+            getattr(it, "_" + n.fn)(n.desc, n.ptrs)
+        return it.outputs()[0].float().clone()
+
+    ref = run(range(len(nodes)))
+    rng = random.Random(7)
+    for trial in range(4):
+        queues = {}
+        for i, n in enumerate(nodes):
+            queues.setdefault(n.stream, []).append(i)
+        done, order = set(), []
+        while len(order) < len(nodes):
+            ready = [k for k, q in queues.items() if q and all(j in done for j in deps[q[0]] if nodes[j].stream != k)]
+            assert ready, "dependency cycle"
+            # bias towards the side branches so that they run as EARLY as the edges allow
+            k = rng.choice([s for s in ready if s] or ready) if trial % 2 == 0 else rng.choice(ready)
+            i = queues[k].pop(0)
+            order.append(i)
+            done.add(i)
+        assert order != list(range(len(nodes)))
+        assert torch.equal(run(order), ref), trial
