@@ -41,6 +41,8 @@ class Predictor:
         self.batch, self.imgsz, self.input_u8 = batch, imgsz, input_u8
         if model.training:
             model.eval()
+        nc = int(getattr(list(model.model)[-1], "nc", 0) or 0)
+        self.names = getattr(model, "names", None) or {i: f"{i}" for i in range(nc)}  # tasks.py:371 default names
         with torch.cuda.device(self.device):
             plan = compile_model(model, batch, imgsz[0], imgsz[1], precision, self.device, input_u8=input_u8,
                                  nms=dict(conf=conf, iou=iou, max_det=max_det, agnostic=agnostic_nms,
@@ -156,12 +158,14 @@ class Predictor:
                 P["done"][pending % 2].synchronize()
                 yield P["h_det"][pending % 2], P["h_cnt"][pending % 2]
 
-    def predict(self, images):
+    def predict(self, images, as_results: bool = False, names=None, paths=None):
         """The reference's ``YOLO(...).predict(list_of_bgr_frames)`` for raw uint8 HWC BGR images of any size (at most
         ``batch`` of them): LetterBox + BGR->RGB on the GPU (fce_letterbox) -> forward + decode + NMS (one CUDA graph) ->
         ops.scale_boxes + clip on the GPU (fce_scale_boxes) -> one D2H of the padded detections.  Returns the
         reference's list of ``[n_i, 6]`` (x1, y1, x2, y2, conf, cls) tensors in ORIGINAL image coordinates
-        (engine/predictor.py:151-201, models/yolo/detect/predict.py:33-122)."""
+        (engine/predictor.py:151-201, models/yolo/detect/predict.py:33-122).  ``as_results=True`` wraps them like
+        ``DetectionPredictor.construct_result`` does (predict.py:109-122): a list of ``results.Results`` whose ``.boxes``
+        mirror the reference's ``Boxes`` accessors (xyxy / conf / cls / xywh / xyxyn / xywhn)."""
         from .preprocess import LetterBoxGPU
 
         n = len(images)
@@ -187,7 +191,14 @@ class Predictor:
             self.h_det.copy_(self.det, non_blocking=True)
             self.h_count.copy_(self.count, non_blocking=True)
         self.stream.synchronize()
-        return [self.h_det[b, :c].clone() for b, c in enumerate(self.h_count[:n].tolist())]
+        dets = [self.h_det[b, :c].clone() for b, c in enumerate(self.h_count[:n].tolist())]
+        if not as_results:
+            return dets
+        from .results import Results
+
+        names = names if names is not None else getattr(self, "names", None)
+        return [Results(im.shape[:2], d, names=names, path=(paths[i] if paths else f"image{i}.jpg"), orig_img=im)
+                for i, (im, d) in enumerate(zip(images, dets))]
 
     def __call__(self, images: torch.Tensor):
         det, count = self.infer(images)
