@@ -3,7 +3,9 @@
 round trips.  ``match_predictions`` turns the padded NMS output of a whole batch into the ``tp [n, 10]`` matrix in
 one launch; ``ValStats`` accumulates the reference's ``stats`` dict (tp, conf, pred_cls, target_cls, target_img -
 ultralytics/utils/metrics.py:1118) and gathers it to rank 0 over NCCL (runner.gather_stats_to_rank0) in place of
-the pickled ``dist.gather_object`` of val.py:222-242.  ``ap_per_class`` itself (metrics.py:817) stays on the host."""
+the pickled ``dist.gather_object`` of val.py:222-242.  ``ap_per_class`` itself (metrics.py:817) stays on the host:
+``ValStats.metrics()`` hands the gathered statistics to ``metrics.detection_metrics`` (numpy restatement, checked
+against the live reference to 1e-12)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -76,3 +78,14 @@ class ValStats:
             return None
         out["tp"] = out["tp"].bool()
         return out
+
+    def metrics(self, group=None):
+        """mp / mr / mAP50 / mAP50-95 and the per-class table (``metrics.detection_metrics``) from everything
+        accumulated so far; on rank 0 only when torch.distributed is initialised (None elsewhere) - the reference's
+        ``DetectionValidator.get_stats`` (val.py:244-262) after ``gather_stats``."""
+        from .metrics import detection_metrics
+
+        st = self.result(group)
+        if st is None:
+            return None
+        return detection_metrics(st["tp"], st["conf"], st["pred_cls"], st["target_cls"])
