@@ -356,6 +356,16 @@ def main():
                 **({"GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
                     "hbm_frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"], 3)} if v["bytes"] else {})}
             for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}
+        try:  # measured DRAM MB per step next to every class's algorithmic figures (same ncu capture as `traffic`)
+            tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+            if tj.get("workload") == name:
+                for k, v in roof["classes"].items():
+                    tc = tj.get("classes", {}).get(k)
+                    if tc:
+                        v["dram_mb_per_step"] = round(tc["dram_bytes_per_step"] / 1e6, 1)
+                        v["algorithmic_mb_per_step"] = round(classes[k]["bytes"] / 1e6, 1)
+        except (OSError, ValueError, KeyError):
+            pass
         if a.kernel_times:
             with open(a.kernel_times, "w") as f:
                 f.write("tag,fn,ms,gflop,mbytes\n")
