@@ -99,13 +99,18 @@ class YOLO:
     __call__ = predict
 
     def val(self, batches, imgsz=640, conf: float = 0.001, iou: float = 0.7, max_det: int = 300, batch: int | None = None):
-        """``batches``: iterable of (frames, labels) with ``frames`` a list of uint8 HWC BGR images and ``labels`` a
+        """``batches``: the path of a YOLO-format ``data.yaml`` (read by ``data.iter_val_batches``), or any
+        iterable of (frames, labels) with ``frames`` a list of uint8 HWC BGR images and ``labels`` a
         list of float arrays [n_i, 5] = (cls, x1, y1, x2, y2) in ORIGINAL image pixels.  Validator settings of the
         reference (val.py:105-126: conf 0.001, multi-label NMS).  Returns ``metrics.detection_metrics``'s dict (on
         rank 0 when torch.distributed is initialised, None elsewhere)."""
         from .val import ValStats
 
         hw = self._imgsz(imgsz)
+        if isinstance(batches, (str, os.PathLike, dict)):  # a data.yaml (YOLO-format dataset): Model.val(data=...)
+            from .data import iter_val_batches
+
+            batches = iter_val_batches(batches, batch=int(batch) if batch else 16)
         stats, p = ValStats(), None
         for frames, labels in batches:
             frames = self._frames(frames)
