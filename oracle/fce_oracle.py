@@ -286,14 +286,15 @@ def detect_decode(raw, strides, reg_max=16):
     box, cls = x_cat.split((reg_max * 4, no - reg_max * 4), 1)
     A = box.shape[-1]
     prob = box.view(B, 4, reg_max, A).softmax(2)
-    dist = (prob * torch.arange(reg_max, dtype=prob.dtype).view(1, 1, reg_max, 1)).sum(2)  # [B,4,A]
+    dev = prob.device  # device-agnostic so that tools/torch_gpu_baseline.py can time these very ops through cuDNN
+    dist = (prob * torch.arange(reg_max, dtype=prob.dtype, device=dev).view(1, 1, reg_max, 1)).sum(2)  # [B,4,A]
     pts, st = [], []
     for r, s in zip(raw, strides):
         h, w = r.shape[2:]
-        sy, sx = torch.meshgrid(torch.arange(h, dtype=torch.float32) + 0.5,
-                                torch.arange(w, dtype=torch.float32) + 0.5, indexing="ij")
+        sy, sx = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=dev) + 0.5,
+                                torch.arange(w, dtype=torch.float32, device=dev) + 0.5, indexing="ij")
         pts.append(torch.stack((sx, sy), -1).view(-1, 2))
-        st.append(torch.full((h * w,), float(s)))
+        st.append(torch.full((h * w,), float(s), device=dev))
     anchors = torch.cat(pts).t().unsqueeze(0)  # [1,2,A]
     st = torch.cat(st).view(1, 1, A)
     lt, rb = dist.chunk(2, 1)
