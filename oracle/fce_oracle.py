@@ -286,7 +286,7 @@ def detect_decode(raw, strides, reg_max=16):
     box, cls = x_cat.split((reg_max * 4, no - reg_max * 4), 1)
     A = box.shape[-1]
     prob = box.view(B, 4, reg_max, A).softmax(2)
-    dev = prob.device  # device-agnostic so that tools/torch_gpu_baseline.py can time these very ops through cuDNN
+    dev = prob.device  # device-agnostic so that tests/torch_gpu_baseline.py can time these very ops through cuDNN
     dist = (prob * torch.arange(reg_max, dtype=prob.dtype, device=dev).view(1, 1, reg_max, 1)).sum(2)  # [B,4,A]
     pts, st = [], []
     for r, s in zip(raw, strides):

@@ -3,8 +3,9 @@
 torch forward (test infrastructure, oracle/fce_oracle.py: F.conv2d / softmax / max_pool2d / interpolate ...) moved to
 the device in bf16 with channels_last tensors, i.e. cuDNN / cuBLAS kernels launched op by op like the reference's eager
 predict path, + torchvision's batched NMS when it is installed.  Prints one JSON line; never imported by the package.
+Lives under tests/ because it executes the oracle (test infrastructure) - it is a measurement aid, not a test.
 
-    python tools/torch_gpu_baseline.py [--config N] [--batch B] [--steps K] [--dtype bf16|fp16|fp32] [--device cuda:0]
+    python tests/torch_gpu_baseline.py [--config N] [--batch B] [--steps K] [--dtype bf16|fp16|fp32] [--device cuda:0]
 
 Not part of bench.py's contract: a reference point for profiles/README.md (run by tools/gpu_job.sh)."""
 import argparse

@@ -12,7 +12,7 @@ python bench.py --kernel-times gpurun_out/ktimes_$TAG.csv > gpurun_out/bench_$TA
 if [ "$2" == "quick" ]; then cat gpurun_out/bench_$TAG.json; exit 0; fi
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"
 # the "kernel to beat" (SURVEY 8d): the same graph through stock PyTorch (cuDNN, bf16 channels_last) on this GPU
-timeout 300 python tools/torch_gpu_baseline.py > gpurun_out/torch_eager_$TAG.json 2> gpurun_out/torch_eager_$TAG.err; echo "torch eager rc=$?"
+timeout 300 python tests/torch_gpu_baseline.py > gpurun_out/torch_eager_$TAG.json 2> gpurun_out/torch_eager_$TAG.err; echo "torch eager rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$TAG.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-latency > gpurun_out/ncu_l_$TAG.log 2>&1; echo "ncu launches rc=$?"
 # full-set capture: first 14 conv launches (stem .. layer 4: halo, im2col s2 and 1x1 kernels) + every non-conv kernel
