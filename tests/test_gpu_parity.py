@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-4
 BF16_TOL = 2e-2
+E2E_BF16_MIN_FRAC = {}  # per-case exceptions to the 99.5 % box criterion of test_end_to_end_bf16 (none)
 
 
 def dev():
@@ -88,7 +89,7 @@ def test_end_to_end_fp32_vs_golden(name):
     assert torch.equal(y, y2)
 
 
-@pytest.mark.parametrize("name", ["n_fce_64", "m_bifpn_64", "n_fce_640"])
+@pytest.mark.parametrize("name", ["n_fce_64", "s_coordatt_64", "s_cca_bicca8_64", "m_bifpn_64", "x_fce_64", "n_fce_640"])
 def test_end_to_end_bf16(name):
     """bf16 mode end to end.  The reference's own bf16 forward drifts up to 0.16 relL2 from its fp32 forward
     (SURVEY E.2), so the end-to-end bound is loose; boxes are checked by IoU against the fp32 oracle."""
@@ -114,7 +115,16 @@ def test_end_to_end_bf16(name):
     iou = inter / ((ax2 - ax1) * (ay2 - ay1) + (bx2 - bx1) * (by2 - by1) - inter)
     frac = (iou >= 0.99).float().mean().item()
     print(name, "bf16 boxes with IoU>=0.99:", frac, "min IoU", iou.min().item())
-    assert frac >= 0.90  # teacher-forced layers meet 2e-2; end-to-end bf16 drift is inherent (SURVEY finding 5)
+    import json
+    import os
+
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_e2e_bf16_pytest.jsonl"), "a") as f:
+            f.write(json.dumps({"case": name, "frac_iou99_per_anchor": frac, "min_iou": iou.min().item()}) + "\n")
+    # north_star: IoU >= 0.99 for >= 99.5 % - per ANCHOR here (every decoded box, no NMS selection), against the fp32
+    # oracle; the matched-detection form of the criterion at BASELINE image sizes is tests/test_gpu_detections.py
+    assert frac >= E2E_BF16_MIN_FRAC.get(name, 0.995)
 
 
 @pytest.mark.parametrize("name", list(MODULE_CASES))
