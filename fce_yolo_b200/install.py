@@ -42,6 +42,9 @@ def _fast_predict_once(self, x, profile=False, visualize=False, embed=None):
     if prec is None:  # follow the model's dtype, as AutoBackend's .half()/.float() would (autobackend.py:208,219)
         prec = "fp32" if next(self.parameters()).dtype == torch.float32 else "bf16"
     y, raw = run_model(self, x, precision=prec)
+    # run_model's outputs alias the executor's arena and are overwritten by the next forward; the reference returns fresh
+    # tensors (callers keep predictions across batches, compare two forwards, do TTA) - so this boundary copies
+    y, raw = y.clone(), [r.clone() for r in raw]
     det = self.model[-1]
     if getattr(det, "export", False):
         return y.to(x.dtype) if x.dtype != torch.uint8 else y

@@ -25,7 +25,7 @@ from oracle import fce_oracle as O  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, default=1)
+    ap.add_argument("--config", type=int, default=None)
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--steps", type=int, default=10)
@@ -33,10 +33,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--device", default="cuda:0")
     a = ap.parse_args()
-    w = dict(bench.WORKLOAD)
-    if a.config != 1:
-        w.update(bench.OTHER_CONFIGS[a.config])
-    w.pop("name", None)
+    w, _ = bench.workload(a.config)
     if a.batch:
         w["batch"] = a.batch
     if a.size:

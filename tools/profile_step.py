@@ -20,8 +20,9 @@ ap.add_argument("--batch", type=int, default=None)
 ap.add_argument("--yaml", default=None)
 ap.add_argument("--size", type=int, default=None)
 ap.add_argument("--nodes", default=None, help="write the node order to this file")
+ap.add_argument("--config", type=int, default=None, help="BASELINE.json configs[i] (default: bench.py's workload)")
 a = ap.parse_args()
-w = dict(bench.WORKLOAD)
+w, _ = bench.workload(a.config)
 if a.yaml:
     w["yaml"], w["variant"] = a.yaml, None
 if a.batch:
