@@ -114,8 +114,8 @@ _SIGS = {
     "fce_match_predictions": (C.c_int, [_P, _P, _P, _P, _P, _P, i32, i32, i32, i32, _P, _P]),
     "fce_scale_boxes": (C.c_int, [_P, _P, _P, i32, i32, _P]),
     "fce_letterbox": (C.c_int, [_P, _P, _P, i32, i32, i32, i32, _P, _P]),
-    "fce_conv_tc_set_profile": (None, [C.c_int]),
-    "fce_conv_tc_profile": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
+    "fce_conv2d_route": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P]),
+    "fce_conv_stats": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "fce_dwconv3x3": (C.c_int, [C.POINTER(DwconvDesc), _P, _P, _P, _P, _P, _P]),
     "fce_sppf_pool": (C.c_int, [C.POINTER(SppfDesc), _P, _P]),
     "fce_upsample2x": (C.c_int, [C.POINTER(UpsampleDesc), _P, _P, _P]),
@@ -154,6 +154,12 @@ def load(check_device: bool = False):
             except AttributeError as e:
                 raise FceLibraryError(f"{LIB_PATH} does not export {name}") from e
             fn.restype, fn.argtypes = res, args
+        # debug builds only (FCE_DEBUG=1 python fce_yolo_b200/build.py): not part of the product ABI, not in the header
+        for name, (res, args) in {"fce_conv_tc_set_profile": (None, [C.c_int]),
+                                  "fce_conv_tc_profile": (C.c_int, [C.POINTER(C.c_longlong), C.c_int])}.items():
+            fn = getattr(lib, name, None)
+            if fn is not None:
+                fn.restype, fn.argtypes = res, args
         _lib = lib
     if check_device and not _lib.fce_device_ok():
         raise FceLibraryError("fce_yolo_b200 kernels are built for sm_100a (B200) only; no such device is current")

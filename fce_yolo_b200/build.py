@@ -13,6 +13,8 @@ LIB = os.path.join(HERE, "libfce_yolo_b200.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("FCE_DEBUG") == "1":  # per-role cycle accounting + load / store / math switch-off bits (tools/conv_bench.py)
+    NVCC_FLAGS.append("-DFCE_DEBUG")
 
 
 def _sources():

@@ -1,4 +1,6 @@
 // C-ABI glue: version / error reporting and the convolution front door (kernel selection).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace fce {
@@ -10,9 +12,11 @@ int conv2d_simt(const fce_conv_desc*, const void*, const void*, const float*, co
 int conv2d_tc(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t,
               const fce_detect_epi_desc* epi = nullptr);
 bool conv2d_tc_supported(const fce_conv_desc*, const void*, const void*, const void*, const void*);
+extern std::atomic<long long> g_conv_stats[4];
+#ifdef FCE_DEBUG
 void conv_tc_set_profile(int on);
-void conv_halo_set_mode(int mode);
 int conv_tc_profile(long long* out, int n);
+#endif
 
 }  // namespace fce
 
@@ -44,9 +48,27 @@ extern "C" int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, 
         if (!tc_ok || d->k != 1 || d->impl == 1 || d->out_dtype != FCE_BF16) return FCE_ERR_UNSUPPORTED;
         return conv2d_tc(d, x, w, bias, res, y, st);
     }
-    if (d->impl == 2) return tc_ok ? conv2d_tc(d, x, w, bias, res, y, st) : FCE_ERR_UNSUPPORTED;
+    if (d->impl >= 2) return tc_ok ? conv2d_tc(d, x, w, bias, res, y, st) : FCE_ERR_UNSUPPORTED;
     if (d->impl == 0 && tc_ok) return conv2d_tc(d, x, w, bias, res, y, st);
+    g_conv_stats[3].fetch_add(1, std::memory_order_relaxed);
     return conv2d_simt(d, x, w, bias, res, y, st);
+}
+
+// Would fce_conv2d run this descriptor on the tensor cores?  1 = tcgen05 kernel, 0 = the CUDA-core route (fp32 mode,
+// strips, channel counts that are not multiples of 16, ...).  Pure function of the descriptor and pointer alignment: the
+// plan compiler calls it to count (or, in strict mode, reject) bf16 convs that would silently leave the tensor pipe.
+extern "C" int fce_conv2d_route(const fce_conv_desc* d, const void* x, const void* w, const void* res, const void* y) {
+    if (!d) return FCE_ERR_BAD_ARG;
+    if (d->impl == 1) return 0;
+    return conv2d_tc_supported(d, x, w, res, y) ? 1 : 0;
+}
+
+// Launch counters since the last call with reset != 0: out[0] tcgen05 single-CTA launches, [1] tcgen05 CTA-pair launches,
+// [2] tcgen05 3x3 strip-kernel launches, [3] CUDA-core (SIMT) launches.
+extern "C" int fce_conv_stats(long long* out, int reset) {
+    if (!out) return FCE_ERR_BAD_ARG;
+    for (int i = 0; i < 4; ++i) out[i] = reset ? g_conv_stats[i].exchange(0) : g_conv_stats[i].load();
+    return FCE_OK;
 }
 
 // Last conv of a Detect branch with the decode fused into the tcgen05 epilogue (conv_tc.cu): y is the prediction
@@ -71,10 +93,12 @@ extern "C" int fce_conv2d_detect(const fce_conv_desc* d, const fce_detect_epi_de
     return conv2d_tc(&dd, x, w, bias, nullptr, y, (cudaStream_t)stream, e);
 }
 
+#ifdef FCE_DEBUG
+// Debug builds only (python fce_yolo_b200/build.py with FCE_DEBUG=1; not declared in the public header): per-role cycle
+// accounting and switches that make the tcgen05 kernels skip loads / stores / epilogue math - the results are GARBAGE,
+// they exist to time one pipeline stage at a time (tools/conv_bench.py --prof / --dbg).
 extern "C" void fce_conv_tc_set_profile(int on) {
     conv_tc_set_profile(on & 15);  // bit 0 profile, bit 1 skip TMA loads, bit 2 skip TMA stores, bit 3 skip epilogue math
-    // bit 4: disable the 3x3 strip kernel (everything goes through the TMA-im2col kernel)
-    // bit 5: strip kernel only with resident weights (the streamed-weight shapes go back to the TMA-im2col kernel)
-    conv_halo_set_mode(((on >> 4) & 1) ? 0 : (((on >> 5) & 1) ? 2 : 1));
 }
 extern "C" int fce_conv_tc_profile(long long* out, int n) { return out ? conv_tc_profile(out, n) : FCE_ERR_BAD_ARG; }
+#endif

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/fce_yolo_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -15,6 +17,21 @@ namespace fce {
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 void set_cuda_error(cudaError_t e);
+
+// cudaFuncSetAttribute (the > 48 KB dynamic shared-memory opt-in) applies to the CURRENT device only: one process driving
+// several GPUs must repeat it per device.  Bit d of the mask = done on device d; setting twice is harmless, so two
+// threads racing through pending() at worst both set the attributes.
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool pending(int* dev) {
+        *dev = 0;
+        if (cudaGetDevice(dev) != cudaSuccess || *dev < 0 || *dev > 63) return true;
+        return ((mask.load(std::memory_order_acquire) >> *dev) & 1ull) == 0;
+    }
+    void done(int dev) {
+        if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release);
+    }
+};
 
 inline int check_launch() {
     cudaError_t e = cudaGetLastError();

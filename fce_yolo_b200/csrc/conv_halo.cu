@@ -57,11 +57,17 @@ struct HaloParams {
 // debug cycle accounting, same slot layout as conv_tc.cu: [4] MMA wait-full [5] MMA wait-tmem [6] MMA total
 // [7] epilogue wait-tmem-full [8] epilogue total [9] epilogue wait-staging [10] DMA wait-written [11] DMA total
 constexpr int PROF_SLOTS = 16;
+#ifdef FCE_DEBUG
+constexpr bool PROF = true;
 __device__ long long g_hprof[kNumSMs * PROF_SLOTS];
+#else
+constexpr bool PROF = false;
+__device__ long long g_hprof[1];
+#endif
 #define HP_T0() long long _t0 = 0; if (PROF) _t0 = clock64()
 #define HP_ACC(var) if (PROF) (var) += clock64() - _t0
 
-template <int KK, bool PROF>
+template <int KK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const HaloParams p,
@@ -386,14 +392,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 bool g_halo_prof = false, g_halo_last = false;
-int g_halo_mode = 1;  // 0 = kernel disabled (debug: everything through the TMA-im2col kernel), 1 = on
+// Kernel-selection knob (same results either way): FCE_HALO_MODE = 0 strip kernel off (every 3x3 through the TMA-im2col
+// kernel), 1 on (default), 2 on with resident weights only.  Read once.
+const int g_halo_mode = [] {
+    const char* e = getenv("FCE_HALO_MODE");
+    return e && *e ? atoi(e) : 1;
+}();
 
 }  // namespace
 
-void conv_halo_set_mode(int mode) { g_halo_mode = mode; }
-void conv_halo_set_profile(bool on) { g_halo_prof = on; }
 bool conv_halo_ran_last() { return g_halo_last; }
 void conv_halo_clear_last() { g_halo_last = false; }
+#ifdef FCE_DEBUG
+void conv_halo_set_profile(bool on) { g_halo_prof = on; }
 int conv_halo_profile(long long* out, int n) {
     if (n > kNumSMs * PROF_SLOTS) n = kNumSMs * PROF_SLOTS;
     cudaError_t e = cudaMemcpyFromSymbol(out, g_hprof, (size_t)n * sizeof(long long));
@@ -403,6 +414,7 @@ int conv_halo_profile(long long* out, int n) {
     }
     return n;
 }
+#endif
 
 // Band height for a given K chunk / weight mode; returns the efficiency estimate (0 = does not fit).
 static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool stream, HaloParams& p) {
@@ -561,18 +573,18 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
     }
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const HaloParams,
                              const float*);
-    static const KernelFn table[6] = {conv_halo_kernel<1, false>, conv_halo_kernel<2, false>, conv_halo_kernel<4, false>,
-                                      conv_halo_kernel<1, true>,  conv_halo_kernel<2, true>,  conv_halo_kernel<4, true>};
-    static bool attr_set = false;
-    if (!attr_set) {
-        for (int v = 0; v < 6; ++v) {
+    static const KernelFn table[3] = {conv_halo_kernel<1>, conv_halo_kernel<2>, conv_halo_kernel<4>};
+    static DeviceOnce attr_once;  // the shared-memory opt-in is a per-device attribute
+    int dev = 0;
+    if (attr_once.pending(&dev)) {
+        for (int v = 0; v < 3; ++v) {
             cudaError_t e = cudaFuncSetAttribute(table[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) {
                 set_cuda_error(e);
                 return FCE_ERR_CUDA;
             }
         }
-        attr_set = true;
+        attr_once.done(dev);
     }
     const size_t smem = (size_t)A_STAGES * p.strip_bytes + p.b_total + (size_t)p.n_stg * p.n_slabs * p.slab_bytes +
                         p.bias_bytes + 1024 + 256;
@@ -581,8 +593,7 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
     if (g_halo_prof)
         fprintf(stderr, "[halo] R=%d bands=%d nb=%d units=%d acc_sets=%d n_stg=%d slab_cols=%d smem=%zu\n", p.R, p.bands, p.nb,
                 p.units, p.acc_sets, p.n_stg, p.slab_cols, smem);
-    return launch_pdl(table[(kc == 16 ? 0 : (kc == 32 ? 1 : 2)) + (g_halo_prof ? 3 : 0)], grid, NUM_THREADS, smem, st, tmA,
-                      tmB, tmC, tmR, p, bias);
+    return launch_pdl(table[kc == 16 ? 0 : (kc == 32 ? 1 : 2)], grid, NUM_THREADS, smem, st, tmA, tmB, tmC, tmR, p, bias);
 }
 
 }  // namespace fce

@@ -21,6 +21,19 @@
 //       warp 15    : TMEM allocator
 //   * Shared-memory tiles use the hardware swizzle that matches the K chunk (128B / 64B / 32B for
 //     kc = 64 / 32 / 16 channels), identical in the TMA descriptor and the UMMA shared-memory descriptor.
+//   * CTA PAIRS (template PAIR, cta_group::2): two CTAs of a {2,1,1} cluster - the two SMs of a TPC - own a 256-pixel
+//     M tile.  Each CTA stages ITS 128 pixels of A and HALF of the [bn, kc] weight tile (bn/2 rows); the leader CTA
+//     (cluster rank 0) issues ONE tcgen05.mma.cta_group::2 of M = 256 per K step, which reads both halves of B across
+//     the pair and accumulates 128 rows in each CTA's TMEM.  Per K step an SM reads 4 KB of A + bn*16 bytes of B from
+//     shared memory instead of 4 KB + bn*32 (the SS-mode operand bandwidth that capped the N <= 128 layers), and the
+//     L2 -> SM weight traffic per output pixel halves (what capped the long-K 3x3 layers: a 128 x 256 tile moves
+//     (128 + 256) * kc * 2 bytes per K step, a pair (256 + 256) for twice the work).  Barriers: TMA loads of both
+//     CTAs complete on the LEADER's full barrier (.cta_group::2 loads, the leader's producers post the expected
+//     bytes of both CTAs); the leader's commits are multicast to the empty / accumulator-full barriers of both CTAs;
+//     the epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier (remote arrive).  The epilogue
+//     itself is unchanged: every CTA drains its own 128 TMEM lanes and stores its own rows.
+#include <atomic>
+
 #include "tc_common.cuh"
 
 namespace fce {
@@ -56,6 +69,7 @@ struct TcParams {
     uint32_t bias_bytes;
     uint32_t tmem_cols;
     int acc_stages;    // TMEM accumulator stages: tile `it` of a CTA accumulates in stage it % acc_stages
+    int m_units;       // M work units: m_tiles for single CTAs, ceil(m_tiles / 2) for CTA pairs
     int out_pitch, res_pitch, act, out_f32;
     uint32_t desc_hi;  // upper 32 bits of the UMMA shared-memory descriptor (SBO, version, swizzle)
     uint32_t idesc;    // UMMA instruction descriptor
@@ -69,11 +83,18 @@ struct TcParams {
     int res_up;        // res is a half-resolution map read through a nearest 2x upsample
 };
 
-// Optional per-role cycle accounting (debug entry points fce_conv_tc_set_profile / fce_conv_tc_profile):
+// Per-role cycle accounting and the load / store / math switch-off bits exist in -DFCE_DEBUG builds only (debug entry
+// points fce_conv_tc_set_profile / fce_conv_tc_profile, declared in api.cu, NOT in the public header):
 // [cta][0..1] A producer wait/total, [4..6] MMA wait-full / wait-tmem-empty / total,
 // [7..8] epilogue warp 0 wait-tmem-full / total.
 constexpr int PROF_SLOTS = 16;
+#ifdef FCE_DEBUG
+constexpr bool PROF = true, DBG = true;
 __device__ long long g_prof[kNumSMs * PROF_SLOTS];
+#else
+constexpr bool PROF = false, DBG = false;
+__device__ long long g_prof[1];
+#endif
 
 #define PROF_T0() long long _t0 = 0; if (PROF) _t0 = clock64()
 #define PROF_ACC(var) if (PROF) (var) += clock64() - _t0
@@ -85,7 +106,7 @@ __device__ long long g_prof[kNumSMs * PROF_SLOTS];
 // instructions take uniform registers) instead of a per-thread dependent chain with R2UR moves.
 // KK = K chunk / 16 (UMMA instructions per K step), S = K steps per pipeline stage: compile-time so that the
 // issue loops are straight-line code (descriptor = base + constant).
-template <int KK, int S, bool PROF>
+template <int KK, int S, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcParams p, const float* __restrict__ bias,
@@ -104,17 +125,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    // work units: (M unit, N tile).  Single CTA: M unit = one 128-row tile, CTA b takes units b, b + grid, ...  Pair: M unit
+    // = two consecutive 128-row tiles (rank r of the pair owns tile 2 * unit + r), pair q = blockIdx.x / 2 takes units
+    // q, q + grid / 2, ... - BOTH CTAs of a pair walk the same unit sequence (same ring / accumulator phases).
+    constexpr int NCTA = PAIR ? 2 : 1;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int total_tiles = p.m_units * p.n_tiles;
+    // barriers the PEER must reach live in the leader's shared memory
+    const uint32_t full0_sig = PAIR ? mapa_shared(full0, 0) : full0;      // TMA completion target
+    const uint32_t bfull_sig = PAIR ? mapa_shared(bfull, 0) : bfull;
+    const uint32_t tempty0_sig = PAIR ? mapa_shared(tempty0, 0) : tempty0;  // epilogue -> MMA issuer
 
     pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel's tail
     if (warp == WARP_PROD_A && lane == 0) {
         for (int i = 0; i < p.stages; ++i) {
-            mbar_init(full0 + 8 * i, p.b_resident ? 1 : 2);
+            mbar_init(full0 + 8 * i, p.b_resident ? 1 : 2);  // arrivals: this CTA's producers (pair: the leader's only)
             mbar_init(empty0 + 8 * i, 1);
         }
         for (int a = 0; a < MAX_ACC; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, 4);  // one group of four epilogue warps drains an accumulator
+            mbar_init(tempty0 + 8 * a, 4 * NCTA);  // one group of four epilogue warps (per CTA) drains an accumulator
         }
         mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -123,16 +156,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmC);
     }
     if (warp == WARP_ALLOC) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {  // one warp of EACH CTA of the pair: the allocation is made in both tensor memories at once
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     {   // bias pre-scaled for the epilogue: x 1/2 for SiLU (epi_math16), x -log2(e) for the fused class sigmoid
         const float bsc = p.epi_mode == 1 ? -1.4426950408889634f : epi_bias_scale(p.act);
         for (int i = threadIdx.x; i < (int)(p.bias_bytes >> 2); i += NUM_THREADS) bias_s[i] = i < p.Cout ? bias[i] * bsc : 0.f;
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // barrier inits and the TMEM allocation of BOTH CTAs are visible to both
+    else __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -143,12 +183,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int kc = KK * 16;
         constexpr uint32_t a_sub = BM * kc * 2, a_stage = S * a_sub;
         const int hw = p.Ho * p.Wo, groups = p.groups, chunks = p.chunks, ksz = p.ksz;
-        const bool is_1x1 = p.taps == 1, skip = (p.dbg & 1) != 0;
+        const bool is_1x1 = p.taps == 1, skip = DBG && (p.dbg & 1) != 0;
         const int n_tiles = p.n_tiles, nstages = p.stages;
         long long pw = 0, pt0 = PROF ? clock64() : 0;
         pdl_wait();  // activations are produced by the previous kernel (weights / bias above are constants)
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m0 = (n_tiles == 1 ? tile : tile / n_tiles) * BM;
+        for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+            int mt = (n_tiles == 1 ? tile : tile / n_tiles) * NCTA + (int)cta_rank;
+            if (PAIR && mt >= p.m_tiles) mt = p.m_tiles - 1;  // odd tile count: the pair's last half re-reads valid rows (never stored)
+            const int m0 = mt * BM;
             int img = 0, w0 = 0, h0 = 0;
             if (!is_1x1) {
                 img = m0 / hw;
@@ -167,15 +209,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     PROF_ACC(pw);
                 }
                 const uint32_t dst = sA + r.stage * a_stage;
+                const uint32_t fsig = full0_sig + 8 * r.stage;
                 if (elect_one()) {
                     if (skip) {
-                        mbar_arrive(fb);
+                        if (leader) mbar_arrive(fb);
                     } else {
-                        mbar_expect_tx(fb, a_stage);
+                        if (leader) mbar_expect_tx(fb, a_stage * NCTA);  // the bytes of both CTAs' A tiles
                         int c_ = ch, kw_ = kw, kh_ = kh;
 #pragma unroll
                         for (int q = 0; q < S; ++q) {
-                            if (is_1x1)
+                            if (PAIR) {
+                                if (is_1x1)
+                                    tma_load_2d_cg2(dst + q * a_sub, &tmA, fsig, c_ * kc, m0);
+                                else
+                                    tma_load_im2col_cg2(dst + q * a_sub, &tmA, fsig, c_ * kc, w0, h0, img, (uint16_t)kw_,
+                                                        (uint16_t)kh_);
+                            } else if (is_1x1)
                                 tma_load_2d(dst + q * a_sub, &tmA, fb, c_ * kc, m0);
                             else
                                 tma_load_im2col(dst + q * a_sub, &tmA, fb, c_ * kc, w0, h0, img, (uint16_t)kw_,
@@ -212,32 +261,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int kc = KK * 16;
         const int k_steps = p.groups * S;
         const uint32_t b_sub = p.b_sub;
-        const bool skip = (p.dbg & 1) != 0;
+        const bool skip = DBG && (p.dbg & 1) != 0;
+        const int nrow0 = (int)cta_rank * (p.bn / NCTA);  // pair: this CTA stages rows [rank * bn/2, +bn/2) of the weight tile
         if (p.b_resident) {
-            // weight-stationary: one load of the whole [Cout, K] matrix for all tiles of this CTA
+            // weight-stationary: one load of the whole [Cout, K] matrix (pair: this CTA's half of the rows) for all tiles
             if (elect_one()) {
-                mbar_expect_tx(bfull, (uint32_t)k_steps * b_sub);
-                for (int it = 0; it < k_steps; ++it) tma_load_2d(sB + it * b_sub, &tmB, bfull, it * kc, 0);
+                if (leader) mbar_expect_tx(bfull, (uint32_t)k_steps * b_sub * NCTA);
+                for (int it = 0; it < k_steps; ++it) {
+                    if (PAIR) tma_load_2d_cg2(sB + it * b_sub, &tmB, bfull_sig, it * kc, nrow0);
+                    else tma_load_2d(sB + it * b_sub, &tmB, bfull, it * kc, 0);
+                }
             }
         } else {
             Ring r;
             const int groups = p.groups, n_tiles = p.n_tiles, nstages = p.stages, bn = p.bn;
             const uint32_t b_stage = p.b_stage;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n0 = (n_tiles == 1 ? 0 : tile % n_tiles) * bn;
+            for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+                const int n0 = (n_tiles == 1 ? 0 : tile % n_tiles) * bn + nrow0;
                 int kcol = 0;
 #pragma unroll 1
                 for (int g = 0; g < groups; ++g) {
                     const uint32_t fb = full0 + 8 * r.stage;
                     mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
                     const uint32_t dst = sB + r.stage * b_stage;
+                    const uint32_t fsig = full0_sig + 8 * r.stage;
                     if (elect_one()) {
                         if (skip) {
-                            mbar_arrive(fb);
+                            if (leader) mbar_arrive(fb);
                         } else {
-                            mbar_expect_tx(fb, b_stage);
+                            if (leader) mbar_expect_tx(fb, b_stage * NCTA);
 #pragma unroll
-                            for (int q = 0; q < S; ++q) tma_load_2d(dst + q * b_sub, &tmB, fb, kcol + q * kc, n0);
+                            for (int q = 0; q < S; ++q) {
+                                if (PAIR) tma_load_2d_cg2(dst + q * b_sub, &tmB, fsig, kcol + q * kc, n0);
+                                else tma_load_2d(dst + q * b_sub, &tmB, fb, kcol + q * kc, n0);
+                            }
                         }
                     }
                     kcol += S * kc;
@@ -245,8 +302,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == WARP_MMA) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp == WARP_MMA && leader) {
+        // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA's only)
         Ring r;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -261,7 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(bfull, 0);
             tc_fence_after();
         }
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = unit0; tile < total_tiles; tile += unit_step) {
             {
                 PROF_T0();
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
@@ -285,12 +342,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int q = 0; q < S; ++q) {
 #pragma unroll
                         for (int k = 0; k < KK; ++k) {
-                            umma_bf16(d_tmem, make_desc(dhi, a_lo + q * (a_sub >> 4) + 2 * k),
-                                      make_desc(dhi, b_lo + q * b_sub16 + 2 * k), idesc, (g | q | k) != 0);
+                            const uint64_t ad = make_desc(dhi, a_lo + q * (a_sub >> 4) + 2 * k);
+                            const uint64_t bd = make_desc(dhi, b_lo + q * b_sub16 + 2 * k);
+                            if (PAIR) umma_bf16_cg2(d_tmem, ad, bd, idesc, (g | q | k) != 0);
+                            else umma_bf16(d_tmem, ad, bd, idesc, (g | q | k) != 0);
                         }
                     }
-                    umma_commit(empty0 + 8 * r.stage);  // frees the smem slot when these MMAs retire
-                    if (g == groups - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
+                    if (PAIR) {  // multicast: the same barrier offsets in both CTAs of the pair
+                        umma_commit_cg2(empty0 + 8 * r.stage);
+                        if (g == groups - 1) umma_commit_cg2(tfull0 + 8 * acc);
+                    } else {
+                        umma_commit(empty0 + 8 * r.stage);  // frees the smem slot when these MMAs retire
+                        if (g == groups - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
+                    }
                 }
                 __syncwarp();
                 r.advance(nstages);
@@ -321,7 +385,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int group = e >> 2;      // which accumulator stage
         const int n_tiles = p.n_tiles, bn = p.bn, Cout = p.Cout, act = p.act;
         const bool has_res = res != nullptr, out_f32 = p.out_f32 != 0;
-        const bool dbg_nostore = (p.dbg & 2) != 0, dbg_nomath = (p.dbg & 4) != 0;  // debug timing only
+        const bool dbg_nostore = DBG && (p.dbg & 2) != 0, dbg_nomath = DBG && (p.dbg & 4) != 0;  // debug timing only
         const int slab_cols = out_f32 ? 16 : 32;  // 64 bytes of output per row
         const int n_slabs = (bn + slab_cols - 1) / slab_cols;
         const uint32_t stg0 = sC + e * 2 * STG_BYTES;
@@ -333,7 +397,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int it = 0;
         long long ew = 0, et0 = PROF ? clock64() : 0;
         pdl_wait();  // residual reads and output stores touch buffers the previous kernel may still be using
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
             // group g owns accumulator stage g: every barrier has ONE waiting group that sees its phases in order (a
             // group waiting two phases ahead of a barrier would be fooled by the parity wrap-around).  With two
             // stages (bn > 170) the third group idles.
@@ -345,8 +409,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 acc_phase ^= 1;
             }
             if (!mine) continue;
-            const int mt = n_tiles == 1 ? tile : tile / n_tiles;
-            const int n0 = n_tiles == 1 ? 0 : (tile - mt * n_tiles) * bn;
+            const int mu = n_tiles == 1 ? tile : tile / n_tiles;
+            const int n0 = n_tiles == 1 ? 0 : (tile - mu * n_tiles) * bn;
+            const int mt = mu * NCTA + (int)cta_rank;  // this CTA's 128-row tile (pair, odd tile count: may be past M)
             const int m_warp = mt * BM + quarter * 32;
             const int m = m_warp + lane;
             const bool m_ok = m < p.M;
@@ -444,7 +509,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * my_acc);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(tempty0_sig + 8 * my_acc);
+                    else mbar_arrive(tempty0 + 8 * my_acc);
+                }
                 continue;
             }
 #pragma unroll 1
@@ -496,7 +564,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0 && !dbg_nostore) {
+                if (lane == 0 && !dbg_nostore && m_warp < p.M) {
                     tma_store_2d(&tmC, stg0 + buf * STG_BYTES, n, m_warp);  // rows >= M / cols >= Cout are clipped
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
@@ -504,7 +572,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * my_acc);  // this warp has drained its part of the accumulator
+            if (lane == 0) {  // this warp has drained its part of the accumulator
+                if (PAIR) mbar_arrive_cluster(tempty0_sig + 8 * my_acc);
+                else mbar_arrive(tempty0 + 8 * my_acc);
+            }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
         if (PROF && warp == WARP_EPI0 && lane == 0) {
@@ -514,21 +585,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's shared memory and barriers are in use until the last MMA / arrive
+    else __syncthreads();
     tc_fence_after();
     if (warp == WARP_ALLOC) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
 
 // ------------------------------------------------------------------------------------------------ host
-bool g_profile_on = false;
+#ifdef FCE_DEBUG
 int g_debug_flags = 0;
-
+#endif
 
 int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
 
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
 }  // namespace
+
+// Launch counters of the convolution front door (fce_conv_stats): how many launches took which route since the last
+// reset.  A bf16 conv that silently left the tensor cores (SIMT route) must be visible to the plan compiler / tests.
+std::atomic<long long> g_conv_stats[4];  // 0 tcgen05 single CTA, 1 tcgen05 CTA pair, 2 tcgen05 3x3 strip kernel, 3 SIMT
 
 bool conv2d_tc_supported(const fce_conv_desc* d, const void* x, const void* w, const void* res, const void* y) {
     if (d->in_dtype != FCE_BF16 || d->w_dtype != FCE_BF16 || d->in_layout != FCE_NHWC) return false;
@@ -544,17 +628,25 @@ bool conv2d_tc_supported(const fce_conv_desc* d, const void* x, const void* w, c
 }
 
 bool conv2d_halo_supported(const fce_conv_desc* d, bool has_res);
-void conv_halo_set_profile(bool on);
 bool conv_halo_ran_last();
 void conv_halo_clear_last();
+#ifdef FCE_DEBUG
+void conv_halo_set_profile(bool on);
 int conv_halo_profile(long long* out, int n);
+#endif
 int conv2d_halo(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
 
 int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res, void* y,
               cudaStream_t st, const fce_detect_epi_desc* epi) {
     if (!bias) return FCE_ERR_BAD_ARG;
     // thin 3x3 stride-1 convs: input strip resident in shared memory (conv_halo.cu)
-    if (!epi && conv2d_halo_supported(d, res != nullptr)) return conv2d_halo(d, x, w, bias, res, y, st);
+    // impl: 0 / 2 automatic kernel choice, 3 = CTA-pair kernel required (error when the shape has no legal pair tiling),
+    // 4 = single-CTA implicit-GEMM kernel required; 3 and 4 bypass the strip kernel (tests, A/B timing)
+    const bool force_pair = d->impl == 3, force_single = d->impl == 4;
+    if (!epi && !force_pair && !force_single && conv2d_halo_supported(d, res != nullptr)) {
+        g_conv_stats[2].fetch_add(1, std::memory_order_relaxed);
+        return conv2d_halo(d, x, w, bias, res, y, st);
+    }
     conv_halo_clear_last();
     const DriverApi& api = driver();
     if (!api.ok) return FCE_ERR_CUDA;
@@ -574,32 +666,49 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     p.kc = pick_kc(d->Cin);
     p.chunks = d->Cin / p.kc;
     p.m_tiles = ceil_div(M, BM);
-    static const int bn_cap = [] {  // experiment knob: FCE_BN_MAX=128 forces N tiles of at most 128 columns
-        const char* e = getenv("FCE_BN_MAX");
-        const int v = e ? atoi(e) : 0;
-        return v >= 32 ? v : 256;
-    }();
-    // short-K 1x1 layers are HBM / epilogue bound: 128-column tiles keep three TMEM stages (and all twelve epilogue
-    // warps) busy; re-reading the small [128, Cin] A tile for the second N tile is an L2 hit.  Long-K 1x1s and 3x3
-    // layers keep 256 columns (their A tiles are large, and each extra N tile re-reads them).
-    static const int cap1x1_k = [] {  // 1x1 layers with at most this many input channels use 128-column tiles
-        const char* e = getenv("FCE_1X1_CAP_K");
-        return e ? atoi(e) : 256;
-    }();
-    p.n_tiles = ceil_div(d->Cout, d->k == 1 && d->Cin <= cap1x1_k && bn_cap > 128 ? 128 : bn_cap);
-    // N tiles that do not end the channel range must end on a 32-column staging-slab boundary
-    p.bn = p.n_tiles == 1 ? d->Cout : ceil_div(ceil_div(d->Cout, p.n_tiles), 32) * 32;
-    // small problems: narrower N tiles give the persistent grid more tiles to balance over 148 SMs
-    while ((long long)p.m_tiles * p.n_tiles < 2 * kNumSMs && p.bn >= 128 && (p.bn / 2) % 32 == 0) {
-        p.bn /= 2;
-        p.n_tiles = ceil_div(d->Cout, p.bn);
-    }
+    // Kernel-selection knobs (they change WHICH kernel computes the same result, never the result): FCE_BN_MAX=128 caps
+    // the N tile; FCE_1X1_CAP_K: 1x1 layers with at most this many input channels use 128-column tiles;
+    // FCE_PAIR = 0 never / 1 whenever legal / unset: automatic.
+    static const int bn_cap = [] { const int v = env_int("FCE_BN_MAX", 0); return v >= 32 ? v : 256; }();
+    static const int cap1x1_k = env_int("FCE_1X1_CAP_K", 256);
+    static const int pair_mode = env_int("FCE_PAIR", -1);
+    // CTA pairs: legal when the pair's 256 x bn MMA exists (bn % 16, each CTA stages bn / 2 rows = whole 8-row swizzle
+    // atoms) and there are at least two M tiles.
     const int k_steps = p.taps * p.chunks;
+    auto plan_tiles = [&](bool pair) {
+        // short-K 1x1 layers are HBM / epilogue bound: 128-column tiles keep three TMEM stages (and all twelve epilogue
+        // warps) busy; re-reading the small [128, Cin] A tile for the second N tile is an L2 hit.  Long-K 1x1s and 3x3
+        // layers keep 256 columns (their A tiles are large, and each extra N tile re-reads them).
+        p.n_tiles = ceil_div(d->Cout, d->k == 1 && d->Cin <= cap1x1_k && bn_cap > 128 ? 128 : bn_cap);
+        // N tiles that do not end the channel range must end on a 32-column staging-slab boundary
+        p.bn = p.n_tiles == 1 ? d->Cout : ceil_div(ceil_div(d->Cout, p.n_tiles), 32) * 32;
+        p.m_units = pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
+        const int workers = pair ? kNumSMs / 2 : kNumSMs;
+        // small problems: narrower N tiles give the persistent grid more units to balance over the SMs
+        while ((long long)p.m_units * p.n_tiles < 2 * workers && p.bn >= 128 && (p.bn / 2) % 32 == 0) {
+            p.bn /= 2;
+            p.n_tiles = ceil_div(d->Cout, p.bn);
+        }
+    };
+    plan_tiles(false);
+    bool pair = false;
+    if ((pair_mode != 0 || force_pair) && !force_single && p.m_tiles >= 2) {
+        plan_tiles(true);
+        pair = p.bn % 16 == 0 && p.bn >= 32;
+        if (pair && pair_mode < 0 && !force_pair) {
+            // automatic: pairs pay where the tensor pipe / operand feed is the limit - long K (3x3, wide 1x1) or wide
+            // tiles; short-K 1x1 layers are HBM / epilogue bound either way and keep the single-CTA schedule
+            pair = k_steps * p.kc >= env_int("FCE_PAIR_MIN_K", 256) && p.m_units * p.n_tiles >= kNumSMs / 4;
+        }
+        if (!pair) plan_tiles(false);
+    }
+    if (force_pair && !pair) return FCE_ERR_UNSUPPORTED;
+    const int ncta = pair ? 2 : 1;
     // narrow K chunks: put three K steps behind one barrier round trip (one kernel row of a 3x3 / a 96-wide 1x1)
     p.S = (p.kc < 64 && k_steps % 3 == 0) ? 3 : 1;
     p.groups = k_steps / p.S;
     p.a_sub = BM * p.kc * 2;
-    p.b_sub = p.bn * p.kc * 2;
+    p.b_sub = (p.bn / ncta) * p.kc * 2;  // per CTA: a pair stages half of the weight tile's rows in each CTA
     p.a_stage = p.S * p.a_sub;
     p.b_stage = p.S * p.b_sub;
     const uint32_t w_bytes = (uint32_t)k_steps * p.b_sub;
@@ -623,7 +732,9 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     p.res_pitch = d->res_pitch;
     p.act = d->act;
     p.out_f32 = d->out_dtype == FCE_F32;
+#ifdef FCE_DEBUG
     p.dbg = g_debug_flags;
+#endif
     p.out_scale = d->weighted ? d->out_scale : 1.f;
     p.res_scale = d->weighted ? d->res_scale : 1.f;
     p.res_up = d->res_up;
@@ -639,7 +750,8 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);  // UMMA LayoutType
     const uint32_t sbo = 8 * row_bytes;                                         // 8-row core-matrix group pitch
     p.desc_hi = (sbo >> 4) | (1u << 14) | (layout << 29);
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // instruction descriptor: fp32 accumulate, bf16 A / B, K-major both, N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 for a pair)
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((BM * ncta) >> 4) << 24);
 
     const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                    : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -676,7 +788,7 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
         const cuuint64_t K = (cuuint64_t)p.taps * d->Cin;
         const cuuint64_t gdim[2] = {K, (cuuint64_t)d->Cout};
         const cuuint64_t gstr[1] = {K * 2};
-        const cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)p.bn};
+        const cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)(p.bn / ncta)};
         const cuuint32_t est[2] = {1, 1};
         cr = api.tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, est,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -703,14 +815,15 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     const size_t smem = (size_t)p.stages * p.a_stage + p.b_total + NUM_EPI_WARPS * 2 * STG_BYTES + p.bias_bytes + 1024 + 256;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*,
                              const __nv_bfloat16*, float*);
-    // (KK, S) variants: S = 3 only with narrow K chunks
+    // [single CTA | CTA pair] x (KK, S) variants: S = 3 only with narrow K chunks
     static const KernelFn table[2][5] = {
         {conv_tc_kernel<1, 1, false>, conv_tc_kernel<2, 1, false>, conv_tc_kernel<4, 1, false>,
          conv_tc_kernel<1, 3, false>, conv_tc_kernel<2, 3, false>},
         {conv_tc_kernel<1, 1, true>, conv_tc_kernel<2, 1, true>, conv_tc_kernel<4, 1, true>,
          conv_tc_kernel<1, 3, true>, conv_tc_kernel<2, 3, true>}};
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;  // the shared-memory opt-in is a per-device attribute
+    int dev = 0;
+    if (attr_once.pending(&dev)) {
         for (int a = 0; a < 2; ++a)
             for (int v = 0; v < 5; ++v) {
                 cudaError_t e = cudaFuncSetAttribute(table[a][v], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -719,20 +832,25 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
                     return FCE_ERR_CUDA;
                 }
             }
-        attr_set = true;
+        attr_once.done(dev);
     }
     const int kk = p.kc >> 4;
     const int variant = p.S == 1 ? (kk == 1 ? 0 : (kk == 2 ? 1 : 2)) : (kk == 1 ? 3 : 4);
-    const int total = p.m_tiles * p.n_tiles;
-    const int grid = total < kNumSMs ? total : kNumSMs;
+    const int total = p.m_units * p.n_tiles;
     const __nv_bfloat16* rp = res ? reinterpret_cast<const __nv_bfloat16*>(res) + d->res_off : nullptr;
     float* ydet = epi ? reinterpret_cast<float*>(y) : nullptr;
-    return launch_pdl(table[g_profile_on ? 1 : 0][variant], grid, NUM_THREADS, smem, st, tmA, tmB, tmC, p, bias, rp, ydet);
+    g_conv_stats[pair ? 1 : 0].fetch_add(1, std::memory_order_relaxed);
+    if (pair) {
+        const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
+        return launch_pdl_cluster(table[1][variant], 2 * pairs, NUM_THREADS, smem, st, 2, tmA, tmB, tmC, p, bias, rp, ydet);
+    }
+    const int grid = total < kNumSMs ? total : kNumSMs;
+    return launch_pdl(table[0][variant], grid, NUM_THREADS, smem, st, tmA, tmB, tmC, p, bias, rp, ydet);
 }
 
+#ifdef FCE_DEBUG
 void conv_tc_set_profile(int on) {
-    g_profile_on = (on & 1) != 0;
-    conv_halo_set_profile(g_profile_on);
+    conv_halo_set_profile((on & 1) != 0);
     g_debug_flags = on >> 1;  // bit 1 of `on`: skip TMA loads (debug timing only - results are garbage)
 }
 
@@ -746,5 +864,6 @@ int conv_tc_profile(long long* out, int n) {
     }
     return n;
 }
+#endif
 
 }  // namespace fce

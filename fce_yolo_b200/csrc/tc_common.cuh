@@ -74,6 +74,42 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
         "l"(tm), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
         : "memory");
 }
+// ---- CTA pairs (cta_group::2): two CTAs of a {2,1,1} cluster on the two SMs of one TPC run ONE tcgen05.mma of M = 256.
+// Each CTA stages its own 128 rows of A and HALF of the B tile; the leader (cluster rank 0) issues the MMAs and its
+// commits arrive on the barriers of both CTAs.  TMA loads of either CTA signal the LEADER's full barrier.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// data lands in THIS CTA's shared memory; the completion bytes go to `bar`, a shared::cluster address that may be the
+// peer CTA's barrier (what .cta_group::2 permits)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_cg2(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h,
+                                                    int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+        "l"(tm), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -94,6 +130,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 // Arrives on the mbarrier once every MMA issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// The pair forms: D[256 x N] over the TMEM of both CTAs (128 lanes each), A = 128 rows per CTA, B = N/2 rows per CTA.
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far retire.
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
@@ -281,6 +334,43 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // Host: launch with the programmatic-stream-serialization attribute (see pdl_wait above).  Captured into CUDA
 // graphs as a programmatic dependency edge.  FCE_NO_PDL=1 in the environment falls back to plain launches (A/B).
+// `cluster` > 1: thread-block clusters of that many CTAs along x (CTA pairs: 2).
+template <typename... KArgs, typename... Args>
+inline int launch_pdl_cluster(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, int cluster,
+                              Args... args) {
+    static const bool no_pdl = [] {
+        const char* e = getenv("FCE_NO_PDL");
+        return e && e[0] == '1';
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)cluster;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (!no_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) {
+        set_cuda_error(e);
+        return FCE_ERR_CUDA;
+    }
+    return check_launch();
+}
+
 template <typename... KArgs, typename... Args>
 inline int launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
     static const bool no_pdl = [] {

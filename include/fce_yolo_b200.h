@@ -58,7 +58,9 @@ int fce_device_ok(void);
  * residual adds (block.py:474-476, 1352-1353) and torch.cat/chunk fused as view offsets.
  * Weights are OHWI: w[co][kh][kw][ci], dense.  y = act(conv(x*in_scale) + bias) (+ res), optionally as a weighted sum
  * (out_scale / res_scale / res_up below).
- * impl: 0 = auto, 1 = force the fp32-accurate SIMT kernel, 2 = force the tcgen05 kernel.
+ * impl: 0 = auto, 1 = force the fp32-accurate SIMT kernel, 2 = force a tcgen05 kernel (strip / single-CTA / CTA-pair chosen
+ *       automatically), 3 = force the CTA-pair (cta_group::2) implicit-GEMM kernel, 4 = force the single-CTA
+ *       implicit-GEMM kernel.  2-4 return FCE_ERR_UNSUPPORTED when the shape has no such kernel.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t B, H, W;          /* input spatial size */
@@ -128,11 +130,17 @@ typedef struct {
 int fce_letterbox(const fce_letterbox_item* items, const int32_t* xtab, const int32_t* ytab, int32_t B, int32_t out_h,
                   int32_t out_w, int32_t pad_value, uint8_t* out, void* stream);
 
-/* Debug aid for the tcgen05 convolution: when switched on, the next fce_conv2d launches record per-CTA, per-role
- * cycle counts (16 int64 slots per CTA: A-producer wait/total, -, -, MMA wait-full/wait-tmem/total, epilogue
- * wait/total); fce_conv_tc_profile copies n slots of the last launch to a HOST buffer and returns n. */
-void fce_conv_tc_set_profile(int on);
-int fce_conv_tc_profile(long long* out, int n);
+/* Which route fce_conv2d takes for a descriptor: 1 = tcgen05 tensor-core kernel, 0 = CUDA-core kernel (fp32 mode,
+ * pooled strips, channel counts that are not multiples of 16 ...), < 0 = fce_status.  Pure function of the descriptor and
+ * the pointers' alignment (nothing is launched): lets the caller SEE a bf16 convolution that would leave the tensor
+ * pipe instead of finding out from a profile. */
+int fce_conv2d_route(const fce_conv_desc* d, const void* x, const void* w, const void* res, const void* y);
+
+/* Launch counters of fce_conv2d / fce_conv2d_detect since the last call with reset != 0:
+ * out[0] tcgen05 single-CTA launches, out[1] tcgen05 CTA-pair (cta_group::2) launches, out[2] tcgen05 3x3 strip-kernel
+ * launches, out[3] CUDA-core launches.  (Monotonic counters; the only process-wide state of the library besides its
+ * immutable kernel / tensor-map setup.) */
+int fce_conv_stats(long long* out, int reset);
 
 /* Depthwise 3x3 stride 1 (+bias, +SiLU, + optional add of a second map).  Replaces DWConv
  * (conv.py:185-199) in Detect.cv3 (head.py:101-102) and Attention.pe with its add

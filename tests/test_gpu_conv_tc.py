@@ -48,6 +48,32 @@ CASES = [
 ]
 
 
+# CTA-pair (cta_group::2) kernel, forced with impl = 3: odd tile counts (the pair's last half is past M), every N-tile
+# shape (Cout = 32 ... 512: bn = 32, 48, 80, 128, 192, 256, two N tiles), resident and streamed weights, 1x1 / 3x3 s1 / s2,
+# residual, fp32 output, channel-slice views, kc = 16 / 32 / 64
+PAIR_CASES = [
+    (2, 16, 16, 64, 64, 1, 1, 1, False, False, 0, 0),        # 4 tiles = 2 pairs, weights resident
+    (3, 16, 16, 64, 128, 1, 1, 1, False, False, 0, 0),       # 6 tiles
+    (2, 20, 20, 64, 128, 1, 1, 1, False, False, 0, 0),       # M = 800: 7 tiles (odd), ragged last tile
+    (1, 24, 16, 32, 48, 1, 1, 1, False, False, 0, 0),        # 3 tiles (odd), kc = 32, bn = 48
+    (2, 12, 12, 16, 32, 1, 1, 0, False, False, 0, 0),        # kc = 16, bn = 32 (16 rows of B per CTA)
+    (2, 12, 12, 96, 80, 1, 1, 1, False, False, 32, 64),      # S = 3, Cout = 80 (40 rows per CTA), channel-slice views
+    (1, 40, 40, 256, 512, 1, 1, 1, False, False, 0, 0),      # two N tiles of 256, streamed weights, 13 tiles (odd)
+    (1, 40, 40, 128, 64, 1, 1, 0, False, True, 0, 80),       # fp32 output into a wider buffer
+    (2, 16, 16, 128, 128, 1, 1, 1, True, False, 0, 128),     # residual
+    (2, 24, 24, 768, 512, 1, 1, 1, False, False, 0, 0),      # long-K 1x1, two N tiles
+    (1, 16, 16, 192, 384, 1, 1, 2, False, False, 0, 0),      # sigmoid, bn = 192
+    (2, 20, 20, 64, 64, 3, 1, 1, True, False, 64, 0),        # 3x3 s1 through TMA-im2col, tiles cross rows and images
+    (1, 80, 80, 128, 128, 3, 1, 1, False, False, 0, 0),      # 50 tiles, streamed weights
+    (2, 40, 40, 256, 256, 3, 1, 1, True, False, 0, 0),       # C3k bottleneck at m scale: K = 2304, bn = 256
+    (2, 32, 32, 64, 128, 3, 2, 1, False, False, 0, 0),       # stride 2
+    (3, 40, 24, 128, 256, 3, 2, 1, False, False, 0, 0),      # stride 2, H != W, 6 tiles
+    (5, 20, 20, 256, 512, 3, 2, 1, False, False, 0, 0),      # stride 2, two N tiles, M = 500 (4 tiles, ragged)
+    (4, 20, 20, 512, 512, 3, 1, 1, False, False, 0, 0),      # long K, two N tiles, 13 tiles (odd)
+    (2, 24, 24, 32, 16, 3, 1, 1, False, False, 0, 0),        # bn = 16: no legal pair tiling -> FCE_ERR_UNSUPPORTED
+]
+
+
 def run_case(lib, L, case, impl):
     B, H, W, Cin, Cout, k, s, act, has_res, out_f32, ipx, opx = case
     dev = torch.device("cuda:0")
@@ -107,17 +133,52 @@ def test_conv_tc_vs_torch(lib, case):
     assert err_l2 < (2e-5 if case[9] else 4e-3), case
 
 
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[f"p{i}" for i in range(len(PAIR_CASES))])
+def test_conv_tc_pair_vs_torch(lib, case):
+    """The cta_group::2 kernel against torch, and against the single-CTA kernel (same MMA arithmetic: the accumulation
+    order over K is identical, so the two must agree to the last bit)."""
+    l, L = lib
+    if case[4] < 32:
+        with pytest.raises(ValueError):
+            run_case(l, L, case, impl=3)
+        return
+    buf = (C.c_longlong * 4)()
+    l.fce_conv_stats(buf, 1)
+    err_max, err_l2, untouched = run_case(l, L, case, impl=3)
+    l.fce_conv_stats(buf, 0)
+    assert buf[1] == 1 and buf[0] == 0 and buf[2] == 0 and buf[3] == 0, list(buf)  # it really was the pair kernel
+    print(case, f"max {err_max:.2e} l2 {err_l2:.2e}")
+    assert untouched
+    assert err_max < 1e-2, case
+    assert err_l2 < (2e-5 if case[9] else 4e-3), case
+    e1 = run_case(l, L, case, impl=4)
+    assert (err_max, err_l2) == (e1[0], e1[1]), (case, err_max, e1)
+
+
+def test_conv_stats_show_the_route(lib):
+    """fce_conv2d_route / fce_conv_stats make the kernel choice visible: a bf16 conv with 8 output channels leaves the
+    tensor cores (SIMT), a 64-channel one does not."""
+    l, L = lib
+    buf = (C.c_longlong * 4)()
+    l.fce_conv_stats(buf, 1)
+    run_case(l, L, (1, 16, 16, 64, 64, 1, 1, 1, False, False, 0, 0), impl=0)
+    l.fce_conv_stats(buf, 1)
+    assert buf[0] + buf[1] + buf[2] == 1 and buf[3] == 0
+    run_case(l, L, (1, 16, 16, 64, 8, 1, 1, 1, False, False, 0, 0), impl=0)
+    l.fce_conv_stats(buf, 1)
+    assert buf[3] == 1 and buf[0] + buf[1] + buf[2] == 0
+
+
 if __name__ == "__main__":  # quick report: python tests/test_gpu_conv_tc.py
     import sys
     sys.path.insert(0, ".")
     from fce_yolo_b200 import _lib as L
     torch.backends.cudnn.allow_tf32 = False
     l = L.load(check_device=True)
-    if len(sys.argv) > 1:
-        l.fce_conv_tc_set_profile(int(sys.argv[1]) << 4)  # 1 = strip kernel off
-    for i, case in enumerate(CASES):
+    tc_impl = int(sys.argv[1]) if len(sys.argv) > 1 else 2  # 3 = CTA-pair kernel, 4 = single-CTA kernel (no strip kernel)
+    for i, case in enumerate(CASES + PAIR_CASES):
         try:
-            em, el, ut = run_case(l, L, case, impl=2)
+            em, el, ut = run_case(l, L, case, impl=tc_impl)
             es, esl, _ = run_case(l, L, case, impl=1)
             print(f"c{i} {case}: tc max {em:.3e} l2 {el:.3e} untouched {ut} | simt max {es:.3e} l2 {esl:.3e}", flush=True)
         except Exception as e:  # noqa

@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""A/B timing of every DISTINCT dense-conv node of a bench workload's plan under the kernel choices of fce_conv2d:
+automatic (impl 0/2: strip kernel / single CTA / CTA pair as the library decides), single-CTA implicit GEMM (impl 4) and
+CTA-pair implicit GEMM (impl 3).  The nodes run on the plan's own buffers with their own descriptors, one at a time,
+L2 flushed between repetitions, CUDA events.  Drives the pair / strip heuristics in csrc/conv_tc.cu.
+
+    python tools/plan_conv_ab.py --config 2 [--batch 64] [--reps 5] [--csv out.csv]
+"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from fce_yolo_b200 import _lib as L  # noqa: E402
+from fce_yolo_b200.predict import Predictor  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--csv", default=None)
+    a = ap.parse_args()
+    w, name = bench.workload(a.config)
+    if a.batch:
+        w["batch"] = a.batch
+    lib = L.load(check_device=True)
+    dev = torch.device("cuda:0")
+    cfg, model, sd = bench.build_model(w)
+    pred = Predictor(model, w["batch"], w["size"], precision="bf16", device=dev, use_graph=False)
+    pred.run_device()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    pk = bench.peaks()
+    seen = {}
+    rows = []
+    tot = {"auto": 0.0, "single": 0.0, "pair": 0.0, "best": 0.0}
+    for fn, args, n in pred.ex._calls:
+        if n.fn not in ("fce_conv2d", "fce_conv2d_detect"):
+            continue
+        d = n.desc
+        if d.in_dtype != L.BF16 or d.w_dtype != L.BF16:
+            continue
+        key = (n.fn, d.B, d.H, d.W, d.Cin, d.Cout, d.k, d.stride, d.res_pitch != 0, d.out_dtype, d.weighted, d.res_up)
+        if key in seen:
+            seen[key][0] += 1
+            continue
+        res = {}
+        for label, impl in (("auto", 0), ("single", 4), ("pair", 3)):
+            saved = d.impl
+            d.impl = impl
+            rc = fn(*args, st)
+            torch.cuda.synchronize()
+            if rc != 0:
+                res[label] = None
+                d.impl = saved
+                continue
+            ms = []
+            for _ in range(a.reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(*args, st)
+                e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+            ms.sort()
+            res[label] = ms[len(ms) // 2]
+            d.impl = saved
+        seen[key] = [1, n.tag, res, n.flops, n.bytes]
+    print(f"{'node':30s} {'shape':34s} cnt {'auto us':>9s} {'single':>9s} {'pair':>9s}  auto TF  best TF  roofline us")
+    for key, (cnt, tag, res, fl, by) in seen.items():
+        _, B, H, W, Cin, Cout, k, s, has_res, odt, wt, ru = key
+        shape = f"{k}x{k}s{s} {Cin}->{Cout} @{H}x{W}" + (" +res" if has_res else "") + (" f32" if odt == L.F32 else "")
+        roof = max(fl / (pk["tf_sustained"] * 1e12), by / (pk["hbm"] * 1e9)) * 1e6
+        vals = {k_: v for k_, v in res.items() if v is not None}
+        best = min(vals.values())
+        f = lambda v: f"{v * 1e3:9.1f}" if v is not None else "        -"  # noqa: E731
+        print(f"{tag:30s} {shape:34s} {cnt:3d} {f(res['auto'])} {f(res['single'])} {f(res['pair'])}  "
+              f"{fl / res['auto'] / 1e9:7.0f} {fl / best / 1e9:8.0f}  {roof:9.1f}", flush=True)
+        for k_ in ("auto", "single", "pair"):
+            tot[k_] += cnt * (res[k_] if res[k_] is not None else res["auto"])
+        tot["best"] += cnt * best
+        rows.append((tag, shape, cnt, res["auto"], res["single"], res["pair"], fl, by))
+    print("TOTAL ms per step: " + "  ".join(f"{k_} {v:.3f}" for k_, v in tot.items()))
+    if a.csv:
+        with open(a.csv, "w") as fcsv:
+            fcsv.write("tag,shape,count,auto_ms,single_ms,pair_ms,gflop,mbytes\n")
+            for r in rows:
+                fcsv.write(",".join(str(x) for x in r[:3]) + "," + ",".join("" if x is None else f"{x:.5f}" for x in r[3:6]) +
+                           f",{r[6] / 1e9:.3f},{r[7] / 1e6:.3f}\n")
+
+
+if __name__ == "__main__":
+    main()
