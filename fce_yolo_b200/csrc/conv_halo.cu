@@ -488,7 +488,10 @@ static bool halo_plan(const fce_conv_desc* d, bool has_res, HaloParams& p) {
     // weights streamed with the strip: worth it for narrow outputs (measured: Cout = 64: 117 -> 82 us, Cout = 128 on a
     // 20x20 map: 26.6 -> 20.5 us), where the TMA-im2col kernel's nine reads of the input per output pixel dominate;
     // wider outputs amortise them over the MMA work and keep the im2col kernel
-    if (d->Cout > g_stream_max_cout || (d->Cout > 64 && d->H * d->W > 1600)) return false;  // 65..128 outputs: small maps only
+    // 65..128 outputs: small maps of small batches only - from ~600 128-row tiles on, the CTA-pair im2col kernel is faster
+    // (m scale, batch 256, 128->128 at 40x40: 146 us streamed strips vs 122 us pairs; at batch 64, 20x20: 20.5 vs 22.7 us)
+    if (d->Cout > g_stream_max_cout || (d->Cout > 64 && (d->H * d->W > 1600 || (long long)d->B * d->H * d->W >= 75000)))
+        return false;
     HaloParams best{};
     double best_eff = 0.0;
     for (int kc = 64; kc >= 32; kc >>= 1) {

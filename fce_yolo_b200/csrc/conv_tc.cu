@@ -670,7 +670,7 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     // the N tile; FCE_1X1_CAP_K: 1x1 layers with at most this many input channels use 128-column tiles;
     // FCE_PAIR = 0 never / 1 whenever legal / unset: automatic.
     static const int bn_cap = [] { const int v = env_int("FCE_BN_MAX", 0); return v >= 32 ? v : 256; }();
-    static const int cap1x1_k = env_int("FCE_1X1_CAP_K", 256);
+    static const int cap1x1_k = env_int("FCE_1X1_CAP_K", 384);  // (384->512 at 80x80, batch 256: 955 -> 904 us with 128-column tiles)
     static const int pair_mode = env_int("FCE_PAIR", -1);
     // CTA pairs: legal when the pair's 256 x bn MMA exists (bn % 16, each CTA stages bn / 2 rows = whole 8-row swizzle
     // atoms) and there are at least two M tiles.
@@ -696,9 +696,14 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
         plan_tiles(true);
         pair = p.bn % 16 == 0 && p.bn >= 32;
         if (pair && pair_mode < 0 && !force_pair) {
-            // automatic: pairs pay where the tensor pipe / operand feed is the limit - long K (3x3, wide 1x1) or wide
-            // tiles; short-K 1x1 layers are HBM / epilogue bound either way and keep the single-CTA schedule
-            pair = k_steps * p.kc >= env_int("FCE_PAIR_MIN_K", 256) && p.m_units * p.n_tiles >= kNumSMs / 4;
+            // automatic (measured per layer on B200 with tools/plan_conv_ab.py, profiles/r02_conv_ab_*.csv): pairs win
+            // wherever the operand feed - shared-memory reads of A + B per MMA, L2 -> SM weight traffic per tile - is the
+            // limit: every 3x3 with Cin >= 64 (m scale, batch 256: 3x3/s2 512->512 1748 -> 1230 us, 256->256 1684 -> 1324 us,
+            // 3x3/s1 128->128 146 -> 122 us) and 1x1 layers with K >= 512 (768->512: 341 -> 296 us).  Short-K 1x1 layers
+            // are HBM / epilogue bound and LOSE 10-20 % to the coupling of the two CTAs' epilogues (256->256: 386 -> 460 us),
+            // the 32-channel 3x3/s2 is bound by the TMA-im2col request rate either way.
+            pair = (d->k == 3 ? d->Cin >= 64 : d->Cin >= env_int("FCE_PAIR_MIN_K1", 512)) &&
+                   p.m_units * p.n_tiles >= kNumSMs / 4;
         }
         if (!pair) plan_tiles(false);
     }

@@ -115,6 +115,7 @@ class Plan:
     HEAD_STREAMS_MAX_PIXELS = 8 * 640 * 640  # automatic mode: batch * H * W of the network input
     FUSED_BIFPN = True  # False: realign convs + fce_bifpn_fuse as separate launches (A/B timing, cross-check)
     FUSED_COORDATT_MLP = True  # False: cv1 / cv_h / cv_w as three strip convs (A/B timing, cross-check)
+    FUSED_C3K_IN = True  # False: C3k.cv1 and C3k.cv2 as two launches (A/B timing, cross-check)
     FUSED_STEM = True  # False: stem = fce_stem_pack + K=32 tcgen05 conv (kept for A/B timing and as a cross-check)
 
     def __init__(self, batch: int, precision: str, device, impl: int = 0):
@@ -338,13 +339,27 @@ class Plan:
 
     def c3k(self, m, x: View, dst=None, tag="") -> View:
         c_ = m.cv1.conv.out_channels
-        cat = self.new_buf(x.H, x.W, 2 * c_)
-        a = self.conv(m.cv1, x, tag=tag + ".cv1")
         blocks = list(m.m)
-        for j, blk in enumerate(blocks):
-            a = self.bottleneck(blk, a, dst=cat.ch(0, c_) if j == len(blocks) - 1 else None, tag=f"{tag}.m.{j}")
         if not blocks:
             raise PlanError("C3k without bottlenecks")
+        p1, p2 = self.conv_params(m.cv1), self.conv_params(m.cv2)
+        if (self.FUSED_C3K_IN and p1[2:] == p2[2:] and p1[2:5] == (1, 1, 1) and p1[0].shape == p2[0].shape
+                and c_ % 8 == 0):
+            # cv1 and cv2 are 1x1 convs of the SAME input (block.py:338-340): ONE launch with the weights stacked reads x
+            # once instead of twice (both layers sit left of the ridge: HBM-bound).  Buffer layout [chain out | cv2(x) |
+            # cv1(x)]: the stacked conv writes channels [c_, 3c_), the bottleneck chain reads the last slice and ends in the
+            # first, cv3 reads the first two - still no concat copy anywhere.
+            buf = self.new_buf(x.H, x.W, 3 * c_)
+            self.conv(None, x, dst=buf.ch(c_, 3 * c_), w_override=torch.cat([p2[0], p1[0]]),
+                      b_override=torch.cat([p2[1], p1[1]]), act=p1[5], tag=tag + ".cv2+cv1")
+            a = buf.ch(2 * c_, 3 * c_)
+            for j, blk in enumerate(blocks):
+                a = self.bottleneck(blk, a, dst=buf.ch(0, c_) if j == len(blocks) - 1 else None, tag=f"{tag}.m.{j}")
+            return self.conv(m.cv3, buf.ch(0, 2 * c_), dst=dst, tag=tag + ".cv3")
+        cat = self.new_buf(x.H, x.W, 2 * c_)
+        a = self.conv(m.cv1, x, tag=tag + ".cv1")
+        for j, blk in enumerate(blocks):
+            a = self.bottleneck(blk, a, dst=cat.ch(0, c_) if j == len(blocks) - 1 else None, tag=f"{tag}.m.{j}")
         with self.branch():  # independent of the bottleneck chain: same input, its own half of the concat buffer
             self.conv(m.cv2, x, dst=cat.ch(c_, 2 * c_), tag=tag + ".cv2")
         return self.conv(m.cv3, cat, dst=dst, tag=tag + ".cv3")

@@ -166,11 +166,25 @@ def test_detect_branches_and_dependencies():
     cfg, scale = load_cfg(case)
     model = DetectionModel(cfg, scale=scale).fuse().eval()
     saved, Plan.HEAD_STREAMS = Plan.HEAD_STREAMS, True
+    saved_c3k, Plan.FUSED_C3K_IN = Plan.FUSED_C3K_IN, False  # the unfused C3k: cv2 is a branch of its own
     try:
         plan = compile_model(model, 2, 64, 64, "bf16", torch.device("cpu"), fuse_decode=True,
                              nms=dict(conf=0.25, iou=0.7, max_det=300))
+        Plan.FUSED_C3K_IN = True
+        fused = compile_model(model, 2, 64, 64, "bf16", torch.device("cpu"), fuse_decode=True,
+                              nms=dict(conf=0.25, iou=0.7, max_det=300))
     finally:
         Plan.HEAD_STREAMS = saved
+        Plan.FUSED_C3K_IN = saved_c3k
+    # fused C3k input convs (the default): one stacked launch per C3k feeds both the bottleneck chain and cv3
+    fdeps = fused.dependencies()
+    stacked = [i for i, n in enumerate(fused.nodes) if n.tag.endswith(".cv2+cv1")]
+    assert stacked and len(fused.nodes) == len(plan.nodes) - len(stacked)
+    for i in stacked:
+        base = fused.nodes[i].tag[:-len(".cv2+cv1")]
+        chain = [j for j, n in enumerate(fused.nodes) if n.tag.startswith(base + ".m.")]
+        cv3 = next(j for j, n in enumerate(fused.nodes) if n.tag == base + ".cv3")
+        assert i in fdeps[chain[0]] and i in fdeps[cv3] and chain[-1] in fdeps[cv3]
     nodes, deps = plan.nodes, plan.dependencies()
     by_stream = {}
     for i, n in enumerate(nodes):
