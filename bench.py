@@ -309,7 +309,7 @@ def measure(w, steps, warm, rank, world, dev, opts, sampler=None):
     import torch.distributed as dist
 
     from fce_yolo_b200.predict import Predictor
-    from fce_yolo_b200.runner import gather_detections
+    from fce_yolo_b200.runner import DetectionGather
     from fce_yolo_b200.weights import synth_images
 
     cfg, model, sd = build_model(w)
@@ -323,11 +323,13 @@ def measure(w, steps, warm, rank, world, dev, opts, sampler=None):
     pred.inp.copy_(h_img)
     torch.cuda.synchronize()
 
+    gatherer = DetectionGather(pred.ex) if world > 1 else None  # one collective per step, out of the NMS's own buffer
+
     def step_device():
-        det, keep, count = pred.run_device()
+        pred.run_device()
         if world > 1:
             with torch.cuda.stream(pred._out_stream()):  # behind this step's NMS (its side stream in overlap mode)
-                gather_detections(det, count)
+                gatherer.gather()
 
     def barrier():
         if world > 1:

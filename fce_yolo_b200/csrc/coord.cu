@@ -389,11 +389,12 @@ extern "C" int fce_strip_attn(const fce_strip_attn_desc* d, const float* q, cons
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = sizeof(float) * ((size_t)2 * d->Lk * d->dh + (AT / 32) * (size_t)d->Lk + (AT / 32) * (size_t)d->dh);
     if (smem > 200 * 1024) return FCE_ERR_UNSUPPORTED;
-    static std::atomic<bool> attr_done{false};
-    if (!attr_done.load(std::memory_order_acquire)) {
+    static DeviceOnce attr_once;  // per-device attribute
+    int dev_ = 0;
+    if (attr_once.pending(&dev_)) {
         cudaError_t e = cudaFuncSetAttribute(strip_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_cuda_error(e); return FCE_ERR_CUDA; }
-        attr_done.store(true, std::memory_order_release);
+        attr_once.done(dev_);
     }
     int qblocks = (d->Lq + (AT / 32) - 1) / (AT / 32);
     // enough CTAs to cover the SMs, without re-loading K/V more often than needed
@@ -419,11 +420,12 @@ extern "C" int fce_coordatt_mlp(const fce_coordatt_mlp_desc* d, const float* str
     const size_t smem = sizeof(float) * ((size_t)d->mip * (d->C + d->oup) + d->oup + (MT / 32) * 2 * (size_t)d->C +
                                          MIP_MAX + (MT / 32) * 2 * MIP_MAX);
     if (smem > 200 * 1024) return FCE_ERR_UNSUPPORTED;
-    static std::atomic<bool> attr_done{false};
-    if (!attr_done.load(std::memory_order_acquire)) {
+    static DeviceOnce attr_once;  // per-device attribute
+    int dev_ = 0;
+    if (attr_once.pending(&dev_)) {
         cudaError_t e = cudaFuncSetAttribute(coordatt_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_cuda_error(e); return FCE_ERR_CUDA; }
-        attr_done.store(true, std::memory_order_release);
+        attr_once.done(dev_);
     }
     // one CTA per SM and row range: the weights are read once per CTA, row pairs are dealt to warps round-robin
     const int seg = d->rows_h > d->rows_w ? d->rows_h : d->rows_w;

@@ -165,14 +165,15 @@ extern "C" int fce_detect_decode(const fce_decode_desc* d, const float* raw0, co
     if (d->B > 65535) return FCE_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(NT / 32) * 32 * ((4 * d->reg_max + d->nc) / 4 + 1) * sizeof(float4);
     if (smem > 200 * 1024) return FCE_ERR_UNSUPPORTED;
-    static size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
+    static DeviceOnce attr_once;  // per-device attribute
+    int dev_ = 0;
+    if (smem > 48 * 1024 && attr_once.pending(&dev_)) {
         cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) {
             set_cuda_error(e);
             return FCE_ERR_CUDA;
         }
-        attr_smem = 200 * 1024;
+        attr_once.done(dev_);
     }
     dim3 grid(blk[d->nl], d->B);
     decode_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(*d, raw0, raw1, raw2, raw3, y, A, blk[1], blk[2], blk[3]);

@@ -260,8 +260,9 @@ int dwconv3x3_tma(const fce_dwconv_desc* d, const void* x, const float* w, const
     static const KernelFn table[2][2] = {
         {(KernelFn)(void*)dwconv_tma_kernel<__nv_bfloat16, 2>, (KernelFn)(void*)dwconv_tma_kernel<__nv_bfloat16, 3>},
         {(KernelFn)(void*)dwconv_tma_kernel<float, 2>, (KernelFn)(void*)dwconv_tma_kernel<float, 3>}};
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;  // per-device attribute
+    int dev_ = 0;
+    if (attr_once.pending(&dev_)) {
         for (int a = 0; a < 2; ++a)
             for (int b = 0; b < 2; ++b) {
                 cudaError_t e = cudaFuncSetAttribute((const void*)table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -271,7 +272,7 @@ int dwconv3x3_tma(const fce_dwconv_desc* d, const void* x, const float* w, const
                     return FCE_ERR_CUDA;
                 }
             }
-        attr_set = true;
+        attr_once.done(dev_);
     }
     int grid = (stages == 2 ? 3 : 2) * kNumSMs;
     if (grid > p.units) grid = p.units;

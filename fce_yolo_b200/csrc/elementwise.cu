@@ -722,15 +722,16 @@ extern "C" int fce_sppf_pool(const fce_sppf_desc* d, void* buf, void* stream) {
             size_t sm2 = (size_t)2 * d->H * d->W * vpc * 16;
             if (sm2 > 110 * 1024) { vpc = 1; sm2 /= 2; }  // very large maps: one vector per CTA
             if (sm2 <= 220 * 1024) {
-                static bool attr2[2] = {false, false};
+                static DeviceOnce attr2[2];  // per-device attribute, one flag set per element type
                 constexpr int ti2 = sizeof(T) == 2 ? 0 : 1;
-                if (!attr2[ti2]) {
+                int dev2 = 0;
+                if (attr2[ti2].pending(&dev2)) {
                     cudaError_t e = cudaFuncSetAttribute(sppf_v2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
                     if (e != cudaSuccess) {
                         set_cuda_error(e);
                         return FCE_ERR_CUDA;
                     }
-                    attr2[ti2] = true;
+                    attr2[ti2].done(dev2);
                 }
                 const int chunks2 = (d->C + vpc * N - 1) / (vpc * N);
                 sppf_v2_kernel<T><<<d->B * chunks2, NT, sm2, st>>>(*d, (T*)buf, vpc);
@@ -742,15 +743,16 @@ extern "C" int fce_sppf_pool(const fce_sppf_desc* d, void* buf, void* stream) {
         const int HW = d->H * d->W;
         const size_t smem = (size_t)2 * HW * SPPF_CH * sizeof(float);
         if (smem > 200 * 1024) return FCE_ERR_UNSUPPORTED;
-        static bool attr_set[2] = {false, false};
+        static DeviceOnce attr_set[2];
         constexpr int ti = sizeof(T) == 2 ? 0 : 1;
-        if (!attr_set[ti]) {
+        int dev_ = 0;
+        if (attr_set[ti].pending(&dev_)) {
             cudaError_t e = cudaFuncSetAttribute(sppf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) {
                 set_cuda_error(e);
                 return FCE_ERR_CUDA;
             }
-            attr_set[ti] = true;
+            attr_set[ti].done(dev_);
         }
         const int chunks = (d->C + SPPF_CH - 1) / SPPF_CH;
         sppf_kernel<T><<<d->B * chunks, NT, smem, st>>>(*d, (T*)buf);

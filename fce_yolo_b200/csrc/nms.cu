@@ -186,7 +186,9 @@ __global__ void __launch_bounds__(NT) nms_kernel(const fce_nms_desc d, const flo
         int need = target;
         // fast path (the usual predict case: a few hundred candidates): everything still unprocessed fits one
         // round, so the rank-`target` composite need not be found - take them all
-        const bool take_all = s_valid - processed <= TSEL;
+        // (<= target, not <= TSEL: when max_nms cuts the list, limit - processed < remaining candidates and the BEST
+        // `target` of them must be selected - nms.py:136-140 keeps the top max_nms by score)
+        const bool take_all = s_valid - processed <= target;
         if (take_all) prefix = ~0ull;
         for (int shift = 56; shift >= 0 && !take_all; shift -= 8) {
             if (tid < 256) hist[tid] = 0;
@@ -419,11 +421,12 @@ extern "C" int fce_nms(const fce_nms_desc* d, const float* pred, const int32_t* 
     if (ws_bytes < fce_nms_workspace(d)) return FCE_ERR_WORKSPACE;
     const size_t smem = kept_smem(d->max_det);
     if (smem > 96 * 1024) return FCE_ERR_UNSUPPORTED;
-    static std::atomic<bool> attr_done{false};
-    if (!attr_done.load(std::memory_order_acquire)) {
+    static DeviceOnce attr_once;  // per-device attribute
+    int dev_ = 0;
+    if (attr_once.pending(&dev_)) {
         cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         if (e != cudaSuccess) { set_cuda_error(e); return FCE_ERR_CUDA; }
-        attr_done.store(true, std::memory_order_release);
+        attr_once.done(dev_);
     }
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* keys = (uint32_t*)ws;

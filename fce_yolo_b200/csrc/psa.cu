@@ -308,12 +308,13 @@ extern "C" int fce_psa_attention(const fce_psa_desc* d, const void* qkv, void* o
     dim3 grid((d->N + BR - 1) / BR, d->heads, d->B);
     constexpr size_t smem = sizeof(float) * (KD * (BR + 4) + KD * (BC + 4) + BC * (HD + 4) + BR * (BC + 4));
     static_assert(smem <= 100 * 1024, "psa smem");
-    static std::atomic<bool> attr_done{false};  // set once per process (not during graph capture replays)
-    if (!attr_done.load(std::memory_order_acquire)) {
+    static DeviceOnce attr_once;  // once per DEVICE (the attribute is per device; never during graph capture replays)
+    int dev_ = 0;
+    if (attr_once.pending(&dev_)) {
         cudaError_t e1 = cudaFuncSetAttribute(psa_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaError_t e2 = cudaFuncSetAttribute(psa_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e1 != cudaSuccess || e2 != cudaSuccess) { set_cuda_error(e1 != cudaSuccess ? e1 : e2); return FCE_ERR_CUDA; }
-        attr_done.store(true, std::memory_order_release);
+        attr_once.done(dev_);
     }
     const bool vec_ok = d->qkv_pitch % 8 == 0 && d->q_off % 8 == 0 && d->k_off % 8 == 0 && d->v_off % 8 == 0 &&
                         d->out_pitch % 2 == 0 && d->out_off % 2 == 0 && (uintptr_t)qkv % 16 == 0 && (uintptr_t)out % 4 == 0;

@@ -117,13 +117,20 @@ class Arena:
         b = self.plan.inputs[i].buf
         return self._flat(b).view(b.B, b.H, b.W, b.C)  # for the NCHW image buffer this *is* [B, C, H, W]
 
+    def bytes(self, v: View) -> torch.Tensor:
+        """Flat uint8 view over a byte-buffer view (plan.raw_buf and channel slices of it)."""
+        b = v.buf
+        if b.dtype != L.U8 or v.row0:
+            raise ValueError("bytes() is for untyped byte buffers")
+        return self.mem[b.offset + v.c0:b.offset + v.c0 + v.C]
+
     def detections(self):
         """(det [B,max_det,6] fp32, keep [B,max_det] int64, count [B] int32) views, if the plan ends in NMS."""
         o = self.plan.outputs
         B, md = self.plan.B, o["max_det"]
-        det = self._flat(o["det"].buf).view(torch.float32).view(B, md, 6)
-        keep = self._flat(o["keep"].buf).view(torch.int64).view(B, md)
-        count = self._flat(o["count"].buf).view(torch.int32).view(B)
+        det = self.bytes(o["det"]).view(torch.float32).view(B, md, 6)
+        keep = self.bytes(o["keep"]).view(torch.int64).view(B, md)
+        count = self.bytes(o["count"]).view(torch.int32).view(B)
         return det, keep, count
 
     def outputs(self):

@@ -110,3 +110,22 @@ def load_packed(path: str):
         raise ValueError(f"{path}: state dict mismatch (missing {missing[:3]}..., unexpected {extra[:3]}...)")
     model.load_state_dict({k: v.to(own[k].dtype) for k, v in sd.items()}, strict=True)
     return model
+
+
+def convert_checkpoint(pt_path: str, out_path: str, dtype: torch.dtype | None = None) -> dict:
+    """Reference checkpoint ingestion: a ``.pt`` written by the reference's trainer (engine/trainer.py:584-623) is a
+    pickled dict whose ``ema`` / ``model`` entries are whole ``nn.Module`` objects (fp16), which only deserialise where
+    the reference package is importable at its original class paths (nn/tasks.py:1371-1486 ``torch_safe_load`` /
+    ``load_checkpoint``).  This reads one - preferring the EMA weights like ``load_checkpoint`` does (tasks.py:1467) -,
+    casts to fp32, folds BatchNorm and writes the pickle-free ``.fcepack`` twin.  Run it ONCE wherever ``ultralytics`` (the
+    reference) can be imported; serving then needs neither pickle nor the reference."""
+    try:
+        import ultralytics  # noqa: F401  (the unpickler resolves ultralytics.nn.tasks.DetectionModel etc.)
+    except ImportError as e:
+        raise RuntimeError("convert_checkpoint() unpickles reference nn.Modules: the reference package (ultralytics) must be "
+                           "importable here; the resulting .fcepack file no longer needs it") from e
+    ckpt = torch.load(pt_path, map_location="cpu", weights_only=False)
+    model = ckpt.get("ema") or ckpt["model"] if isinstance(ckpt, dict) else ckpt
+    model = model.float().eval()
+    meta = {"source": "reference .pt", "epoch": ckpt.get("epoch") if isinstance(ckpt, dict) else None}
+    return save_packed(model, out_path, dtype=dtype, meta=meta)

@@ -719,13 +719,16 @@ class Plan:
                       max_wh=float(max_wh), n_classes=0)
         cap = A * nc if d.multi_label else A
         ws_bytes = B * cap * 16
-        det = self.raw_buf(B * max_det * 6 * 4)
+        # det and count back to back in ONE buffer: the NMS kernel writes straight into the send buffer of the multi-GPU
+        # gather (runner.DetectionGather: one collective, no packing copy)
+        nd = B * max_det * 6 * 4
+        detcount = self.raw_buf(nd + B * 4)
+        det, count = detcount.ch(0, nd), detcount.ch(nd, nd + B * 4)
         keep = self.raw_buf(B * max_det * 8)
-        count = self.raw_buf(B * 4)
         ws = self.raw_buf(ws_bytes)
         self.add(Node("fce_nms", d, [y, None, det, keep, count, ws, ws_bytes], reads=[y],
                       writes=[det, keep, count, ws], tag=tag, bytes=B * ((4.0 + nc) * A * 4 + max_det * 6 * 4)))
-        self.outputs.update({"det": det, "keep": keep, "count": count, "max_det": max_det})
+        self.outputs.update({"det": det, "keep": keep, "count": count, "max_det": max_det, "detcount": detcount})
         return det, keep, count
 
     # ------------------------------------------------------------------ dispatch

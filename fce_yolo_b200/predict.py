@@ -53,12 +53,19 @@ class Predictor:
             self.stream_ = self.stream
             self.inp = self.ex.input_tensor()
             self.det, self.keep, self.count = self.ex.detections()
-            self.h_det = torch.empty(self.det.shape, dtype=torch.float32).pin_memory()
-            self.h_count = torch.empty(self.count.shape, dtype=torch.int32).pin_memory()
+            # det and count sit back to back in one arena buffer (plan.Plan.nms): ONE device->host copy per call
+            self.detcount = self.ex.bytes(plan.outputs["detcount"])
+            self.h_det, self.h_count, self._h_dc = self._host_slot()
             self.overlap = bool(overlap_nms and use_graph)
             if self.overlap:  # NMS of call i runs on a side stream underneath the forward of call i+1 (engine.py)
                 self.ex.enable_overlap()
         self.launches_per_call = self.ex.launches_per_run
+
+    def _host_slot(self):
+        """Pinned host mirror of the packed (det, count) buffer: (det view [B,max_det,6], count view [B], raw bytes)."""
+        raw = torch.empty(self.detcount.numel(), dtype=torch.uint8).pin_memory()
+        nd = self.det.numel() * 4
+        return (raw[:nd].view(torch.float32).view(self.det.shape), raw[nd:nd + 4 * self.batch].view(torch.int32), raw)
 
     def _run(self):
         if self.overlap:
@@ -94,8 +101,7 @@ class Predictor:
             self.inp.copy_(images, non_blocking=True)
             self._run()
             self.join()
-            self.h_det.copy_(self.det, non_blocking=True)
-            self.h_count.copy_(self.count, non_blocking=True)
+            self._h_dc.copy_(self.detcount, non_blocking=True)
         self.stream.synchronize()
         return self.h_det, self.h_count
 
@@ -103,7 +109,8 @@ class Predictor:
         """Pipelined inference over an iterable of host batches (each shaped like ``input_shape``, ideally pinned):
         the host->device copy of batch i+1 runs on a copy stream while batch i is in the graph, and the padded
         detections of batch i come back device->host on the compute stream.  Yields, per batch and in order, pinned
-        host tensors (det [B,max_det,6], count [B]) - valid until the next-but-one ``next()`` (two result slots).
+        host tensors (det [B,max_det,6], count [B]) - valid until the next-but-one ``next()`` (three result slots: the
+        device->host copy of batch i+2 is enqueued while the caller still holds batch i, into a different slot).
         Every batch still crosses PCIe inside the call: this is the end-to-end path, only overlapped."""
         dev = self.device
         with torch.cuda.device(dev):
@@ -111,11 +118,10 @@ class Predictor:
                 self._pipe = dict(
                     copy_stream=torch.cuda.Stream(dev),
                     stage=[torch.empty_like(self.inp) for _ in range(2)],
-                    h_det=[torch.empty(self.det.shape, dtype=torch.float32).pin_memory() for _ in range(2)],
-                    h_cnt=[torch.empty(self.count.shape, dtype=torch.int32).pin_memory() for _ in range(2)],
+                    slot=[self._host_slot() for _ in range(3)],
                     copied=[torch.cuda.Event() for _ in range(2)],
                     consumed=[torch.cuda.Event() for _ in range(2)],
-                    done=[torch.cuda.Event() for _ in range(2)])
+                    done=[torch.cuda.Event() for _ in range(3)])
             P = self._pipe
             cs, ms = P["copy_stream"], self.stream_
             it = iter(batches)
@@ -144,19 +150,18 @@ class Predictor:
                     P["consumed"][cur_i % 2].record(ms)
                     self._run()
                     with torch.cuda.stream(self._out_stream()):  # in overlap mode: behind the NMS, on its side stream
-                        P["h_det"][cur_i % 2].copy_(self.det, non_blocking=True)
-                        P["h_cnt"][cur_i % 2].copy_(self.count, non_blocking=True)
-                        P["done"][cur_i % 2].record(torch.cuda.current_stream(dev))
+                        P["slot"][cur_i % 3][2].copy_(self.detcount, non_blocking=True)  # det + count: one copy
+                        P["done"][cur_i % 3].record(torch.cuda.current_stream(dev))
                 if nxt is not None:
                     upload(cur_i + 1, nxt)  # overlaps the graph that was just launched
                 if pending is not None:
-                    P["done"][pending % 2].synchronize()
-                    yield P["h_det"][pending % 2], P["h_cnt"][pending % 2]
+                    P["done"][pending % 3].synchronize()
+                    yield P["slot"][pending % 3][0], P["slot"][pending % 3][1]
                 pending = cur_i
                 i += 1
             if pending is not None:
-                P["done"][pending % 2].synchronize()
-                yield P["h_det"][pending % 2], P["h_cnt"][pending % 2]
+                P["done"][pending % 3].synchronize()
+                yield P["slot"][pending % 3][0], P["slot"][pending % 3][1]
 
     def predict(self, images, as_results: bool = False, names=None, paths=None):
         """The reference's ``YOLO(...).predict(list_of_bgr_frames)`` for raw uint8 HWC BGR images of any size (at most
@@ -188,8 +193,7 @@ class Predictor:
                                           C.c_void_p(self._meta_dev.data_ptr()), n, self.det.shape[1],
                                           C.c_void_p(self.stream.cuda_stream))
             L.check(st, "fce_scale_boxes")
-            self.h_det.copy_(self.det, non_blocking=True)
-            self.h_count.copy_(self.count, non_blocking=True)
+            self._h_dc.copy_(self.detcount, non_blocking=True)
         self.stream.synchronize()
         dets = [self.h_det[b, :c].clone() for b, c in enumerate(self.h_count[:n].tolist())]
         if not as_results:
@@ -208,4 +212,4 @@ class Predictor:
         return self.inp.numel() * self.inp.element_size()
 
     def d2h_bytes(self):
-        return self.h_det.numel() * 4 + self.h_count.numel() * 4
+        return self._h_dc.numel()

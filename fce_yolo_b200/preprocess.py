@@ -71,6 +71,7 @@ class LetterBoxGPU:
             raise RuntimeError("fce_yolo_b200 preprocessing runs on the GPU only (no CPU fallback)")
         self.lib = L.load(check_device=True)
         self._pin = self._dev = None  # staging: [meta int32 | images uint8], grown on demand
+        self._h2d_done = None         # event behind the last host->device copy out of the pinned staging buffer
 
     def _staging(self, nbytes: int):
         if self._pin is None or self._pin.numel() < nbytes:
@@ -100,6 +101,10 @@ class LetterBoxGPU:
         for im in images:
             img_offs.append(cur)
             cur = (cur + im.shape[0] * im.shape[1] * 3 + 15) & ~15
+        if self._h2d_done is not None:
+            # the previous call's non_blocking copy may still be reading the pinned buffer: rewriting it now would corrupt
+            # that batch (two back-to-back standalone calls) - wait for the DMA, not for the whole stream
+            self._h2d_done.synchronize()
         pin, dev = self._staging(cur)
         pin_np = pin.numpy()
         base = dev.data_ptr()
@@ -121,6 +126,9 @@ class LetterBoxGPU:
             raise ValueError(f"out must be a contiguous uint8 tensor of shape {(B, out_h, out_w, 3)}")
         with torch.cuda.device(self.device):
             dev[:cur].copy_(pin[:cur], non_blocking=True)
+            if self._h2d_done is None:
+                self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record(torch.cuda.current_stream(self.device))
             st = self.lib.fce_letterbox(C.c_void_p(base), C.c_void_p(base + off_x), C.c_void_p(base + off_y), B, out_h,
                                         out_w, PAD_VALUE, C.c_void_p(out.data_ptr()),
                                         C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))

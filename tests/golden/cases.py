@@ -78,6 +78,9 @@ NMS_CASES = {
     "class79": dict(make=_class79, kw=dict(conf_thres=0.25, iou_thres=0.7, max_det=300)),
     "empty": dict(make=_empty, kw=dict(conf_thres=0.25, iou_thres=0.7)),
     "maxdet20": dict(make=lambda: synth_predictions(14, 1, 8400), kw=dict(conf_thres=0.25, iou_thres=0.7, max_det=20)),
+    # max_nms below the candidate count, both <= 1024: the kept set must be the BEST max_nms by score (nms.py:136-140)
+    "maxnms_cut": dict(make=lambda: synth_predictions(16, 2, 700, sharp=4.0),
+                       kw=dict(conf_thres=0.25, iou_thres=0.7, max_det=300, max_nms=150), tie_perm=True),
     "a33600": dict(make=lambda: synth_predictions(15, 1, 33600, imgsz=1280, sharp=1.5),
                    kw=dict(conf_thres=0.25, iou_thres=0.7, max_det=300), tie_perm=True),
 }

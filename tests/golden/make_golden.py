@@ -148,3 +148,6 @@ if __name__ == "__main__":
     if "nms" in which:
         for n, c in NMS_CASES.items():
             nms_case(n, c)
+    for w in which:  # a single NMS case by name: python make_golden.py nms:maxnms_cut
+        if w.startswith("nms:"):
+            nms_case(w[4:], NMS_CASES[w[4:]])

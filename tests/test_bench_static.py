@@ -5,7 +5,7 @@ import os
 
 from helpers import ROOT
 
-COLLECTIVE_CALLS = {"step_device", "gather_detections", "barrier", "all_reduce", "all_gather", "all_gather_into_tensor",
+COLLECTIVE_CALLS = {"step_device", "gather_detections", "gather", "barrier", "all_reduce", "all_gather", "all_gather_into_tensor",
                     "broadcast", "gather_stats_to_rank0", "init_process_group", "destroy_process_group"}
 
 

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fce_yolo_b200.runner import gather_detections, gather_stats_to_rank0, shard_range
+from fce_yolo_b200.runner import DetectionGather, gather_detections, gather_stats_to_rank0, shard_range
 
 
 def test_shard_range_matches_contiguous_sampler():
@@ -45,6 +45,26 @@ def _worker(rank, world, port, q):
             gr = torch.Generator().manual_seed(100 + r)
             ok &= torch.equal(all_det[r * B:(r + 1) * B], torch.rand(B, max_det, 6, generator=gr))
             ok &= all_cnt[r * B:(r + 1) * B].tolist() == [r + 1, 0, max_det]
+        # the zero-copy per-step gatherer on a stand-in executor: det and count adjacent in one byte buffer
+        nd = B * max_det * 24
+        packed = torch.cat([det.view(-1).view(torch.uint8), count.view(torch.uint8)])
+
+        class _Plan:
+            outputs = {"detcount": "dc", "max_det": max_det}
+
+        _Plan.B = B
+
+        class _Ex:
+            plan = _Plan
+
+            @staticmethod
+            def bytes(v):
+                return packed
+
+        dg = DetectionGather(_Ex)
+        d4, c2 = dg.gather()
+        ok &= d4.shape == (world, B, max_det, 6) and c2.shape == (world, B) and dg.send.numel() == nd + 4 * B
+        ok &= torch.equal(d4.reshape(world * B, max_det, 6), all_det) and torch.equal(c2.reshape(-1), all_cnt)
         # ragged validation statistics (different n per rank, one rank empty-ish)
         n = 4 if rank == 0 else 1
         stats = {"tp": torch.full((n, 10), bool(rank)), "conf": torch.arange(n, dtype=torch.float32) + 10 * rank,
