@@ -527,6 +527,7 @@ def main():
             "impl_detail": {"cuda_graph": not a.no_graph, "arena_mb": round(pred.ex.nbytes / 2 ** 20, 1),
                             "nms_overlap": "NMS of step i runs on a side stream under the forward of step i+1; the last "
                                            "step's NMS is inside the timed region" if pred.overlap else False,
+                            "bf16_convs_on_cuda_cores": len(pred.ex.simt_bf16_convs),
                             "detections_per_image": round(m["detections_per_image"], 1),
                             "nms_candidates_per_image": round(m["candidates_per_image"], 1)},
             "e2e": {"value": round(m["e2e"], 2), "unit": "images/s",

@@ -20,6 +20,15 @@
 //
 // Each input element crosses L2 -> SM (R+2)/R times instead of 9, and the producer issues one TMA per
 // (band, chunk) instead of nine per 128 pixels.  Warp roles as in conv_tc.cu.
+//
+// CTA PAIRS (template PAIR, cta_group::2): the two CTAs of a {2,1,1} cluster each own a band (units 2q and 2q+1) with the
+// SAME geometry, stage their own strip and HALF of the rows of every weight tile; the leader issues tcgen05.mma of
+// M = 256 whose shifted-strip descriptors address both CTAs' shared memory at the same offsets.  Per K = 16 step an SM
+// reads 4 KB of A + Cout * 16 bytes of B instead of Cout * 32 (Cout = 64: 160 instead of 192 B/clk against the 128 B/clk
+// shared-memory port), parked weights take half the shared memory, and streamed weights cross L2 -> SM once per TWO bands:
+// 128 -> 128 channels at 40x40 moves 0.97 KB per output pixel instead of the 3.4 KB of the TMA-im2col pair kernel.
+// Barrier protocol as in conv_tc.cu: loads of both CTAs complete on the leader's full barrier, commits are multicast,
+// epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
 #include <cstdio>
 
 #include "tc_common.cuh"
@@ -43,7 +52,8 @@ struct HaloParams {
     int units;         // B * bands
     int acc_sets;      // 1 or 2 accumulator sets of nb * Cout TMEM columns
     uint32_t strip_bytes, strip_tx;  // shared-memory bytes of one strip stage / bytes one TMA box delivers
-    uint32_t b_sub;                  // bytes of one (tap, chunk) weight tile: Cout x kc bf16
+    uint32_t b_sub;                  // bytes of one (tap, chunk) weight tile PER CTA: Cout (pair: Cout / 2) x kc bf16
+    int pair_units;                  // ceil(units / 2): work items of a CTA pair
     uint32_t b_total, bias_bytes;
     int kc;        // channels per K chunk
     int b_stream;  // weights too large to park: the 9 tap tiles of chunk c travel with strip chunk c (same ring stage)
@@ -67,7 +77,7 @@ __device__ long long g_hprof[1];
 #define HP_T0() long long _t0 = 0; if (PROF) _t0 = clock64()
 #define HP_ACC(var) if (PROF) (var) += clock64() - _t0
 
-template <int KK>
+template <int KK, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const HaloParams p,
@@ -88,6 +98,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Work items: single CTA b walks units b, b + grid, ...; a pair q = blockIdx.x / 2 walks pair-units q, q + grid / 2, ...
+    // and its CTA of rank r owns unit 2 * item + r (an odd unit count leaves the last pair's rank 1 with a dummy: it
+    // re-reads the last unit's strip for the joint MMA and stores nothing).
+    constexpr int NCTA = PAIR ? 2 : 1;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_items = PAIR ? p.pair_units : p.units;
+    const uint32_t full0_sig = PAIR ? mapa_shared(full0, 0) : full0;      // barriers of the LEADER that the peer signals
+    const uint32_t bfull_sig = PAIR ? mapa_shared(bfull, 0) : bfull;
+    const uint32_t tempty0_sig = PAIR ? mapa_shared(tempty0, 0) : tempty0;
 
     pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel's tail
     if (warp == WARP_PROD_A && lane == 0) {
@@ -97,7 +119,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, NUM_EPI_WARPS);
+            mbar_init(tempty0 + 8 * a, NUM_EPI_WARPS * NCTA);
         }
         mbar_init(bfull, 1);
         for (int a = 0; a < 2; ++a) {
@@ -111,13 +133,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.has_res) tma_prefetch_desc(&tmR);
     }
     if (warp == WARP_ALLOC) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     for (int i = threadIdx.x; i < (int)(p.bias_bytes >> 2); i += NUM_THREADS) bias_s[i] = i < p.Cout ? bias[i] * epi_bias_scale(p.act) : 0.f;  // pre-scaled for epi_math16
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -127,19 +156,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == WARP_PROD_A) {
         // ------------------------------------------------------------------ strip producer
         Ring r;
+        const int nrow0 = (int)cta_rank * (p.Cout / NCTA);  // pair: this CTA stages rows [rank * Cout/2, +Cout/2) of each tile
         pdl_wait();  // activations come from the previous kernel (the weights loaded by the B producer do not)
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        for (int it = item0; it < n_items; it += item_step) {
+            int u = it * NCTA + (int)cta_rank;
+            if (u >= units) u = units - 1;  // the dummy half of the last pair
             const int b = u / p.bands, band = u - b * p.bands;
             const int h0 = band * p.R;
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
                 if (elect_one()) {
-                    const uint32_t fb = full0 + 8 * r.stage;
-                    mbar_expect_tx(fb, p.b_stream ? p.strip_tx + 9u * p.b_sub : p.strip_tx);
-                    tma_load_4d(sA + r.stage * p.strip_bytes, &tmA, fb, c * kc, -1, h0 - 1, b);
+                    const uint32_t fb = full0 + 8 * r.stage, fsig = full0_sig + 8 * r.stage;
+                    if (leader) mbar_expect_tx(fb, (p.b_stream ? p.strip_tx + 9u * p.b_sub : p.strip_tx) * NCTA);
+                    if (PAIR) tma_load_4d_cg2(sA + r.stage * p.strip_bytes, &tmA, fsig, c * kc, -1, h0 - 1, b);
+                    else tma_load_4d(sA + r.stage * p.strip_bytes, &tmA, fb, c * kc, -1, h0 - 1, b);
                     if (p.b_stream) {  // this chunk's nine weight tiles ride in the same stage
                         const uint32_t bdst = sB + r.stage * 9u * p.b_sub;
-                        for (int t = 0; t < 9; ++t) tma_load_2d(bdst + t * p.b_sub, &tmB, fb, t * p.Cin + c * kc, 0);
+                        for (int t = 0; t < 9; ++t) {
+                            if (PAIR) tma_load_2d_cg2(bdst + t * p.b_sub, &tmB, fsig, t * p.Cin + c * kc, nrow0);
+                            else tma_load_2d(bdst + t * p.b_sub, &tmB, fb, t * p.Cin + c * kc, 0);
+                        }
                     }
                 }
                 r.advance(A_STAGES);
@@ -149,14 +185,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ------------------------------------------------------------------ weights: parked once
         if (!p.b_stream && elect_one()) {
             const int tiles = 9 * chunks;
-            mbar_expect_tx(bfull, (uint32_t)tiles * p.b_sub);
+            const int nrow0 = (int)cta_rank * (p.Cout / NCTA);
+            if (leader) mbar_expect_tx(bfull, (uint32_t)tiles * p.b_sub * NCTA);
             // tile index = chunk * 9 + tap ; K column of the OHWI matrix = tap * Cin + chunk * kc
             for (int c = 0; c < chunks; ++c)
-                for (int t = 0; t < 9; ++t)
-                    tma_load_2d(sB + (c * 9 + t) * p.b_sub, &tmB, bfull, t * p.Cin + c * kc, 0);
+                for (int t = 0; t < 9; ++t) {
+                    if (PAIR) tma_load_2d_cg2(sB + (c * 9 + t) * p.b_sub, &tmB, bfull_sig, t * p.Cin + c * kc, nrow0);
+                    else tma_load_2d(sB + (c * 9 + t) * p.b_sub, &tmB, bfull, t * p.Cin + c * kc, 0);
+                }
         }
-    } else if (warp == WARP_MMA) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp == WARP_MMA && leader) {
+        // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA's only)
         Ring r;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -170,7 +209,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
         }
         long long wf = 0, we = 0, mt0 = PROF ? clock64() : 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        for (int it = item0; it < n_items; it += item_step) {
             {
                 HP_T0();
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
@@ -203,13 +242,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             const uint32_t bs = b16 + t * b_sub16;
 #pragma unroll
                             for (int k = 0; k < KK; ++k) {
-                                umma_bf16(d_tmem, make_desc(hi, ((as + 2 * k) & 0x3FFF) | (1u << 16)),
-                                          make_desc(dhi, ((bs + 2 * k) & 0x3FFF) | (1u << 16)), idesc, (c | t | k) != 0);
+                                const uint64_t ad = make_desc(hi, ((as + 2 * k) & 0x3FFF) | (1u << 16));
+                                const uint64_t bd = make_desc(dhi, ((bs + 2 * k) & 0x3FFF) | (1u << 16));
+                                if (PAIR) umma_bf16_cg2(d_tmem, ad, bd, idesc, (c | t | k) != 0);
+                                else umma_bf16(d_tmem, ad, bd, idesc, (c | t | k) != 0);
                             }
                         }
                     }
-                    umma_commit(empty0 + 8 * r.stage);
-                    if (c == chunks - 1) umma_commit(tfull0 + 8 * acc);
+                    if (PAIR) {
+                        umma_commit_cg2(empty0 + 8 * r.stage);
+                        if (c == chunks - 1) umma_commit_cg2(tfull0 + 8 * acc);
+                    } else {
+                        umma_commit(empty0 + 8 * r.stage);
+                        if (c == chunks - 1) umma_commit(tfull0 + 8 * acc);
+                    }
                 }
                 __syncwarp();
                 r.advance(A_STAGES);
@@ -247,16 +293,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t ph[2] = {0, 0};
         int i = 0;
         long long dw = 0, dt0 = PROF ? clock64() : 0;
+        // this CTA's unit of work item `it`; -1 = the dummy half of the last pair (no residual, no store)
+        auto unit_of = [&](int it) { const int u = it * NCTA + (int)cta_rank; return u < units ? u : -1; };
+        auto ready_or_free = [&](int it, int buf) {  // executed by one elected lane
+            const int u = unit_of(it);
+            if (u >= 0) make_ready(u, buf);
+            else mbar_arrive(stg_ready0 + 8 * buf);
+        };
         pdl_wait();  // residual reads and output stores touch buffers the previous kernel may still be using
-        if (blockIdx.x < units && elect_one()) make_ready(blockIdx.x, 0);
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ++i) {
+        if (item0 < n_items && elect_one()) ready_or_free(item0, 0);
+        for (int it = item0; it < n_items; it += item_step, ++i) {
+            const int u = unit_of(it);
             const int buf = n_stg == 2 ? (i & 1) : 0;
             if (n_stg == 2) {
                 // the other buffer's last store (band i-1) must have drained it before band i+1 may load into it
-                const int un = u + gridDim.x;
+                const int itn = it + item_step;
                 if (elect_one()) {
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    if (un < units) make_ready(un, buf ^ 1);
+                    if (itn < n_items) ready_or_free(itn, buf ^ 1);
                 }
             }
             {
@@ -266,14 +320,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             ph[buf] ^= 1;
             if (elect_one()) {
-                const int b = u / p.bands, band = u - b * p.bands;
-                for (int sl = 0; sl < n_slabs; ++sl)
-                    tma_store_4d(&tmC, sStg + buf * stg_bytes + sl * p.slab_bytes, sl * slab_cols, 0, band * p.R, b);
+                if (u >= 0) {
+                    const int b = u / p.bands, band = u - b * p.bands;
+                    for (int sl = 0; sl < n_slabs; ++sl)
+                        tma_store_4d(&tmC, sStg + buf * stg_bytes + sl * p.slab_bytes, sl * slab_cols, 0, band * p.R, b);
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 if (n_stg == 1) {
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    const int un = u + gridDim.x;
-                    if (un < units) make_ready(un, 0);
+                    const int itn = it + item_step;
+                    if (itn < n_items) ready_or_free(itn, 0);
                 }
             }
             __syncwarp();
@@ -298,7 +354,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int acc = 0, i = 0;
         uint32_t acc_phase = 0, sph[2] = {0, 0};
         long long ew = 0, es = 0, et0 = PROF ? clock64() : 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ++i) {
+        for (int it = item0; it < n_items; it += item_step, ++i) {
+            const int u_raw = it * NCTA + (int)cta_rank;
+            const bool live = u_raw < units;  // false: the dummy half of the last pair
+            const int u = live ? u_raw : units - 1;
             const int band = u % p.bands;
             const int h0 = band * R;
             const int buf = p.n_stg == 2 ? (i & 1) : 0;
@@ -316,7 +375,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             sph[buf] ^= 1;
             tc_fence_after();
 #pragma unroll 1
-            for (int item = grp; item < items; item += NUM_GROUPS) {
+            for (int item = grp; item < (live ? items : 0); item += NUM_GROUPS) {
                 const int blk = item / pairs;
                 const int j = (item - blk * pairs) * 2;
                 const int o = blk * 128 + quarter * 32 + lane;  // padded-flat output index inside the band
@@ -366,7 +425,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(tempty0 + 8 * acc);
+                if (PAIR) mbar_arrive_cluster(tempty0_sig + 8 * acc);
+                else mbar_arrive(tempty0 + 8 * acc);
                 mbar_arrive(stg_written0 + 8 * buf);
             }
             if (p.acc_sets == 2) {
@@ -384,10 +444,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     if (warp == WARP_ALLOC) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
 
@@ -417,10 +481,10 @@ int conv_halo_profile(long long* out, int n) {
 #endif
 
 // Band height for a given K chunk / weight mode; returns the efficiency estimate (0 = does not fit).
-static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool stream, HaloParams& p) {
+static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool stream, int ncta, HaloParams& p) {
     const int chunks = d->Cin / kc;
     const uint32_t row_b = kc * 2;
-    const uint32_t b_sub = (uint32_t)d->Cout * row_b;
+    const uint32_t b_sub = (uint32_t)(d->Cout / ncta) * row_b;  // a pair stages half of every weight tile's rows per CTA
     const uint32_t b_total = ((stream ? (uint32_t)A_STAGES * 9u : 9u * chunks) * b_sub + 1023u) & ~1023u;
     const uint32_t bias_bytes = ((uint32_t)d->Cout * 4 + 1023u) & ~1023u;
     const int Wp = d->W + 2;
@@ -455,6 +519,7 @@ static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool s
     p.nb = (best_R * Wp + 127) / 128;
     p.chunks = chunks;
     p.units = d->B * p.bands;
+    p.pair_units = (p.units + 1) / 2;
     p.acc_sets = 2 * p.nb * d->Cout <= 512 ? 2 : 1;
     p.strip_bytes = ((128u * p.nb + 2u * Wp + 2u) * row_b + 1023u) & ~1023u;
     p.strip_tx = row_b * (uint32_t)Wp * (uint32_t)(best_R + 2);
@@ -477,27 +542,39 @@ static const int g_stream_max_cout = [] {  // widest output the streamed-weight 
     return e ? atoi(e) : 128;
 }();
 
+// Automatic pair rule, from per-layer A/B timings on B200 (tools/plan_conv_ab.py, profiles/r02_conv_ab_*_v3.csv; m scale,
+// batch 256): pairs pay where the operand feed limits the single CTA - 64 -> 64 at 80x80: 193 -> 173 us; Detect box branch
+// 256 -> 64 at 80x80 (streamed weights): 546 -> 405 us, 512 -> 64 at 40x40: 316 -> 235 us; 128 -> 128 at 40x40: 136 us against
+// 140 us of the im2col pair kernel (155 vs 169 us with the residual).  Thin layers (Cin or Cout of 32 and less) are HBM /
+// epilogue bound and LOSE to the coupling of the two CTAs' epilogues (32 -> 32 at 160x160 with residual: 267 -> 351 us).
+static bool halo_pair_pays(const fce_conv_desc* d, const HaloParams& q) {
+    (void)q;
+    return d->Cout >= 64 && d->Cin >= 64;
+}
+
 // Picks the weight mode, the K chunk and the band height; returns false when the shape does not fit this kernel.
-static bool halo_plan(const fce_conv_desc* d, bool has_res, HaloParams& p) {
+// ncta = 2 plans the CTA-pair variant (half of each weight tile per CTA: more shapes park their weights).
+static bool halo_plan(const fce_conv_desc* d, bool has_res, int ncta, HaloParams& p) {
     if (g_halo_mode == 0) return false;
     if (d->k != 3 || d->stride != 1) return false;
     if (d->Cout > 256 || d->W + 2 > 256 || d->out_dtype != FCE_BF16) return false;
+    if (ncta == 2 && (d->Cout % 16 || d->Cout < 32)) return false;  // M = 256 MMAs: N % 16, whole swizzle atoms per CTA
     const int kc0 = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
-    if (halo_plan_one(d, has_res, kc0, false, p) >= 0.55) return true;  // weights parked in shared memory
-    if (g_halo_mode == 2) return false;                                // debug: streaming mode off
-    // weights streamed with the strip: worth it for narrow outputs (measured: Cout = 64: 117 -> 82 us, Cout = 128 on a
-    // 20x20 map: 26.6 -> 20.5 us), where the TMA-im2col kernel's nine reads of the input per output pixel dominate;
-    // wider outputs amortise them over the MMA work and keep the im2col kernel
-    // 65..128 outputs: small maps of small batches only - from ~600 128-row tiles on, the CTA-pair im2col kernel is faster
-    // (m scale, batch 256, 128->128 at 40x40: 146 us streamed strips vs 122 us pairs; at batch 64, 20x20: 20.5 vs 22.7 us)
-    if (d->Cout > g_stream_max_cout || (d->Cout > 64 && (d->H * d->W > 1600 || (long long)d->B * d->H * d->W >= 75000)))
-        return false;
+    if (halo_plan_one(d, has_res, kc0, false, ncta, p) >= 0.55) return true;  // weights parked in shared memory
+    if (g_halo_mode == 2) return false;                                      // debug: streaming mode off
+    // weights streamed with the strip.  Single CTA: worth it for narrow outputs (measured: Cout = 64: 117 -> 82 us, Cout =
+    // 128 on a 20x20 map: 26.6 -> 20.5 us), where the TMA-im2col kernel's nine reads of the input per output pixel
+    // dominate; 65..128 outputs only on small maps of small batches - from ~600 128-row tiles on, the CTA-pair im2col
+    // kernel is faster (m scale, batch 256, 128->128 at 40x40: 146 us streamed strips vs 122 us pairs).  A PAIR streams
+    // half of the weights per CTA and band: up to 128 outputs at any size.
+    if (d->Cout > g_stream_max_cout) return false;
+    if (ncta == 1 && d->Cout > 64 && (d->H * d->W > 1600 || (long long)d->B * d->H * d->W >= 75000)) return false;
     HaloParams best{};
     double best_eff = 0.0;
     for (int kc = 64; kc >= 32; kc >>= 1) {
         if (d->Cin % kc) continue;
         HaloParams q{};
-        const double e = halo_plan_one(d, has_res, kc, true, q);
+        const double e = halo_plan_one(d, has_res, kc, true, ncta, q);
         if (e > best_eff + 0.05) {  // prefer the wider chunk unless the narrower one buys a clearly better band
             best_eff = e;
             best = q;
@@ -508,16 +585,34 @@ static bool halo_plan(const fce_conv_desc* d, bool has_res, HaloParams& p) {
     return true;
 }
 
-bool conv2d_halo_supported(const fce_conv_desc* d, bool has_res) {
+// 0 = not a strip-kernel shape, 1 = single CTA, 2 = CTA pair.  Automatic choice (mode 0) from per-layer A/B timings
+// (tools/plan_conv_ab.py); mode 1 / 2 force single / pair.
+static int halo_choice(const fce_conv_desc* d, bool has_res, int mode, HaloParams& p) {
+    static const int pair_env = [] { const char* e = getenv("FCE_HALO_PAIR"); return e && *e ? atoi(e) : -1; }();
+    if (mode == 1) return halo_plan(d, has_res, 1, p) ? 1 : 0;
+    if (mode == 2) return (halo_plan(d, has_res, 2, p) && p.units >= 2) ? 2 : 0;
+    if (pair_env != 0) {
+        HaloParams q{};
+        if (halo_plan(d, has_res, 2, q) && q.units >= kNumSMs / 2 && (pair_env == 1 || halo_pair_pays(d, q))) {
+            p = q;
+            return 2;
+        }
+    }
+    return halo_plan(d, has_res, 1, p) ? 1 : 0;
+}
+
+int conv2d_halo_choice(const fce_conv_desc* d, bool has_res, int mode) {
     HaloParams p{};
-    return halo_plan(d, has_res, p);
+    return halo_choice(d, has_res, mode, p);
 }
 
 int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res, void* y,
-                cudaStream_t st) {
+                cudaStream_t st, int mode) {
     const DriverApi& api = driver();
     HaloParams p{};
-    if (!api.ok || !halo_plan(d, res != nullptr, p)) return FCE_ERR_UNSUPPORTED;
+    const int choice = api.ok ? halo_choice(d, res != nullptr, mode, p) : 0;
+    if (!choice) return FCE_ERR_UNSUPPORTED;
+    const int ncta = choice;
     const int kc = p.kc;
     const uint32_t row_b = kc * 2;
     p.act = d->act;
@@ -525,7 +620,7 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
     const uint32_t layout = row_b == 128 ? 2u : (row_b == 64 ? 4u : 6u);
     const uint32_t sbo = 8 * row_b;
     p.desc_hi = (sbo >> 4) | (1u << 14) | (layout << 29);
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->Cout >> 3) << 17) | ((uint32_t)((128 * ncta) >> 4) << 24);
     const CUtensorMapSwizzle swz = row_b == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                    : row_b == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -567,7 +662,7 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
         const cuuint64_t K = 9ull * d->Cin;
         const cuuint64_t gdim[2] = {K, (cuuint64_t)d->Cout};
         const cuuint64_t gstr[1] = {K * 2};
-        const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)d->Cout};
+        const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(d->Cout / ncta)};
         const cuuint32_t est[2] = {1, 1};
         if (api.tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, est,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -576,11 +671,12 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
     }
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const HaloParams,
                              const float*);
-    static const KernelFn table[3] = {conv_halo_kernel<1>, conv_halo_kernel<2>, conv_halo_kernel<4>};
+    static const KernelFn table[6] = {conv_halo_kernel<1, false>, conv_halo_kernel<2, false>, conv_halo_kernel<4, false>,
+                                      conv_halo_kernel<1, true>,  conv_halo_kernel<2, true>,  conv_halo_kernel<4, true>};
     static DeviceOnce attr_once;  // the shared-memory opt-in is a per-device attribute
     int dev = 0;
     if (attr_once.pending(&dev)) {
-        for (int v = 0; v < 3; ++v) {
+        for (int v = 0; v < 6; ++v) {
             cudaError_t e = cudaFuncSetAttribute(table[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) {
                 set_cuda_error(e);
@@ -591,12 +687,17 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
     }
     const size_t smem = (size_t)A_STAGES * p.strip_bytes + p.b_total + (size_t)p.n_stg * p.n_slabs * p.slab_bytes +
                         p.bias_bytes + 1024 + 256;
-    const int grid = p.units < kNumSMs ? p.units : kNumSMs;
     g_halo_last = true;
     if (g_halo_prof)
-        fprintf(stderr, "[halo] R=%d bands=%d nb=%d units=%d acc_sets=%d n_stg=%d slab_cols=%d smem=%zu\n", p.R, p.bands, p.nb,
-                p.units, p.acc_sets, p.n_stg, p.slab_cols, smem);
-    return launch_pdl(table[kc == 16 ? 0 : (kc == 32 ? 1 : 2)], grid, NUM_THREADS, smem, st, tmA, tmB, tmC, tmR, p, bias);
+        fprintf(stderr, "[halo] ncta=%d R=%d bands=%d nb=%d units=%d acc_sets=%d n_stg=%d slab_cols=%d stream=%d smem=%zu\n", ncta,
+                p.R, p.bands, p.nb, p.units, p.acc_sets, p.n_stg, p.slab_cols, p.b_stream, smem);
+    const int kv = kc == 16 ? 0 : (kc == 32 ? 1 : 2);
+    if (ncta == 2) {
+        const int pairs = p.pair_units < kNumSMs / 2 ? p.pair_units : kNumSMs / 2;
+        return launch_pdl_cluster(table[3 + kv], 2 * pairs, NUM_THREADS, smem, st, 2, tmA, tmB, tmC, tmR, p, bias);
+    }
+    const int grid = p.units < kNumSMs ? p.units : kNumSMs;
+    return launch_pdl(table[kv], grid, NUM_THREADS, smem, st, tmA, tmB, tmC, tmR, p, bias);
 }
 
 }  // namespace fce

@@ -627,25 +627,34 @@ bool conv2d_tc_supported(const fce_conv_desc* d, const void* x, const void* w, c
     return driver().ok;
 }
 
-bool conv2d_halo_supported(const fce_conv_desc* d, bool has_res);
+int conv2d_halo_choice(const fce_conv_desc* d, bool has_res, int mode);  // 0 no strip kernel, 1 single CTA, 2 CTA pair
 bool conv_halo_ran_last();
 void conv_halo_clear_last();
 #ifdef FCE_DEBUG
 void conv_halo_set_profile(bool on);
 int conv_halo_profile(long long* out, int n);
 #endif
-int conv2d_halo(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+int conv2d_halo(const fce_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t, int mode);
 
 int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float* bias, const void* res, void* y,
               cudaStream_t st, const fce_detect_epi_desc* epi) {
     if (!bias) return FCE_ERR_BAD_ARG;
     // thin 3x3 stride-1 convs: input strip resident in shared memory (conv_halo.cu)
     // impl: 0 / 2 automatic kernel choice, 3 = CTA-pair kernel required (error when the shape has no legal pair tiling),
-    // 4 = single-CTA implicit-GEMM kernel required; 3 and 4 bypass the strip kernel (tests, A/B timing)
+    // 4 = single-CTA implicit-GEMM kernel required (3 and 4 bypass the strip kernel), 5 / 6 = single-CTA / CTA-pair 3x3 strip
+    // kernel required (tests, A/B timing)
     const bool force_pair = d->impl == 3, force_single = d->impl == 4;
-    if (!epi && !force_pair && !force_single && conv2d_halo_supported(d, res != nullptr)) {
-        g_conv_stats[2].fetch_add(1, std::memory_order_relaxed);
-        return conv2d_halo(d, x, w, bias, res, y, st);
+    if (d->impl == 5 || d->impl == 6) {
+        if (epi || !conv2d_halo_choice(d, res != nullptr, d->impl - 4)) return FCE_ERR_UNSUPPORTED;
+        g_conv_stats[d->impl == 6 ? 1 : 2].fetch_add(1, std::memory_order_relaxed);
+        return conv2d_halo(d, x, w, bias, res, y, st, d->impl - 4);
+    }
+    if (!epi && !force_pair && !force_single) {
+        const int hc = conv2d_halo_choice(d, res != nullptr, 0);
+        if (hc) {
+            g_conv_stats[hc == 2 ? 1 : 2].fetch_add(1, std::memory_order_relaxed);
+            return conv2d_halo(d, x, w, bias, res, y, st, 0);
+        }
     }
     conv_halo_clear_last();
     const DriverApi& api = driver();

@@ -145,7 +145,7 @@ class Arena:
 class Executor(Arena):
     """Binds a Plan to device memory and runs it through the C ABI."""
 
-    def __init__(self, plan: Plan, reuse_memory: bool = True, use_graph: bool = True):
+    def __init__(self, plan: Plan, reuse_memory: bool = True, use_graph: bool = True, strict_tc: bool = False):
         self.lib = L.load(check_device=True)
         super().__init__(plan, reuse_memory)
         base = self.base
@@ -167,6 +167,17 @@ class Executor(Arena):
                 else:
                     args.append(C.c_size_t(int(p)))
             self._calls.append((fn, args, n))
+        # Which bf16 convs leave the tensor cores?  fce_conv2d falls through to the CUDA-core kernel when the tcgen05 path
+        # rejects a shape (channel counts that are not multiples of 16, unaligned views ...): that must be VISIBLE, not
+        # found in a profile.  (fp32-mode plans and the fp32 pooled strips are CUDA-core work by design.)
+        self.simt_bf16_convs = []
+        for fn, args, n in self._calls:
+            d = n.desc
+            if n.fn == "fce_conv2d" and d.in_dtype == L.BF16 and d.w_dtype == L.BF16 and d.impl == 0:
+                if self.lib.fce_conv2d_route(*args[:3], args[4], args[5]) == 0:
+                    self.simt_bf16_convs.append(n.tag)
+        if strict_tc and self.simt_bf16_convs:
+            raise PlanError(f"bf16 convolutions off the tensor cores: {self.simt_bf16_convs}")
         self.use_graph = use_graph
         self._side_streams = {}  # branch id -> torch stream (plans with Node.stream > 0, graph mode only)
         self.graph = None

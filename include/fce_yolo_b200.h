@@ -60,7 +60,8 @@ int fce_device_ok(void);
  * (out_scale / res_scale / res_up below).
  * impl: 0 = auto, 1 = force the fp32-accurate SIMT kernel, 2 = force a tcgen05 kernel (strip / single-CTA / CTA-pair chosen
  *       automatically), 3 = force the CTA-pair (cta_group::2) implicit-GEMM kernel, 4 = force the single-CTA
- *       implicit-GEMM kernel.  2-4 return FCE_ERR_UNSUPPORTED when the shape has no such kernel.
+ *       implicit-GEMM kernel, 5 / 6 = force the 3x3 stride-1 strip kernel as single CTAs / CTA pairs.  2-6 return
+ *       FCE_ERR_UNSUPPORTED when the shape has no such kernel.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t B, H, W;          /* input spatial size */

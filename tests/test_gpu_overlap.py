@@ -108,3 +108,20 @@ def test_head_branches_match_single_stream(overlap):
         assert torch.equal(preds[False].ex.outputs()[0], preds[True].ex.outputs()[0]), it
         total += int(c0.sum())
     assert total > 0
+
+
+def test_bf16_convs_that_leave_the_tensor_cores_are_reported():
+    """Executor.simt_bf16_convs lists the bf16 convs fce_conv2d would route to the CUDA-core kernel (n scale: the 8-channel
+    bottleneck convs, Cout % 16 != 0); the m-scale graph has none, and strict_tc=True turns a non-empty list into an error."""
+    from fce_yolo_b200.engine import Executor
+    from fce_yolo_b200.plan import PlanError, compile_model
+    from fce_yolo_b200.tasks import DetectionModel
+
+    dev = torch.device("cuda:0")
+    n_model = _model()
+    ex = Executor(compile_model(n_model, 1, 64, 64, "bf16", dev), use_graph=False)
+    assert ex.simt_bf16_convs and all(".m." in t for t in ex.simt_bf16_convs)
+    with pytest.raises(PlanError):
+        Executor(compile_model(n_model, 1, 64, 64, "bf16", dev), use_graph=False, strict_tc=True)
+    m_model = DetectionModel("yolo11m-bifpn.yaml").fuse().eval()
+    assert Executor(compile_model(m_model, 1, 64, 64, "bf16", dev), use_graph=False, strict_tc=True).simt_bf16_convs == []

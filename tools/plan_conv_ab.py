@@ -41,7 +41,7 @@ def main():
     pk = bench.peaks()
     seen = {}
     rows = []
-    tot = {"auto": 0.0, "single": 0.0, "pair": 0.0, "best": 0.0}
+    tot = {"auto": 0.0, "single": 0.0, "pair": 0.0, "strip": 0.0, "strip2": 0.0, "best": 0.0}
     for fn, args, n in pred.ex._calls:
         if n.fn not in ("fce_conv2d", "fce_conv2d_detect"):
             continue
@@ -53,7 +53,7 @@ def main():
             seen[key][0] += 1
             continue
         res = {}
-        for label, impl in (("auto", 0), ("single", 4), ("pair", 3)):
+        for label, impl in (("auto", 0), ("single", 4), ("pair", 3), ("strip", 5), ("strip2", 6)):
             saved = d.impl
             d.impl = impl
             rc = fn(*args, st)
@@ -75,7 +75,7 @@ def main():
             res[label] = ms[len(ms) // 2]
             d.impl = saved
         seen[key] = [1, n.tag, res, n.flops, n.bytes]
-    print(f"{'node':30s} {'shape':34s} cnt {'auto us':>9s} {'single':>9s} {'pair':>9s}  auto TF  best TF  roofline us")
+    print(f"{'node':30s} {'shape':34s} cnt {'auto us':>9s} {'single':>9s} {'pair':>9s} {'strip':>9s} {'strip2':>9s}  auto TF  best TF  roofline us")
     for key, (cnt, tag, res, fl, by) in seen.items():
         _, B, H, W, Cin, Cout, k, s, has_res, odt, wt, ru = key
         shape = f"{k}x{k}s{s} {Cin}->{Cout} @{H}x{W}" + (" +res" if has_res else "") + (" f32" if odt == L.F32 else "")
@@ -83,19 +83,19 @@ def main():
         vals = {k_: v for k_, v in res.items() if v is not None}
         best = min(vals.values())
         f = lambda v: f"{v * 1e3:9.1f}" if v is not None else "        -"  # noqa: E731
-        print(f"{tag:30s} {shape:34s} {cnt:3d} {f(res['auto'])} {f(res['single'])} {f(res['pair'])}  "
+        print(f"{tag:30s} {shape:34s} {cnt:3d} {f(res['auto'])} {f(res['single'])} {f(res['pair'])} {f(res['strip'])} {f(res['strip2'])}  "
               f"{fl / res['auto'] / 1e9:7.0f} {fl / best / 1e9:8.0f}  {roof:9.1f}", flush=True)
-        for k_ in ("auto", "single", "pair"):
+        for k_ in ("auto", "single", "pair", "strip", "strip2"):
             tot[k_] += cnt * (res[k_] if res[k_] is not None else res["auto"])
         tot["best"] += cnt * best
-        rows.append((tag, shape, cnt, res["auto"], res["single"], res["pair"], fl, by))
+        rows.append((tag, shape, cnt, res["auto"], res["single"], res["pair"], res["strip"], res["strip2"], fl, by))
     print("TOTAL ms per step: " + "  ".join(f"{k_} {v:.3f}" for k_, v in tot.items()))
     if a.csv:
         with open(a.csv, "w") as fcsv:
-            fcsv.write("tag,shape,count,auto_ms,single_ms,pair_ms,gflop,mbytes\n")
+            fcsv.write("tag,shape,count,auto_ms,single_ms,pair_ms,strip_ms,strip_pair_ms,gflop,mbytes\n")
             for r in rows:
-                fcsv.write(",".join(str(x) for x in r[:3]) + "," + ",".join("" if x is None else f"{x:.5f}" for x in r[3:6]) +
-                           f",{r[6] / 1e9:.3f},{r[7] / 1e6:.3f}\n")
+                fcsv.write(",".join(str(x) for x in r[:3]) + "," + ",".join("" if x is None else f"{x:.5f}" for x in r[3:8]) +
+                           f",{r[8] / 1e9:.3f},{r[9] / 1e6:.3f}\n")
 
 
 if __name__ == "__main__":
