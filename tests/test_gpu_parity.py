@@ -225,7 +225,10 @@ def test_large_batch_properties():
     xb = x.repeat(64, 1, 1, 1)
     yb, _ = run_model(model, xb.to(dev()), precision="bf16")
     assert torch.equal(yb[0], yb[63])
-    assert rel_l2(yb[0:1].cpu(), y1.cpu()) < 1e-6
+    # batch 1 and batch 64 may run a layer on DIFFERENT kernels (strip / im2col, single CTA / CTA pair are chosen by
+    # problem size) whose fp32 accumulation order over K differs: equal up to bf16 rounding of a few elements, far below
+    # the 2e-2 bf16 tolerance - not bit-equal
+    assert rel_l2(yb[0:1].cpu(), y1.cpu()) < 2e-3
     assert torch.isfinite(yb).all()
 
 
