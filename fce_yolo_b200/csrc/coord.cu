@@ -332,6 +332,10 @@ __global__ void __launch_bounds__(MT) coordatt_mlp_kernel(const fce_coordatt_mlp
 }  // namespace
 }  // namespace fce
 
+namespace fce {
+int coord_pool_tma(const fce_pool_desc* d, const void* x, float* strip, cudaStream_t st);  // coord_pool_tma.cu
+}
+
 using namespace fce;
 
 extern "C" size_t fce_coord_pool_workspace(const fce_pool_desc* d) {
@@ -347,6 +351,10 @@ extern "C" int fce_coord_pool(const fce_pool_desc* d, const void* x, float* stri
     const int n = d->dtype == FCE_BF16 ? 8 : 4;
     if (d->dtype != FCE_BF16 && d->dtype != FCE_F32) return FCE_ERR_UNSUPPORTED;
     if ((d->C % n) || (d->pitch % n) || (d->off % n) || (((uintptr_t)x) & 15)) return FCE_ERR_ALIGNMENT;
+    {   // bf16, enough (image, 64-channel chunk) pairs to fill the GPU: the TMA-fed kernel (asynchronous loads)
+        const int rc = coord_pool_tma(d, x, strip, st);
+        if (rc != FCE_ERR_UNSUPPORTED) return rc;
+    }
     // widest channel group whose sweep (3 column groups of PT / cvt slots) still covers W
     const int cvt = (d->W <= 24 && d->C >= 32 * n) ? 32 : ((d->W <= 48 && d->C >= 16 * n) ? 16 : 8);
     const int cc = cvt * n;

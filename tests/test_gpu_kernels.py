@@ -254,7 +254,11 @@ def test_gate_apply_vs_torch(lib, B, H, W, Cc, mode, dtype):
 
 # ------------------------------------------------------------------------------------------------ coordinate pooling
 @pytest.mark.parametrize("B,H,W,Cc", [(2, 80, 80, 256), (64, 40, 40, 512), (3, 20, 20, 512), (1, 160, 160, 64),
-                                      (2, 13, 27, 128), (1, 7, 100, 40), (5, 33, 50, 256)])
+                                      (2, 13, 27, 128), (1, 7, 100, 40), (5, 33, 50, 256),
+                                      # large (image, chunk) counts: the TMA-fed kernel (bf16) - every (RB, NCOL) variant,
+                                      # ragged last band, partial last channel chunk, W not a multiple of 16
+                                      (64, 80, 80, 128), (32, 160, 160, 64), (48, 20, 20, 256), (40, 33, 50, 200),
+                                      (100, 7, 100, 40), (128, 40, 40, 64)])
 @pytest.mark.parametrize("dtype", ["bf16", "fp32"])
 def test_coord_pool_vs_torch(lib, B, H, W, Cc, dtype):
     """fce_coord_pool: strip[b, 0:H] = mean over W, strip[B*H + b*W ...] = mean over H (fce_block.py:101-102), every
