@@ -86,8 +86,9 @@ def gather_stats_to_rank0(stats: dict, group=None):
     n_all = torch.empty((world, len(keys)), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(n_all.view(-1), n_local, group=group)
     n_all = n_all.tolist()  # the one host sync
-    row_bytes = [stats[k][0:1].numel() * stats[k].element_size() if stats[k].ndim > 1 else stats[k].element_size()
-                 for k in keys]
+    import math
+
+    row_bytes = [math.prod(stats[k].shape[1:]) * stats[k].element_size() for k in keys]  # (an empty tensor has rows too)
     n_max = [max(n_all[r][i] for r in range(world)) for i in range(len(keys))]
     seg = [-(-(n_max[i] * row_bytes[i]) // 16) * 16 for i in range(len(keys))]  # 16-byte aligned segments
     send = torch.zeros(max(sum(seg), 16), dtype=torch.uint8, device=dev)

@@ -53,8 +53,12 @@ def match_predictions(det: torch.Tensor, count: torch.Tensor, gt_boxes: torch.Te
 class ValStats:
     """Accumulates the reference's validation statistics over batches on the device."""
 
-    def __init__(self):
+    def __init__(self, device=None):
         self.parts = {k: [] for k in ("tp", "conf", "pred_cls", "target_cls", "target_img")}
+        # where EMPTY statistics live: a rank whose shard holds no batch (more ranks than batches) still takes part in the
+        # collectives of result(), and NCCL needs its (empty) tensors on this rank's GPU
+        self.device = torch.device(device) if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
 
     def update(self, det, count, gt_boxes, gt_cls, gt_offsets):
         tp = match_predictions(det, count, gt_boxes, gt_cls, gt_offsets)
@@ -70,7 +74,7 @@ class ValStats:
 
     def result(self, group=None):
         """Concatenated stats, gathered to rank 0 when torch.distributed is initialised (None on other ranks)."""
-        dev = next((p[0].device for p in self.parts.values() if p), torch.device("cpu"))
+        dev = next((p[0].device for p in self.parts.values() if p), self.device)
         stats = {k: (torch.cat(v) if v else torch.zeros((0, 10) if k == "tp" else (0,), device=dev)) for k, v in self.parts.items()}
         stats["tp"] = stats["tp"].to(torch.uint8)
         out = gather_stats_to_rank0(stats, group)

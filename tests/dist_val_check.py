@@ -36,7 +36,8 @@ def main():
     from fce_yolo_b200.val import ValStats
     from fce_yolo_b200.weights import load_synthetic, synth_images
 
-    N_IMG, B, S = 56, 8, 320  # 7 batches: ranks get unequal shares
+    # 7 batches by default: ranks get unequal shares; FCE_DIST_VAL_IMAGES=8 leaves every rank but the first WITHOUT a batch
+    N_IMG, B, S = int(os.environ.get("FCE_DIST_VAL_IMAGES", 56)), 8, 320
     model = DetectionModel("yolo11n-fce.yaml").fuse().eval()
     load_synthetic(model, 0)
     pred = Predictor(model, B, S, precision="bf16", device=dev, conf=0.001, iou=0.7, max_det=300, multi_label=True,

@@ -76,6 +76,12 @@ def _worker(rank, world, port, q):
                 and not merged["tp"][:4].any().item()
         else:
             ok &= merged is None
+        # a rank with NO statistics at all (more ranks than batches) still joins the collectives
+        empty = {"tp": torch.zeros((0, 10), dtype=torch.uint8), "conf": torch.zeros(0)} if rank == 1 else \
+            {"tp": torch.ones((2, 10), dtype=torch.uint8), "conf": torch.tensor([0.5, 0.25])}
+        m2 = gather_stats_to_rank0(empty)
+        if rank == 0:
+            ok &= m2["tp"].shape == (2, 10) and m2["conf"].tolist() == [0.5, 0.25]
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
