@@ -54,6 +54,7 @@ struct HaloParams {
     uint32_t strip_bytes, strip_tx;  // shared-memory bytes of one strip stage / bytes one TMA box delivers
     uint32_t b_sub;                  // bytes of one (tap, chunk) weight tile PER CTA: Cout (pair: Cout / 2) x kc bf16
     int pair_units;                  // ceil(units / 2): work items of a CTA pair
+    int issuers;                     // 1 or 2 MMA-issuing warps (2: 128-row blocks alternate between them)
     uint32_t b_total, bias_bytes;
     int kc;        // channels per K chunk
     int b_stream;  // weights too large to park: the 9 tap tiles of chunk c travel with strip chunk c (same ring stage)
@@ -115,10 +116,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == WARP_PROD_A && lane == 0) {
         for (int i = 0; i < A_STAGES; ++i) {
             mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, p.issuers);  // every issuing warp commits once per stage
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(tfull0 + 8 * a, 1);
+            mbar_init(tfull0 + 8 * a, p.issuers);
             mbar_init(tempty0 + 8 * a, NUM_EPI_WARPS * NCTA);
         }
         mbar_init(bfull, 1);
@@ -181,25 +182,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 r.advance(A_STAGES);
             }
         }
-    } else if (warp == WARP_PROD_B) {
-        // ------------------------------------------------------------------ weights: parked once
-        if (!p.b_stream && elect_one()) {
-            const int tiles = 9 * chunks;
-            const int nrow0 = (int)cta_rank * (p.Cout / NCTA);
-            if (leader) mbar_expect_tx(bfull, (uint32_t)tiles * p.b_sub * NCTA);
-            // tile index = chunk * 9 + tap ; K column of the OHWI matrix = tap * Cin + chunk * kc
-            for (int c = 0; c < chunks; ++c)
-                for (int t = 0; t < 9; ++t) {
-                    if (PAIR) tma_load_2d_cg2(sB + (c * 9 + t) * p.b_sub, &tmB, bfull_sig, t * p.Cin + c * kc, nrow0);
-                    else tma_load_2d(sB + (c * 9 + t) * p.b_sub, &tmB, bfull, t * p.Cin + c * kc, 0);
-                }
+    } else if (warp == WARP_PROD_B || warp == WARP_MMA) {
+        if (warp == WARP_PROD_B) {
+            // -------------------------------------------------------------- weights: parked once
+            if (!p.b_stream && elect_one()) {
+                const int tiles = 9 * chunks;
+                const int nrow0 = (int)cta_rank * (p.Cout / NCTA);
+                if (leader) mbar_expect_tx(bfull, (uint32_t)tiles * p.b_sub * NCTA);
+                // tile index = chunk * 9 + tap ; K column of the OHWI matrix = tap * Cin + chunk * kc
+                for (int c = 0; c < chunks; ++c)
+                    for (int t = 0; t < 9; ++t) {
+                        if (PAIR) tma_load_2d_cg2(sB + (c * 9 + t) * p.b_sub, &tmB, bfull_sig, t * p.Cin + c * kc, nrow0);
+                        else tma_load_2d(sB + (c * 9 + t) * p.b_sub, &tmB, bfull, t * p.Cin + c * kc, 0);
+                    }
+            }
+            __syncwarp();
         }
-    } else if (warp == WARP_MMA && leader) {
-        // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA's only)
+        // ------------------------------------------------------------------ MMA issuers (pair: the leader CTA's only)
+        // p.issuers == 2 (experiment, off by default - see the host code): the weight-producer warp, idle after its one
+        // load, issues the odd 128-row blocks and this warp the even ones; each block's accumulation stays in one thread's
+        // program order, each issuer commits its own MMAs (the stage-empty / accumulator-full barriers count both).
+        const int me = warp == WARP_MMA ? 0 : 1;
+        if (leader && me < p.issuers) {
         Ring r;
         int acc = 0;
         uint32_t acc_phase = 0;
         const uint32_t dhi = p.desc_hi, idesc = p.idesc, b_sub16 = p.b_sub >> 4;
+        const int blk_step = p.issuers;
         // strip-row offset of every tap, in 16-byte units
         uint32_t tap16[9];
 #pragma unroll
@@ -228,7 +237,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t b16 = (sB + (p.b_stream ? r.stage : c) * 9 * p.b_sub) >> 4;
                 if (elect_one()) {
 #pragma unroll 1
-                    for (int blk = 0; blk < nb; ++blk) {
+                    for (int blk = me; blk < nb; blk += blk_step) {
                         const uint32_t d_tmem = d0 + blk * bn;
                         const uint32_t blk16 = a16 + (uint32_t)blk * (128u * (row_b >> 4));
 #pragma unroll
@@ -267,10 +276,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 acc_phase ^= 1;
             }
         }
-        if (PROF && lane == 0) {
+        if (PROF && lane == 0 && me == 0) {
             g_hprof[blockIdx.x * PROF_SLOTS + 4] = wf;
             g_hprof[blockIdx.x * PROF_SLOTS + 5] = we;
             g_hprof[blockIdx.x * PROF_SLOTS + 6] = clock64() - mt0;
+        }
         }
     } else if (warp == WARP_ALLOC) {
         // ------------------------------------------------------------------ staging DMA: residual in, result out
@@ -617,6 +627,12 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
     const uint32_t row_b = kc * 2;
     p.act = d->act;
     p.has_res = res != nullptr;
+    // One issuing warp.  FCE_HALO_ISSUERS=2 lets the (idle) weight-producer warp issue every other 128-row block - an
+    // experiment that did NOT pay (m scale, batch 256, same box: 64->64 at 80x80 157 -> 177 us, 128->128 at 40x40 138 -> 146 us,
+    // with residual 159 -> 142 us; step total 20.61 -> 20.86 ms): the short-MMA layers are paced by the tensor core's own
+    // dispatch rate, not by the issuing thread's instruction stream (4-5 uniform-datapath instructions per UTCHMMA).
+    static const int issuers_env = [] { const char* e = getenv("FCE_HALO_ISSUERS"); return e && *e ? atoi(e) : 1; }();
+    p.issuers = issuers_env >= 2 && p.nb >= 2 ? 2 : 1;
     const uint32_t layout = row_b == 128 ? 2u : (row_b == 64 ? 4u : 6u);
     const uint32_t sbo = 8 * row_b;
     p.desc_hi = (sbo >> 4) | (1u << 14) | (layout << 29);
