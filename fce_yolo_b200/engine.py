@@ -11,6 +11,7 @@ CUDA graph (350-590 eager ATen launches in the reference become one graph launch
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -19,6 +20,7 @@ from . import _lib as L
 from .plan import Buf, Plan, PlanError, View, compile_model, compile_module, DT_SIZE, TORCH_DT
 
 ALIGN = 1024
+NVTX = os.environ.get("FCE_NVTX") == "1"
 _DEFAULT_PRECISION = "bf16"
 
 
@@ -187,6 +189,15 @@ class Executor(Arena):
     # -- execution ----------------------------------------------------------------------------------
     def _launch_all(self, stream_ptr):
         s = C.c_void_p(stream_ptr)
+        if NVTX:  # FCE_NVTX=1: one NVTX range per plan node (entry point + layer tag) around eager launches, so that
+            # a timeline / ncu --nvtx capture maps kernels back to reference layers
+            for fn, args, n in self._calls:
+                torch.cuda.nvtx.range_push(f"{n.fn}:{n.tag}")
+                st = fn(*args, s)
+                torch.cuda.nvtx.range_pop()
+                if st != 0:
+                    L.check(st, f"{n.fn} [{n.tag}]")
+            return
         for fn, args, n in self._calls:
             st = fn(*args, s)
             if st != 0:
