@@ -778,8 +778,11 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
         const cuuint64_t gstr[1] = {(cuuint64_t)d->in_pitch * 2};
         const cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)BM};
         const cuuint32_t est[2] = {1, 1};
+        static const int a_promo = env_int("FCE_A_L2PROMO", 128);
         cr = api.tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)xin, gdim, gstr, box, est,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                       a_promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                      : (a_promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B),
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         const cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};

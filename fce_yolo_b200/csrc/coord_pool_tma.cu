@@ -140,10 +140,8 @@ int coord_pool_tma(const fce_pool_desc* d, const void* x, float* strip, cudaStre
     int rb, variant;
     // stages of at most 20 KB: three CTAs (3 x 3 stages) per SM - a single CTA per SM with 40 KB stages reached only half
     // of an SM's share of the HBM bandwidth (latency-bound ring), and 256 CTAs on 148 SMs quantise badly
-    if (ncol <= 2) { rb = 8; variant = 0; }
-    else if (ncol <= 3) { rb = 4; variant = 1; }
-    else if (ncol <= 5) { rb = 2; variant = 2; }
-    else { rb = 1; variant = 3; }
+    if (ncol <= 5) { rb = 2; variant = 0; }  // 49..80 columns
+    else { rb = 1; variant = 1; }            // 81..160 columns
     CUtensorMap tm;
     {
         const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x) + d->off;
@@ -158,12 +156,11 @@ int coord_pool_tma(const fce_pool_desc* d, const void* x, float* strip, cudaStre
             return FCE_ERR_UNSUPPORTED;
     }
     typedef void (*KernelFn)(const CUtensorMap, const fce_pool_desc, float*, int, int);
-    static const KernelFn table[4] = {coord_pool_tma_kernel<8, 2>, coord_pool_tma_kernel<4, 3>, coord_pool_tma_kernel<2, 5>,
-                                      coord_pool_tma_kernel<1, 10>};
+    static const KernelFn table[2] = {coord_pool_tma_kernel<2, 5>, coord_pool_tma_kernel<1, 10>};
     static DeviceOnce attr_once;
     int dev = 0;
     if (attr_once.pending(&dev)) {
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < 2; ++v) {
             cudaError_t e = cudaFuncSetAttribute(table[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
             if (e != cudaSuccess) {
                 set_cuda_error(e);
