@@ -24,3 +24,24 @@ def test_val_stats_and_detection_gather_over_nccl(images):
     assert r.returncode == 0 and line, (r.stdout[-1500:], r.stderr[-1500:])
     out = json.loads(line)
     assert out["dist_val"] == "ok" and out["world"] == n and out["n_pred"] >= 300 * images * 0.9, out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least two GPUs")
+def test_two_devices_in_one_process():
+    """One process driving two GPUs: the > 48 KB dynamic shared-memory opt-in (cudaFuncSetAttribute) is a per-device
+    attribute - every kernel family must repeat it on the second device (the tcgen05 convs ask for up to 227 KB).  Same
+    model, same batch on cuda:0 and cuda:1: identical detections."""
+    import detection_parity as DP
+    from fce_yolo_b200.predict import Predictor
+
+    case = dict(DP.CONFIGS["cfg1_s_coordatt"], size=320, batch=4)
+    _, model, _ = DP.build(case)
+    x = DP.u8_batch(9, 4, 320).pin_memory()
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        p = Predictor(model, 4, 320, precision="bf16", device=torch.device(dev), conf=0.25, iou=0.7, overlap_nms=True)
+        det, cnt = p.infer(x)
+        outs.append((det.clone(), cnt.clone(), p.keep.cpu().clone()))
+    assert int(outs[0][1].sum()) > 100
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
