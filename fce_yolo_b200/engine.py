@@ -251,6 +251,14 @@ class Executor(Arena):
         for k in used:
             main.wait_stream(side[k])
 
+    def _capture_stream(self):
+        """Capture stream on THIS executor's device.  torch.cuda.graph() otherwise re-uses one class-level stream created
+        on whatever device was current the first time any graph was captured in the process: on a second GPU the plan's
+        launches would then miss the capture (invalid resource handle on the first side-branch launch)."""
+        if getattr(self, "_cap_stream", None) is None:
+            self._cap_stream = torch.cuda.Stream(self.device)
+        return self._cap_stream
+
     def run(self):
         stream = torch.cuda.current_stream(self.device)
         if not self._warm:
@@ -259,7 +267,7 @@ class Executor(Arena):
             self._warm = True
             if self.use_graph:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=self._capture_stream()):
                     self._launch_branched(0, len(self._calls))
                 self.graph = g
                 self.graph.replay()  # outputs of this call come from the replayed graph
@@ -303,7 +311,7 @@ class Executor(Arena):
             self._segs = []
             for lo, hi in ((0, k), (k, n - 1), (n - 1, n)):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=self._capture_stream()):
                     self._launch_branched(lo, hi)
                 self._segs.append(g)
             self.nms_done.record(stream)
