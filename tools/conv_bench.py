@@ -61,10 +61,15 @@ def main():
     ap.add_argument("--skip-tma", action="store_true", help="debug: producers skip the loads (MMA+epilogue rate)")
     ap.add_argument("--dbg", type=int, default=0, help="debug bits for timed runs: 1 skip TMA loads, 2 skip TMA stores, "
                                                       "4 skip epilogue math (results are garbage)")
-    ap.add_argument("--nohalo", action="store_true")
-    ap.add_argument("--nostream", action="store_true", help="strip kernel only with resident weights")
+    ap.add_argument("--nohalo", action="store_true", help="strip kernel off (sets FCE_HALO_MODE=0 before the library loads)")
+    ap.add_argument("--nostream", action="store_true", help="strip kernel only with resident weights (FCE_HALO_MODE=2)")
     a = ap.parse_args()
+    if a.nohalo or a.nostream:  # kernel-selection knob of conv_halo.cu, read once at load time
+        os.environ["FCE_HALO_MODE"] = "0" if a.nohalo else "2"
     lib = L.load(check_device=True)
+    debug = hasattr(lib, "fce_conv_tc_set_profile") and lib.fce_conv_tc_set_profile.argtypes is not None
+    if (a.prof or a.dbg or a.skip_tma) and not debug:
+        sys.exit("--prof / --dbg / --skip-tma need a debug build of the library: FCE_DEBUG=1 python fce_yolo_b200/build.py")
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
@@ -107,7 +112,8 @@ def main():
             print(f"{name:34s} tiles/CTA {tiles/148:6.1f} | A-prod wait {m[0]:9.0f} / {m[1]:9.0f} | MMA wait-full {m[4]:9.0f} "
                   f"wait-tmem {m[5]:9.0f} / {m[6]:9.0f} | epi wait {m[7]:9.0f} / {m[8]:9.0f} stg-wait {m[9]:9.0f} | dma wait {m[10]:9.0f} / {m[11]:9.0f}", flush=True)
             continue
-        lib.fce_conv_tc_set_profile((a.dbg << 1) | (16 if a.nohalo else 0) | (32 if a.nostream else 0))
+        if debug:
+            lib.fce_conv_tc_set_profile(a.dbg << 1)
         for _ in range(2):
             L.check(lib.fce_conv2d(*args), name)
         ms = []
@@ -120,7 +126,8 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms.append(e0.elapsed_time(e1))
-        lib.fce_conv_tc_set_profile(0)
+        if debug:
+            lib.fce_conv_tc_set_profile(0)
         ms.sort()
         t = ms[len(ms) // 2]
         flops = 2.0 * B * Ho * Wo * Cout * Cin * k * k

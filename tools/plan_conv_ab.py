@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--csv", default=None)
+    ap.add_argument("--only", default=None, help="comma-separated substrings of node tags to time")
     a = ap.parse_args()
     w, name = bench.workload(a.config)
     if a.batch:
@@ -47,6 +48,8 @@ def main():
             continue
         d = n.desc
         if d.in_dtype != L.BF16 or d.w_dtype != L.BF16:
+            continue
+        if a.only and not any(t in n.tag for t in a.only.split(",")):
             continue
         key = (n.fn, d.B, d.H, d.W, d.Cin, d.Cout, d.k, d.stride, d.res_pitch != 0, d.out_dtype, d.weighted, d.res_up)
         if key in seen:
