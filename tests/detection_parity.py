@@ -42,6 +42,9 @@ CONFIGS = {
     "cfg3_s_cca_bicca8": dict(yaml="yolo11s-fce.yaml", size=640, batch=4, seed=1,
                               variant={5: ("CoordCrossAtt", [512, 16, 2]), 8: ("BiCoordCrossAtt", [512, 8, 8])}),
     "cfg4_x_fce_1280": dict(yaml="yolo11x-fce.yaml", variant=None, size=1280, batch=2, seed=1),
+    # beyond BASELINE.json: the remaining scale of the FCE graph (l: two repeats, C3k everywhere) and the stock Concat neck
+    "extra_l_fce_320": dict(yaml="yolo11l-fce.yaml", variant=None, size=320, batch=2, seed=2),
+    "extra_s_stock_320": dict(yaml="yolo11s.yaml", variant=None, size=320, batch=2, seed=3),
 }
 CONF, IOU, MAX_DET = 0.25, 0.7, 300
 
