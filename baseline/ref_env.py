@@ -108,3 +108,23 @@ def reference_yolo(yaml_name: str, variant=None, seed: int | None = 0):
     m.task = "detect"
     y.model = m
     return y
+
+
+def offline_val_env():
+    """What the reference's ``YOLO.val()`` needs to run offline in this image: it dies in ``check_det_dataset`` ->
+    ``check_font`` (data/utils.py:475, utils/checks.py:308-336) because matplotlib is not installed and no font can be
+    downloaded.  A zero-byte ``Arial.ttf`` in the config directory is found first (checks.py:322-325), and a stub
+    ``matplotlib.font_manager`` satisfies the import.  TEST / MEASUREMENT infrastructure only."""
+    import types
+
+    import_reference()
+    d = os.path.join(os.environ["YOLO_CONFIG_DIR"], "Ultralytics")
+    os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, "Arial.ttf"), "a").close()
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        m, fm = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.font_manager")
+        fm.findSystemFonts = lambda *a, **k: []
+        m.font_manager = fm
+        sys.modules["matplotlib"], sys.modules["matplotlib.font_manager"] = m, fm
