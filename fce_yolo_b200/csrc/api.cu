@@ -45,6 +45,7 @@ extern "C" int fce_conv2d(const fce_conv_desc* d, const void* x, const void* w, 
     const bool weighted = d->weighted != 0 || d->res_up != 0;
     if (weighted) {  // BiFPN-fused epilogue: 1x1 convs on the tcgen05 kernel only
         if (d->res_up && (!res || (d->H & 1) || (d->W & 1))) return FCE_ERR_BAD_ARG;
+        if (d->weighted < 0 || d->weighted > 2 || (d->weighted == 2 && !res)) return FCE_ERR_BAD_ARG;
         if (!tc_ok || d->k != 1 || d->impl == 1 || d->out_dtype != FCE_BF16) return FCE_ERR_UNSUPPORTED;
         return conv2d_tc(d, x, w, bias, res, y, st);
     }

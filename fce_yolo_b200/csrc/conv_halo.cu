@@ -45,7 +45,8 @@ constexpr int A_STAGES = 2;
 constexpr int SMEM_LIMIT = 222 * 1024;
 
 struct HaloParams {
-    int B, H, W, Wp;  // Wp = W + 2
+    int B, H, W, Wp;  // Wp = Wt + 2: padded width of one strip
+    int Wt, wtiles;   // column tiles of Wt output columns (maps wider than 254 columns: the TMA box holds at most 256)
     int Cin, Cout;
     int R, bands, nb;  // rows per band, bands per image, 128-row MMA blocks per band
     int chunks;        // K chunks (kc channels each)
@@ -162,15 +163,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int it = item0; it < n_items; it += item_step) {
             int u = it * NCTA + (int)cta_rank;
             if (u >= units) u = units - 1;  // the dummy half of the last pair
-            const int b = u / p.bands, band = u - b * p.bands;
-            const int h0 = band * p.R;
+            const int ub = p.wtiles == 1 ? u : u / p.wtiles, wt = u - ub * p.wtiles;  // one tile: no division
+            const int b = ub / p.bands, band = ub - b * p.bands;
+            const int h0 = band * p.R, w0 = wt * p.Wt;
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(empty0 + 8 * r.stage, r.phase ^ 1);
                 if (elect_one()) {
                     const uint32_t fb = full0 + 8 * r.stage, fsig = full0_sig + 8 * r.stage;
                     if (leader) mbar_expect_tx(fb, (p.b_stream ? p.strip_tx + 9u * p.b_sub : p.strip_tx) * NCTA);
-                    if (PAIR) tma_load_4d_cg2(sA + r.stage * p.strip_bytes, &tmA, fsig, c * kc, -1, h0 - 1, b);
-                    else tma_load_4d(sA + r.stage * p.strip_bytes, &tmA, fb, c * kc, -1, h0 - 1, b);
+                    if (PAIR) tma_load_4d_cg2(sA + r.stage * p.strip_bytes, &tmA, fsig, c * kc, w0 - 1, h0 - 1, b);
+                    else tma_load_4d(sA + r.stage * p.strip_bytes, &tmA, fb, c * kc, w0 - 1, h0 - 1, b);
                     if (p.b_stream) {  // this chunk's nine weight tiles ride in the same stage
                         const uint32_t bdst = sB + r.stage * 9u * p.b_sub;
                         for (int t = 0; t < 9; ++t) {
@@ -288,14 +290,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // free) -> stg_ready; the eight epilogue warps fill it -> stg_written; one bulk store per slab.  With two
         // staging buffers the residual of band i+1 is fetched while band i is still in the epilogue.
         const int n_stg = p.n_stg, n_slabs = p.n_slabs, slab_cols = p.slab_cols;
-        const uint32_t res_tx = (uint32_t)n_slabs * (uint32_t)(slab_cols * 2) * (uint32_t)p.W * (uint32_t)p.R;
+        const uint32_t res_tx = (uint32_t)n_slabs * (uint32_t)(slab_cols * 2) * (uint32_t)p.Wt * (uint32_t)p.R;
         auto make_ready = [&](int u, int buf) {  // executed by one elected lane
             if (p.has_res) {
-                const int b = u / p.bands, band = u - b * p.bands;
+                const int ub = p.wtiles == 1 ? u : u / p.wtiles, wt = u - ub * p.wtiles;  // one tile: no division
+                const int b = ub / p.bands, band = ub - b * p.bands;
                 mbar_expect_tx(stg_ready0 + 8 * buf, res_tx);
                 for (int sl = 0; sl < n_slabs; ++sl)
-                    tma_load_4d(sStg + buf * stg_bytes + sl * p.slab_bytes, &tmR, stg_ready0 + 8 * buf, sl * slab_cols, 0,
-                                band * p.R, b);
+                    tma_load_4d(sStg + buf * stg_bytes + sl * p.slab_bytes, &tmR, stg_ready0 + 8 * buf, sl * slab_cols,
+                                wt * p.Wt, band * p.R, b);
             } else {
                 mbar_arrive(stg_ready0 + 8 * buf);
             }
@@ -331,9 +334,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ph[buf] ^= 1;
             if (elect_one()) {
                 if (u >= 0) {
-                    const int b = u / p.bands, band = u - b * p.bands;
-                    for (int sl = 0; sl < n_slabs; ++sl)
-                        tma_store_4d(&tmC, sStg + buf * stg_bytes + sl * p.slab_bytes, sl * slab_cols, 0, band * p.R, b);
+                    const int ub = p.wtiles == 1 ? u : u / p.wtiles, wt = u - ub * p.wtiles;  // one tile: no division
+                    const int b = ub / p.bands, band = ub - b * p.bands;
+                    for (int sl = 0; sl < n_slabs; ++sl)  // columns past W (ragged last tile) are clipped by the TMA unit
+                        tma_store_4d(&tmC, sStg + buf * stg_bytes + sl * p.slab_bytes, sl * slab_cols, wt * p.Wt, band * p.R, b);
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 if (n_stg == 1) {
@@ -355,7 +359,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // TMEM -> registers -> bias / activation (+ residual, read from the staged tile) -> staging, compacted from the
         // padded-flat accumulator rows to [R][W] so that ONE 4-D bulk store per 32-column slab writes the band.
         const int quarter = warp & 3, grp = warp >> 2;
-        const int n_chunks = bn >> 4, act = p.act, Wp = p.Wp, W = p.W, R = p.R, H = p.H;
+        const int n_chunks = bn >> 4, act = p.act, Wp = p.Wp, W = p.W, Wt = p.Wt, R = p.R, H = p.H;
         const int pairs = (n_chunks + 1) >> 1;  // work item = (128-row block, pair of 16-column chunks), dealt round-robin
         const int items = nb * pairs;           // to the three warp groups
         const bool has_res = p.has_res != 0;
@@ -368,8 +372,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int u_raw = it * NCTA + (int)cta_rank;
             const bool live = u_raw < units;  // false: the dummy half of the last pair
             const int u = live ? u_raw : units - 1;
-            const int band = u % p.bands;
-            const int h0 = band * R;
+            const int ub = p.wtiles == 1 ? u : u / p.wtiles;  // one column tile (maps up to 254 wide): no division
+            const int band = ub % p.bands;
+            const int h0 = band * R, w0 = (u - ub * p.wtiles) * Wt;
+            const int wlim = min(Wt, W - w0), rlim = min(R, H - h0);  // valid columns / rows of this unit
             const int buf = p.n_stg == 2 ? (i & 1) : 0;
             const uint32_t stg = sStg + buf * stg_bytes;
             {
@@ -390,8 +396,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int j = (item - blk * pairs) * 2;
                 const int o = blk * 128 + quarter * 32 + lane;  // padded-flat output index inside the band
                 const int ro = o / Wp, co = o - ro * Wp;
-                const bool ok = co < W && ro < R && h0 + ro < H;
-                const uint32_t lin = (uint32_t)(ro * W + co) * row_bytes;  // byte offset of this pixel's row in a slab
+                const bool ok = co < wlim && ro < rlim;
+                const uint32_t lin = (uint32_t)(ro * Wt + co) * row_bytes;  // byte offset of this pixel's row in a slab
                 const uint32_t swz = ((lin >> 7) & swz_mask) << 4;           // swizzle: address bits 7.. -> bits 4..
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * nb + blk) * bn;
                 {
@@ -497,7 +503,11 @@ static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool s
     const uint32_t b_sub = (uint32_t)(d->Cout / ncta) * row_b;  // a pair stages half of every weight tile's rows per CTA
     const uint32_t b_total = ((stream ? (uint32_t)A_STAGES * 9u : 9u * chunks) * b_sub + 1023u) & ~1023u;
     const uint32_t bias_bytes = ((uint32_t)d->Cout * 4 + 1023u) & ~1023u;
-    const int Wp = d->W + 2;
+    // column tiles: a TMA box dimension holds at most 256 elements, so maps wider than 254 columns (320 x 320 maps of
+    // 1280^2 inputs) are cut into the fewest equal tiles; every tile is its own unit with its own halo columns
+    const int wtiles = (d->W + 253) / 254;
+    const int Wt = (d->W + wtiles - 1) / wtiles;
+    const int Wp = Wt + 2;
     int best_R = 0;
     double best_eff = 0.0;
     for (int R = 1; R <= d->H && R + 2 <= 256; ++R) {
@@ -506,14 +516,14 @@ static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool s
         const uint32_t rows = 128u * nb + 2u * Wp + 2u;
         const uint32_t strip = (rows * row_b + 1023u) & ~1023u;
         const uint32_t slab_cols = d->Cout % 64 == 0 ? 64u : 32u;
-        const uint32_t slab = ((uint32_t)R * d->W * slab_cols * 2u + 1023u) & ~1023u;
+        const uint32_t slab = ((uint32_t)R * Wt * slab_cols * 2u + 1023u) & ~1023u;
         const uint32_t n_slabs = ((uint32_t)d->Cout + slab_cols - 1) / slab_cols;
         // with a residual the staging is double buffered (the next band's residual streams in during the epilogue)
         const uint32_t n_stg = has_res ? 2u : 1u;
         if ((size_t)A_STAGES * strip + b_total + n_stg * n_slabs * slab + bias_bytes + 2048 > (size_t)SMEM_LIMIT) break;
         // useful fraction of the issued MMA rows, discounted by the halo re-read
         const int bands = (d->H + R - 1) / R;
-        const double eff = (double)d->H * d->W / ((double)bands * nb * 128) * (0.75 + 0.25 * R / (R + 2.0));
+        const double eff = (double)d->H * d->W / ((double)bands * wtiles * nb * 128) * (0.75 + 0.25 * R / (R + 2.0));
         if (eff > best_eff + 1e-9) {
             best_eff = eff;
             best_R = R;
@@ -521,6 +531,7 @@ static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool s
     }
     if (best_R == 0) return 0.0;
     p.B = d->B; p.H = d->H; p.W = d->W; p.Wp = Wp;
+    p.Wt = Wt; p.wtiles = wtiles;
     p.Cin = d->Cin; p.Cout = d->Cout;
     p.kc = kc;
     p.b_stream = stream ? 1 : 0;
@@ -528,7 +539,7 @@ static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool s
     p.bands = (d->H + best_R - 1) / best_R;
     p.nb = (best_R * Wp + 127) / 128;
     p.chunks = chunks;
-    p.units = d->B * p.bands;
+    p.units = d->B * p.bands * wtiles;
     p.pair_units = (p.units + 1) / 2;
     p.acc_sets = 2 * p.nb * d->Cout <= 512 ? 2 : 1;
     p.strip_bytes = ((128u * p.nb + 2u * Wp + 2u) * row_b + 1023u) & ~1023u;
@@ -537,7 +548,7 @@ static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool s
     p.b_total = b_total;
     p.bias_bytes = bias_bytes;
     p.slab_cols = d->Cout % 64 == 0 ? 64 : 32;
-    p.slab_bytes = ((uint32_t)best_R * d->W * (uint32_t)p.slab_cols * 2u + 1023u) & ~1023u;
+    p.slab_bytes = ((uint32_t)best_R * Wt * (uint32_t)p.slab_cols * 2u + 1023u) & ~1023u;
     p.n_slabs = (d->Cout + p.slab_cols - 1) / p.slab_cols;
     // a second staging buffer (residual prefetch / store overlap) when shared memory allows
     p.n_stg = ((size_t)A_STAGES * p.strip_bytes + b_total + 2ull * p.n_slabs * p.slab_bytes + bias_bytes + 2048 <=
@@ -567,7 +578,7 @@ static bool halo_pair_pays(const fce_conv_desc* d, const HaloParams& q) {
 static bool halo_plan(const fce_conv_desc* d, bool has_res, int ncta, HaloParams& p) {
     if (g_halo_mode == 0) return false;
     if (d->k != 3 || d->stride != 1) return false;
-    if (d->Cout > 256 || d->W + 2 > 256 || d->out_dtype != FCE_BF16) return false;
+    if (d->Cout > 256 || d->W > 2032 || d->out_dtype != FCE_BF16) return false;
     if (ncta == 2 && (d->Cout % 16 || d->Cout < 32)) return false;  // M = 256 MMAs: N % 16, whole swizzle atoms per CTA
     const int kc0 = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
     if (halo_plan_one(d, has_res, kc0, false, ncta, p) >= 0.55) return true;  // weights parked in shared memory
@@ -654,7 +665,7 @@ int conv2d_halo(const fce_conv_desc* d, const void* x, const void* w, const floa
                            : (void*)(reinterpret_cast<__nv_bfloat16*>(y) + d->out_off);
         const cuuint64_t gdim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
         const cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)d->W * pitch * 2, (cuuint64_t)d->H * d->W * pitch * 2};
-        const cuuint32_t box[4] = {(cuuint32_t)p.slab_cols, (cuuint32_t)d->W, (cuuint32_t)p.R, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)p.slab_cols, (cuuint32_t)p.Wt, (cuuint32_t)p.R, 1};
         const cuuint32_t est[4] = {1, 1, 1, 1};
         if (api.tiled(is_res ? &tmR : &tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, gdim, gstr, box, est,
                       CU_TENSOR_MAP_INTERLEAVE_NONE,

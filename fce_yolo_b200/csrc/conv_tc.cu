@@ -81,6 +81,8 @@ struct TcParams {
     // weighted-sum epilogue (BiFPN fused into its realign conv): y = out_scale * act(..) + res_scale * res
     float out_scale, res_scale;
     int res_up;        // res is a half-resolution map read through a nearest 2x upsample
+    int res_wide;      // residual rows are 32-byte aligned: 256-bit loads
+    int res_pre;       // res joins the accumulator before bias + activation (fce_conv_desc.weighted == 2)
 };
 
 // Per-role cycle accounting and the load / store / math switch-off bits exist in -DFCE_DEBUG builds only (debug entry
@@ -384,7 +386,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may read
         const int group = e >> 2;      // which accumulator stage
         const int n_tiles = p.n_tiles, bn = p.bn, Cout = p.Cout, act = p.act;
-        const bool has_res = res != nullptr, out_f32 = p.out_f32 != 0;
+        const bool has_res = res != nullptr, out_f32 = p.out_f32 != 0, res_pre = p.res_pre != 0;
         const bool dbg_nostore = DBG && (p.dbg & 2) != 0, dbg_nomath = DBG && (p.dbg & 4) != 0;  // debug timing only
         const int slab_cols = out_f32 ? 16 : 32;  // 64 bytes of output per row
         const int n_slabs = (bn + slab_cols - 1) / slab_cols;
@@ -423,6 +425,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ridx = ((size_t)bimg * (p.Ho >> 1) + (ph >> 1)) * (p.Wo >> 1) + (pw >> 1);
             }
             const __nv_bfloat16* rrow = res + ridx * p.res_pitch;
+            // Residual of slab `s`, fetched ONE SLAB AHEAD (slab 0 before the accumulator wait): the four 16-byte loads of
+            // a lane touch a row of their own (32 sectors per request) and come from L2 - issued at the top of their own
+            // slab, their latency was exposed once per slab (1x1 512 -> 256 at 80x80, residual at half resolution:
+            // 725 us against 498 us without the residual).
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+            auto res_fetch = [&](int s) {
+                const int c0 = s * slab_cols, n = n0 + c0;
+                if (s >= n_slabs || n >= Cout || !m_ok) return;
+                const uint4* rp = reinterpret_cast<const uint4*>(rrow + n);
+                const bool four = !out_f32 && c0 + 16 < bn && n + 16 < Cout;
+                if (p.res_wide) {  // 32-byte aligned rows: 256-bit loads, half the requests (L2 only, like __ldcg below)
+                    ldcg256(rp, q0, q1);
+                    if (four) ldcg256(rp + 2, q2, q3);
+                    return;
+                }
+                q0 = __ldcg(rp);  // L2 only: with PDL this SM's L1 may still hold the previous grid's lines
+                q1 = __ldcg(rp + 1);
+                if (four) {
+                    q2 = __ldcg(rp + 2);
+                    q3 = __ldcg(rp + 3);
+                }
+            };
+            if (has_res && p.epi_mode == 0) res_fetch(0);
             {
                 PROF_T0();
                 mbar_wait(tfull0 + 8 * my_acc, my_phase);
@@ -521,16 +546,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int n = n0 + c0;
                 if (n >= Cout) break;
                 const bool two = !out_f32 && (c0 + 16 < bn);
-                uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
-                if (has_res && m_ok) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(rrow + n);
-                    r0 = __ldcg(rp);  // L2 only: with PDL this SM's L1 may still hold the previous grid's lines
-                    r1 = __ldcg(rp + 1);
-                    if (two && n + 16 < Cout) {
-                        r2 = __ldcg(rp + 2);
-                        r3 = __ldcg(rp + 3);
-                    }
-                }
+                const uint4 r0 = q0, r1 = q1, r2 = q2, r3 = q3;
+                if (has_res) res_fetch(sl + 1);
                 uint32_t v0[16], v1[16];
                 tmem_ld16(t_row + c0, v0);
                 if (two) tmem_ld16(t_row + c0 + 16, v1);
@@ -551,12 +568,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     float f[16];
                     uint32_t o[8];
-                    epi_math16(v0, bias_s + n, act, has_res, r0, r1, f, p.out_scale, p.res_scale);
+                    epi_math16(v0, bias_s + n, act, has_res, r0, r1, f, p.out_scale, p.res_scale, res_pre);
                     pack16(f, o);
                     st_shared_v4(rowp + ((0 ^ swz) << 4), o[0], o[1], o[2], o[3]);
                     st_shared_v4(rowp + ((1 ^ swz) << 4), o[4], o[5], o[6], o[7]);
                     if (two) {
-                        epi_math16(v1, bias_s + n + 16, act, has_res, r2, r3, f, p.out_scale, p.res_scale);
+                        epi_math16(v1, bias_s + n + 16, act, has_res, r2, r3, f, p.out_scale, p.res_scale, res_pre);
                         pack16(f, o);
                         st_shared_v4(rowp + ((2 ^ swz) << 4), o[0], o[1], o[2], o[3]);
                         st_shared_v4(rowp + ((3 ^ swz) << 4), o[4], o[5], o[6], o[7]);
@@ -744,14 +761,16 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     while (p.tmem_cols < (uint32_t)(p.acc_stages * p.bn)) p.tmem_cols <<= 1;
     p.out_pitch = d->out_pitch;
     p.res_pitch = d->res_pitch;
+    p.res_wide = res && d->res_pitch % 16 == 0 && d->res_off % 16 == 0 && (reinterpret_cast<uintptr_t>(res) & 31) == 0;
     p.act = d->act;
     p.out_f32 = d->out_dtype == FCE_F32;
 #ifdef FCE_DEBUG
     p.dbg = g_debug_flags;
 #endif
-    p.out_scale = d->weighted ? d->out_scale : 1.f;
-    p.res_scale = d->weighted ? d->res_scale : 1.f;
+    p.out_scale = d->weighted == 1 ? d->out_scale : 1.f;
+    p.res_scale = d->weighted == 1 ? d->res_scale : 1.f;
     p.res_up = d->res_up;
+    p.res_pre = d->weighted == 2 ? 1 : 0;
     if (epi) {
         if (p.n_tiles != 1 && epi->mode == 2) return FCE_ERR_UNSUPPORTED;
         p.epi_mode = epi->mode;

@@ -221,6 +221,12 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
     return r;
 }
+// 32 bytes from L2 in one request (sm_100: LDG.256); p must be 32-byte aligned
+__device__ __forceinline__ void ldcg256(const uint4* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(src),
                  "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -241,9 +247,26 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
 // conversions and was 5% slower - the epilogue is issue-bound, not MUFU-bound.)
 __host__ __device__ __forceinline__ float epi_bias_scale(int act) { return act == FCE_ACT_SILU ? 0.5f : 1.f; }
 // osc / rsc: weighted-sum epilogue y = osc * act(..) + rsc * res (BiFPN fusion); both 1 for the plain conv.
-__device__ __forceinline__ void epi_math16(const uint32_t* v, const float* sbias, int act, bool has_res, uint4 r0,
-                                           uint4 r1, float* f, float osc = 1.f, float rsc = 1.f) {
+// pre: the residual joins the accumulator BEFORE bias and activation, y = act(acc + res + bias) - the second half of a
+// 1x1 conv over a weighted sum of two maps (BiFPN node folded into its consumer).
+__device__ __forceinline__ void epi_math16(const uint32_t* vin, const float* sbias, int act, bool has_res, uint4 r0,
+                                           uint4 r1, float* f, float osc = 1.f, float rsc = 1.f, bool pre = false) {
     float2 o[8];
+    uint32_t v[16];
+    if (pre && has_res) {
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 a = __fadd2_rn(make_float2(__uint_as_float(vin[2 * i]), __uint_as_float(vin[2 * i + 1])),
+                                        make_float2(__uint_as_float(rr[i] << 16), __uint_as_float(rr[i] & 0xffff0000u)));
+            v[2 * i] = __float_as_uint(a.x);
+            v[2 * i + 1] = __float_as_uint(a.y);
+        }
+        has_res = false;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = vin[i];
+    }
     if (act == FCE_ACT_SILU) {
         const float2 half2 = make_float2(0.5f, 0.5f);
 #pragma unroll

@@ -88,6 +88,18 @@ class LazyUp:
 
 
 @dataclass
+class LazySum:
+    """A two-input BiFPN_Concat node with identity realigns, sum_i wn[i] * x_i (fce_block.py:55-63), that has not been
+    materialised: a 1x1-conv consumer folds it into two convs (Plan.conv_of_sum) and the fused map is never stored."""
+    terms: list             # [(View, weight, upsampled)]
+    H: int
+    W: int
+    C: int
+    tag: str = ""
+    mat: View | None = None
+
+
+@dataclass
 class Node:
     fn: str                 # C-ABI symbol
     desc: object            # ctypes struct
@@ -114,6 +126,8 @@ class Plan:
     HEAD_STREAMS = {"0": False, "1": True}.get(os.environ.get("FCE_HEAD_STREAMS", ""), None)
     HEAD_STREAMS_MAX_PIXELS = 8 * 640 * 640  # automatic mode: batch * H * W of the network input
     FUSED_BIFPN = True  # False: realign convs + fce_bifpn_fuse as separate launches (A/B timing, cross-check)
+    # False (or FCE_FUSED_SUM=0): identity-realign BiFPN nodes always run fce_bifpn_fuse (A/B timing, cross-check)
+    FUSED_SUM = os.environ.get("FCE_FUSED_SUM", "1") != "0"
     FUSED_COORDATT_MLP = True  # False: cv1 / cv_h / cv_w as three strip convs (A/B timing, cross-check)
     FUSED_C3K_IN = True  # False: C3k.cv1 and C3k.cv2 as two launches (A/B timing, cross-check)
     FUSED_STEM = True  # False: stem = fce_stem_pack + K=32 tcgen05 conv (kept for A/B timing and as a cross-check)
@@ -246,7 +260,7 @@ class Plan:
 
     def conv(self, m, x: View, dst: View | None = None, res: View | None = None, out_dtype=None, act=None,
              w_override=None, b_override=None, in_layout=L.NHWC, in_scale=1.0, tag="", out_scale=1.0, res_scale=1.0,
-             res_up=False) -> View:
+             res_up=False, res_pre=False) -> View:
         w, b, k, s, g, a = self.conv_params(m) if m is not None else (w_override, b_override, 1, 1, 1, L.ACT_NONE)
         if w_override is not None:
             w, b = w_override, b_override
@@ -275,7 +289,7 @@ class Plan:
         d = L.ConvDesc(B=x.B, H=x.H, W=x.W, Cin=Cin, Cout=Cout, in_pitch=x.pitch, in_off=0, out_pitch=dst.pitch,
                        out_off=0, res_pitch=res.pitch if res is not None else 0, res_off=0, k=k, stride=s, act=a,
                        in_dtype=x.dtype, w_dtype=w_dt, out_dtype=dst.dtype, in_layout=in_layout, in_scale=in_scale,
-                       impl=self.impl, weighted=1 if (out_scale != 1.0 or res_scale != 1.0) else 0,
+                       impl=self.impl, weighted=2 if res_pre else (1 if (out_scale != 1.0 or res_scale != 1.0) else 0),
                        out_scale=float(out_scale), res_scale=float(res_scale), res_up=1 if res_up else 0)
         rs = 2 if res_up else 1
         if res is not None and (res.C != Cout or res.dtype != dst.dtype or (res.H * rs, res.W * rs) != (Ho, Wo)):
@@ -364,10 +378,13 @@ class Plan:
             self.conv(m.cv2, x, dst=cat.ch(c_, 2 * c_), tag=tag + ".cv2")
         return self.conv(m.cv3, cat, dst=dst, tag=tag + ".cv3")
 
-    def c3k2(self, m, x: View, dst=None, tag="") -> View:
+    def c3k2(self, m, x, dst=None, tag="") -> View:
         c, n = m.c, len(m.m)
         cat = self.new_buf(x.H, x.W, (2 + n) * c)
-        self.conv(m.cv1, x, dst=cat.ch(0, 2 * c), tag=tag + ".cv1")
+        if isinstance(x, LazySum):  # BiFPN node in front: folded into cv1
+            self.conv_of_sum(m.cv1, x, dst=cat.ch(0, 2 * c), tag=tag + ".cv1")
+        else:
+            self.conv(m.cv1, x, dst=cat.ch(0, 2 * c), tag=tag + ".cv1")
         prev = cat.ch(c, 2 * c)
         for j, blk in enumerate(m.m):
             out = cat.ch((2 + j) * c, (3 + j) * c)
@@ -432,6 +449,12 @@ class Plan:
             return dst
         if x.mat is not None and dst is None:
             return x.mat
+        if isinstance(x, LazySum):
+            views, ups, wn = [t[0] for t in x.terms], [1 if t[2] else 0 for t in x.terms], [t[1] for t in x.terms]
+            out = self._fuse_node(views, ups, wn, x.H, x.W, x.C, dst, x.tag)
+            if dst is None:
+                x.mat = out
+            return out
         s = x.src
         out = dst if dst is not None else self.new_buf(2 * s.H, 2 * s.W, s.C, dtype=s.dtype)
         d = L.UpsampleDesc(B=s.B, H=s.H, W=s.W, C=s.C, in_pitch=s.pitch, in_off=0, out_pitch=out.pitch, out_off=0,
@@ -512,9 +535,19 @@ class Plan:
                                 tag=f"{tag}.realign.{i}+fuse")
                 acc_w, acc_up = 1.0, False
             return acc
+        identity = all(isinstance(r, nn.Identity) for r in m.realign_convs)
+        if (dst is None and self.FUSED_SUM and self.act_dt == L.BF16 and self.impl != 1 and len(xs) == 2 and identity
+                and C % 16 == 0 and sum(ups) == 1):
+            # nothing to compute yet: a 1x1-conv consumer (C3k2.cv1) takes the two maps directly.  Only with ONE upsampled
+            # operand - its half of the conv then runs on a quarter of the pixels.  Two full-resolution operands: the
+            # second conv costs what the fusion launch costs (m scale, batch 256, 20x20: 138 us separate, 167 us folded)
+            return LazySum([(v, wn[i], bool(ups[i])) for i, v in enumerate(views)], H, W, C, tag)
+        return self._fuse_node(views, ups, wn, H, W, C, dst, tag)
+
+    def _fuse_node(self, views, ups, wn, H, W, C, dst, tag) -> View:
         if dst is None:
             dst = self.new_buf(H, W, C)
-        d = L.BifpnDesc(B=self.B, H=H, W=W, C=C, n=len(xs), out_pitch=dst.pitch, out_off=0, dtype=dst.dtype)
+        d = L.BifpnDesc(B=self.B, H=H, W=W, C=C, n=len(views), out_pitch=dst.pitch, out_off=0, dtype=dst.dtype)
         for i, (v, u) in enumerate(zip(views, ups)):
             d.pitch[i], d.off[i], d.up[i], d.wn[i] = v.pitch, 0, u, wn[i]
         ptrs = views + [None] * (3 - len(views)) + [dst]
@@ -522,6 +555,21 @@ class Plan:
         alg = sum(v.B * v.H * v.W * v.C for v in views) * esz + self.B * H * W * C * esz
         self.add(Node("fce_bifpn_fuse", d, ptrs, reads=views, writes=[dst], tag=tag + ".fuse", bytes=alg))
         return dst
+
+    def conv_of_sum(self, m, x: LazySum, dst: View | None = None, tag="") -> View:
+        """1x1 Conv over a weighted sum of two maps without forming the sum:
+        act(W (w0 a + w1 b) + bias) = act((w1 W) b + [(w0 W) a] + bias).  The bracket runs first as a plain conv with no
+        bias / activation - at LOW resolution when a is the upsampled operand (a 1x1 conv commutes with nearest
+        upsampling) - and joins the main conv's accumulator in its epilogue (fce_conv_desc.weighted == 2)."""
+        w, b, k, s, g, a = self.conv_params(m)
+        if (k, s, g) != (1, 1, 1) or w.shape[0] % 16:
+            return self.conv(m, self.materialize(x), dst=dst, tag=tag)
+        (v0, w0, u0), (v1, w1, u1) = x.terms
+        if u1:  # the main conv runs on the full-resolution operand
+            (v0, w0, u0), (v1, w1, u1) = (v1, w1, u1), (v0, w0, u0)
+        side = self.conv(None, v0, w_override=w * w0, b_override=torch.zeros_like(b), act=L.ACT_NONE, tag=tag + ".side")
+        return self.conv(None, v1, dst=dst, res=side, res_up=u0, res_pre=True, w_override=w * w1, b_override=b, act=a,
+                         tag=tag + "+sum")
 
     # ------------------------------------------------------------------ coordinate attention family
     def _pool(self, x: View, tag) -> View:
@@ -735,6 +783,8 @@ class Plan:
     def emit(self, m, x, tag=""):
         """x: View | LazyUp | list of those.  Returns View | LazyUp | (y, raws) for Detect."""
         name = type(m).__name__
+        if isinstance(x, list):  # only a single 1x1-conv consumer folds a pending BiFPN sum
+            x = [self.materialize(e) if isinstance(e, LazySum) else e for e in x]
         if name == "Upsample":
             sf = m.scale_factor
             if m.mode != "nearest" or float(sf if not isinstance(sf, tuple) else sf[0]) != 2.0:
@@ -746,6 +796,8 @@ class Plan:
             return self.concat(m, list(x), tag=tag)
         if name == "Detect":
             return self.detect(m, list(x), tag=tag)
+        if name == "C3k2" and isinstance(x, LazySum):
+            return self.c3k2(m, x, tag=tag)
         x = self.materialize(x)
         if name in ("Conv", "Conv2d"):
             if name == "Conv" and m.conv.groups != 1:

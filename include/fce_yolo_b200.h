@@ -76,7 +76,10 @@ typedef struct {
     float in_scale;           /* 1.0, or 1/255 for u8 images */
     int32_t impl;
     /* Weighted-sum epilogue (BiFPN_Concat.forward, fce_block.py:55-63, fused into its realign conv), when
-     * weighted != 0:   y = out_scale * act(conv(x) + bias) + res_scale * res     (a scale of 0 is legitimate: relu(w) = 0)
+     * weighted == 1:   y = out_scale * act(conv(x) + bias) + res_scale * res     (a scale of 0 is legitimate: relu(w) = 0)
+     * weighted == 2:   y = act(conv(x) + res + bias): res is the partial sum W' x' of the OTHER input of a two-input BiFPN
+     *                  node whose consumer is this 1x1 conv (conv(w0 a + w1 b) = (w0 W) a + (w1 W) b; the node's scales are
+     *                  folded into the two weight matrices by the caller, the fused map is never stored)
      * res_up = 1: res is a [B, Ho/2, Wo/2, Cout] map read through a nearest 2x upsample (the Upsample layer in front of
      * the BiFPN node, yolo11-fce.yaml:40,44).  weighted / res_up: 1x1 convs on the tcgen05 path only
      * (FCE_ERR_UNSUPPORTED otherwise). */

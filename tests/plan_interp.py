@@ -36,12 +36,17 @@ class Interp(Arena):
         xin = xin * d.in_scale
         wt = w.float().permute(0, 3, 1, 2)  # OHWI -> OIHW
         o = F.conv2d(xin, wt, b.float(), stride=d.stride, padding=d.k // 2)
-        o = _act(o, d.act) * (d.out_scale if d.weighted else 1.0)
+        r = None
         if res is not None:
             r = self.t(res).permute(0, 3, 1, 2).float()
             if d.res_up:
                 r = F.interpolate(r, scale_factor=2, mode="nearest")
-            o = o + r * (d.res_scale if d.weighted else 1.0)
+        if d.weighted == 2:  # the residual joins before the activation (BiFPN node folded into its consumer)
+            o = _act(o + r, d.act)
+        else:
+            o = _act(o, d.act) * (d.out_scale if d.weighted else 1.0)
+            if r is not None:
+                o = o + r * (d.res_scale if d.weighted else 1.0)
         self.t(y).copy_(o.permute(0, 2, 3, 1))
 
     def _fce_stem_pack(self, d, p):

@@ -169,6 +169,11 @@ HALO_PAIR_CASES = [
     (3, 20, 20, 128, 128, 3, 1, 1, True, False, 0, 0),       # C3k bottleneck: 128 outputs streamed, residual
     (2, 40, 40, 128, 128, 3, 1, 1, False, False, 0, 0),      # the m-scale 128 -> 128 layers
     (2, 40, 40, 192, 96, 3, 1, 1, False, False, 64, 32),
+    # maps wider than one TMA box (254 output columns): column tiles, each with its own halo columns
+    (1, 24, 320, 48, 48, 3, 1, 1, True, False, 0, 0),        # x-scale L2 bottleneck at 1280^2: two tiles of 160
+    (2, 11, 300, 64, 64, 3, 1, 1, False, False, 0, 32),      # 2 x 150
+    (1, 9, 515, 32, 64, 3, 1, 1, True, False, 32, 0),        # 3 x 172, ragged last tile (171 columns)
+    (1, 7, 255, 64, 32, 3, 1, 1, False, False, 0, 0),        # just past one box: 128 + 127
 ]
 
 

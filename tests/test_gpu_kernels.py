@@ -396,6 +396,42 @@ def test_conv_weighted_sum_epilogue(lib, B, H, W, Cin, Cout, res_up, scales):
     assert (err <= 2 ** -7 * ref.abs() + 2e-2).all(), err.max().item()
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 80, 80, 512, 256), (3, 20, 20, 512, 512), (1, 6, 10, 64, 32),
+                                            (5, 40, 40, 384, 128)])
+@pytest.mark.parametrize("res_up", [0, 1])
+@pytest.mark.parametrize("impl", [0, 3, 4])
+def test_conv_pre_activation_residual(lib, B, H, W, Cin, Cout, res_up, impl):
+    """fce_conv2d with weighted = 2: y = SiLU(conv1x1(x) + res + b) - the second half of a 1x1 conv over a two-input
+    BiFPN sum (conv(w0 a + w1 b) = (w0 W) a + (w1 W) b), res optionally at half resolution (the upsampled operand: a
+    1x1 conv commutes with nearest upsampling).  Single-CTA and CTA-pair kernels."""
+    l, L = lib
+    g = torch.Generator().manual_seed(B + H + Cin + Cout + res_up)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(Cout, 1, 1, Cin, generator=g) / math.sqrt(Cin)).to(torch.bfloat16).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    rh, rw = (H // 2, W // 2) if res_up else (H, W)
+    res = torch.randn(B, rh, rw, Cout, generator=g).to(torch.bfloat16).cuda()
+    y = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16).cuda()
+    d = L.ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=Cout, in_pitch=Cin, in_off=0, out_pitch=Cout, out_off=0, res_pitch=Cout,
+                   res_off=0, k=1, stride=1, act=L.ACT_SILU, in_dtype=L.BF16, w_dtype=L.BF16, out_dtype=L.BF16,
+                   in_layout=L.NHWC, in_scale=1.0, impl=impl, weighted=2, out_scale=1.0, res_scale=1.0, res_up=res_up)
+    st = l.fce_conv2d(C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
+                      C.c_void_p(res.data_ptr()), C.c_void_p(y.data_ptr()), _stream())
+    if impl == 3 and st == -2:
+        pytest.skip("no CTA-pair tiling for this shape")
+    L.check(st, "fce_conv2d pre-activation residual")
+    torch.cuda.synchronize()
+    r = res.float().permute(0, 3, 1, 2)
+    if res_up:
+        r = F.interpolate(r, scale_factor=2, mode="nearest")
+    ref = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b) + r).permute(0, 2, 3, 1)
+    err = (y.float() - ref).abs()
+    assert (err <= 2 ** -7 * ref.abs() + 2e-2).all(), err.max().item()
+    d.weighted = 2
+    assert l.fce_conv2d(C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()), None,
+                        C.c_void_p(y.data_ptr()), _stream()) == -1  # weighted = 2 without a residual
+
+
 def test_conv_weighted_sum_needs_the_tensor_core_1x1(lib):
     l, L = lib
     t = torch.zeros(1 << 16, dtype=torch.bfloat16).cuda()

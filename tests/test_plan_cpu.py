@@ -132,11 +132,11 @@ def test_bifpn_fused_into_realign_convs(name):
     x = synth_images(case["img_seed"], case["batch"], case["size"], case["size"])
     ys, counts = {}, {}
     for fused in (False, True):
-        Plan.FUSED_BIFPN = fused
+        Plan.FUSED_BIFPN, Plan.FUSED_SUM = fused, False  # FUSED_SUM: layer outputs of the BiFPN nodes are read back below
         try:
             plan = compile_model(model, case["batch"], case["size"], case["size"], "bf16", torch.device("cpu"))
         finally:
-            Plan.FUSED_BIFPN = True
+            Plan.FUSED_BIFPN = Plan.FUSED_SUM = True
         counts[fused] = sum(1 for n in plan.nodes if n.fn == "fce_bifpn_fuse")
         it = Interp(plan, reuse_memory=False)  # layer outputs are read back after the run
         it.input_tensor().copy_(x)
@@ -151,6 +151,42 @@ def test_bifpn_fused_into_realign_convs(name):
     for a, b in zip(ys[True][1], ys[False][1]):
         assert rel_l2(a, b) < 2e-2
     assert rel_l2(ys[True][0], ys[False][0]) < 5e-2  # end to end: two bf16 evaluation orders of the same graph
+
+
+@pytest.mark.parametrize("name", ["m_bifpn_64", "n_fce_64"])
+def test_bifpn_sum_folded_into_consumer(name):
+    """Two-input BiFPN nodes with identity realigns (m scale: SURVEY A.1-3) never store their weighted sum: the C3k2.cv1
+    behind them runs as (w0 W) a [at a's resolution] + (w1 W) b with the first product joining the second conv's
+    accumulator (fce_conv_desc.weighted == 2).  Same predictions as the fce_bifpn_fuse route up to bf16 rounding."""
+    from fce_yolo_b200.plan import Plan
+
+    case = FORWARD_CASES[name]
+    cfg, scale = load_cfg(case)
+    model = DetectionModel(cfg, scale=scale).fuse().eval()
+    load_synthetic(model, case["seed"])
+    x = synth_images(case["img_seed"], case["batch"], case["size"], case["size"])
+    ys, fuse_nodes, folded = {}, {}, {}
+    for fused in (False, True):
+        Plan.FUSED_SUM = fused
+        try:
+            plan = compile_model(model, case["batch"], case["size"], case["size"], "bf16", torch.device("cpu"))
+        finally:
+            Plan.FUSED_SUM = True
+        fuse_nodes[fused] = sum(1 for n in plan.nodes if n.fn == "fce_bifpn_fuse")
+        folded[fused] = sum(1 for n in plan.nodes if n.fn == "fce_conv2d" and n.desc.weighted == 2)
+        it = Interp(plan, reuse_memory=True)
+        it.input_tensor().copy_(x)
+        it.run()
+        ys[fused] = it.outputs()[0].float()
+    assert folded[False] == 0
+    if name == "m_bifpn_64":
+        assert folded[True] == 2 and fuse_nodes[True] == fuse_nodes[False] - 2  # three-input / same-resolution nodes keep the kernel
+    else:
+        assert folded[True] == fuse_nodes[False] - fuse_nodes[True]
+    assert rel_l2(ys[True], ys[False]) < 5e-2
+    # fp32 plans keep the separate launch
+    assert all(n.desc.weighted != 2 for n in compile_model(model, 1, 64, 64, "fp32", torch.device("cpu")).nodes
+               if n.fn == "fce_conv2d")
 
 
 def test_detect_branches_and_dependencies():
