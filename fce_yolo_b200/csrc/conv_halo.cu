@@ -496,16 +496,18 @@ int conv_halo_profile(long long* out, int n) {
 }
 #endif
 
-// Band height for a given K chunk / weight mode; returns the efficiency estimate (0 = does not fit).
-static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool stream, int ncta, HaloParams& p) {
+static const int g_halo_wtiles_max = [] {  // extra column tiles tried when the plain plan does not fit (FCE_HALO_WTILES=1: off)
+    const char* e = getenv("FCE_HALO_WTILES");
+    return e && *e ? atoi(e) : 4;
+}();
+
+// Band height for a given K chunk / weight mode / column-tile count; returns the efficiency estimate (0 = does not fit).
+static double halo_plan_tiles(const fce_conv_desc* d, bool has_res, int kc, bool stream, int ncta, int wtiles, HaloParams& p) {
     const int chunks = d->Cin / kc;
     const uint32_t row_b = kc * 2;
     const uint32_t b_sub = (uint32_t)(d->Cout / ncta) * row_b;  // a pair stages half of every weight tile's rows per CTA
     const uint32_t b_total = ((stream ? (uint32_t)A_STAGES * 9u : 9u * chunks) * b_sub + 1023u) & ~1023u;
     const uint32_t bias_bytes = ((uint32_t)d->Cout * 4 + 1023u) & ~1023u;
-    // column tiles: a TMA box dimension holds at most 256 elements, so maps wider than 254 columns (320 x 320 maps of
-    // 1280^2 inputs) are cut into the fewest equal tiles; every tile is its own unit with its own halo columns
-    const int wtiles = (d->W + 253) / 254;
     const int Wt = (d->W + wtiles - 1) / wtiles;
     const int Wp = Wt + 2;
     int best_R = 0;
@@ -523,7 +525,8 @@ static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool s
         if ((size_t)A_STAGES * strip + b_total + n_stg * n_slabs * slab + bias_bytes + 2048 > (size_t)SMEM_LIMIT) break;
         // useful fraction of the issued MMA rows, discounted by the halo re-read
         const int bands = (d->H + R - 1) / R;
-        const double eff = (double)d->H * d->W / ((double)bands * wtiles * nb * 128) * (0.75 + 0.25 * R / (R + 2.0));
+        const double eff = (double)d->H * d->W / ((double)bands * wtiles * nb * 128) * (0.75 + 0.25 * R / (R + 2.0)) *
+                           (wtiles == 1 ? 1.0 : 0.75 + 0.25 * Wt / (Wt + 2.0));
         if (eff > best_eff + 1e-9) {
             best_eff = eff;
             best_R = R;
@@ -556,6 +559,25 @@ static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool s
     p.tmem_cols = 32;
     while (p.tmem_cols < (uint32_t)(p.acc_sets * p.nb * d->Cout)) p.tmem_cols <<= 1;
     return best_eff;
+}
+
+// Column tiles: a TMA box dimension holds at most 256 elements, so maps wider than 254 columns (320 x 320 maps of 1280^2
+// inputs) are cut into the fewest equal tiles; every tile is its own unit with its own halo columns.  More tiles than
+// that only where the plain plan does not fit the accumulator: 96 outputs leave room for two 128-row blocks per
+// accumulator set - one 160-wide row wastes 38 % of them, three rows of an 80-wide tile 6 %.
+static double halo_plan_one(const fce_conv_desc* d, bool has_res, int kc, bool stream, int ncta, HaloParams& p) {
+    const int wmin = (d->W + 253) / 254;
+    double best = halo_plan_tiles(d, has_res, kc, stream, ncta, wmin, p);
+    if (best >= 0.55 || g_halo_wtiles_max <= 1) return best;
+    for (int wt = wmin + 1; wt <= wmin + g_halo_wtiles_max - 1 && d->W / wt >= 32; ++wt) {
+        HaloParams q{};
+        const double e = halo_plan_tiles(d, has_res, kc, stream, ncta, wt, q);
+        if (e > best + 1e-9) {
+            best = e;
+            p = q;
+        }
+    }
+    return best;
 }
 
 static const int g_stream_max_cout = [] {  // widest output the streamed-weight mode takes (FCE_STREAM_MAX_COUT to vary)
@@ -612,6 +634,10 @@ static int halo_choice(const fce_conv_desc* d, bool has_res, int mode, HaloParam
     static const int pair_env = [] { const char* e = getenv("FCE_HALO_PAIR"); return e && *e ? atoi(e) : -1; }();
     if (mode == 1) return halo_plan(d, has_res, 1, p) ? 1 : 0;
     if (mode == 2) return (halo_plan(d, has_res, 2, p) && p.units >= 2) ? 2 : 0;
+    // 128 outputs and more WITH a residual on a large problem: the im2col CTA-pair kernel (conv_tc.cu), whose epilogue now
+    // prefetches the residual with 32-byte loads, is ahead of the streamed-weight pair strips (m scale, batch 256,
+    // 128 -> 128 at 40x40 + res: 153 us against 163 us; equal at 20x20)
+    if (has_res && d->Cout >= 128 && (long long)d->B * d->H * d->W >= 200000) return 0;
     if (pair_env != 0) {
         HaloParams q{};
         if (halo_plan(d, has_res, 2, q) && q.units >= kNumSMs / 2 && (pair_env == 1 || halo_pair_pays(d, q))) {

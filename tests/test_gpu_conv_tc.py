@@ -174,6 +174,10 @@ HALO_PAIR_CASES = [
     (2, 11, 300, 64, 64, 3, 1, 1, False, False, 0, 32),      # 2 x 150
     (1, 9, 515, 32, 64, 3, 1, 1, True, False, 32, 0),        # 3 x 172, ragged last tile (171 columns)
     (1, 7, 255, 64, 32, 3, 1, 1, False, False, 0, 0),        # just past one box: 128 + 127
+    # more column tiles than the box needs, where one row would waste the 96-output accumulator (x scale)
+    (2, 24, 160, 96, 96, 3, 1, 1, False, False, 0, 0),
+    (2, 24, 160, 96, 96, 3, 1, 1, True, False, 96, 0),
+    (1, 17, 100, 96, 96, 3, 1, 1, True, False, 0, 32),       # ragged tiles
 ]
 
 

@@ -56,6 +56,10 @@ def main():
             seen[key][0] += 1
             continue
         res = {}
+        for _ in range(3):  # untimed: the first variant timed after the previous node's runs came out 5-10 % slow
+            flush.zero_()
+            fn(*args, st)
+        torch.cuda.synchronize()
         for label, impl in (("auto", 0), ("single", 4), ("pair", 3), ("strip", 5), ("strip2", 6)):
             saved = d.impl
             d.impl = impl
