@@ -79,6 +79,23 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+def write_only_peak(device):
+    """HBM WRITE-only bandwidth, measured live (GB/s): a fill of 2 GiB.  On these B200s a pure write stream reaches about
+    3.9 TB/s where reads and read+write copies reach 6.5 - 6.6 TB/s, so a kernel that mostly writes (the stem: 0.3 GB
+    in, 3.4 GB out) is bounded by this number, not by MEASURED_PEAKS.json's copy bandwidth.  Reported next to the contract's
+    roofline, never instead of it."""
+    x = torch.empty(2 << 30, dtype=torch.uint8, device=device)
+    x.zero_()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        x.zero_()
+    e1.record()
+    torch.cuda.synchronize(device)
+    return 5 * (2 << 30) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 def build_model(w):
     from fce_yolo_b200.tasks import DetectionModel, variant_cfg, yaml_model_load
     from fce_yolo_b200.weights import load_synthetic
@@ -244,13 +261,20 @@ def kernel_table(pred, name):
                 acc[i] += evs[i].elapsed_time(evs[i + 1]) / reps
     classes, table = {}, []
     pk = peaks()
+    from fce_yolo_b200.plan import DT_SIZE, View
+    wpk = write_only_peak(pred.device)
     for (fn, args, n), ms in zip(ex._calls, acc):
         # the fused Detect epilogues are launches of the same tcgen05 conv kernel: one class
         cls = "fce_conv2d" if n.fn == "fce_conv2d_detect" else n.fn
-        c = classes.setdefault(cls, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, ideal=0.0))
+        c = classes.setdefault(cls, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, ideal=0.0, wbytes=0.0, ideal_w=0.0))
         c["ms"] += ms
         # this launch's own roofline: the slower of its tensor time and its HBM time
-        c["ideal"] += max(n.flops / (pk["tf_sustained"] * 1e12), n.bytes / (pk["hbm"] * 1e9)) * 1e3
+        ideal = max(n.flops / (pk["tf_sustained"] * 1e12), n.bytes / (pk["hbm"] * 1e9)) * 1e3
+        c["ideal"] += ideal
+        # ... and with the write stream held to the measured write-only bandwidth
+        wb = sum(v.B * v.H * v.W * v.C * DT_SIZE[v.dtype] for v in n.writes if isinstance(v, View)) if n.bytes else 0.0
+        c["wbytes"] += wb
+        c["ideal_w"] += max(ideal, wb / (wpk * 1e9) * 1e3)
         c["flops"] += n.flops
         c["bytes"] += n.bytes
         c["launches"] += 1
@@ -287,10 +311,13 @@ def kernel_table(pred, name):
                 roof["algorithmic_bytes_per_launch"] = round(c["bytes"] / c["launches"], 1)
         except (OSError, ValueError, KeyError):
             tj = {}
+    roof["write_only_peak_GB/s"] = round(wpk, 1)
     roof["classes"] = {
         k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total, 3), "launches": v["launches"],
             **({"TFLOP/s": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] else {}),
             "roofline_frac": round(v["ideal"] / v["ms"], 3),
+            **({"write_GB/s": round(v["wbytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                "roofline_frac_write_aware": round(v["ideal_w"] / v["ms"], 3)} if v["wbytes"] else {}),
             **({"GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
                 "hbm_frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"], 3)} if v["bytes"] else {})}
         for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}

@@ -743,6 +743,12 @@ int conv2d_tc(const fce_conv_desc* d, const void* x, const void* w, const float*
     p.a_stage = p.S * p.a_sub;
     p.b_stage = p.S * p.b_sub;
     const uint32_t w_bytes = (uint32_t)k_steps * p.b_sub;
+    // Weights parked in shared memory for the life of the CTA when there is ONE N tile.  (Tried and dropped: with several
+    // N tiles, a grid that is a multiple of n_tiles so that every CTA keeps one tile column and parks its [bn, K] slice.
+    // Isolated, L2 flushed: 1x1 192 -> 256 at 160x160 1149 -> 1086 us, 256 -> 256 at 80x80 357 -> 338 us, but 384 -> 512
+    // at 80x80 842 -> 916 us with only four A stages left; inside the captured step the m-scale forward came out
+    // 0.5 % SLOWER, 10.29k vs 10.35k images/s on the same box - the streamed weight tiles are L2 hits that overlap the A
+    // stream, and the parked slice costs pipeline depth.)
     p.b_resident = (p.n_tiles == 1 && w_bytes <= (uint32_t)B_RESIDENT_MAX) ? 1 : 0;
     p.bias_bytes = (uint32_t)(p.n_tiles * p.bn * 4 + 1023) & ~1023u;
     int room = SMEM_BUDGET - (int)p.bias_bytes;

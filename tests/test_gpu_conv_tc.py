@@ -45,6 +45,15 @@ CASES = [
     (2, 40, 40, 160, 64, 3, 1, 1, False, False, 0, 0),       # Cin % 64 != 0: kc = 32 x5
     (3, 20, 20, 128, 128, 3, 1, 1, True, False, 0, 0),       # C3k bottleneck at P5: 128 outputs, residual
     (2, 40, 40, 192, 96, 3, 1, 1, False, False, 64, 32),
+    # 1x1 layers with several N tiles on a full persistent grid
+    (8, 80, 80, 192, 256, 1, 1, 1, False, False, 0, 0),      # 2 N tiles of 128
+    (4, 80, 80, 256, 512, 1, 1, 1, True, False, 0, 0),       # 4 N tiles, residual
+    (4, 80, 80, 256, 384, 1, 1, 1, False, False, 64, 0),     # 3 N tiles
+    (5, 80, 80, 128, 320, 1, 1, 0, False, False, 0, 64),     # ragged last N tile (320 = 128 + 128 + 64)
+    # strip kernel on maps wider than one TMA box: column tiles
+    (1, 24, 320, 48, 48, 3, 1, 1, True, False, 0, 0),
+    (1, 9, 515, 32, 64, 3, 1, 1, False, False, 0, 0),
+    (2, 24, 160, 96, 96, 3, 1, 1, True, False, 96, 0),       # extra column tiles (96-output accumulator)
 ]
 
 
@@ -70,6 +79,8 @@ PAIR_CASES = [
     (3, 40, 24, 128, 256, 3, 2, 1, False, False, 0, 0),      # stride 2, H != W, 6 tiles
     (5, 20, 20, 256, 512, 3, 2, 1, False, False, 0, 0),      # stride 2, two N tiles, M = 500 (4 tiles, ragged)
     (4, 20, 20, 512, 512, 3, 1, 1, False, False, 0, 0),      # long K, two N tiles, 13 tiles (odd)
+    (8, 80, 80, 256, 512, 1, 1, 1, True, False, 0, 0),       # full grid of pairs: 2 x 256 columns, residual
+    (8, 80, 80, 192, 384, 1, 1, 1, False, False, 0, 0),      # full grid of pairs: 3 x 128 columns
     (2, 24, 24, 32, 16, 3, 1, 1, False, False, 0, 0),        # bn = 16: no legal pair tiling -> FCE_ERR_UNSUPPORTED
 ]
 
