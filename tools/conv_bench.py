@@ -41,6 +41,12 @@ SHAPES = [
     ("Det.cv2.2.0 3x3 512->64@20", 64, 20, 20, 512, 64, 3, 1, 0, 0),
     ("Det.cv3.0.2 1x1 128->80@80", 64, 80, 80, 128, 80, 1, 1, 0, 1),
     ("Det.cv2.0.2 1x1 64->64 @80 f32", 64, 80, 80, 64, 64, 1, 1, 0, 1),
+    # m scale, batch 256 (the north-star configuration): the layers furthest from their own roofline
+    ("M1   3x3s2  64->128 @320 b256", 256, 320, 320, 64, 128, 3, 2, 0, 0),
+    ("M2.cv2 1x1 192->256 @160 b256", 256, 160, 160, 192, 256, 1, 1, 0, 0),
+    ("M4.cv2 1x1 384->512 @80 b256", 256, 80, 80, 384, 512, 1, 1, 0, 0),
+    ("M16.cv2 1x1 384->256 @80 b256", 256, 80, 80, 384, 256, 1, 1, 0, 0),
+    ("M6.cv1 1x1 512->512 @40 b256", 256, 40, 40, 512, 512, 1, 1, 0, 0),
     # L2-resident probes of the TMA feed rate (run with --noflush): A traffic only, tiny N
     ("probe tiled 1x1 1024->16 @80 b4", 4, 80, 80, 1024, 16, 1, 1, 0, 0),
     ("probe im2col 3x3 128->16 @80 b4", 4, 80, 80, 128, 16, 3, 1, 0, 0),
