@@ -50,6 +50,11 @@ class DwconvDesc(C.Structure):
                                    "add_off", "act", "dtype")]
 
 
+class DwpwDesc(C.Structure):
+    _fields_ = [(n, i32) for n in ("B", "H", "W", "C", "Cout", "in_pitch", "in_off", "out_pitch", "out_off", "dw_act",
+                                   "pw_act")]
+
+
 class SppfDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "H", "W", "C", "pitch", "off", "dtype")]
 
@@ -117,6 +122,8 @@ _SIGS = {
     "fce_conv2d_route": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P]),
     "fce_conv_stats": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "fce_dwconv3x3": (C.c_int, [C.POINTER(DwconvDesc), _P, _P, _P, _P, _P, _P]),
+    "fce_dwpw_conv": (C.c_int, [C.POINTER(DwpwDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "fce_dwpw_route": (C.c_int, [C.POINTER(DwpwDesc)]),
     "fce_sppf_pool": (C.c_int, [C.POINTER(SppfDesc), _P, _P]),
     "fce_upsample2x": (C.c_int, [C.POINTER(UpsampleDesc), _P, _P, _P]),
     "fce_bifpn_fuse": (C.c_int, [C.POINTER(BifpnDesc), _P, _P, _P, _P, _P]),

@@ -17,6 +17,7 @@ classes in fce_yolo_b200.modules and the reference's own ultralytics instances (
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from dataclasses import dataclass, field
 
@@ -130,6 +131,8 @@ class Plan:
     FUSED_SUM = os.environ.get("FCE_FUSED_SUM", "1") != "0"
     FUSED_COORDATT_MLP = True  # False: cv1 / cv_h / cv_w as three strip convs (A/B timing, cross-check)
     FUSED_C3K_IN = True  # False: C3k.cv1 and C3k.cv2 as two launches (A/B timing, cross-check)
+    # False (or FCE_FUSED_DWPW=0): Detect's DWConv + 1x1 blocks as two launches (A/B timing, cross-check)
+    FUSED_DWPW = os.environ.get("FCE_FUSED_DWPW", "1") != "0"
     FUSED_STEM = True  # False: stem = fce_stem_pack + K=32 tcgen05 conv (kept for A/B timing and as a cross-check)
 
     def __init__(self, batch: int, precision: str, device, impl: int = 0):
@@ -344,6 +347,32 @@ class Plan:
         esz = DT_SIZE[x.dtype]
         self.add(Node("fce_dwconv3x3", d, [x, wp, bp, add, dst], reads=[x] + ([add] if add is not None else []),
                       writes=[dst], tag=tag, bytes=(2 + (add is not None)) * x.B * x.H * x.W * x.C * esz))
+        return dst
+
+    def dwpw(self, m_dw, m_pw, x: View, dst: View | None = None, tag="") -> View:
+        """DWConv(c, c, 3) followed by Conv(c, c2, 1) (one block of Detect.cv3, head.py:101-102) as ONE launch
+        (fce_dwpw_conv: the depthwise result stays in shared memory) where the kernel takes the shape; two launches
+        otherwise.  Same values either way (tests/test_gpu_dwpw.py)."""
+        wd, bd, kd, sd, gd, ad = self.conv_params(m_dw)
+        wp_, bp_, kp, sp, gp, ap = self.conv_params(m_pw)
+        Cc, Cout = x.C, wp_.shape[0]
+        d = L.DwpwDesc(B=x.B, H=x.H, W=x.W, C=Cc, Cout=Cout, in_pitch=x.pitch, in_off=0,
+                       out_pitch=dst.pitch if dst is not None else Cout, out_off=0, dw_act=ad, pw_act=ap)
+        ok = (self.FUSED_DWPW and self.act_dt == L.BF16 and self.impl in (0, 2) and x.dtype == L.BF16
+              and (kd, sd, gd) == (3, 1, Cc) and wd.shape[0] == Cc and wd.shape[1] == 1
+              and (kp, sp, gp) == (1, 1, 1) and wp_.shape[1] == Cc and (dst is None or dst.dtype == L.BF16)
+              and L.load().fce_dwpw_route(ctypes.byref(d)) == 1)
+        if not ok:
+            t = self.dwconv(m_dw, x, tag=tag + ".0")
+            return self.conv(m_pw, t, dst=dst, tag=tag + ".1")
+        if dst is None:
+            dst = self.new_buf(x.H, x.W, Cout)
+        if (dst.H, dst.W, dst.C, dst.B) != (x.H, x.W, Cout, x.B):
+            raise PlanError(f"{tag}: dwpw output does not fit its destination")
+        ptrs = [x, self._w(wd.view(Cc, 9).t()), self._w(bd), self._w(wp_.view(Cout, Cc), torch.bfloat16), self._w(bp_), dst]
+        px = x.B * x.H * x.W
+        self.add(Node("fce_dwpw_conv", d, ptrs, reads=[x], writes=[dst], tag=tag + ".0+1",
+                      flops=2.0 * px * Cout * Cc, bytes=px * (Cc + Cout) * 2.0 + Cout * Cc * 2.0))
         return dst
 
     # ------------------------------------------------------------------ blocks
@@ -714,8 +743,7 @@ class Plan:
                 blk = m.cv3[i][j]
                 if len(blk) != 2:
                     raise PlanError("legacy Detect heads (dense 3x3 class branch) are outside the path")
-                c = self.dwconv(blk[0], c, tag=f"{tag}.cv3.{i}.{j}.0")
-                c = self.conv(blk[1], c, tag=f"{tag}.cv3.{i}.{j}.1")
+                c = self.dwpw(blk[0], blk[1], c, tag=f"{tag}.cv3.{i}.{j}")
             if fused:
                 tails.append((m.cv3[i][2], c, 1, i, f"{tag}.cv3.{i}.2"))
             else:

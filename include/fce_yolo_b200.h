@@ -157,6 +157,25 @@ typedef struct {
 int fce_dwconv3x3(const fce_dwconv_desc* d, const void* x, const float* w, const float* bias, const void* add,
                   void* y, void* stream);
 
+/* Depthwise 3x3 stride 1 + bias + act FOLLOWED BY a 1x1 conv + bias + act, in one pass: one block of Detect's class
+ * branch, cv3[i][j] = Sequential(DWConv(c, c, 3), Conv(c, c3, 1)) (head.py:101-102; conv.py:185-199, :80-89).  The
+ * depthwise result (rounded to bf16, as the two-launch route stores it) goes straight into the shared-memory A operand
+ * of the 1x1 on the tensor cores and never exists in HBM; results are bit-identical to fce_dwconv3x3 + fce_conv2d.
+ * bf16 NHWC views in and out; w_dw fp32 [9][C] (tap-major), b_dw fp32 [C], w_pw bf16 [Cout][C], b_pw fp32 [Cout].
+ * Shapes: C % 64 == 0, Cout % 16 == 0, Cout <= 256, and the [Cout, C] weights must fit shared memory next to the
+ * pipeline (C * Cout <= 64 Ki elements); anything else returns FCE_ERR_UNSUPPORTED and the caller issues the two
+ * launches.  fce_dwpw_route answers that question without launching (1 = this entry point takes the shape, 0 = not;
+ * pure function of the descriptor). */
+typedef struct {
+    int32_t B, H, W;
+    int32_t C, Cout;
+    int32_t in_pitch, in_off, out_pitch, out_off;
+    int32_t dw_act, pw_act;      /* fce_act of the depthwise conv / of the 1x1 */
+} fce_dwpw_desc;
+int fce_dwpw_conv(const fce_dwpw_desc* d, const void* x, const float* w_dw, const float* b_dw, const void* w_pw,
+                  const float* b_pw, void* y, void* stream);
+int fce_dwpw_route(const fce_dwpw_desc* d);
+
 /* SPPF pyramid: three chained 5x5/s1/p2 max-pools (= 5x5, 9x9, 13x13 windows) of slice 0 of the
  * concat buffer written to slices 1..3 (block.py:228-232).  buf has 4*C channels. */
 typedef struct {

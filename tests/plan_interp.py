@@ -84,6 +84,14 @@ class Interp(Arena):
             o = o + self.t(add).permute(0, 3, 1, 2).float()
         self.t(y).copy_(o.permute(0, 2, 3, 1))
 
+    def _fce_dwpw_conv(self, d, p):
+        x, wd, bd, wp, bp, y = p
+        xin = self.t(x).permute(0, 3, 1, 2).float()
+        t = _act(F.conv2d(xin, wd.float().t().reshape(d.C, 1, 3, 3), bd.float(), padding=1, groups=d.C), d.dw_act)
+        t = t.to(self.t(y).dtype).float()  # the intermediate is rounded to the activation dtype, as the two launches store it
+        o = _act(F.conv2d(t, wp.float().view(d.Cout, d.C, 1, 1), bp.float()), d.pw_act)
+        self.t(y).copy_(o.permute(0, 2, 3, 1))
+
     def _fce_sppf_pool(self, d, p):
         cat = p[0]
         cur = self.t(cat.ch(0, d.C)).permute(0, 3, 1, 2).float()

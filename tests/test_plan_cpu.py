@@ -230,7 +230,9 @@ def test_detect_branches_and_dependencies():
     level_of = {"0": "model.18", "1": "model.21", "2": "model.24"}
     for k, chain in head.items():
         tag = nodes[chain[0]].tag  # model.25.cv2.<level>.0 or model.25.cv3.<level>.0.0
-        assert nodes[chain[-1]].fn == "fce_conv2d_detect" and len(chain) == (3 if ".cv2." in tag else 5)
+        n_dwpw = sum(nodes[i].fn == "fce_dwpw_conv" for i in chain)  # a DWConv + 1x1 block the fused kernel takes is ONE node
+        assert nodes[chain[-1]].fn == "fce_conv2d_detect" and len(chain) == (3 if ".cv2." in tag else 5 - n_dwpw)
+        assert n_dwpw == (0 if ".cv2." in tag else 1)  # n scale: 64 -> 80 fuses, the 80-channel depthwise does not
         (src,) = deps[chain[0]]
         assert nodes[src].stream == 0 and nodes[src].tag.startswith(level_of[tag.split(".")[3]])
         for a, b in zip(chain, chain[1:]):

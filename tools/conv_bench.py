@@ -43,6 +43,10 @@ SHAPES = [
     ("Det.cv2.0.2 1x1 64->64 @80 f32", 64, 80, 80, 64, 64, 1, 1, 0, 1),
     # m scale, batch 256 (the north-star configuration): the layers furthest from their own roofline
     ("M1   3x3s2  64->128 @320 b256", 256, 320, 320, 64, 128, 3, 2, 0, 0),
+    ("M2.m.cv1 3x3 32->32 @160 b256", 256, 160, 160, 32, 32, 3, 1, 0, 0),
+    ("M2.m.cv2 3x3 32->32 @160 b256 +res", 256, 160, 160, 32, 32, 3, 1, 1, 0),
+    ("M2.cv3 1x1 64->64 @160 b256", 256, 160, 160, 64, 64, 1, 1, 0, 0),
+    ("M4.m.cv1 3x3 64->64 @80 b256", 256, 80, 80, 64, 64, 3, 1, 0, 0),
     ("M2.cv2 1x1 192->256 @160 b256", 256, 160, 160, 192, 256, 1, 1, 0, 0),
     ("M4.cv2 1x1 384->512 @80 b256", 256, 80, 80, 384, 512, 1, 1, 0, 0),
     ("M16.cv2 1x1 384->256 @80 b256", 256, 80, 80, 384, 256, 1, 1, 0, 0),
@@ -63,6 +67,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--noflush", action="store_true")
     ap.add_argument("--act", type=int, default=1)
+    ap.add_argument("--in-pitch-mult", type=int, default=1, help="read the input as a channel slice of a buffer this many times wider")
+    ap.add_argument("--out-pitch-mult", type=int, default=1, help="write the output into a channel slice of a wider buffer")
     ap.add_argument("--prof", action="store_true", help="per-role cycle accounting of one launch per shape")
     ap.add_argument("--skip-tma", action="store_true", help="debug: producers skip the loads (MMA+epilogue rate)")
     ap.add_argument("--dbg", type=int, default=0, help="debug bits for timed runs: 1 skip TMA loads, 2 skip TMA stores, "
@@ -87,13 +93,13 @@ def main():
             B = a.batch
         pad = k // 2
         Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
-        x = torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16)
+        x = torch.randn(B, H, W, Cin * a.in_pitch_mult, device=dev).to(torch.bfloat16)
         w = (torch.randn(Cout, k, k, Cin, device=dev) / (k * k * Cin) ** 0.5).to(torch.bfloat16)
         bias = torch.randn(Cout, device=dev)
-        y = torch.empty(B, Ho, Wo, Cout, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+        y = torch.empty(B, Ho, Wo, Cout * a.out_pitch_mult, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
         r = torch.randn(B, Ho, Wo, Cout, device=dev).to(torch.bfloat16) if has_res else None
-        d = L.ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=Cout, in_pitch=Cin, in_off=0, out_pitch=Cout, out_off=0,
-                       res_pitch=Cout if has_res else 0, res_off=0, k=k, stride=s, act=a.act, in_dtype=L.BF16,
+        d = L.ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=Cout, in_pitch=Cin * a.in_pitch_mult, in_off=0,
+                       out_pitch=Cout * a.out_pitch_mult, out_off=0, res_pitch=Cout if has_res else 0, res_off=0, k=k, stride=s, act=a.act, in_dtype=L.BF16,
                        w_dtype=L.BF16, out_dtype=L.F32 if f32 else L.BF16, in_layout=L.NHWC, in_scale=1.0, impl=a.impl)
         args = (C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(bias.data_ptr()),
                 C.c_void_p(r.data_ptr() if has_res else 0), C.c_void_p(y.data_ptr()), C.c_void_p(st))
@@ -137,7 +143,8 @@ def main():
         ms.sort()
         t = ms[len(ms) // 2]
         flops = 2.0 * B * Ho * Wo * Cout * Cin * k * k
-        byts = x.numel() * 2 + y.numel() * y.element_size() + (r.numel() * 2 if has_res else 0) + w.numel() * 2
+        byts = (x.numel() * 2 // a.in_pitch_mult + y.numel() * y.element_size() // a.out_pitch_mult +
+                (r.numel() * 2 if has_res else 0) + w.numel() * 2)
         roof_ms = max(byts / 6553.9e9, flops / 1407e12) * 1e3
         tot_ms += t
         tot_roof += roof_ms

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--csv", default=None)
+    ap.add_argument("--dense", action="store_true", help="also time every conv on dense scratch tensors")
     ap.add_argument("--only", default=None, help="comma-separated substrings of node tags to time")
     a = ap.parse_args()
     w, name = bench.workload(a.config)
@@ -51,7 +52,8 @@ def main():
             continue
         if a.only and not any(t in n.tag for t in a.only.split(",")):
             continue
-        key = (n.fn, d.B, d.H, d.W, d.Cin, d.Cout, d.k, d.stride, d.res_pitch != 0, d.out_dtype, d.weighted, d.res_up)
+        key = (n.fn, d.B, d.H, d.W, d.Cin, d.Cout, d.k, d.stride, d.res_pitch != 0, d.out_dtype, d.weighted, d.res_up) + (
+            (d.in_pitch, d.out_pitch, d.res_pitch) if a.dense else ())
         if key in seen:
             seen[key][0] += 1
             continue
@@ -81,13 +83,55 @@ def main():
             ms.sort()
             res[label] = ms[len(ms) // 2]
             d.impl = saved
-        seen[key] = [1, n.tag, res, n.flops, n.bytes]
+        if a.dense and n.fn == "fce_conv2d":
+            # the same conv on DENSE scratch tensors (pitch = channel count): what the channel-slice views cost
+            import copy
+            dd = copy.copy(d)
+            Ho = (d.H + 2 * (d.k // 2) - d.k) // d.stride + 1
+            Wo = (d.W + 2 * (d.k // 2) - d.k) // d.stride + 1
+            xs = torch.randn(d.B, d.H, d.W, d.Cin, device=dev).to(torch.bfloat16)  # real data: zeros run cooler and faster
+            ys = torch.empty(d.B, Ho, Wo, d.Cout, dtype=torch.float32 if d.out_dtype == L.F32 else torch.bfloat16, device=dev)
+            rs = None
+            if d.res_pitch:
+                q = 2 if d.res_up else 1
+                rs = torch.randn(d.B, Ho // q, Wo // q, d.Cout, device=dev).to(torch.bfloat16)
+            dd.in_pitch, dd.in_off, dd.out_pitch, dd.out_off = d.Cin, 0, d.Cout, 0
+            dd.res_pitch, dd.res_off = (d.Cout if rs is not None else 0), 0
+            dargs = [C.byref(dd), C.c_void_p(xs.data_ptr()), args[2], args[3],
+                     C.c_void_p(rs.data_ptr() if rs is not None else 0), C.c_void_p(ys.data_ptr())]
+            if fn(*dargs, st) == 0:
+                torch.cuda.synchronize()
+                ms = []
+                for _ in range(a.reps):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    fn(*dargs, st)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms.append(e0.elapsed_time(e1))
+                ms.sort()
+                res["dense"] = ms[len(ms) // 2]
+            del xs, ys, rs
+        seen[key] = [1, n.tag, res, n.flops, n.bytes, (d.in_pitch, d.Cin, d.out_pitch, d.Cout)]
     print(f"{'node':30s} {'shape':34s} cnt {'auto us':>9s} {'single':>9s} {'pair':>9s} {'strip':>9s} {'strip2':>9s}  auto TF  best TF  roofline us")
-    for key, (cnt, tag, res, fl, by) in seen.items():
-        _, B, H, W, Cin, Cout, k, s, has_res, odt, wt, ru = key
+    if a.dense:
+        gain = 0.0
+        print("dense-tensor twin of every conv (what the channel-slice views cost):")
+        for key, (cnt, tag, res, fl, by, pit) in seen.items():
+            if res.get("dense") is None:
+                continue
+            g = cnt * (res["auto"] - res["dense"])
+            gain += g
+            if abs(g) > 0.004:
+                print(f"  {tag:30s} x{cnt} in {pit[1]}/{pit[0]} out {pit[3]}/{pit[2]}  views {res['auto']*1e3:8.1f} us  dense "
+                      f"{res['dense']*1e3:8.1f} us  gain {g*1e3:7.1f} us")
+        print(f"  TOTAL gain if every view were dense: {gain:.3f} ms per step")
+    for key, (cnt, tag, res, fl, by, *_r) in seen.items():
+        _, B, H, W, Cin, Cout, k, s, has_res, odt, wt, ru = key[:12]
         shape = f"{k}x{k}s{s} {Cin}->{Cout} @{H}x{W}" + (" +res" if has_res else "") + (" f32" if odt == L.F32 else "")
         roof = max(fl / (pk["tf_sustained"] * 1e12), by / (pk["hbm"] * 1e9)) * 1e6
-        vals = {k_: v for k_, v in res.items() if v is not None}
+        vals = {k_: v for k_, v in res.items() if v is not None and k_ != "dense"}
         best = min(vals.values())
         f = lambda v: f"{v * 1e3:9.1f}" if v is not None else "        -"  # noqa: E731
         print(f"{tag:30s} {shape:34s} {cnt:3d} {f(res['auto'])} {f(res['single'])} {f(res['pair'])} {f(res['strip'])} {f(res['strip2'])}  "
