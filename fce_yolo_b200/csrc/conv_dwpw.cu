@@ -22,16 +22,16 @@
 //   epilogue      eight warps (two per TMEM lane quarter, half of the channels each): tcgen05.ld -> bias + SiLU -> bf16 -> 32-byte global stores (one pixel row per thread; no
 //                   staging buffer: shared memory goes to the parked weights).
 //
-//   CTA PAIRS (template PAIR, cta_group::2): the parked weights are what limits the depth of the input ring (m scale: 128 KB
-//   of weights left room for three boxes, ~20 KB in flight per SM against an HBM latency of ~2000 cycles: 0.60 ms).  In a
-//   pair each CTA parks HALF of the weight rows, owns one unit and produces its own A stage; the leader issues ONE
-//   tcgen05.mma.cta_group::2 of M = 256 per K step once the teams of BOTH CTAs have arrived on its A-full barrier (remote
-//   mbarrier arrive), its commits are multicast to the A-empty / accumulator-full barriers of both CTAs, the epilogue warps
-//   of both arrive on the leader's accumulator-empty barrier.  Input boxes stay CTA-local.
+//   Measured and dropped (git history, commit 7b7fe32): a CTA-pair variant (cta_group::2, half of the weight rows parked
+//   per CTA so that five input stages fit at m scale) - the coupling of the two CTAs' producer teams through the joint
+//   M = 256 MMA cost more than the deeper ring bought (m scale P3 block, batch 256: 690 us against 520 us for single CTAs
+//   with three stages; switching the input loads off entirely changes nothing: the kernel is not paced by them).
 //
 // Algorithmic HBM bytes per output pixel: 2 * C read (+ 1/8 .. 1/4 halo re-read, an L2 hit) + 2 * Cout written.
-// Bound (m scale, C = Cout = 256): HBM 0.26 ms at the copy peak; the SM side is paced by MUFU (one tanh per depthwise
-// and per 1x1 output: 4096 cycles per unit) and instruction issue (~3600), the tensor pipe needs 2200.
+// Bound (m scale, C = Cout = 256, batch 256): HBM 0.26 ms at the copy peak.  Measured 0.52 ms (two launches: 0.74 ms): the
+// SM side has no single saturated pipe (ncu: issue slots 58 %, XU 40 %, FMA 36 %, L1 / shared 68 %, tensor 21 %; the
+// depthwise warps are busy 93 % of the time at ~11 cycles per issued instruction, 1.4 eligible warps per scheduler) -
+// ~21 k warp instructions per unit, of which ~13.5 k are the arithmetic itself.
 #include "tc_common.cuh"
 
 namespace fce {
@@ -53,12 +53,11 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 struct DwpwParams {
     int B, H, W, C, Cout;
     int tiles_h, tiles_w, units, chunks;
-    int pair_units;     // ceil(units / 2): work items of a CTA pair
     int in_stages;      // depth of the input ring
     int out_pitch;
     int dw_act, pw_act;
     uint32_t in_stage;  // bytes of one input stage = one TMA box
-    uint32_t w_chunk;   // bytes of one parked weight chunk PER CTA: Cout (pair: Cout / 2) x 128
+    uint32_t w_chunk;   // bytes of one parked weight chunk : Cout x 128
     uint32_t bias_bytes, tmem_cols;
     uint32_t desc_hi, idesc;
     int wide_store;     // output rows 32-byte aligned: 256-bit stores
@@ -82,26 +81,7 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* o) {
                  : "memory");
 }
 
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// wait on a barrier that CTAs of the whole cluster arrive on (their shared-memory writes must be visible afterwards)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-
-template <int TH, bool PAIR>
+template <int TH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DwpwParams p,
                  const float* __restrict__ w_dw, const float* __restrict__ b_dw, const float* __restrict__ b_pw,
@@ -122,19 +102,8 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - raw0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Work items: single CTA b walks units b, b + grid, ...; pair q = blockIdx.x / 2 walks pair-units q, q + grid / 2, ... and
-    // its CTA of rank r owns unit 2 * item + r (odd unit count: the last pair's rank 1 recomputes the last unit, stores nothing)
-    constexpr int NCTA = PAIR ? 2 : 1;
-    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
-    const bool leader = cta_rank == 0;
-    const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int n_items = PAIR ? p.pair_units : p.units;
+    const int item0 = (int)blockIdx.x, item_step = (int)gridDim.x, n_items = p.units;  // persistent: units b, b + grid, ...
     const int nst = p.in_stages;
-    // barriers of the LEADER that the peer signals
-    const uint32_t a_full0_sig = PAIR ? mapa_shared(a_full0, 0) : a_full0;
-    const uint32_t tempty0_sig = PAIR ? mapa_shared(tempty0, 0) : tempty0;
-    const uint32_t wfull_sig = PAIR ? mapa_shared(wfull, 0) : wfull;
 
     pdl_launch_dependents();
     if (warp == WARP_TMA && lane == 0) {
@@ -143,12 +112,12 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             mbar_init(in_empty0 + 8 * i, TEAM_WARPS);  // the four warps of the team that consumed the stage
         }
         for (int t = 0; t < TEAMS; ++t) {
-            mbar_init(a_full0 + 8 * t, TEAM_WARPS * NCTA);  // pair: the teams of both CTAs arrive on the leader's barrier
+            mbar_init(a_full0 + 8 * t, TEAM_WARPS);
             mbar_init(a_empty0 + 8 * t, 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, NUM_EPI_WARPS * NCTA);
+            mbar_init(tempty0 + 8 * a, NUM_EPI_WARPS);
         }
         mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -156,49 +125,35 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tma_prefetch_desc(&tmW);
     }
     if (warp == WARP_MMA) {
-        if (PAIR) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {
         const float bsc = epi_bias_scale(p.pw_act);  // pre-scaled for epi_math16
         for (int i = threadIdx.x; i < (int)(p.bias_bytes >> 2); i += NUM_THREADS) bias_s[i] = i < p.Cout ? b_pw[i] * bsc : 0.f;
     }
     tc_fence_before();
-    if (PAIR) cluster_sync_all();
-    else __syncthreads();
+    __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     const int chunks = p.chunks, units = p.units;
-    auto unit_coords = [&](int it, int& b, int& h0, int& w0) {  // -> is this CTA's unit of item `it` a real one?
-        const int u_raw = it * NCTA + (int)cta_rank;
-        const int u = u_raw < units ? u_raw : units - 1;
+    auto unit_coords = [&](int u, int& b, int& h0, int& w0) {
         const int tw = u % p.tiles_w;
         const int r = u / p.tiles_w;
         const int th = r % p.tiles_h;
         b = r / p.tiles_h;
         h0 = th * TH;
         w0 = tw * TW;
-        return u_raw < units;
     };
 
     if (warp == WARP_TMA) {
         // ------------------------------------------------------------------ loads: parked 1x1 weights, then input boxes
         if (elect_one()) {
-            if (leader) mbar_expect_tx(wfull, (uint32_t)chunks * p.w_chunk * NCTA);  // the halves of both CTAs
-            const int nrow0 = (int)cta_rank * (p.Cout / NCTA);
-            for (int c = 0; c < chunks; ++c) {
-                if (PAIR) tma_load_2d_cg2(sW + c * p.w_chunk, &tmW, wfull_sig, c * KC, nrow0);
-                else tma_load_2d(sW + c * p.w_chunk, &tmW, wfull, c * KC, 0);
-            }
+            mbar_expect_tx(wfull, (uint32_t)chunks * p.w_chunk);
+            for (int c = 0; c < chunks; ++c) tma_load_2d(sW + c * p.w_chunk, &tmW, wfull, c * KC, 0);
         }
         __syncwarp();
         pdl_wait();  // activations come from the previous kernel (the weights above are constants)
@@ -222,8 +177,7 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
         }
     } else if (warp == WARP_MMA) {
-        // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA's only)
-        if (leader) {
+        // ------------------------------------------------------------------ MMA issuer
         mbar_wait(wfull, 0);
         tc_fence_after();
         int acc = 0, turn = 0;
@@ -242,8 +196,7 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int c = 0; c < chunks; ++c) {
                 {
                     DP_T0();
-                    if (PAIR) mbar_wait_cluster(a_full0 + 8 * turn, (a_phase >> turn) & 1u);
-                    else mbar_wait(a_full0 + 8 * turn, (a_phase >> turn) & 1u);
+                    mbar_wait(a_full0 + 8 * turn, (a_phase >> turn) & 1u);
                     DP_ACC(m_wa);
                 }
                 tc_fence_after();
@@ -251,18 +204,10 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 const uint32_t b_lo = (((sW + c * p.w_chunk) >> 4) & 0x3FFF) | (1u << 16);
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k) {
-                        const uint64_t ad = make_desc(dhi, a_lo + 2 * k), bd = make_desc(dhi, b_lo + 2 * k);
-                        if (PAIR) umma_bf16_cg2(d_tmem, ad, bd, idesc, (c | k) != 0);
-                        else umma_bf16(d_tmem, ad, bd, idesc, (c | k) != 0);
-                    }
-                    if (PAIR) {  // multicast: the same barrier offsets in both CTAs
-                        umma_commit_cg2(a_empty0 + 8 * turn);
-                        if (c == chunks - 1) umma_commit_cg2(tfull0 + 8 * acc);
-                    } else {
-                        umma_commit(a_empty0 + 8 * turn);                   // the team may overwrite its A stage
-                        if (c == chunks - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
-                    }
+                    for (int k = 0; k < KC / 16; ++k)
+                        umma_bf16(d_tmem, make_desc(dhi, a_lo + 2 * k), make_desc(dhi, b_lo + 2 * k), idesc, (c | k) != 0);
+                    umma_commit(a_empty0 + 8 * turn);                   // the team may overwrite its A stage
+                    if (c == chunks - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 a_phase ^= 1u << turn;
@@ -275,7 +220,6 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             g_dprof[blockIdx.x * 16 + 4] = m_wa;
             g_dprof[blockIdx.x * 16 + 5] = m_we;
             g_dprof[blockIdx.x * 16 + 6] = clock64() - m_t0;
-        }
         }
     } else if (warp < WARP_EPI0) {
         // ------------------------------------------------------------------ depthwise teams: input box -> A stage
@@ -365,8 +309,7 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) {
                         mbar_arrive(in_empty0 + 8 * rin.stage);
-                        if (PAIR) mbar_arrive_cluster(a_full0_sig + 8 * team);
-                        else mbar_arrive(a_full0 + 8 * team);
+                        mbar_arrive(a_full0 + 8 * team);
                     }
                     a_phase ^= 1;
                 }
@@ -394,8 +337,8 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         long long e_w = 0, e_t0 = DBG ? clock64() : 0;
         for (int it = item0; it < n_items; it += item_step) {
             int b, h0, w0;
-            const bool live = unit_coords(it, b, h0, w0);
-            const bool ok = live && r < TH && h0 + r < p.H && w0 + cc < p.W;
+            unit_coords(it, b, h0, w0);
+            const bool ok = r < TH && h0 + r < p.H && w0 + cc < p.W;
             __nv_bfloat16* yrow = y + (((size_t)b * p.H + (h0 + r)) * p.W + (w0 + cc)) * p.out_pitch;
             {
                 DP_T0();
@@ -437,10 +380,7 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                if (PAIR) mbar_arrive_cluster(tempty0_sig + 8 * acc);
-                else mbar_arrive(tempty0 + 8 * acc);
-            }
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -451,68 +391,46 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
 
     tc_fence_before();
-    if (PAIR) cluster_sync_all();  // the peer's shared memory and barriers are in use until the last MMA / arrive
-    else __syncthreads();
+    __syncthreads();
     tc_fence_after();
-    if (warp == WARP_MMA) {
-        if (PAIR)
-            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
-        else
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
-    }
+    if (warp == WARP_MMA)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
 }
 
 size_t dwpw_smem(const DwpwParams& p) {
     return (size_t)TEAMS * A_STAGE + (size_t)p.chunks * p.w_chunk + (size_t)p.in_stages * p.in_stage + p.bias_bytes + 256 + 1024;
 }
 
-// Ring depth a (tile height, CTA count) combination leaves room for; 0 = does not fit.
-int dwpw_stages(const fce_dwpw_desc* d, int th, int ncta) {
-    const size_t fixed = (size_t)TEAMS * A_STAGE + (size_t)(d->C / KC) * (size_t)(d->Cout / ncta) * 128u +
+// Ring depth a tile height leaves room for next to the parked weights; 0 = does not fit.
+int dwpw_stages(const fce_dwpw_desc* d, int th) {
+    const size_t fixed = (size_t)TEAMS * A_STAGE + (size_t)(d->C / KC) * (size_t)d->Cout * 128u +
                          (((size_t)d->Cout * 4u + 255u) & ~(size_t)255u) + 256 + 1024;
     if (fixed >= (size_t)SMEM_LIMIT) return 0;
     const int st = (int)(((size_t)SMEM_LIMIT - fixed) / ((size_t)(th + 2) * BC * 128u));
     return st > MAX_IN_STAGES ? MAX_IN_STAGES : st;
 }
 
-// Shape rules, CTA count, tile height and ring depth; pure arithmetic (no CUDA calls): also behind fce_dwpw_route.
-// Returns the tile height (0 = not a shape of this kernel); ncta = 1 or 2.
-// The input ring has to cover the HBM latency: ~20 KB boxes, two of them being consumed, the rest in flight.  Single CTAs
-// where five stages fit next to the parked weights (s scale: 32 - 128 KB of weights); CTA pairs - half of the weight rows
-// per CTA - where they do not (m scale, 256 -> 256: three stages alone, five in a pair).  FCE_DWPW_PAIR=0/1 forces one.
-int dwpw_plan(const fce_dwpw_desc* d, DwpwParams& p, int& ncta) {
+// Shape rules, tile height and ring depth; pure arithmetic (no CUDA calls): also behind fce_dwpw_route.
+// Returns the tile height (0 = not a shape of this kernel).
+int dwpw_plan(const fce_dwpw_desc* d, DwpwParams& p) {
     if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->Cout <= 0) return 0;
     if (d->C % KC || d->Cout % 16 || d->Cout > 256) return 0;
     if (d->in_pitch % 8 || d->in_off % 8 || d->out_pitch % 8 || d->out_off % 8) return 0;
     if (d->dw_act != FCE_ACT_SILU && d->dw_act != FCE_ACT_NONE) return 0;
     if (d->pw_act != FCE_ACT_SILU && d->pw_act != FCE_ACT_NONE && d->pw_act != FCE_ACT_SIGMOID) return 0;
     if (d->H > 32000 || d->W > 32000) return 0;
-    static const int pair_env = [] { const char* e = getenv("FCE_DWPW_PAIR"); return e && *e ? atoi(e) : -1; }();
-    const long long units8 = (long long)d->B * ((d->H + 7) / 8) * ((d->W + TW - 1) / TW);
-    const bool pair_legal = d->Cout >= 32 && units8 >= 2;  // M = 256 MMAs: N % 16, whole 8-row swizzle atoms per CTA
     int TH = 0, stages = 0;
-    ncta = 1;
-    auto pick = [&](int n, int min_stages) {
-        for (int th = 8; th >= 7; --th) {
-            const int st = dwpw_stages(d, th, n);
-            if (st >= min_stages) {
-                TH = th;
-                stages = st;
-                ncta = n;
-                return true;
-            }
+    for (int th = 8; th >= 7 && !TH; --th) {  // at least three input stages: two being consumed, one in flight
+        const int st = dwpw_stages(d, th);
+        if (st >= 3) {
+            TH = th;
+            stages = st;
         }
-        return false;
-    };
-    bool ok = false;
-    if (pair_env == 1 && pair_legal) ok = pick(2, 3);
-    if (!ok && pair_env != 1) ok = pick(1, pair_env == 0 || !pair_legal ? 3 : 5);
-    if (!ok && pair_env != 0 && pair_legal) ok = pick(2, 3);
-    if (!ok) ok = pick(1, 3);
-    if (!ok) return 0;
+    }
+    if (!TH) return 0;
     p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.Cout = d->Cout;
     p.chunks = d->C / KC;
-    p.w_chunk = (uint32_t)(d->Cout / ncta) * 128u;
+    p.w_chunk = (uint32_t)d->Cout * 128u;
     p.bias_bytes = ((uint32_t)d->Cout * 4u + 255u) & ~255u;
     p.out_pitch = d->out_pitch;
     p.dw_act = d->dw_act;
@@ -524,11 +442,10 @@ int dwpw_plan(const fce_dwpw_desc* d, DwpwParams& p, int& ncta) {
     const long long units = (long long)d->B * p.tiles_h * p.tiles_w;
     if (units > 0x7fffffffLL) return 0;
     p.units = (int)units;
-    p.pair_units = (p.units + 1) / 2;
     p.tmem_cols = 32;
     while (p.tmem_cols < 2u * (uint32_t)d->Cout) p.tmem_cols <<= 1;
     p.desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 8 rows x 128 bytes, descriptor version 1, 128B swizzle
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->Cout >> 3) << 17) | ((uint32_t)((128 * ncta) >> 4) << 24);
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     return TH;
 }
 
@@ -547,8 +464,7 @@ extern "C" int fce_dwpw_profile(long long* out, int n) {  // debug builds only, 
 extern "C" int fce_dwpw_route(const fce_dwpw_desc* d) {
     if (!d) return FCE_ERR_BAD_ARG;
     DwpwParams p{};
-    int ncta = 1;
-    return dwpw_plan(d, p, ncta) ? 1 : 0;
+    return dwpw_plan(d, p) ? 1 : 0;
 }
 
 extern "C" int fce_dwpw_conv(const fce_dwpw_desc* d, const void* x, const float* w_dw, const float* b_dw, const void* w_pw,
@@ -556,8 +472,7 @@ extern "C" int fce_dwpw_conv(const fce_dwpw_desc* d, const void* x, const float*
     if (!d || !x || !w_dw || !b_dw || !w_pw || !b_pw || !y) return FCE_ERR_BAD_ARG;
     if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->Cout <= 0) return FCE_ERR_BAD_ARG;
     DwpwParams p{};
-    int ncta = 1;
-    const int TH = dwpw_plan(d, p, ncta);
+    const int TH = dwpw_plan(d, p);
     if (!TH) return FCE_ERR_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(w_pw) || !aligned16(y) || !aligned16(w_dw) || !aligned16(b_dw)) return FCE_ERR_ALIGNMENT;
     const DriverApi& api = driver();
@@ -586,7 +501,7 @@ extern "C" int fce_dwpw_conv(const fce_dwpw_desc* d, const void* x, const float*
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)d->C, (cuuint64_t)d->Cout};
         const cuuint64_t gstr[1] = {(cuuint64_t)d->C * 2};
-        const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(d->Cout / ncta)};
+        const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)d->Cout};
         const cuuint32_t est[2] = {1, 1};
         if (api.tiled(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_pw), gdim, gstr, box, est,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -595,12 +510,11 @@ extern "C" int fce_dwpw_conv(const fce_dwpw_desc* d, const void* x, const float*
     }
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const DwpwParams, const float*, const float*, const float*,
                              __nv_bfloat16*);
-    static const KernelFn table[4] = {conv_dwpw_kernel<7, false>, conv_dwpw_kernel<8, false>, conv_dwpw_kernel<7, true>,
-                                      conv_dwpw_kernel<8, true>};
+    static const KernelFn table[2] = {conv_dwpw_kernel<7>, conv_dwpw_kernel<8>};
     static DeviceOnce attr_once;  // the shared-memory opt-in is a per-device attribute
     int dev = 0;
     if (attr_once.pending(&dev)) {
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < 2; ++v) {
             cudaError_t e = cudaFuncSetAttribute(table[v], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
             if (e != cudaSuccess) {
                 set_cuda_error(e);
@@ -608,11 +522,6 @@ extern "C" int fce_dwpw_conv(const fce_dwpw_desc* d, const void* x, const float*
             }
         }
         attr_once.done(dev);
-    }
-    if (ncta == 2) {
-        const int pairs = p.pair_units < kNumSMs / 2 ? p.pair_units : kNumSMs / 2;
-        return launch_pdl_cluster(table[2 + TH - 7], 2 * pairs, NUM_THREADS, dwpw_smem(p), (cudaStream_t)stream, 2, tmX, tmW, p,
-                                  w_dw, b_dw, b_pw, yout);
     }
     const int grid = p.units < kNumSMs ? p.units : kNumSMs;
     return launch_pdl(table[TH - 7], grid, NUM_THREADS, dwpw_smem(p), (cudaStream_t)stream, tmX, tmW, p, w_dw, b_dw, b_pw, yout);
