@@ -40,6 +40,10 @@ class StemDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "H", "W", "Cout", "out_pitch", "out_off", "act", "in_dtype", "in_layout")]
 
 
+class Stem2Desc(C.Structure):
+    _fields_ = [(n, i32) for n in ("B", "H", "W", "C0", "C1", "out_pitch", "out_off", "act0", "act1")]
+
+
 class LetterboxItem(C.Structure):
     _fields_ = [("src", C.c_uint64)] + [(n, i32) for n in ("src_pitch", "H", "W", "new_w", "new_h", "top", "left",
                                                             "reserved")]
@@ -116,6 +120,8 @@ _SIGS = {
     "fce_conv2d_detect": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(DetectEpiDesc), _P, _P, _P, _P, _P]),
     "fce_stem_pack": (C.c_int, [C.POINTER(PackDesc), _P, _P, _P]),
     "fce_stem_conv": (C.c_int, [C.POINTER(StemDesc), _P, _P, _P, _P, _P]),
+    "fce_stem2_conv": (C.c_int, [C.POINTER(Stem2Desc), _P, _P, _P, _P, _P, _P, _P]),
+    "fce_stem2_route": (C.c_int, [C.POINTER(Stem2Desc)]),
     "fce_match_predictions": (C.c_int, [_P, _P, _P, _P, _P, _P, i32, i32, i32, i32, _P, _P]),
     "fce_scale_boxes": (C.c_int, [_P, _P, _P, i32, i32, _P]),
     "fce_letterbox": (C.c_int, [_P, _P, _P, i32, i32, i32, i32, _P, _P]),

@@ -133,6 +133,8 @@ class Plan:
     FUSED_C3K_IN = True  # False: C3k.cv1 and C3k.cv2 as two launches (A/B timing, cross-check)
     # False (or FCE_FUSED_DWPW=0): Detect's DWConv + 1x1 blocks as two launches (A/B timing, cross-check)
     FUSED_DWPW = os.environ.get("FCE_FUSED_DWPW", "1") != "0"
+    # False (or FCE_FUSED_STEM2=0): the first two convs as two launches (A/B timing, cross-check)
+    FUSED_STEM2 = os.environ.get("FCE_FUSED_STEM2", "1") != "0"
     FUSED_STEM = True  # False: stem = fce_stem_pack + K=32 tcgen05 conv (kept for A/B timing and as a cross-check)
 
     def __init__(self, batch: int, precision: str, device, impl: int = 0):
@@ -333,6 +335,33 @@ class Plan:
         self.add(Node("fce_stem_pack", d, [img, packed], reads=[img], writes=[packed], tag=tag + ".pack",
                       bytes=img.B * (H * W * 3 * DT_SIZE[img.dtype] + Ho * Wo * 64.0)))
         return self.conv(None, packed, w_override=wk, b_override=b, act=a, tag=tag)
+
+    def stem2(self, m0, m1, img: View, in_scale, tag0="", tag1=""):
+        """The first two Convs of the graph (3x3/s2 on the uint8 NHWC image, then 3x3/s2) as ONE launch (fce_stem2_conv:
+        the stem map stays in shared memory).  Returns the second conv's output view, or None when the kernel does not
+        take the shape (the caller then emits the two layers as usual)."""
+        if not (self.FUSED_STEM2 and self.FUSED_STEM and self.act_dt == L.BF16 and self.impl in (0, 2) and img.dtype == L.U8):
+            return None
+        if type(m1).__name__ != "Conv" or getattr(m1, "f", -1) != -1:
+            return None
+        w0, b0, k0, s0, g0, a0 = self.conv_params(m0)
+        w1, b1, k1, s1, g1, a1 = self.conv_params(m1)
+        if (k0, s0, g0, k1, s1, g1) != (3, 2, 1, 3, 2, 1) or w0.shape[1] != 3 or w1.shape[1] != w0.shape[0]:
+            return None
+        C0, C1 = w0.shape[0], w1.shape[0]
+        H, W = img.H, img.W
+        d = L.Stem2Desc(B=img.B, H=H, W=W, C0=C0, C1=C1, out_pitch=C1, out_off=0, act0=a0, act1=a1)
+        if L.load().fce_stem2_route(ctypes.byref(d)) != 1:
+            return None
+        out = self.new_buf(H // 4, W // 4, C1, dtype=L.BF16, B=img.B)
+        wk = torch.zeros(C0, 32, device=w0.device)
+        wk[:, :27] = w0.permute(0, 2, 3, 1).reshape(C0, 27) * in_scale  # as Plan.stem: OHWI rows, input scale folded in
+        ptrs = [img, self._w(wk, torch.bfloat16), self._w(b0), self._w(w1.permute(0, 2, 3, 1), torch.bfloat16), self._w(b1), out]
+        px0, px1 = img.B * (H // 2) * (W // 2), img.B * (H // 4) * (W // 4)
+        self.add(Node("fce_stem2_conv", d, ptrs, reads=[img], writes=[out], tag=f"{tag0}+{tag1}",
+                      flops=2.0 * px0 * C0 * 27 + 2.0 * px1 * C1 * C0 * 9,
+                      bytes=img.B * H * W * 3.0 + px1 * C1 * 2.0 + C1 * C0 * 9 * 2.0))
+        return out
 
     def dwconv(self, m, x: View, dst: View | None = None, add: View | None = None, tag="") -> View:
         w, b, k, s, g, a = self.conv_params(m)
@@ -863,14 +892,23 @@ def compile_model(model, batch: int, height: int, width: int, precision: str, de
     p.inputs = [img]
     ys = []
     x = None
+    # layer 0's map is consumed by layer 1 alone (no later layer routes from it): the pair can run as one launch
+    later_from0 = any(0 in ([f_] if isinstance(f_, int) else list(f_)) for f_ in (getattr(m_, "f", -1) for m_ in layers[2:]))
+    fused01 = None
     for i, m in enumerate(layers):
         f = getattr(m, "f", -1)
         if i == 0:
             xin = View(img.buf, 0, cin, batch, height, width)  # for NCHW the geometry is carried by the desc
-            if input_u8:
+            if input_u8 and len(layers) > 1 and not later_from0:
+                fused01 = p.stem2(m, layers[1], xin, 1.0 / 255.0, tag0="model.0", tag1="model.1")
+            if fused01 is not None:
+                x = None  # the stem map does not exist
+            elif input_u8:
                 x = p.stem(m, xin, L.NHWC, 1.0 / 255.0, tag="model.0")
             else:
                 x = p.stem(m, xin, L.NCHW, 1.0, tag="model.0")
+        elif i == 1 and fused01 is not None:
+            x = fused01
         else:
             if f != -1:
                 x = ys[f] if isinstance(f, int) else [x if j == -1 else ys[j] for j in f]

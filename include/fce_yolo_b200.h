@@ -116,6 +116,23 @@ typedef struct {
 } fce_stem_desc;
 int fce_stem_conv(const fce_stem_desc* d, const void* x, const void* w, const float* bias, void* y, void* stream);
 
+/* The first TWO convolutions of the graph in one pass (yolo11-fce.yaml:20-21; conv.py:80-89): Conv(3, C0, 3, 2) on the
+ * uint8 NHWC image followed by Conv(C0, C1, 3, 2), both + bias + act; the stem map [B, H/2, W/2, C0] stays in shared
+ * memory and never exists in HBM.  w0 / b0 as for fce_stem_conv (bf16 [C0][32] with the input scale folded in, fp32 [C0]);
+ * w1 bf16 OHWI [C1][3][3][C0], b1 fp32 [C1]; y bf16 NHWC view [B, H/4, W/4, C1].  Same values as fce_stem_conv +
+ * fce_conv2d (same stem arithmetic, same bf16 rounding of the intermediate).  Shapes: C0 = 64, C1 % 16 == 0, C1 <= 128
+ * (the nine [C1, C0] tap tiles are parked in shared memory), H and W multiples of 4; anything else returns
+ * FCE_ERR_UNSUPPORTED (fce_stem2_route: 1 = taken, 0 = not, without launching) and the caller issues the two launches. */
+typedef struct {
+    int32_t B, H, W;          /* image size */
+    int32_t C0, C1;
+    int32_t out_pitch, out_off;
+    int32_t act0, act1;
+} fce_stem2_desc;
+int fce_stem2_conv(const fce_stem2_desc* d, const void* x, const void* w0, const float* b0, const void* w1,
+                   const float* b1, void* y, void* stream);
+int fce_stem2_route(const fce_stem2_desc* d);
+
 /* Predict-side preprocessing, the step right before the path (LetterBox, ultralytics/data/augment.py:1589-1631,
  * + the BGR->RGB flip of BasePredictor.preprocess, ultralytics/engine/predictor.py:163-165): a batch of differently
  * sized uint8 HWC BGR images -> uint8 NHWC RGB [B, out_h, out_w, 3], resized with cv2.resize(INTER_LINEAR)'s 8-bit

@@ -75,6 +75,14 @@ class Interp(Arena):
         o = _act(F.conv2d(xin, wt, b.float(), stride=2, padding=1), d.act)
         self.t(y).copy_(o.permute(0, 2, 3, 1))
 
+    def _fce_stem2_conv(self, d, p):
+        x, w0, b0, w1, b1, y = p
+        xin = self._flat(x.buf).view(d.B, d.H, d.W, 3).permute(0, 3, 1, 2).float()
+        wt0 = w0.float()[:, :27].reshape(d.C0, 3, 3, 3).permute(0, 3, 1, 2)
+        t = _act(F.conv2d(xin, wt0, b0.float(), stride=2, padding=1), d.act0).to(torch.bfloat16).float()
+        o = _act(F.conv2d(t, w1.float().permute(0, 3, 1, 2), b1.float(), stride=2, padding=1), d.act1)
+        self.t(y).copy_(o.permute(0, 2, 3, 1))
+
     def _fce_dwconv3x3(self, d, p):
         x, w, b, add, y = p
         xin = self.t(x).permute(0, 3, 1, 2).float()
