@@ -7,19 +7,25 @@
 //
 //   unit = 7 x 16 output pixels of the second conv (M = 112 of the 128 rows of one tcgen05.mma).  It needs a 15 x 33
 //   window of stem pixels, which needs 31 x 67 image pixels.
-//   * stem warps (11): stage the image window as fp16 (byte / 256) in shared memory, then compute the stem window with
-//     warp-level mma.sync m16n8k16 (the arithmetic of stem.cu: same K order, same operand scaling, bias + SiLU on packed
-//     fp32 pairs) in runs of 16 stem pixels, and write bf16 rows of 64 channels (128 bytes) into the STEM TILE.  Stem
-//     pixels outside the stem map are written as zeros: they are the zero padding of the second conv.
-//   * the stem tile is laid out as FOUR PARITY PLANES (stem row parity x column parity), each a padded-flat pixel list
-//     of pitch 17, rows 128B-swizzled by their absolute shared-memory address.  A stride-2 3x3 tap (kh, kw) of output
-//     pixel o = r * 17 + c reads plane (kh & 1, kw & 1) at flat index o + (kh >> 1) * 17 + (kw >> 1): every tap's A operand
-//     is ONE shifted shared-memory descriptor over a plane (conv_halo.cu's trick, per parity) - no im2col traffic at all.
-//     The 17th column of every row produces accumulator rows that are never stored.
-//   * MMA warp: the planes are produced and consumed in the order P11, P10, P01, P00 (1, 2, 2, 4 taps); each plane has its
-//     own full / free barrier, so the stem warps refill plane q for the next unit while the tensor core still works on
-//     planes q+1.. of this one - one stem tile in shared memory behaves like a four-stage ring.  36 tcgen05.mma (M = 128,
-//     N = C1, K = 16) per unit against the PARKED weights (all nine [C1, 64] tap tiles, loaded once per CTA).
+//   * the stem window is itself a small GEMM on the tensor cores: four blocks of 128 stem pixels, [128 x 32] x [32 x 64].
+//     BUILDER warps (2 teams of 4, one stem pixel per thread) read the pixel's 3 x 10 image bytes (L1-cached words, funnel-shifted to
+//     the byte origin), convert them to fp16 (byte / 256, the magic-number trick of stem.cu) and write one 64-byte A row,
+//     K order k' = 10 * kh + j; the stem weights sit in shared memory as the fp16 B operand (x 256).  A first version
+//     computed the stem with warp-level mma.sync like stem.cu: 19 warp instructions per stem pixel made the fused kernel
+//     stem-bound at 2.3 ms; the operand build costs ~3.
+//   * STEM EPILOGUE warps (2 groups of 4, blocks alternate; the bias rides in the GEMM as K column 30): TMEM -> SiLU -> bf16 -> the STEM TILE in shared memory, laid out as FOUR PARITY PLANES
+//     (stem row parity x column parity), each a padded-flat pixel list of pitch 17 with 128-byte rows swizzled by their
+//     absolute shared-memory address.  A stride-2 3x3 tap (kh, kw) of output pixel o = r * 17 + c reads plane
+//     (kh & 1, kw & 1) at flat index o + (kh >> 1) * 17 + (kw >> 1): every tap's A operand is ONE shifted shared-memory
+//     descriptor over a plane (conv_halo.cu's trick, per parity) - no im2col traffic at all.  The 17th column of every row
+//     produces accumulator rows that are never stored.  Stem pixels outside the stem map are written as zeros: they are
+//     the zero padding of the second conv.
+//   * MMA warp: the planes are produced and consumed in the order P11, P10, P01, P00 (1, 2, 2, 4 taps; the four stem blocks
+//     walk the slot list in the same order, so plane q is complete when block q is); each plane has its own full / free
+//     barrier, so the stem epilogue refills plane q for the next unit while the tensor core still works on planes q+1.. of
+//     this one - one stem tile in shared memory behaves like a four-stage ring.  36 tcgen05.mma (M = 128, N = C1, K = 16)
+//     per unit against the PARKED weights (all nine [C1, 64] tap tiles, loaded once per CTA); the stem GEMMs are issued two
+//     blocks ahead of the plane steps that consume them.
 //   * epilogue warps (4): TMEM -> bias + SiLU -> bf16 -> 32-byte global stores, two accumulator stages.
 //
 // HBM bytes per output pixel: 48 image bytes (+ halo, L2) read, 2 * C1 written.  m scale, batch 256: 0.3 + 1.68 GB instead
@@ -33,24 +39,25 @@ using namespace tc;
 namespace {
 
 constexpr int C0 = 64;                      // stem channels = K chunk of the second conv (128-byte rows)
-constexpr int NT = C0 / 8;                  // mma.sync n-tiles of the stem
 constexpr int TH = 7, TW = 16, PW = TW + 1; // unit of the second conv; plane pitch
-constexpr int SR = 2 * TH + 1, SC = 2 * TW + 1;     // stem window 15 x 33
-constexpr int IR = 2 * SR + 1;                      // 31 image rows
-constexpr int ISHIFT = 1;                           // one extra image column on the left: the byte origin is 4-byte aligned
-constexpr int HP = 208;                             // fp16 elements per staged row: element 1 + b holds byte b of the row
-constexpr int NSTEM_WARPS = 11, STEM_THREADS = NSTEM_WARPS * 32;
-constexpr int WARP_MMA = NSTEM_WARPS, WARP_EPI0 = WARP_MMA + 1;  // 12 .. 15: warp & 3 = TMEM lane quarter
-constexpr int NUM_THREADS = (WARP_EPI0 + 4) * 32;   // 512: four warps per scheduler, 128 registers per thread
+constexpr int SC = 2 * TW + 1;                      // stem window: 15 rows x 33 columns
+// warp roles (21 warps: 80 registers per thread)
+constexpr int TEAM_WARPS = 4;                       //     // 0 .. 7: two builder teams (blocks alternate), one stem pixel (A row) per thread
+constexpr int WARP_SEPI0 = 8;                       // 8 .. 15 stem epilogue: warp & 3 = TMEM lane quarter, (warp - 8) >> 2 = group
+constexpr int WARP_EPI0 = 16;                       // 16 .. 19 epilogue of the second conv
+constexpr int WARP_MMA = 20;
+constexpr int NUM_THREADS = 21 * 32;
 // planes in memory order P00, P01, P10, P11 (index = (row parity) * 2 + column parity)
-__host__ __device__ constexpr int pl_rows(int pl) { return pl < 2 ? 8 * PW : 7 * PW; }  // 136 136 119 119 pixel slots
+// (136, 136, 119, 119 pixel slots)
 __host__ __device__ constexpr int pl_base(int pl) { return pl == 0 ? 0 : pl == 1 ? 8 * PW : pl == 2 ? 16 * PW : 23 * PW; }  // 0 136 272 391
 constexpr int ST_ROWS_ALLOC = 520;  // the last descriptor reads rows [391 + 1, +128)
-// production / consumption order q = 0..3 -> plane P11, P10, P01, P00, and the global list of runs (16 slots each): 8, 8, 9, 9
+// Production / consumption order q = 0..3 -> plane P11, P10, P01, P00.  The stem window is computed as FOUR blocks of 128
+// slots of the list [P11 | P10 | P01 | P00] (119 + 119 + 136 + 136 = 510 slots): plane q is complete when block q is.
 __host__ __device__ constexpr int q_plane(int q) { return 3 - q; }
-__host__ __device__ constexpr int q_run0(int q) { return q == 0 ? 0 : q == 1 ? 8 : q == 2 ? 16 : q == 3 ? 25 : 34; }
+constexpr int N_SLOTS = 510;
 constexpr uint32_t STILE_BYTES = ST_ROWS_ALLOC * 128;
-constexpr uint32_t ITILE_BYTES = IR * HP * 2;
+constexpr uint32_t A0_BYTES = 128 * 64;  // stem GEMM A operand: 128 rows x K = 32 fp16 (64-byte rows, 64B swizzle)
+constexpr uint32_t B0_BYTES = C0 * 64;   // stem weights: 64 rows x 32 fp16
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct Stem2Params {
@@ -61,21 +68,35 @@ struct Stem2Params {
     int out_pitch, act0, act1;
     uint32_t w_tile;    // bytes of one tap's weight tile: C1 x 128
     uint32_t bias_bytes, tmem_cols;
-    uint32_t desc_hi, idesc;
+    uint32_t desc_hi, idesc;     // second conv: 128-byte rows, bf16
+    uint32_t desc_hi0, idesc0;   // stem GEMM: 64-byte rows, fp16
     int wide_store;
 };
+
+#ifdef FCE_DEBUG
+constexpr bool DBG = true;
+// per-CTA cycle accounting: [0] builder wait-A-empty [1] builder total | [2] stem epilogue wait-acc [3] wait-plane-free [4] total
+// | [5] MMA wait-A-full [6] wait-stem-acc-empty [7] wait-plane-full [8] wait-acc-empty [9] total | [10] epilogue wait [11] total
+__device__ long long g_sprof[kNumSMs * 16];
+#else
+constexpr bool DBG = false;
+__device__ long long g_sprof[1];
+#endif
+#define SP_T0() long long _t0 = 0; if (DBG) _t0 = clock64()
+#define SP_ACC(var) if (DBG) (var) += clock64() - _t0
 
 __device__ __forceinline__ void st2_global_v8(void* p, const uint32_t* o) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
                  "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
                  : "memory");
 }
-__device__ __forceinline__ void stem_bar() { asm volatile("bar.sync 1, %0;" ::"n"(STEM_THREADS) : "memory"); }
-
-// K axis of the stem GEMM, as in stem.cu: k' 0..23 = the first eight values of patch rows 0 / 1 / 2, k' 24..29 = (value 8,
-// the zero-weight neighbour 9) of rows 0 / 1 / 2, k' 30..31 zero.
-__host__ __device__ constexpr int s2_kh(int kp) { return kp < 24 ? kp / 8 : (kp - 24) / 2; }
-__host__ __device__ constexpr int s2_j(int kp) { return kp < 24 ? kp % 8 : 8 + (kp - 24) % 2; }
+// global slot of the unit's list -> (plane, slot inside the plane); slots >= N_SLOTS give an index past the plane
+__device__ __forceinline__ void slot_to_plane(int gs, int& pl, int& i) {
+    if (gs < 119) { pl = 3; i = gs; }
+    else if (gs < 238) { pl = 2; i = gs - 119; }
+    else if (gs < 374) { pl = 1; i = gs - 238; }
+    else { pl = 0; i = gs - 374; }
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, const uint8_t* __restrict__ x,
@@ -86,11 +107,13 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
     const uint32_t base = (raw0 + 1023u) & ~1023u;
     const uint32_t sW = base;                           // 9 x [C1][64] bf16, 128B-swizzled
     const uint32_t sT = sW + 9 * p.w_tile;              // stem tile: four parity planes, 128-byte rows
-    const uint32_t sI = sT + STILE_BYTES;               // staged image window, fp16 [IR][HP]
-    const uint32_t sBias = sI + ITILE_BYTES;
+    const uint32_t sA = sT + STILE_BYTES;               // stem GEMM A operand (one stage)
+    const uint32_t sB0 = sA + A0_BYTES;                 // stem GEMM B operand
+    const uint32_t sBias = sB0 + B0_BYTES;
     const uint32_t bars = sBias + p.bias_bytes;
-    const uint32_t pfull0 = bars, pfree0 = bars + 32, tfull0 = bars + 64, tempty0 = bars + 80, wfull = bars + 96;
-    const uint32_t tmem_slot = bars + 104;
+    const uint32_t a_full = bars, a_empty0 = bars + 8, s_tfull0 = bars + 24, s_tempty0 = bars + 40;
+    const uint32_t pfull0 = bars + 56, pfree0 = bars + 88, tfull0 = bars + 120, tempty0 = bars + 136, wfull = bars + 152;
+    const uint32_t tmem_slot = bars + 160;
     float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - raw0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,13 +121,17 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
 
     pdl_launch_dependents();
     if (warp == WARP_MMA && lane == 0) {
-        for (int q = 0; q < 4; ++q) {
-            mbar_init(pfull0 + 8 * q, NSTEM_WARPS);
-            mbar_init(pfree0 + 8 * q, 1);
-        }
+        mbar_init(a_full, TEAM_WARPS);
         for (int a = 0; a < 2; ++a) {
+            mbar_init(a_empty0 + 8 * a, 1);
+            mbar_init(s_tfull0 + 8 * a, 1);
+            mbar_init(s_tempty0 + 8 * a, 4);  // the stem-epilogue group that owns the stage
             mbar_init(tfull0 + 8 * a, 1);
             mbar_init(tempty0 + 8 * a, 4);
+        }
+        for (int q = 0; q < 4; ++q) {
+            mbar_init(pfull0 + 8 * q, q == 0 ? 4 : 8);  // the group of block q + (q > 0) the group of block q - 1 (plane head)
+            mbar_init(pfree0 + 8 * q, 1);
         }
         mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -116,8 +143,24 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {
-        const float bsc = epi_bias_scale(p.act1);  // pre-scaled for epi_math16
-        for (int i = threadIdx.x; i < (int)(p.bias_bytes >> 2); i += NUM_THREADS) bias_s[i] = i < p.C1 ? b1[i] * bsc : 0.f;
+        // Stem weights as the B operand of the stem GEMM: fp16 [64][32], K order k' = 10 * kh + j (j = 0..9: the nine values of
+        // patch row kh and their zero-weight neighbour; k' 30 = the bias, 31 zero), x 256 because the A operand holds byte / 256
+        // (bf16 -> fp16 and the power of two are exact; the bias keeps 11 bits - three more than the bf16 result); 64-byte
+        // rows, 64B swizzle (16-byte chunk c of row n at c ^ ((n >> 1) & 3))
+        const unsigned short* wus = reinterpret_cast<const unsigned short*>(w0);
+        for (int idx = threadIdx.x; idx < C0 * 32; idx += NUM_THREADS) {
+            const int n = idx >> 5, kp = idx & 31;
+            const int kh = kp / 10, j = kp - kh * 10;
+            float v = 0.f;
+            if (kp < 30 && j < 9) v = __uint_as_float((uint32_t)__ldg(wus + n * 32 + kh * 9 + j) << 16) * 256.f;
+            if (kp == 30) v = __ldg(b0 + n) * 256.f;  // the bias rides in the GEMM: A column 30 is the constant 1 / 256
+            const __half hv = __float2half_rn(v);
+            const uint32_t addr = sB0 + (uint32_t)n * 64u + ((((uint32_t)kp >> 3) ^ (((uint32_t)n >> 1) & 3u)) << 4) + ((uint32_t)kp & 7u) * 2u;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+        }
+        const float bsc1 = epi_bias_scale(p.act1);  // pre-scaled for epi_math16
+        for (int i = threadIdx.x; i < (int)(p.bias_bytes >> 2); i += NUM_THREADS) bias_s[i] = i < p.C1 ? b1[i] * bsc1 : 0.f;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the B operand is read by the tensor core
     }
     tc_fence_before();
     __syncthreads();
@@ -133,6 +176,16 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
         oh0 = th * TH;
         ow0 = tw * TW;
     };
+    // this thread's stem pixel of block blk: plane, slot in the plane, window coordinates, liveness
+    auto stem_slot = [&](int blk, int row, int& pl, int& i, int& r, int& c) {
+        const int gs = blk * 128 + row;
+        slot_to_plane(gs, pl, i);
+        const int pi = i / PW, pj = i - pi * PW;
+        r = 2 * pi + (pl >> 1);
+        c = 2 * pj + (pl & 1);
+        return gs < N_SLOTS && c < SC;
+    };
+    const int my_units = (int)blockIdx.x < units ? (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == WARP_MMA) {
         // ------------------------------------------------------------------ weights (once), then the MMA issue loop
@@ -143,208 +196,256 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
         __syncwarp();
         mbar_wait(wfull, 0);
         tc_fence_after();
-        const uint32_t dhi = p.desc_hi, idesc = p.idesc;
-        int acc = 0, it = 0;
-        uint32_t acc_phase = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
-            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+        const uint32_t dhi = p.desc_hi, idesc = p.idesc, dhi0 = p.desc_hi0, idesc0 = p.idesc0;
+        const int S = 4 * my_units;  // stem blocks = plane steps of this CTA
+        long long m_af = 0, m_se = 0, m_pf = 0, m_te = 0, m_t0 = DBG ? clock64() : 0;
+        // stem GEMM of block sb: [128 slots x 32] x [32 x 64] -> stem accumulator stage sb & 1 (64 TMEM columns)
+        auto stem_mma = [&](int sb) {
+            const int stage = sb & 1;
+            {
+                SP_T0();
+                mbar_wait(s_tempty0 + 8 * stage, (((uint32_t)sb >> 1) & 1u) ^ 1u);  // the stem epilogue of block sb - 2 has drained it
+                SP_ACC(m_se);
+            }
+            {
+                SP_T0();
+                mbar_wait(a_full, (uint32_t)sb & 1u);
+                SP_ACC(m_af);
+            }
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * p.C1;
-            bool first = true;
+            if (elect_one()) {
+                const uint32_t a16 = sA >> 4, b16 = sB0 >> 4;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                mbar_wait(pfull0 + 8 * q, (uint32_t)it & 1u);
+                for (int k = 0; k < 2; ++k)
+                    umma_bf16(tmem_base + stage * C0, make_desc(dhi0, ((a16 + 2 * k) & 0x3FFF) | (1u << 16)),
+                              make_desc(dhi0, ((b16 + 2 * k) & 0x3FFF) | (1u << 16)), idesc0, (uint32_t)k);
+                umma_commit(a_empty0 + 8 * (sb & 1));  // the OTHER builder team may fill the stage with block sb + 1
+                umma_commit(s_tfull0 + 8 * stage);     // -> stem epilogue
+            }
+            __syncwarp();
+        };
+        // the taps of plane step lp (unit lp >> 2, plane order q = lp & 3) of the second conv
+        auto l1_mma = [&](int lp) {
+            const int q = lp & 3, itu = lp >> 2, acc = itu & 1;
+            if (q == 0) {
+                SP_T0();
+                mbar_wait(tempty0 + 8 * acc, (((uint32_t)itu >> 1) & 1u) ^ 1u);
+                SP_ACC(m_te);
                 tc_fence_after();
-                if (elect_one()) {
-                    const int pl = q_plane(q), pr = pl >> 1, pc = pl & 1;
-#pragma unroll
-                    for (int kh = pr; kh < 3; kh += 2)
-#pragma unroll
-                        for (int kw = pc; kw < 3; kw += 2) {
-                            const uint32_t a16 = (sT + (uint32_t)(pl_base(pl) + (kh >> 1) * PW + (kw >> 1)) * 128u) >> 4;
-                            const uint32_t b16 = (sW + (uint32_t)(kh * 3 + kw) * p.w_tile) >> 4;
-#pragma unroll
-                            for (int k = 0; k < C0 / 16; ++k) {
-                                const uint64_t ad = make_desc(dhi, ((a16 + 2 * k) & 0x3FFF) | (1u << 16));
-                                const uint64_t bd = make_desc(dhi, ((b16 + 2 * k) & 0x3FFF) | (1u << 16));
-                                umma_bf16(d_tmem, ad, bd, idesc, first ? 0u : 1u);
-                                first = false;
-                            }
-                        }
-                    umma_commit(pfree0 + 8 * q);             // the stem warps may refill this plane
-                    if (q == 3) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
-                }
-                __syncwarp();
-                first = false;
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
-        }
-    } else if (warp < NSTEM_WARPS) {
-        // ------------------------------------------------------------------ stem warps
-        const int tid = threadIdx.x, g = lane >> 2, t = lane & 3;
-        // B fragments (stem weights, fp16) in the re-ordered K axis; bf16 -> fp16 is exact, x 256 because the staged image is
-        // byte / 256, x 1/2 for the SiLU form h + h * tanh(h) (stem.cu)
-        uint32_t bf[2][NT][2];
-        float bs[NT][2];
-        {
-            const unsigned short* wus = reinterpret_cast<const unsigned short*>(w0);
-            const float sc = 256.f * (p.act0 == FCE_ACT_SILU ? 0.5f : 1.f);
+            {
+                SP_T0();
+                mbar_wait(pfull0 + 8 * q, (uint32_t)itu & 1u);
+                SP_ACC(m_pf);
+            }
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + 2 * C0 + acc * p.C1;
+                const int pl = q_plane(q), pr = pl >> 1, pc = pl & 1;
+                bool first = q == 0;
+                for (int kh = pr; kh < 3; kh += 2)
+                    for (int kw = pc; kw < 3; kw += 2) {
+                        const uint32_t a16 = (sT + (uint32_t)(pl_base(pl) + (kh >> 1) * PW + (kw >> 1)) * 128u) >> 4;
+                        const uint32_t b16 = (sW + (uint32_t)(kh * 3 + kw) * p.w_tile) >> 4;
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const unsigned short* wr = wus + (nt * 8 + g) * 32;
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        uint32_t v = 0u;
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int kp = ks * 16 + hf * 8 + 2 * t + e;
-                            const int kh = s2_kh(kp), j = s2_j(kp);
-                            if (kp < 30 && j < 9) v |= (uint32_t)__ldg(wr + kh * 9 + j) << (16 * e);
+                        for (int k = 0; k < C0 / 16; ++k) {
+                            umma_bf16(d_tmem, make_desc(dhi, ((a16 + 2 * k) & 0x3FFF) | (1u << 16)),
+                                      make_desc(dhi, ((b16 + 2 * k) & 0x3FFF) | (1u << 16)), idesc, first ? 0u : 1u);
+                            first = false;
                         }
-                        const __half2 h = __floats2half2_rn(__uint_as_float(v << 16) * sc, __uint_as_float(v & 0xffff0000u) * sc);
-                        bf[ks][nt][hf] = *reinterpret_cast<const uint32_t*>(&h);
                     }
-                const float bscale = p.act0 == FCE_ACT_SILU ? 0.5f : 1.f;
-                bs[nt][0] = __ldg(b0 + nt * 8 + 2 * t) * bscale;
-                bs[nt][1] = __ldg(b0 + nt * 8 + 2 * t + 1) * bscale;
+                umma_commit(pfree0 + 8 * q);                // the stem epilogue may refill this plane
+                if (q == 3) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
+            }
+            __syncwarp();
+        };
+        // the stem GEMMs run two blocks ahead of the plane steps that consume their result
+        if (S > 0) {
+            stem_mma(0);
+            stem_mma(1);
+#pragma unroll 1
+            for (int k = 0; k < S; ++k) {
+                l1_mma(k);
+                if (k + 2 < S) stem_mma(k + 2);
             }
         }
-        // this thread's 4 A-fragment word offsets relative to a patch origin (32-bit words of the fp16 window)
-        int aoff[2][2];
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int kp = ks * 16 + hf * 8 + 2 * t;
-                aoff[ks][hf] = kp < 30 ? (s2_kh(kp) * HP + s2_j(kp)) / 2 : -1;
-            }
+        if (DBG && lane == 0) {
+            long long* g = g_sprof + blockIdx.x * 16;
+            g[5] = m_af; g[6] = m_se; g[7] = m_pf; g[8] = m_te; g[9] = clock64() - m_t0;
+        }
+    } else if (warp < WARP_SEPI0) {
+        // ------------------------------------------------------------------ builders: image patches -> A rows of the stem GEMM
+        // Two teams of four warps; team t builds the blocks sb = t, t + 2, ... of the CTA's block sequence: the loads and
+        // conversions of block sb + 1 run while block sb waits for the (single) A stage.
+        const int team = warp / TEAM_WARPS;
+        const int row = (int)threadIdx.x - team * (TEAM_WARPS * 32);  // 0 .. 127
         const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
         const int row_words = p.W * 3 / 4;
-        constexpr int GROUPS = IR * (HP / 8);                          // 806 groups of eight staged values
-        constexpr int TRIPS = (GROUPS + STEM_THREADS - 1) / STEM_THREADS;  // 3
-        uint32_t wa[TRIPS], wb[TRIPS], wc[TRIPS];
-        auto fetch = [&](int u) {  // this thread's words of unit u's image window -> registers
-            int b, oh0, ow0;
-            unit_coords(u, b, oh0, ow0);
-            const int ih0 = 4 * oh0 - 3;
-            const int w_first = (4 * ow0 - 3 - ISHIFT) * 3 / 4;  // exact: (4 ow0 - 4) * 3 is a multiple of 4 (may be negative)
-#pragma unroll
-            for (int k = 0; k < TRIPS; ++k) {
-                const int i = tid + k * STEM_THREADS;
-                const int r = i / (HP / 8), qq = 2 * (i - r * (HP / 8));
-                const int hi = ih0 + r, wq = w_first + qq;
-                wa[k] = wb[k] = wc[k] = 0u;
-                if (i < GROUPS && hi >= 0 && hi < p.H) {
-                    const uint32_t* rowp = xw + (size_t)(b * p.H + hi) * row_words;
-                    if (wq - 1 >= 0 && wq - 1 < row_words) wa[k] = __ldg(rowp + wq - 1);
-                    if (wq >= 0 && wq < row_words) wb[k] = __ldg(rowp + wq);
-                    if (wq + 1 >= 0 && wq + 1 < row_words) wc[k] = __ldg(rowp + wq + 1);
-                }
-            }
-        };
-        uint4* iw = reinterpret_cast<uint4*>(smem_raw + (sI - raw0));
-        const uint32_t* il = reinterpret_cast<const uint32_t*>(smem_raw + (sI - raw0));
         const __half2 four = __float2half2_rn(4.f);
         auto cvt2 = [&](uint32_t v, uint32_t sel) {  // two bytes -> two fp16 (byte / 256): 0x4400 | byte = 4 + byte / 256
             const uint32_t m = __byte_perm(v, 0x44444444u, sel);
             const __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&m), four);
             return *reinterpret_cast<const uint32_t*>(&h);
         };
-        const bool silu = p.act0 == FCE_ACT_SILU;
+        const uint32_t my_row = sA + (uint32_t)row * 64u, sw = ((uint32_t)row >> 1) & 3u;
+        // this thread's two stem pixels (blocks team and team + 2) do not depend on the unit: window coordinates r | c << 8,
+        // -1 = no pixel
+        int slot_rc[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            int pl, i, r, c;
+            slot_rc[j] = stem_slot(2 * j + team, row, pl, i, r, c) ? (r | (c << 8)) : -1;
+        }
+        // next unit's image window -> L1 / L2 while this unit is computed: 31 rows x (up to) three 128-byte lines
+        auto prefetch_window = [&](int u) {
+            int b, oh0, ow0;
+            unit_coords(u, b, oh0, ow0);
+            const int r = row / 3, k = row - 3 * r;  // 93 of the 128 threads: row r, line k
+            const int ih = 4 * oh0 - 3 + r;
+            const long long bcol = 3LL * (4 * ow0 - 3) + 128 * k;
+            if (r < 31 && ih >= 0 && ih < p.H && bcol >= -127 && bcol < 3LL * p.W && (k < 2 || bcol < 3LL * (4 * ow0 + 64))) {
+                const uint8_t* a = x + ((size_t)(b * p.H + ih) * p.W) * 3 + (bcol < 0 ? 0 : bcol);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+            }
+        };
+        long long b_w = 0, b_t0 = DBG ? clock64() : 0;
+        int nb = 0;  // blocks this team has built
         pdl_wait();  // the image comes from the previous work in the stream
-        if ((int)blockIdx.x < units) fetch(blockIdx.x);
-        int it = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
             int b, oh0, ow0;
             unit_coords(u, b, oh0, ow0);
             const int sr0 = 2 * oh0 - 1, sc0 = 2 * ow0 - 1;  // stem coordinates of the window origin
-            // ---- stage this unit's window (already in registers), then prefetch the next unit's
+            if (team == 0 && u + (int)gridDim.x < units) prefetch_window(u + gridDim.x);
 #pragma unroll
-            for (int k = 0; k < TRIPS; ++k) {
-                const int i = tid + k * STEM_THREADS;
-                if (i >= GROUPS) continue;
-                const uint32_t v0 = __funnelshift_l(wa[k], wb[k], 8), v1 = __funnelshift_l(wb[k], wc[k], 8);
-                iw[i] = make_uint4(cvt2(v0, 0x4140), cvt2(v0, 0x4342), cvt2(v1, 0x4140), cvt2(v1, 0x4342));
-            }
-            stem_bar();
-            if (u + (int)gridDim.x < units) fetch(u + gridDim.x);
-            // ---- the stem window, plane by plane (order P11, P10, P01, P00), runs of 16 slots dealt round-robin to the warps
-#pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
-                const int pl = q_plane(q), pr = pl >> 1, pc = pl & 1;
-                mbar_wait(pfree0 + 8 * q, ((uint32_t)it & 1u) ^ 1u);  // the MMAs of the previous unit are done with this plane
-                const int n_slots = pl_rows(pl);
-                const uint32_t pbase = sT + (uint32_t)pl_base(pl) * 128u;
-                const int run_lo = q_run0(q), run_hi = q_run0(q + 1);
-#pragma unroll 1
-                for (int run = run_lo + ((warp - run_lo % NSTEM_WARPS + NSTEM_WARPS) % NSTEM_WARPS); run < run_hi;
-                     run += NSTEM_WARPS) {
-                    const int s0 = (run - run_lo) * 16;
-                    // slots of fragment rows g and g + 8 -> stem window coordinates -> patch origin
-                    int slot[2], po[2];
-                    bool inside[2], live[2];
+            for (int j = 0; j < 2; ++j, ++nb) {  // blocks team and team + 2 of this unit: sb = 2 * nb + team of the CTA's sequence
+                const int rc = slot_rc[j];
+                const int sr = sr0 + (rc & 255), scc = sc0 + (rc >> 8);
+                const bool inside = rc >= 0 && sr >= 0 && sr < p.H0 && scc >= 0 && scc < p.W0;
+                uint32_t hw[16];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int s = s0 + g + 8 * h;
-                        slot[h] = s;
-                        const int pi = s / PW, pj = s - pi * PW;
-                        const int r = 2 * pi + pr, c = 2 * pj + pc;  // stem window coordinates
-                        live[h] = s < n_slots;
-                        const int sr = sr0 + r, scc = sc0 + c;
-                        inside[h] = live[h] && c < SC && sr >= 0 && sr < p.H0 && scc >= 0 && scc < p.W0;
-                        // patch origin: image window row 2 r, element 1 + 3 * (2 c + ISHIFT) (even) -> 32-bit words
-                        const int rr = live[h] && c < SC ? r : 0, cc = live[h] && c < SC ? c : 0;
-                        po[h] = (2 * rr) * (HP / 2) + 3 * cc + (1 + 3 * ISHIFT) / 2;
+                for (int k = 0; k < 16; ++k) hw[k] = 0u;
+                hw[15] = 0x00001C00u;  // k' = 30: fp16 1 / 256, the multiplier of the bias row of B
+                if (inside) {
+                    // patch row kh: image row 2 sr - 1 + kh, bytes [6 sc - 3, +9] (three pixels x 3 channels + one neighbour)
+                    const int bs = 6 * scc - 3, w_lo = bs >> 2;
+                    const uint32_t sh = 8u * (uint32_t)(bs & 3);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const int ih = 2 * sr - 1 + kh;
+                        if (ih < 0 || ih >= p.H) continue;  // zero padding of the stem conv
+                        const uint32_t* rowp = xw + (size_t)(b * p.H + ih) * row_words;
+                        uint32_t wd[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) wd[k] = (w_lo + k >= 0 && w_lo + k < row_words) ? __ldg(rowp + w_lo + k) : 0u;
+                        const uint32_t v0 = __funnelshift_r(wd[0], wd[1], sh), v1 = __funnelshift_r(wd[1], wd[2], sh),
+                                       v2 = __funnelshift_r(wd[2], wd[3], sh);
+                        hw[5 * kh + 0] = cvt2(v0, 0x4140);
+                        hw[5 * kh + 1] = cvt2(v0, 0x4342);
+                        hw[5 * kh + 2] = cvt2(v1, 0x4140);
+                        hw[5 * kh + 3] = cvt2(v1, 0x4342);
+                        hw[5 * kh + 4] = cvt2(v2, 0x4140);
                     }
-                    uint32_t a[2][4];
+                }
+                {
+                    // the stem GEMM of the previous block (sb - 1, built by the other team) has read the stage: its commits go
+                    // to a_empty[(sb - 1) & 1] - a barrier whose every phase this team observes (no parity aliasing)
+                    SP_T0();
+                    mbar_wait(a_empty0 + 8 * (team ^ 1), team ? ((uint32_t)nb & 1u) : (((uint32_t)nb & 1u) ^ 1u));
+                    SP_ACC(b_w);
+                }
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
+                for (int k = 0; k < 4; ++k)
+                    st_shared_v4(my_row + ((((uint32_t)k) ^ sw) << 4), hw[4 * k], hw[4 * k + 1], hw[4 * k + 2], hw[4 * k + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full);
+            }
+        }
+        if (DBG && warp == 0 && lane == 0) {
+            g_sprof[blockIdx.x * 16 + 0] = b_w;
+            g_sprof[blockIdx.x * 16 + 1] = clock64() - b_t0;
+        }
+    } else if (warp < WARP_EPI0) {
+        // ------------------------------------------------------------------ stem epilogue: TMEM -> SiLU -> bf16 -> planes
+        // Two groups of four warps (one warp per TMEM lane quarter); group g drains the blocks g and g + 2 of every unit from
+        // stem accumulator stage g, all 64 channels of its 32 pixels per warp: two blocks are in flight at a time.
+        const int quarter = warp & 3, grp = (warp - WARP_SEPI0) >> 2;
+        const int row = quarter * 32 + lane;
+        const bool silu = p.act0 == FCE_ACT_SILU;
+        // this thread's two stem pixels do not depend on the unit: window coordinates and the row address in the stem tile
+        int slot_rc[2];
+        uint32_t slot_ra[2];
 #pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            const int o = aoff[ks][hf];
-                            a[ks][2 * hf] = o >= 0 ? il[po[0] + o] : 0u;
-                            a[ks][2 * hf + 1] = o >= 0 ? il[po[1] + o] : 0u;
+        for (int j2 = 0; j2 < 2; ++j2) {
+            int pl, i, r, c;
+            const bool live = stem_slot(2 * j2 + grp, row, pl, i, r, c);
+            slot_rc[j2] = r | (c << 8);
+            slot_ra[j2] = live ? sT + (uint32_t)(pl_base(pl) + i) * 128u : 0u;
+        }
+        int itu = 0;
+        long long e_wa = 0, e_wp = 0, e_t0 = DBG ? clock64() : 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++itu) {
+            int b, oh0, ow0;
+            unit_coords(u, b, oh0, ow0);
+            const int sr0 = 2 * oh0 - 1, sc0 = 2 * ow0 - 1;
+#pragma unroll
+            for (int j2 = 0; j2 < 2; ++j2) {
+                const int blk = 2 * j2 + grp;  // block sb = 4 * itu + blk of the CTA's sequence, accumulator stage sb & 1 = grp
+                const uint32_t ra = slot_ra[j2];
+                const int sr = sr0 + (slot_rc[j2] & 255), scc = sc0 + (slot_rc[j2] >> 8);
+                const bool inside = ra != 0u && sr >= 0 && sr < p.H0 && scc >= 0 && scc < p.W0;
+                {
+                    SP_T0();
+                    mbar_wait(s_tfull0 + 8 * grp, (uint32_t)(2 * itu + j2) & 1u);  // this stage's (2 itu + j2)-th completion
+                    SP_ACC(e_wa);
+                }
+                {
+                    // the MMAs of the previous unit are done with the planes this block writes: plane step blk, head of blk + 1
+                    SP_T0();
+                    mbar_wait(pfree0 + 8 * blk, ((uint32_t)itu & 1u) ^ 1u);
+                    if (blk < 3) mbar_wait(pfree0 + 8 * (blk + 1), ((uint32_t)itu & 1u) ^ 1u);
+                    SP_ACC(e_wp);
+                }
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + grp * C0;
+                const uint32_t xr = (ra >> 7) & 7u;
+#pragma unroll
+                for (int cg = 0; cg < 4; ++cg) {  // 16 channels = two 16-byte chunks of the pixel's row at a time
+                    uint32_t v[16], o[8];
+                    tmem_ld16(t_row + 16 * cg, v);
+                    tmem_ld_wait();
+                    if (cg == 3) {  // the accumulator is in registers: the stage is free for block sb + 2
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(s_tempty0 + 8 * grp);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float2 a = make_float2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+                        if (silu) {  // h + h * tanh(h), h = a / 2 (the bias is already in the accumulator)
+                            const float2 h = __fmul2_rn(a, make_float2(0.5f, 0.5f));
+                            a = __ffma2_rn(h, make_float2(tanh_fast(h.x), tanh_fast(h.y)), h);
                         }
-                    // swizzled row addresses of the two pixels (absolute address bits 7..9 select the XOR)
-                    const uint32_t row0 = pbase + (uint32_t)slot[0] * 128u, row1 = pbase + (uint32_t)slot[1] * 128u;
-                    const uint32_t x0 = (row0 >> 7) & 7u, x1 = (row1 >> 7) & 7u;
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        float c[4] = {bs[nt][0], bs[nt][1], bs[nt][0], bs[nt][1]};
-                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                                     : "r"(a[0][0]), "r"(a[0][1]), "r"(a[0][2]), "r"(a[0][3]), "r"(bf[0][nt][0]), "r"(bf[0][nt][1]));
-                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                                     : "r"(a[1][0]), "r"(a[1][1]), "r"(a[1][2]), "r"(a[1][3]), "r"(bf[1][nt][0]), "r"(bf[1][nt][1]));
-                        if (silu) {  // c holds h = v / 2: silu(v) = h + h * tanh(h), on packed pairs
-#pragma unroll
-                            for (int j = 0; j < 4; j += 2) {
-                                const float2 h = make_float2(c[j], c[j + 1]);
-                                const float2 o = __ffma2_rn(h, make_float2(tanh_fast(h.x), tanh_fast(h.y)), h);
-                                c[j] = o.x;
-                                c[j + 1] = o.y;
-                            }
-                        }
-                        __nv_bfloat162 lo = __floats2bfloat162_rn(c[0], c[1]), hi = __floats2bfloat162_rn(c[2], c[3]);
-                        const uint32_t vlo = inside[0] ? *reinterpret_cast<uint32_t*>(&lo) : 0u;  // outside the stem map: the
-                        const uint32_t vhi = inside[1] ? *reinterpret_cast<uint32_t*>(&hi) : 0u;  // second conv's zero padding
-                        if (live[0])
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(row0 + ((((uint32_t)nt ^ x0) << 4) | (uint32_t)(t << 2))), "r"(vlo)
-                                         : "memory");
-                        if (live[1])
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(row1 + ((((uint32_t)nt ^ x1) << 4) | (uint32_t)(t << 2))), "r"(vhi)
-                                         : "memory");
+                        __nv_bfloat162 ob = __floats2bfloat162_rn(a.x, a.y);
+                        o[k] = inside ? *reinterpret_cast<uint32_t*>(&ob) : 0u;  // outside the stem map: the second conv's zero padding
+                    }
+                    if (ra != 0u) {
+                        st_shared_v4(ra + (((uint32_t)(2 * cg) ^ xr) << 4), o[0], o[1], o[2], o[3]);
+                        st_shared_v4(ra + (((uint32_t)(2 * cg + 1) ^ xr) << 4), o[4], o[5], o[6], o[7]);
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(pfull0 + 8 * q);
+                if (lane == 0) {  // plane step blk is complete once blocks blk - 1 (its head) and blk are
+                    mbar_arrive(pfull0 + 8 * blk);
+                    if (blk < 3) mbar_arrive(pfull0 + 8 * (blk + 1));
+                }
             }
-            stem_bar();  // every warp is done reading the staged window
+        }
+        if (DBG && warp == WARP_SEPI0 && lane == 0) {
+            g_sprof[blockIdx.x * 16 + 2] = e_wa;
+            g_sprof[blockIdx.x * 16 + 3] = e_wp;
+            g_sprof[blockIdx.x * 16 + 4] = clock64() - e_t0;
         }
     } else {
         // ------------------------------------------------------------------ epilogue: TMEM -> bias + act -> bf16 -> global
@@ -355,14 +456,19 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
         int acc = 0;
         uint32_t acc_phase = 0;
         pdl_wait();  // the output buffer may still be in use by the previous kernel (arena buffers are recycled)
+        long long l_w = 0, l_t0 = DBG ? clock64() : 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             int b, oh0, ow0;
             unit_coords(u, b, oh0, ow0);
             const bool ok = r < TH && cc < TW && oh0 + r < p.H1 && ow0 + cc < p.W1;
             __nv_bfloat16* yrow = y + (((size_t)b * p.H1 + (oh0 + r)) * p.W1 + (ow0 + cc)) * p.out_pitch;
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            {
+                SP_T0();
+                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                SP_ACC(l_w);
+            }
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C1n;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + 2 * C0 + acc * C1n;
             const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
             for (int n = 0; n < C1n; n += 32) {
@@ -400,6 +506,10 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (DBG && warp == WARP_EPI0 && lane == 0) {
+            g_sprof[blockIdx.x * 16 + 10] = l_w;
+            g_sprof[blockIdx.x * 16 + 11] = clock64() - l_t0;
+        }
     }
 
     tc_fence_before();
@@ -410,7 +520,7 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
 }
 
 size_t stem2_smem(const Stem2Params& p) {
-    return 9ull * p.w_tile + STILE_BYTES + ITILE_BYTES + p.bias_bytes + 256 + 1024;
+    return 9ull * p.w_tile + STILE_BYTES + A0_BYTES + B0_BYTES + p.bias_bytes + 256 + 1024;
 }
 
 // Shape rules; pure arithmetic (also behind fce_stem2_route).
@@ -437,9 +547,11 @@ bool stem2_plan(const fce_stem2_desc* d, Stem2Params& p) {
     p.bias_bytes = ((uint32_t)d->C1 * 4u + 255u) & ~255u;
     if (stem2_smem(p) > (size_t)SMEM_LIMIT) return false;
     p.tmem_cols = 32;
-    while (p.tmem_cols < 2u * (uint32_t)d->C1) p.tmem_cols <<= 1;
+    while (p.tmem_cols < 2u * C0 + 2u * (uint32_t)d->C1) p.tmem_cols <<= 1;  // two stem stages + two accumulator stages
     p.desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 8 rows x 128 bytes, descriptor version 1, 128B swizzle
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->C1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.desc_hi0 = (512u >> 4) | (1u << 14) | (4u << 29);  // stem GEMM: 8 rows x 64 bytes, 64B swizzle
+    p.idesc0 = (1u << 4) | ((uint32_t)(C0 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // fp16 A / B, fp32 accumulate, N = 64
     return true;
 }
 
@@ -447,6 +559,13 @@ bool stem2_plan(const fce_stem2_desc* d, Stem2Params& p) {
 }  // namespace fce
 
 using namespace fce;
+
+#ifdef FCE_DEBUG
+extern "C" int fce_stem2_profile(long long* out, int n) {  // debug builds only, not in the public header
+    if (n > kNumSMs * 16) n = kNumSMs * 16;
+    return cudaMemcpyFromSymbol(out, g_sprof, (size_t)n * sizeof(long long)) == cudaSuccess ? n : FCE_ERR_CUDA;
+}
+#endif
 
 extern "C" int fce_stem2_route(const fce_stem2_desc* d) {
     if (!d) return FCE_ERR_BAD_ARG;

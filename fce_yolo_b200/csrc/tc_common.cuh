@@ -42,24 +42,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// try_wait with a suspend-time hint (ns): the waiting thread sleeps in hardware until the phase completes or the time is up,
-// instead of coming back every few hundred cycles.  Measured on the fused depthwise + 1x1 kernel (ncu source view): the
-// spinning slow path of the idle roles (TMA / MMA / epilogue warps between tiles) was 25 % of all issued instructions.
-__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(ns)
-        : "memory");
-    return ok != 0;
-}
 // Bounded wait: a protocol bug must fault the launch (reported through the C ABI), never hang the GPU.
+// The clock is read once per 256 polls: with clock64() and a 64-bit compare in every iteration the idle roles' spin loops were
+// 25 - 40 % of all issued instructions of the fused producer kernels (ncu source view of conv_dwpw / conv_stem2), taking
+// issue slots from the warps that do the work.  (A try_wait with a suspend-time hint compiled to NANOSLEEP.SYNCS + the same
+// clock arithmetic and polled just as often.)
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
-    while (!mbar_try_wait_hint(bar, parity, 200000u)) {
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 256; ++i) {
+            if (mbar_try_wait(bar, parity)) return;  // (a __nanosleep(40) back-off here measured 6 % SLOWER on conv_stem2)
+        }
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }

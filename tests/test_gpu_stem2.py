@@ -1,8 +1,10 @@
 """fce_stem2_conv (the first two convs of the graph in one pass: Conv(3, 64, 3, 2) on the uint8 image + Conv(64, C1, 3, 2),
-yolo11-fce.yaml:20-21, conv.py:80-89) against (a) the two-launch route fce_stem_conv + fce_conv2d - same stem arithmetic and
-same bf16 rounding of the stem map; the second conv accumulates its nine taps in a different order (parity plane by parity
-plane), so the fp32 sums differ in the last bits: at most ONE bf16 ulp on at most 1 % of the outputs, and (b) a torch fp32
-reference of the two layers with the tolerance of two bf16 roundings."""
+yolo11-fce.yaml:20-21, conv.py:80-89) against (a) the two-launch route fce_stem_conv + fce_conv2d: same operands and the
+same bf16 rounding of the stem map, but the stem GEMM runs on tcgen05 instead of mma.sync (its bias enters as an fp16 K
+column) and the second conv accumulates its taps plane by plane - a stem value now and then rounds to the neighbouring
+bf16, so the outputs agree to rounding noise, not bit for bit: relative L2 <= 2e-3, no output off by more than 2 % of the
+largest magnitude; and (b) a torch fp32 reference of the two layers with the tolerance of two bf16 roundings (the same bound
+the two-launch route meets)."""
 import ctypes as C
 
 import pytest
@@ -72,13 +74,8 @@ def test_stem2_equals_two_launches(lib, B, H, W, C1, acts, sliced):
     a, b = y1[..., oo:oo + C1], y2[..., oo:oo + C1]
     assert torch.isfinite(a.float()).all()
     af, bfl = a.float(), b.float()
-    diff = (af - bfl).abs()
-    # one bf16 ulp is at most 2^-7 of the magnitude; outputs that cancel to ~0 carry the fp32 summation-order noise of the
-    # 576-term sum itself (terms of magnitude ~0.1: a few 1e-7 absolute, measured 1.5e-7), far above their own ulp
-    ulp = torch.maximum(af.abs(), bfl.abs()) * 2.0 ** -7 + 5e-5
-    bad = (diff > ulp).nonzero()
-    assert bad.numel() == 0, f"{bad.shape[0]} outputs differ by more than one bf16 ulp, first {bad[:5].tolist()}"
-    assert (diff > 0).float().mean().item() < 0.01
+    assert ((af - bfl).norm() / bfl.norm()).item() < 2e-3
+    assert ((af - bfl).abs().max() / bfl.abs().max()).item() < 2e-2
     # torch fp32 reference (bf16 operands, bf16 stem map)
     xr = x.float().permute(0, 3, 1, 2)
     w0r = wk_d.float().cpu()[:, :27].reshape(C0, 3, 3, 3).permute(0, 3, 1, 2)
@@ -88,7 +85,9 @@ def test_stem2_equals_two_launches(lib, B, H, W, C1, acts, sliced):
     ref = F.silu(ref) if act1 == 1 else ref
     out = a.float().cpu().permute(0, 3, 1, 2)
     l2 = ((out - ref).norm() / ref.norm()).item()
-    assert l2 < 6e-3, l2
+    l2_two = ((b.float().cpu().permute(0, 3, 1, 2) - ref).norm() / ref.norm()).item()
+    assert l2 < 6e-3, (l2, l2_two)
+    assert l2 < 1.25 * l2_two + 1e-4, (l2, l2_two)  # no less accurate than the two launches
 
 
 def test_stem2_route_rejects(lib):
