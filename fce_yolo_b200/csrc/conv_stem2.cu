@@ -24,8 +24,8 @@
 //     walk the slot list in the same order, so plane q is complete when block q is); each plane has its own full / free
 //     barrier, so the stem epilogue refills plane q for the next unit while the tensor core still works on planes q+1.. of
 //     this one - one stem tile in shared memory behaves like a four-stage ring.  36 tcgen05.mma (M = 128, N = C1, K = 16)
-//     per unit against the PARKED weights (all nine [C1, 64] tap tiles, loaded once per CTA); the stem GEMMs are issued two
-//     blocks ahead of the plane steps that consume them.
+//     per unit against the PARKED weights (all nine [C1, 64] tap tiles, loaded once per CTA); the stem GEMMs (four TMEM
+//     stages) and the plane steps are two independent instruction streams of this warp, each issued when its barriers allow.
 //   * epilogue warps (4): TMEM -> bias + SiLU -> bf16 -> 32-byte global stores, two accumulator stages.
 //
 // HBM bytes per output pixel: 48 image bytes (+ halo, L2) read, 2 * C1 written.  m scale, batch 256: 0.3 + 1.68 GB instead
@@ -41,10 +41,11 @@ namespace {
 constexpr int C0 = 64;                      // stem channels = K chunk of the second conv (128-byte rows)
 constexpr int TH = 7, TW = 16, PW = TW + 1; // unit of the second conv; plane pitch
 constexpr int SC = 2 * TW + 1;                      // stem window: 15 rows x 33 columns
-// warp roles (21 warps: 80 registers per thread)
+// warp roles (21 warps: 80 registers per thread; 25 warps with eight epilogue warps measured slower: the SM is paced by
+// its aggregate instruction rate, more warps only dilute it)
 constexpr int TEAM_WARPS = 4;                       //     // 0 .. 7: two builder teams (blocks alternate), one stem pixel (A row) per thread
 constexpr int WARP_SEPI0 = 8;                       // 8 .. 15 stem epilogue: warp & 3 = TMEM lane quarter, (warp - 8) >> 2 = group
-constexpr int WARP_EPI0 = 16;                       // 16 .. 19 epilogue of the second conv
+constexpr int WARP_EPI0 = 16, NEPI_WARPS = 4;       // 16 .. 19 epilogue of the second conv
 constexpr int WARP_MMA = 20;
 constexpr int NUM_THREADS = 21 * 32;
 // planes in memory order P00, P01, P10, P11 (index = (row parity) * 2 + column parity)
@@ -56,6 +57,7 @@ constexpr int ST_ROWS_ALLOC = 520;  // the last descriptor reads rows [391 + 1, 
 __host__ __device__ constexpr int q_plane(int q) { return 3 - q; }
 constexpr int N_SLOTS = 510;
 constexpr uint32_t STILE_BYTES = ST_ROWS_ALLOC * 128;
+constexpr int STEM_STAGES = 4;           // stem accumulator stages in TMEM (64 columns each): block blk of a unit -> stage blk
 constexpr uint32_t A0_BYTES = 128 * 64;  // stem GEMM A operand: 128 rows x K = 32 fp16 (64-byte rows, 64B swizzle)
 constexpr uint32_t B0_BYTES = C0 * 64;   // stem weights: 64 rows x 32 fp16
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -85,6 +87,19 @@ __device__ long long g_sprof[1];
 #define SP_T0() long long _t0 = 0; if (DBG) _t0 = clock64()
 #define SP_ACC(var) if (DBG) (var) += clock64() - _t0
 
+// non-blocking phase test (try_wait may suspend the thread for a hardware-defined time before it reports failure)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 __device__ __forceinline__ void st2_global_v8(void* p, const uint32_t* o) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
                  "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
@@ -111,9 +126,9 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
     const uint32_t sB0 = sA + A0_BYTES;                 // stem GEMM B operand
     const uint32_t sBias = sB0 + B0_BYTES;
     const uint32_t bars = sBias + p.bias_bytes;
-    const uint32_t a_full = bars, a_empty0 = bars + 8, s_tfull0 = bars + 24, s_tempty0 = bars + 40;
-    const uint32_t pfull0 = bars + 56, pfree0 = bars + 88, tfull0 = bars + 120, tempty0 = bars + 136, wfull = bars + 152;
-    const uint32_t tmem_slot = bars + 160;
+    const uint32_t a_full = bars, a_empty0 = bars + 8, s_tfull0 = bars + 24, s_tempty0 = bars + 56;
+    const uint32_t pfull0 = bars + 88, pfree0 = bars + 120, tfull0 = bars + 152, tempty0 = bars + 168, wfull = bars + 184;
+    const uint32_t tmem_slot = bars + 192;
     float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - raw0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,10 +139,12 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
         mbar_init(a_full, TEAM_WARPS);
         for (int a = 0; a < 2; ++a) {
             mbar_init(a_empty0 + 8 * a, 1);
-            mbar_init(s_tfull0 + 8 * a, 1);
-            mbar_init(s_tempty0 + 8 * a, 4);  // the stem-epilogue group that owns the stage
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, 4);
+            mbar_init(tempty0 + 8 * a, NEPI_WARPS);
+        }
+        for (int a = 0; a < STEM_STAGES; ++a) {
+            mbar_init(s_tfull0 + 8 * a, 1);
+            mbar_init(s_tempty0 + 8 * a, 4);  // the stem-epilogue group that drains the stage
         }
         for (int q = 0; q < 4; ++q) {
             mbar_init(pfull0 + 8 * q, q == 0 ? 4 : 8);  // the group of block q + (q > 0) the group of block q - 1 (plane head)
@@ -144,16 +161,17 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
     }
     {
         // Stem weights as the B operand of the stem GEMM: fp16 [64][32], K order k' = 10 * kh + j (j = 0..9: the nine values of
-        // patch row kh and their zero-weight neighbour; k' 30 = the bias, 31 zero), x 256 because the A operand holds byte / 256
+        // patch row kh and their zero-weight neighbour; k' 30 = the bias, 31 zero), x 256 (x 128 with SiLU) because the A operand holds byte / 256
         // (bf16 -> fp16 and the power of two are exact; the bias keeps 11 bits - three more than the bf16 result); 64-byte
         // rows, 64B swizzle (16-byte chunk c of row n at c ^ ((n >> 1) & 3))
         const unsigned short* wus = reinterpret_cast<const unsigned short*>(w0);
+        const float wsc = p.act0 == FCE_ACT_SILU ? 128.f : 256.f;  // SiLU as h + h * tanh(h): the GEMM produces h = v / 2 directly
         for (int idx = threadIdx.x; idx < C0 * 32; idx += NUM_THREADS) {
             const int n = idx >> 5, kp = idx & 31;
             const int kh = kp / 10, j = kp - kh * 10;
             float v = 0.f;
-            if (kp < 30 && j < 9) v = __uint_as_float((uint32_t)__ldg(wus + n * 32 + kh * 9 + j) << 16) * 256.f;
-            if (kp == 30) v = __ldg(b0 + n) * 256.f;  // the bias rides in the GEMM: A column 30 is the constant 1 / 256
+            if (kp < 30 && j < 9) v = __uint_as_float((uint32_t)__ldg(wus + n * 32 + kh * 9 + j) << 16) * wsc;
+            if (kp == 30) v = __ldg(b0 + n) * wsc;  // the bias rides in the GEMM: A column 30 is the constant 1 / 256
             const __half hv = __float2half_rn(v);
             const uint32_t addr = sB0 + (uint32_t)n * 64u + ((((uint32_t)kp >> 3) ^ (((uint32_t)n >> 1) & 3u)) << 4) + ((uint32_t)kp & 7u) * 2u;
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
@@ -198,75 +216,68 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
         tc_fence_after();
         const uint32_t dhi = p.desc_hi, idesc = p.idesc, dhi0 = p.desc_hi0, idesc0 = p.idesc0;
         const int S = 4 * my_units;  // stem blocks = plane steps of this CTA
-        long long m_af = 0, m_se = 0, m_pf = 0, m_te = 0, m_t0 = DBG ? clock64() : 0;
-        // stem GEMM of block sb: [128 slots x 32] x [32 x 64] -> stem accumulator stage sb & 1 (64 TMEM columns)
-        auto stem_mma = [&](int sb) {
-            const int stage = sb & 1;
-            {
-                SP_T0();
-                mbar_wait(s_tempty0 + 8 * stage, (((uint32_t)sb >> 1) & 1u) ^ 1u);  // the stem epilogue of block sb - 2 has drained it
-                SP_ACC(m_se);
+        long long m_af = 0, m_se = 0, m_pf = 0, m_te = 0, m_t0 = DBG ? clock64() : 0;  // (the waits of this warp are polls now)
+        // Two instruction streams share this warp: the stem GEMMs (block sb: [128 slots x 32] x [32 x 64] -> stem accumulator
+        // stage sb & 3) and the plane steps of the second conv (step lp: the taps of plane order q = lp & 3 of unit lp >> 2).
+        // Each is issued as soon as ITS barriers allow (non-blocking tests): a blocking wait for one stream would hold back the
+        // other - the first version waited in program order and the stem epilogue sat idle 38 % of the time.
+        auto ready = [&](uint32_t bar, uint32_t parity) { return __all_sync(0xffffffffu, mbar_test(bar, parity)) != 0; };
+        int sb = 0, lp = 0;
+        (void)m_af; (void)m_se; (void)m_pf; (void)m_te;
+        long long t_prog = clock64();  // bounded like every other wait: a protocol bug faults the launch instead of hanging
+        int idle = 0;
+        while (lp < S) {
+            if (++idle == 4096) {
+                idle = 0;
+                if (clock64() - t_prog > 4000000000LL) __trap();
             }
-            {
-                SP_T0();
-                mbar_wait(a_full, (uint32_t)sb & 1u);
-                SP_ACC(m_af);
-            }
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t a16 = sA >> 4, b16 = sB0 >> 4;
+            if (sb < S && sb < lp + STEM_STAGES) {
+                const int stage = sb & 3;
+                // the stem epilogue has drained the stage (block sb - 4), the builders have filled the A operand
+                if (ready(s_tempty0 + 8 * stage, (((uint32_t)sb >> 2) & 1u) ^ 1u) && ready(a_full, (uint32_t)sb & 1u)) {
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a16 = sA >> 4, b16 = sB0 >> 4;
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    umma_bf16(tmem_base + stage * C0, make_desc(dhi0, ((a16 + 2 * k) & 0x3FFF) | (1u << 16)),
-                              make_desc(dhi0, ((b16 + 2 * k) & 0x3FFF) | (1u << 16)), idesc0, (uint32_t)k);
-                umma_commit(a_empty0 + 8 * (sb & 1));  // the OTHER builder team may fill the stage with block sb + 1
-                umma_commit(s_tfull0 + 8 * stage);     // -> stem epilogue
-            }
-            __syncwarp();
-        };
-        // the taps of plane step lp (unit lp >> 2, plane order q = lp & 3) of the second conv
-        auto l1_mma = [&](int lp) {
-            const int q = lp & 3, itu = lp >> 2, acc = itu & 1;
-            if (q == 0) {
-                SP_T0();
-                mbar_wait(tempty0 + 8 * acc, (((uint32_t)itu >> 1) & 1u) ^ 1u);
-                SP_ACC(m_te);
-                tc_fence_after();
-            }
-            {
-                SP_T0();
-                mbar_wait(pfull0 + 8 * q, (uint32_t)itu & 1u);
-                SP_ACC(m_pf);
-            }
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t d_tmem = tmem_base + 2 * C0 + acc * p.C1;
-                const int pl = q_plane(q), pr = pl >> 1, pc = pl & 1;
-                bool first = q == 0;
-                for (int kh = pr; kh < 3; kh += 2)
-                    for (int kw = pc; kw < 3; kw += 2) {
-                        const uint32_t a16 = (sT + (uint32_t)(pl_base(pl) + (kh >> 1) * PW + (kw >> 1)) * 128u) >> 4;
-                        const uint32_t b16 = (sW + (uint32_t)(kh * 3 + kw) * p.w_tile) >> 4;
-#pragma unroll
-                        for (int k = 0; k < C0 / 16; ++k) {
-                            umma_bf16(d_tmem, make_desc(dhi, ((a16 + 2 * k) & 0x3FFF) | (1u << 16)),
-                                      make_desc(dhi, ((b16 + 2 * k) & 0x3FFF) | (1u << 16)), idesc, first ? 0u : 1u);
-                            first = false;
-                        }
+                        for (int k = 0; k < 2; ++k)
+                            umma_bf16(tmem_base + stage * C0, make_desc(dhi0, ((a16 + 2 * k) & 0x3FFF) | (1u << 16)),
+                                      make_desc(dhi0, ((b16 + 2 * k) & 0x3FFF) | (1u << 16)), idesc0, (uint32_t)k);
+                        umma_commit(a_empty0 + 8 * (sb & 1));  // the OTHER builder team may fill the stage with block sb + 1
+                        umma_commit(s_tfull0 + 8 * stage);     // -> stem epilogue
                     }
-                umma_commit(pfree0 + 8 * q);                // the stem epilogue may refill this plane
-                if (q == 3) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
+                    __syncwarp();
+                    ++sb;
+                    idle = 0;
+                    t_prog = clock64();
+                }
             }
-            __syncwarp();
-        };
-        // the stem GEMMs run two blocks ahead of the plane steps that consume their result
-        if (S > 0) {
-            stem_mma(0);
-            stem_mma(1);
-#pragma unroll 1
-            for (int k = 0; k < S; ++k) {
-                l1_mma(k);
-                if (k + 2 < S) stem_mma(k + 2);
+            {
+                const int q = lp & 3, itu = lp >> 2, acc = itu & 1;
+                // the plane is complete; for the first plane of a unit the epilogue has drained the accumulator stage
+                if ((q != 0 || ready(tempty0 + 8 * acc, (((uint32_t)itu >> 1) & 1u) ^ 1u)) && ready(pfull0 + 8 * q, (uint32_t)itu & 1u)) {
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t d_tmem = tmem_base + STEM_STAGES * C0 + acc * p.C1;
+                        const int pl = q_plane(q), pr = pl >> 1, pc = pl & 1;
+                        bool first = q == 0;
+                        for (int kh = pr; kh < 3; kh += 2)
+                            for (int kw = pc; kw < 3; kw += 2) {
+                                const uint32_t a16 = (sT + (uint32_t)(pl_base(pl) + (kh >> 1) * PW + (kw >> 1)) * 128u) >> 4;
+                                const uint32_t b16 = (sW + (uint32_t)(kh * 3 + kw) * p.w_tile) >> 4;
+#pragma unroll
+                                for (int k = 0; k < C0 / 16; ++k) {
+                                    umma_bf16(d_tmem, make_desc(dhi, ((a16 + 2 * k) & 0x3FFF) | (1u << 16)),
+                                              make_desc(dhi, ((b16 + 2 * k) & 0x3FFF) | (1u << 16)), idesc, first ? 0u : 1u);
+                                    first = false;
+                                }
+                            }
+                        umma_commit(pfree0 + 8 * q);                // the stem epilogue may refill this plane
+                        if (q == 3) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
+                    }
+                    __syncwarp();
+                    ++lp;
+                    idle = 0;
+                }
             }
         }
         if (DBG && lane == 0) {
@@ -309,57 +320,78 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
             }
         };
         long long b_w = 0, b_t0 = DBG ? clock64() : 0;
-        int nb = 0;  // blocks this team has built
-        pdl_wait();  // the image comes from the previous work in the stream
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        // Software pipeline over this team's block sequence (block n: unit blockIdx.x + (n >> 1) * grid, slot j = n & 1): the
+        // twelve image words of block n + 1 are requested before block n is converted and stored, so that their latency (L2
+        // or HBM: ~2.7 k cycles per block were spent here) hides behind a whole block of work.
+        uint32_t wd[3][4];
+        uint32_t sh = 0;
+        bool inside = false;
+        auto request = [&](int n) {  // loads of block n -> wd / sh / inside
+            const int u = (int)blockIdx.x + (n >> 1) * (int)gridDim.x;
+            inside = false;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) wd[kh][k] = 0u;
+            if (u >= units) return;
             int b, oh0, ow0;
             unit_coords(u, b, oh0, ow0);
-            const int sr0 = 2 * oh0 - 1, sc0 = 2 * ow0 - 1;  // stem coordinates of the window origin
-            if (team == 0 && u + (int)gridDim.x < units) prefetch_window(u + gridDim.x);
+            const int rc = slot_rc[n & 1];
+            const int sr = 2 * oh0 - 1 + (rc & 255), scc = 2 * ow0 - 1 + (rc >> 8);  // stem coordinates of this thread's pixel
+            inside = rc >= 0 && sr >= 0 && sr < p.H0 && scc >= 0 && scc < p.W0;
+            if (!inside) return;
+            // patch row kh: image row 2 sr - 1 + kh, bytes [6 sc - 3, +9] (three pixels x 3 channels + one neighbour)
+            const int bs = 6 * scc - 3, w_lo = bs >> 2;
+            sh = 8u * (uint32_t)(bs & 3);
 #pragma unroll
-            for (int j = 0; j < 2; ++j, ++nb) {  // blocks team and team + 2 of this unit: sb = 2 * nb + team of the CTA's sequence
-                const int rc = slot_rc[j];
-                const int sr = sr0 + (rc & 255), scc = sc0 + (rc >> 8);
-                const bool inside = rc >= 0 && sr >= 0 && sr < p.H0 && scc >= 0 && scc < p.W0;
-                uint32_t hw[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) hw[k] = 0u;
-                hw[15] = 0x00001C00u;  // k' = 30: fp16 1 / 256, the multiplier of the bias row of B
-                if (inside) {
-                    // patch row kh: image row 2 sr - 1 + kh, bytes [6 sc - 3, +9] (three pixels x 3 channels + one neighbour)
-                    const int bs = 6 * scc - 3, w_lo = bs >> 2;
-                    const uint32_t sh = 8u * (uint32_t)(bs & 3);
-#pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
-                        const int ih = 2 * sr - 1 + kh;
-                        if (ih < 0 || ih >= p.H) continue;  // zero padding of the stem conv
-                        const uint32_t* rowp = xw + (size_t)(b * p.H + ih) * row_words;
-                        uint32_t wd[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) wd[k] = (w_lo + k >= 0 && w_lo + k < row_words) ? __ldg(rowp + w_lo + k) : 0u;
-                        const uint32_t v0 = __funnelshift_r(wd[0], wd[1], sh), v1 = __funnelshift_r(wd[1], wd[2], sh),
-                                       v2 = __funnelshift_r(wd[2], wd[3], sh);
-                        hw[5 * kh + 0] = cvt2(v0, 0x4140);
-                        hw[5 * kh + 1] = cvt2(v0, 0x4342);
-                        hw[5 * kh + 2] = cvt2(v1, 0x4140);
-                        hw[5 * kh + 3] = cvt2(v1, 0x4342);
-                        hw[5 * kh + 4] = cvt2(v2, 0x4140);
-                    }
-                }
-                {
-                    // the stem GEMM of the previous block (sb - 1, built by the other team) has read the stage: its commits go
-                    // to a_empty[(sb - 1) & 1] - a barrier whose every phase this team observes (no parity aliasing)
-                    SP_T0();
-                    mbar_wait(a_empty0 + 8 * (team ^ 1), team ? ((uint32_t)nb & 1u) : (((uint32_t)nb & 1u) ^ 1u));
-                    SP_ACC(b_w);
-                }
+            for (int kh = 0; kh < 3; ++kh) {
+                const int ih = 2 * sr - 1 + kh;
+                if (ih < 0 || ih >= p.H) continue;  // zero padding of the stem conv
+                const uint32_t* rowp = xw + (size_t)(b * p.H + ih) * row_words;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    st_shared_v4(my_row + ((((uint32_t)k) ^ sw) << 4), hw[4 * k], hw[4 * k + 1], hw[4 * k + 2], hw[4 * k + 3]);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a_full);
+                    if (w_lo + k >= 0 && w_lo + k < row_words) wd[kh][k] = __ldg(rowp + w_lo + k);
             }
+        };
+        const int n_blocks = 2 * my_units;
+        pdl_wait();  // the image comes from the previous work in the stream
+        if (n_blocks > 0) request(0);
+#pragma unroll 1
+        for (int nb = 0; nb < n_blocks; ++nb) {  // block sb = 2 * nb + team of the CTA's sequence
+            if (team == 0 && (nb & 1) == 0) {
+                const int un = (int)blockIdx.x + ((nb >> 1) + 1) * (int)gridDim.x;
+                if (un < units) prefetch_window(un);
+            }
+            uint32_t hw[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) hw[k] = 0u;
+            hw[15] = 0x00001C00u;  // k' = 30: fp16 1 / 256, the multiplier of the bias row of B
+            if (inside) {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const uint32_t v0 = __funnelshift_r(wd[kh][0], wd[kh][1], sh), v1 = __funnelshift_r(wd[kh][1], wd[kh][2], sh),
+                                   v2 = __funnelshift_r(wd[kh][2], wd[kh][3], sh);
+                    hw[5 * kh + 0] = cvt2(v0, 0x4140);
+                    hw[5 * kh + 1] = cvt2(v0, 0x4342);
+                    hw[5 * kh + 2] = cvt2(v1, 0x4140);
+                    hw[5 * kh + 3] = cvt2(v1, 0x4342);
+                    hw[5 * kh + 4] = cvt2(v2, 0x4140);
+                }
+            }
+            request(nb + 1);  // in flight across the wait, the stores and the hand-over below
+            {
+                // the stem GEMM of the previous block (sb - 1, built by the other team) has read the stage: its commits go
+                // to a_empty[(sb - 1) & 1] - a barrier whose every phase this team observes (no parity aliasing)
+                SP_T0();
+                mbar_wait(a_empty0 + 8 * (team ^ 1), team ? ((uint32_t)nb & 1u) : (((uint32_t)nb & 1u) ^ 1u));
+                SP_ACC(b_w);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                st_shared_v4(my_row + ((((uint32_t)k) ^ sw) << 4), hw[4 * k], hw[4 * k + 1], hw[4 * k + 2], hw[4 * k + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
         }
         if (DBG && warp == 0 && lane == 0) {
             g_sprof[blockIdx.x * 16 + 0] = b_w;
@@ -390,13 +422,13 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
             const int sr0 = 2 * oh0 - 1, sc0 = 2 * ow0 - 1;
 #pragma unroll
             for (int j2 = 0; j2 < 2; ++j2) {
-                const int blk = 2 * j2 + grp;  // block sb = 4 * itu + blk of the CTA's sequence, accumulator stage sb & 1 = grp
+                const int blk = 2 * j2 + grp;  // block sb = 4 * itu + blk of the CTA's sequence, stem accumulator stage blk
                 const uint32_t ra = slot_ra[j2];
                 const int sr = sr0 + (slot_rc[j2] & 255), scc = sc0 + (slot_rc[j2] >> 8);
                 const bool inside = ra != 0u && sr >= 0 && sr < p.H0 && scc >= 0 && scc < p.W0;
                 {
                     SP_T0();
-                    mbar_wait(s_tfull0 + 8 * grp, (uint32_t)(2 * itu + j2) & 1u);  // this stage's (2 itu + j2)-th completion
+                    mbar_wait(s_tfull0 + 8 * blk, (uint32_t)itu & 1u);  // one completion of stage blk per unit
                     SP_ACC(e_wa);
                 }
                 {
@@ -407,27 +439,30 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
                     SP_ACC(e_wp);
                 }
                 tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + grp * C0;
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + blk * C0;
                 const uint32_t xr = (ra >> 7) & 7u;
+                // 16 channels (two 16-byte chunks of the pixel's row) at a time.  (Keeping the TMEM load of group cg + 1 in flight
+                // while group cg is computed measured SLOWER: 1.32 -> 1.52 ms.)
 #pragma unroll
-                for (int cg = 0; cg < 4; ++cg) {  // 16 channels = two 16-byte chunks of the pixel's row at a time
+                for (int cg = 0; cg < 4; ++cg) {
                     uint32_t v[16], o[8];
                     tmem_ld16(t_row + 16 * cg, v);
                     tmem_ld_wait();
-                    if (cg == 3) {  // the accumulator is in registers: the stage is free for block sb + 2
+                    if (cg == 3) {  // the accumulator is in registers: the stage is free for block sb + 4
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(s_tempty0 + 8 * grp);
+                        if (lane == 0) mbar_arrive(s_tempty0 + 8 * blk);
                     }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         float2 a = make_float2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
-                        if (silu) {  // h + h * tanh(h), h = a / 2 (the bias is already in the accumulator)
-                            const float2 h = __fmul2_rn(a, make_float2(0.5f, 0.5f));
-                            a = __ffma2_rn(h, make_float2(tanh_fast(h.x), tanh_fast(h.y)), h);
-                        }
+                        if (silu) a = __ffma2_rn(a, make_float2(tanh_fast(a.x), tanh_fast(a.y)), a);  // the accumulator is h = v / 2
                         __nv_bfloat162 ob = __floats2bfloat162_rn(a.x, a.y);
-                        o[k] = inside ? *reinterpret_cast<uint32_t*>(&ob) : 0u;  // outside the stem map: the second conv's zero padding
+                        o[k] = *reinterpret_cast<uint32_t*>(&ob);
+                    }
+                    if (!inside) {  // outside the stem map: the second conv's zero padding
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[k] = 0u;
                     }
                     if (ra != 0u) {
                         st_shared_v4(ra + (((uint32_t)(2 * cg) ^ xr) << 4), o[0], o[1], o[2], o[3]);
@@ -452,6 +487,7 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
         const int quarter = warp & 3;
         const int o = quarter * 32 + lane, r = o / PW, cc = o - r * PW;  // padded-flat output index -> (row, column) of the unit
         const int act = p.act1, C1n = p.C1;
+        const int n_lo = 0, n_hi = C1n;
         const bool wide = p.wide_store != 0;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -468,11 +504,11 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
                 SP_ACC(l_w);
             }
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + 2 * C0 + acc * C1n;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + STEM_STAGES * C0 + acc * C1n;
             const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-            for (int n = 0; n < C1n; n += 32) {
-                const bool two = n + 16 < C1n;
+            for (int n = n_lo; n < n_hi; n += 32) {
+                const bool two = n + 16 < n_hi;
                 uint32_t v0[16], v1[16];
                 tmem_ld16(t_row + n, v0);
                 if (two) tmem_ld16(t_row + n + 16, v1);
@@ -547,7 +583,7 @@ bool stem2_plan(const fce_stem2_desc* d, Stem2Params& p) {
     p.bias_bytes = ((uint32_t)d->C1 * 4u + 255u) & ~255u;
     if (stem2_smem(p) > (size_t)SMEM_LIMIT) return false;
     p.tmem_cols = 32;
-    while (p.tmem_cols < 2u * C0 + 2u * (uint32_t)d->C1) p.tmem_cols <<= 1;  // two stem stages + two accumulator stages
+    while (p.tmem_cols < (uint32_t)STEM_STAGES * C0 + 2u * (uint32_t)d->C1) p.tmem_cols <<= 1;  // stem stages + two accumulator stages
     p.desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 8 rows x 128 bytes, descriptor version 1, 128B swizzle
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->C1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.desc_hi0 = (512u >> 4) | (1u << 14) | (4u << 29);  // stem GEMM: 8 rows x 64 bytes, 64B swizzle
