@@ -38,7 +38,8 @@ namespace fce {
 using namespace tc;
 namespace {
 
-constexpr int C0 = 64;                      // stem channels = K chunk of the second conv (128-byte rows)
+// C0 (template): stem channels = K chunk of the second conv: 64 (m / l scale: 128-byte rows, 128B swizzle) or 32 (s scale:
+// 64-byte rows, 64B swizzle)
 constexpr int TH = 7, TW = 16, PW = TW + 1; // unit of the second conv; plane pitch
 constexpr int SC = 2 * TW + 1;                      // stem window: 15 rows x 33 columns
 // warp roles (21 warps: 80 registers per thread; 25 warps with eight epilogue warps measured slower: the SM is paced by
@@ -56,10 +57,9 @@ constexpr int ST_ROWS_ALLOC = 520;  // the last descriptor reads rows [391 + 1, 
 // slots of the list [P11 | P10 | P01 | P00] (119 + 119 + 136 + 136 = 510 slots): plane q is complete when block q is.
 __host__ __device__ constexpr int q_plane(int q) { return 3 - q; }
 constexpr int N_SLOTS = 510;
-constexpr uint32_t STILE_BYTES = ST_ROWS_ALLOC * 128;
 constexpr int STEM_STAGES = 4;           // stem accumulator stages in TMEM (64 columns each): block blk of a unit -> stage blk
 constexpr uint32_t A0_BYTES = 128 * 64;  // stem GEMM A operand: 128 rows x K = 32 fp16 (64-byte rows, 64B swizzle)
-constexpr uint32_t B0_BYTES = C0 * 64;   // stem weights: 64 rows x 32 fp16
+// stem weights (B operand of the stem GEMM): C0 rows x 32 fp16 = C0 x 64 bytes
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct Stem2Params {
@@ -113,14 +113,18 @@ __device__ __forceinline__ void slot_to_plane(int gs, int& pl, int& i) {
     else { pl = 0; i = gs - 374; }
 }
 
+template <int C0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, const uint8_t* __restrict__ x,
                   const __nv_bfloat16* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ b1,
                   __nv_bfloat16* __restrict__ y) {
+    constexpr uint32_t RB = C0 * 2;              // bytes of one stem-tile / weight row = swizzle span
+    constexpr uint32_t SWZ = RB == 128 ? 7u : 3u;  // 16-byte chunk c of a row lives at c ^ ((address >> 7) & SWZ)
+    constexpr uint32_t STILE_BYTES = (ST_ROWS_ALLOC * RB + 1023u) & ~1023u, B0_BYTES = C0 * 64;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw0 = smem_u32(smem_raw);
     const uint32_t base = (raw0 + 1023u) & ~1023u;
-    const uint32_t sW = base;                           // 9 x [C1][64] bf16, 128B-swizzled
+    const uint32_t sW = base;                           // 9 x [C1][C0] bf16, swizzled
     const uint32_t sT = sW + 9 * p.w_tile;              // stem tile: four parity planes, 128-byte rows
     const uint32_t sA = sT + STILE_BYTES;               // stem GEMM A operand (one stage)
     const uint32_t sB0 = sA + A0_BYTES;                 // stem GEMM B operand
@@ -262,7 +266,7 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
                         bool first = q == 0;
                         for (int kh = pr; kh < 3; kh += 2)
                             for (int kw = pc; kw < 3; kw += 2) {
-                                const uint32_t a16 = (sT + (uint32_t)(pl_base(pl) + (kh >> 1) * PW + (kw >> 1)) * 128u) >> 4;
+                                const uint32_t a16 = (sT + (uint32_t)(pl_base(pl) + (kh >> 1) * PW + (kw >> 1)) * RB) >> 4;
                                 const uint32_t b16 = (sW + (uint32_t)(kh * 3 + kw) * p.w_tile) >> 4;
 #pragma unroll
                                 for (int k = 0; k < C0 / 16; ++k) {
@@ -412,7 +416,7 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
             int pl, i, r, c;
             const bool live = stem_slot(2 * j2 + grp, row, pl, i, r, c);
             slot_rc[j2] = r | (c << 8);
-            slot_ra[j2] = live ? sT + (uint32_t)(pl_base(pl) + i) * 128u : 0u;
+            slot_ra[j2] = live ? sT + (uint32_t)(pl_base(pl) + i) * RB : 0u;
         }
         int itu = 0;
         long long e_wa = 0, e_wp = 0, e_t0 = DBG ? clock64() : 0;
@@ -440,15 +444,15 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
                 }
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + blk * C0;
-                const uint32_t xr = (ra >> 7) & 7u;
+                const uint32_t xr = (ra >> 7) & SWZ;
                 // 16 channels (two 16-byte chunks of the pixel's row) at a time.  (Keeping the TMEM load of group cg + 1 in flight
                 // while group cg is computed measured SLOWER: 1.32 -> 1.52 ms.)
 #pragma unroll
-                for (int cg = 0; cg < 4; ++cg) {
+                for (int cg = 0; cg < C0 / 16; ++cg) {
                     uint32_t v[16], o[8];
                     tmem_ld16(t_row + 16 * cg, v);
                     tmem_ld_wait();
-                    if (cg == 3) {  // the accumulator is in registers: the stage is free for block sb + 4
+                    if (cg == C0 / 16 - 1) {  // the accumulator is in registers: the stage is free for block sb + 4
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(s_tempty0 + 8 * blk);
@@ -555,14 +559,15 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmW, const Stem2Params p, 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
 }
 
-size_t stem2_smem(const Stem2Params& p) {
-    return 9ull * p.w_tile + STILE_BYTES + A0_BYTES + B0_BYTES + p.bias_bytes + 256 + 1024;
+size_t stem2_smem(const Stem2Params& p, int c0) {
+    return 9ull * p.w_tile + (((size_t)ST_ROWS_ALLOC * c0 * 2 + 1023) & ~(size_t)1023) + A0_BYTES + (size_t)c0 * 64 + p.bias_bytes + 256 + 1024;
 }
 
 // Shape rules; pure arithmetic (also behind fce_stem2_route).
 bool stem2_plan(const fce_stem2_desc* d, Stem2Params& p) {
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return false;
-    if (d->C0 != C0 || d->C1 % 16 || d->C1 < 16 || d->C1 > 256) return false;
+    if ((d->C0 != 64 && d->C0 != 32) || d->C1 % 16 || d->C1 < 16 || d->C1 > 256) return false;
+    const int C0 = d->C0;
     if (d->H % 4 || d->W % 4 || d->H > 16000 || d->W > 16000) return false;  // whole words per image row, both strides exact
     if (d->out_pitch % 8 || d->out_off % 8) return false;
     if (d->act0 != FCE_ACT_SILU && d->act0 != FCE_ACT_NONE) return false;
@@ -579,15 +584,17 @@ bool stem2_plan(const fce_stem2_desc* d, Stem2Params& p) {
     p.out_pitch = d->out_pitch;
     p.act0 = d->act0;
     p.act1 = d->act1;
-    p.w_tile = (uint32_t)d->C1 * 128u;
+    p.w_tile = (uint32_t)d->C1 * (uint32_t)C0 * 2u;
     p.bias_bytes = ((uint32_t)d->C1 * 4u + 255u) & ~255u;
-    if (stem2_smem(p) > (size_t)SMEM_LIMIT) return false;
+    if (stem2_smem(p, C0) > (size_t)SMEM_LIMIT) return false;
+    if (STEM_STAGES * C0 + 2 * d->C1 > 512) return false;  // tensor memory: four stem stages + two accumulator stages
     p.tmem_cols = 32;
     while (p.tmem_cols < (uint32_t)STEM_STAGES * C0 + 2u * (uint32_t)d->C1) p.tmem_cols <<= 1;  // stem stages + two accumulator stages
-    p.desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 8 rows x 128 bytes, descriptor version 1, 128B swizzle
+    // SBO = 8 rows of the swizzle span, descriptor version 1, 128B (layout 2) / 64B (layout 4) swizzle
+    p.desc_hi = C0 == 64 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : ((512u >> 4) | (1u << 14) | (4u << 29));
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->C1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.desc_hi0 = (512u >> 4) | (1u << 14) | (4u << 29);  // stem GEMM: 8 rows x 64 bytes, 64B swizzle
-    p.idesc0 = (1u << 4) | ((uint32_t)(C0 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // fp16 A / B, fp32 accumulate, N = 64
+    p.idesc0 = (1u << 4) | ((uint32_t)(C0 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // fp16 A / B, fp32 accumulate, N = C0
     return true;
 }
 
@@ -623,27 +630,33 @@ extern "C" int fce_stem2_conv(const fce_stem2_desc* d, const void* x, const void
     p.wide_store = (d->out_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(yout) & 31) == 0) ? 1 : 0;
     alignas(64) CUtensorMap tmW;
     {
+        const int C0 = d->C0;
         const cuuint64_t K = 9ull * C0;
         const cuuint64_t gdim[2] = {K, (cuuint64_t)d->C1};
         const cuuint64_t gstr[1] = {K * 2};
         const cuuint32_t box[2] = {(cuuint32_t)C0, (cuuint32_t)d->C1};
         const cuuint32_t est[2] = {1, 1};
         if (api.tiled(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w1), gdim, gstr, box, est,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, C0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return FCE_ERR_UNSUPPORTED;
     }
+    typedef void (*KernelFn)(const CUtensorMap, const Stem2Params, const uint8_t*, const __nv_bfloat16*, const float*,
+                             const float*, __nv_bfloat16*);
+    static const KernelFn table[2] = {conv_stem2_kernel<32>, conv_stem2_kernel<64>};
     static DeviceOnce attr_once;  // the shared-memory opt-in is a per-device attribute
     int dev = 0;
     if (attr_once.pending(&dev)) {
-        cudaError_t e = cudaFuncSetAttribute(conv_stem2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e != cudaSuccess) {
-            set_cuda_error(e);
-            return FCE_ERR_CUDA;
+        for (int v = 0; v < 2; ++v) {
+            cudaError_t e = cudaFuncSetAttribute(table[v], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+            if (e != cudaSuccess) {
+                set_cuda_error(e);
+                return FCE_ERR_CUDA;
+            }
         }
         attr_once.done(dev);
     }
     const int grid = p.units < kNumSMs ? p.units : kNumSMs;
-    return launch_pdl(conv_stem2_kernel, grid, NUM_THREADS, stem2_smem(p), (cudaStream_t)stream, tmW, p,
+    return launch_pdl(table[d->C0 == 64 ? 1 : 0], grid, NUM_THREADS, stem2_smem(p, d->C0), (cudaStream_t)stream, tmW, p,
                       reinterpret_cast<const uint8_t*>(x), reinterpret_cast<const __nv_bfloat16*>(w0), b0, b1, yout);
 }

@@ -120,8 +120,9 @@ int fce_stem_conv(const fce_stem_desc* d, const void* x, const void* w, const fl
  * uint8 NHWC image followed by Conv(C0, C1, 3, 2), both + bias + act; the stem map [B, H/2, W/2, C0] stays in shared
  * memory and never exists in HBM.  w0 / b0 as for fce_stem_conv (bf16 [C0][32] with the input scale folded in, fp32 [C0]);
  * w1 bf16 OHWI [C1][3][3][C0], b1 fp32 [C1]; y bf16 NHWC view [B, H/4, W/4, C1].  Same values as fce_stem_conv +
- * fce_conv2d (same stem arithmetic, same bf16 rounding of the intermediate).  Shapes: C0 = 64, C1 % 16 == 0, C1 <= 128
- * (the nine [C1, C0] tap tiles are parked in shared memory), H and W multiples of 4; anything else returns
+ * fce_conv2d up to rounding noise (same operands, same bf16 rounding of the intermediate; tests/test_gpu_stem2.py).
+ * Shapes: C0 in {32, 64}, C1 % 16 == 0, C1 <= 128 for C0 = 64 / <= 192 for C0 = 32 (the nine [C1, C0] tap tiles are parked
+ * in shared memory, 4 * C0 + 2 * C1 <= 512 tensor-memory columns), H and W multiples of 4; anything else returns
  * FCE_ERR_UNSUPPORTED (fce_stem2_route: 1 = taken, 0 = not, without launching) and the caller issues the two launches. */
 typedef struct {
     int32_t B, H, W;          /* image size */

@@ -30,19 +30,20 @@ def _p(t):
     return C.c_void_p(t.data_ptr() if t is not None else 0)
 
 
-# (B, H, W, C1): the m-scale pair at full size (one image: 230 units), small maps (one unit, ragged units on both borders),
-# H / W multiples of 4 only, several units per CTA (batch 40 at 160^2: 600 units), narrow outputs
-SHAPES = [(1, 640, 640, 128), (2, 64, 64, 128), (1, 96, 160, 128), (1, 68, 36, 64), (3, 32, 32, 16), (1, 4, 4, 32),
-          (40, 160, 160, 128), (2, 128, 256, 96)]
+# (B, H, W, C0, C1): the m-scale pair (64 -> 128) and the s-scale pair (32 -> 64) at full size (one image: 230 units), small maps
+# (one unit, ragged units on both borders), H / W multiples of 4 only, several units per CTA (batch 40 at 160^2: 600 units),
+# narrow and wide outputs
+SHAPES = [(1, 640, 640, 64, 128), (2, 64, 64, 64, 128), (1, 96, 160, 64, 128), (1, 68, 36, 64, 64), (3, 32, 32, 64, 16),
+          (1, 4, 4, 64, 32), (40, 160, 160, 64, 128), (2, 128, 256, 64, 96),
+          (1, 640, 640, 32, 64), (2, 64, 64, 32, 64), (1, 68, 36, 32, 48), (40, 160, 160, 32, 64), (2, 96, 128, 32, 192)]
 
 
-@pytest.mark.parametrize("B,H,W,C1", SHAPES)
+@pytest.mark.parametrize("B,H,W,C0,C1", SHAPES)
 @pytest.mark.parametrize("acts", [(1, 1), (0, 0)])
 @pytest.mark.parametrize("sliced", [False, True])
-def test_stem2_equals_two_launches(lib, B, H, W, C1, acts, sliced):
+def test_stem2_equals_two_launches(lib, B, H, W, C0, C1, acts, sliced):
     l, L = lib
     act0, act1 = acts
-    C0 = 64
     g = torch.Generator().manual_seed(B * 7 + H * 100 + W + C1)
     x = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
     w0 = torch.randn(C0, 3, 3, 3, generator=g) * 0.3
@@ -92,7 +93,8 @@ def test_stem2_equals_two_launches(lib, B, H, W, C1, acts, sliced):
 
 def test_stem2_route_rejects(lib):
     l, L = lib
-    for kw in [dict(C0=32, C1=64), dict(C0=64, C1=192), dict(C0=64, C1=40), dict(C0=64, C1=128, H=66)]:
+    for kw in [dict(C0=16, C1=32), dict(C0=96, C1=192), dict(C0=64, C1=192), dict(C0=32, C1=256), dict(C0=64, C1=40),
+               dict(C0=64, C1=128, H=66)]:
         args = dict(B=1, H=64, W=64, C0=64, C1=128, out_pitch=256, out_off=0, act0=1, act1=1)
         args.update(kw)
         assert l.fce_stem2_route(C.byref(L.Stem2Desc(**args))) == 0

@@ -8,6 +8,7 @@ import re
 import sys
 
 CLASS = [("conv_tc_kernel|conv_halo_kernel|strip_gemm_kernel|conv_simt|conv_direct", "fce_conv2d"),
+         ("conv_dwpw_kernel", "fce_dwpw_conv"), ("conv_stem2_kernel", "fce_stem2_conv"),
          ("dwconv", "fce_dwconv3x3"), ("stem_fused", "fce_stem_conv"), ("decode_kernel", "fce_detect_decode"),
          ("gate_", "fce_gate_apply"), ("bifpn_kernel", "fce_bifpn_fuse"), ("coord_pool", "fce_coord_pool"),
          ("coordatt_mlp", "fce_coordatt_mlp"), ("psa_", "fce_psa_attention"), ("sppf", "fce_sppf_pool"),
