@@ -244,12 +244,15 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int c = 0; c < chunks; ++c) {
                 if (turn == team) {
                     // depthwise taps / bias of this lane's two channels: constants (L1 hits), in flight across the wait below
+                    // With SiLU the taps and the bias are halved (exact), so the accumulator IS h = a / 2 of silu(a) = h + h * tanh(h):
+                    // the same values as dwconv_tma.cu's a * 0.5 afterwards, one multiply per pair less.
                     float2 wt[9], bs;
                     {
                         const int ch = c * KC + lane * 2;
+                        const float2 hs = silu ? make_float2(0.5f, 0.5f) : make_float2(1.f, 1.f);
 #pragma unroll
-                        for (int t = 0; t < 9; ++t) wt[t] = __ldg(reinterpret_cast<const float2*>(w_dw + t * p.C + ch));
-                        bs = __ldg(reinterpret_cast<const float2*>(b_dw + ch));
+                        for (int t = 0; t < 9; ++t) wt[t] = __fmul2_rn(__ldg(reinterpret_cast<const float2*>(w_dw + t * p.C + ch)), hs);
+                        bs = __fmul2_rn(__ldg(reinterpret_cast<const float2*>(b_dw + ch)), hs);
                     }
                     {
                         DP_T0();
@@ -291,10 +294,8 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
                                 for (int q = 0; q < 2; ++q) {
                                     float2 out = acc[o % 3][q];
-                                    if (silu) {  // h + h * tanh(h), h = a / 2: one MUFU per element
-                                        const float2 h = __fmul2_rn(out, make_float2(0.5f, 0.5f));
-                                        out = __ffma2_rn(h, make_float2(tanh_fast(h.x), tanh_fast(h.y)), h);
-                                    }
+                                    if (silu)  // h + h * tanh(h), the accumulator is h: one MUFU per element
+                                        out = __ffma2_rn(out, make_float2(tanh_fast(out.x), tanh_fast(out.y)), out);
                                     acc[o % 3][q] = bs;
                                     __nv_bfloat162 ob = __floats2bfloat162_rn(out.x, out.y);
                                     asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_col[q] + (uint32_t)o * (TW * 128u)),
