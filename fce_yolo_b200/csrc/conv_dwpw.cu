@@ -10,7 +10,8 @@
 //            one tcgen05.mma (rows past TH * 16 are never stored)
 //   K loop = C / 64 chunks of 64 channels (128-byte rows):
 //     TMA warp      one tiled 4-D box {64 channels, 18 columns, TH + 2 rows} of the NHWC input per (unit, chunk); the TMA
-//                   unit's out-of-bounds zero fill is the conv padding.  Three-stage ring.
+//                   unit's out-of-bounds zero fill is the conv padding.  Ring of three to eight stages (what fits next to the
+//                   parked weights).
 //     DW teams      two teams of eight warps; team t takes chunks t, t + 2, ... of the (unit, chunk) sequence.  A warp owns two
 //                   adjacent columns, a lane two channels (every shared-memory access of a warp is one 128-byte pixel row:
 //                   no bank conflicts); it walks down the box rows with three rolling accumulator rows on
@@ -19,8 +20,9 @@
 //                   layout a TMA load of the stored map would have produced.
 //     MMA warp      4 x tcgen05.mma (M = 128, N = Cout, K = 16) per chunk from the A stage and the PARKED 1x1 weights
 //                   ([Cout, C] bf16, loaded once per CTA), accumulator in TMEM, two accumulator stages.
-//   epilogue      eight warps (two per TMEM lane quarter, half of the channels each): tcgen05.ld -> bias + SiLU -> bf16 -> 32-byte global stores (one pixel row per thread; no
-//                   staging buffer: shared memory goes to the parked weights).
+//   epilogue      eight warps (two per TMEM lane quarter, half of the channels each): tcgen05.ld -> bias + SiLU -> bf16 ->
+//                   32-byte global stores (one pixel row per thread; no staging buffer: shared memory goes to the parked
+//                   weights).
 //
 //   Measured and dropped (git history, commit 7b7fe32): a CTA-pair variant (cta_group::2, half of the weight rows parked
 //   per CTA so that five input stages fit at m scale) - the coupling of the two CTAs' producer teams through the joint
