@@ -356,3 +356,43 @@ def test_predict_plan_bf16_all_families(name):
     # fused vs unfused plan: two bf16 evaluation orders of the same graph
     assert rel_l2(ys[True][:, :4], ys[False][:, :4]) < 3e-3   # measured 3e-8 .. 4e-4
     assert rel_l2(ys[True][:, 4:], ys[False][:, 4:]) < 3e-2   # measured 0 .. 5e-3
+
+
+@pytest.mark.parametrize("name", ["m_bifpn_64", "s_coordatt_64", "n_fce_64"])
+def test_fused_producer_nodes_in_u8_plans(name):
+    """uint8-input bf16 plans: the first two convs become ONE fce_stem2_conv node where the kernel takes the stem width (32 /
+    64 channels: s, m, l scale - not the 16-channel n-scale stem) and every DWConv + 1x1 block of Detect's class branch ONE
+    fce_dwpw_conv node where it takes the channel counts; the interpreted plan gives the predictions of the plan with the
+    two-launch routes (same layer arithmetic, interpreted in fp32 with bf16 storage)."""
+    from fce_yolo_b200.plan import Plan
+
+    case = FORWARD_CASES[name]
+    cfg, scale = load_cfg(case)
+    model = DetectionModel(cfg, scale=scale).fuse().eval()
+    load_synthetic(model, case["seed"])
+    B, S = case["batch"], case["size"]
+    x = (synth_images(case["img_seed"], B, S, S) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    saved = (Plan.FUSED_STEM2, Plan.FUSED_DWPW)
+    plans = {}
+    try:
+        for fused in (False, True):
+            Plan.FUSED_STEM2 = Plan.FUSED_DWPW = fused
+            plans[fused] = compile_model(model, B, S, S, "bf16", torch.device("cpu"), input_u8=True)
+    finally:
+        Plan.FUSED_STEM2, Plan.FUSED_DWPW = saved
+    fns = {f: [n.fn for n in p.nodes] for f, p in plans.items()}
+    assert "fce_stem2_conv" not in fns[False] and "fce_dwpw_conv" not in fns[False]
+    stem_width = model.model[0].conv.out_channels
+    assert ("fce_stem2_conv" in fns[True]) == (stem_width in (32, 64))
+    n_dwpw = fns[True].count("fce_dwpw_conv")
+    assert 1 <= n_dwpw <= 6
+    assert len(fns[True]) == len(fns[False]) - n_dwpw - ("fce_stem2_conv" in fns[True])
+    if "fce_stem2_conv" in fns[True]:
+        assert fns[True][0] == "fce_stem2_conv" and "fce_stem_conv" not in fns[True]
+    ys = {}
+    for f, plan in plans.items():
+        it = Interp(plan, reuse_memory=True)
+        it.input_tensor().copy_(x)
+        it.run()
+        ys[f] = it.outputs()[0].float()
+    assert rel_max(ys[True], ys[False]) < 1e-5  # the interpreter runs the same fp32 arithmetic with the same bf16 roundings
