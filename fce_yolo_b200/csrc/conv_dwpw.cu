@@ -19,7 +19,8 @@
 //                   bias + SiLU -> bf16 -> its team's A stage [128 rows x 128 bytes], 128B-swizzled K-major - exactly the
 //                   layout a TMA load of the stored map would have produced.
 //     MMA warp      4 x tcgen05.mma (M = 128, N = Cout, K = 16) per chunk from the A stage and the PARKED 1x1 weights
-//                   ([Cout, C] bf16, loaded once per CTA), accumulator in TMEM, two accumulator stages.
+//                   ([Cout, C] bf16, loaded once per CTA; where they do not fit - 512 -> 256: 256 KB - chunk c of the weights
+//                   is streamed with input chunk c through a three-stage ring), accumulator in TMEM, two accumulator stages.
 //   epilogue      eight warps (two per TMEM lane quarter, half of the channels each): tcgen05.ld -> bias + SiLU -> bf16 ->
 //                   32-byte global stores (one pixel row per thread; no staging buffer: shared memory goes to the parked
 //                   weights).
@@ -49,6 +50,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int WARP_TMA = WARP_EPI0 + NUM_EPI_WARPS, WARP_MMA = WARP_TMA + 1;
 constexpr int NUM_THREADS = (WARP_MMA + 1) * 32;  // 832
 constexpr int MAX_IN_STAGES = 8;
+constexpr int W_STAGES = 3;            // streamed weights: ring of [Cout, 64] chunks
 constexpr uint32_t A_STAGE = 128 * 128;  // one A stage: 128 rows x 128 bytes
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -59,7 +61,8 @@ struct DwpwParams {
     int out_pitch;
     int dw_act, pw_act;
     uint32_t in_stage;  // bytes of one input stage = one TMA box
-    uint32_t w_chunk;   // bytes of one parked weight chunk : Cout x 128
+    uint32_t w_chunk;   // bytes of one weight chunk: Cout x 128
+    int w_stream;       // the [Cout, C] weights do not fit next to the pipeline: chunk c travels with input chunk c (W_STAGES ring)
     uint32_t bias_bytes, tmem_cols;
     uint32_t desc_hi, idesc;
     int wide_store;     // output rows 32-byte aligned: 256-bit stores
@@ -93,14 +96,15 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t raw0 = smem_u32(smem_raw);
     const uint32_t base = (raw0 + 1023u) & ~1023u;
     const uint32_t sA = base;                              // TEAMS x A_STAGE
-    const uint32_t sW = sA + TEAMS * A_STAGE;              // chunks x [Cout][64] bf16, 128B-swizzled
-    const uint32_t sIn = sW + p.chunks * p.w_chunk;        // in_stages x [BR][BC][64] bf16
+    const uint32_t sW = sA + TEAMS * A_STAGE;              // chunks (parked) or W_STAGES (streamed) x [Cout][64] bf16, 128B-swizzled
+    const uint32_t sIn = sW + (p.w_stream ? W_STAGES : p.chunks) * p.w_chunk;  // in_stages x [BR][BC][64] bf16
     const uint32_t sBias = sIn + p.in_stages * p.in_stage;
     const uint32_t bars = sBias + p.bias_bytes;
     const uint32_t in_full0 = bars, in_empty0 = bars + 8 * MAX_IN_STAGES;
     const uint32_t a_full0 = in_empty0 + 8 * MAX_IN_STAGES, a_empty0 = a_full0 + 8 * TEAMS;
     const uint32_t tfull0 = a_empty0 + 8 * TEAMS, tempty0 = tfull0 + 16;
     const uint32_t wfull = tempty0 + 16, tmem_slot = wfull + 8;
+    const uint32_t ws_full0 = tmem_slot + 8, ws_empty0 = ws_full0 + 8 * W_STAGES;  // streamed-weight ring
     float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - raw0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -122,6 +126,10 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             mbar_init(tempty0 + 8 * a, NUM_EPI_WARPS);
         }
         mbar_init(wfull, 1);
+        for (int i = 0; i < W_STAGES; ++i) {
+            mbar_init(ws_full0 + 8 * i, 1);
+            mbar_init(ws_empty0 + 8 * i, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
@@ -153,17 +161,27 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
     if (warp == WARP_TMA) {
         // ------------------------------------------------------------------ loads: parked 1x1 weights, then input boxes
-        if (elect_one()) {
+        const bool w_stream = p.w_stream != 0;
+        if (!w_stream && elect_one()) {
             mbar_expect_tx(wfull, (uint32_t)chunks * p.w_chunk);
             for (int c = 0; c < chunks; ++c) tma_load_2d(sW + c * p.w_chunk, &tmW, wfull, c * KC, 0);
         }
         __syncwarp();
         pdl_wait();  // activations come from the previous kernel (the weights above are constants)
-        Ring r;
+        Ring r, rw;
         for (int it = item0; it < n_items; it += item_step) {
             int b, h0, w0;
             unit_coords(it, b, h0, w0);
             for (int c = 0; c < chunks; ++c) {
+                if (w_stream) {  // this chunk's weights (an L2 hit after the first unit): consumed by the MMA warp
+                    mbar_wait(ws_empty0 + 8 * rw.stage, rw.phase ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(ws_full0 + 8 * rw.stage, p.w_chunk);
+                        tma_load_2d(sW + rw.stage * p.w_chunk, &tmW, ws_full0 + 8 * rw.stage, c * KC, 0);
+                    }
+                    __syncwarp();
+                    rw.advance(W_STAGES);
+                }
                 mbar_wait(in_empty0 + 8 * r.stage, r.phase ^ 1);
                 if (elect_one()) {
                     const uint32_t fb = in_full0 + 8 * r.stage;
@@ -180,8 +198,12 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
     } else if (warp == WARP_MMA) {
         // ------------------------------------------------------------------ MMA issuer
-        mbar_wait(wfull, 0);
-        tc_fence_after();
+        const bool w_stream = p.w_stream != 0;
+        if (!w_stream) {
+            mbar_wait(wfull, 0);
+            tc_fence_after();
+        }
+        Ring rw;
         int acc = 0, turn = 0;
         uint32_t acc_phase = 0, a_phase = 0;  // bit t of a_phase: parity of team t's A-full barrier
         const uint32_t dhi = p.desc_hi, idesc = p.idesc;
@@ -201,19 +223,22 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     mbar_wait(a_full0 + 8 * turn, (a_phase >> turn) & 1u);
                     DP_ACC(m_wa);
                 }
+                if (w_stream) mbar_wait(ws_full0 + 8 * rw.stage, rw.phase);
                 tc_fence_after();
                 const uint32_t a_lo = (((sA + turn * A_STAGE) >> 4) & 0x3FFF) | (1u << 16);
-                const uint32_t b_lo = (((sW + c * p.w_chunk) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t b_lo = (((sW + (w_stream ? rw.stage : c) * p.w_chunk) >> 4) & 0x3FFF) | (1u << 16);
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k)
                         umma_bf16(d_tmem, make_desc(dhi, a_lo + 2 * k), make_desc(dhi, b_lo + 2 * k), idesc, (c | k) != 0);
                     umma_commit(a_empty0 + 8 * turn);                   // the team may overwrite its A stage
+                    if (w_stream) umma_commit(ws_empty0 + 8 * rw.stage);  // the weight stage may be refilled
                     if (c == chunks - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 a_phase ^= 1u << turn;
                 if (++turn == TEAMS) turn = 0;
+                if (w_stream) rw.advance(W_STAGES);
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -401,13 +426,14 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 }
 
 size_t dwpw_smem(const DwpwParams& p) {
-    return (size_t)TEAMS * A_STAGE + (size_t)p.chunks * p.w_chunk + (size_t)p.in_stages * p.in_stage + p.bias_bytes + 256 + 1024;
+    return (size_t)TEAMS * A_STAGE + (size_t)(p.w_stream ? W_STAGES : p.chunks) * p.w_chunk + (size_t)p.in_stages * p.in_stage +
+           p.bias_bytes + 512 + 1024;
 }
 
-// Ring depth a tile height leaves room for next to the parked weights; 0 = does not fit.
-int dwpw_stages(const fce_dwpw_desc* d, int th) {
-    const size_t fixed = (size_t)TEAMS * A_STAGE + (size_t)(d->C / KC) * (size_t)d->Cout * 128u +
-                         (((size_t)d->Cout * 4u + 255u) & ~(size_t)255u) + 256 + 1024;
+// Ring depth a tile height leaves room for next to the weights (parked, or the streamed ring); 0 = does not fit.
+int dwpw_stages(const fce_dwpw_desc* d, int th, bool stream) {
+    const size_t fixed = (size_t)TEAMS * A_STAGE + (size_t)(stream ? W_STAGES : d->C / KC) * (size_t)d->Cout * 128u +
+                         (((size_t)d->Cout * 4u + 255u) & ~(size_t)255u) + 512 + 1024;
     if (fixed >= (size_t)SMEM_LIMIT) return 0;
     const int st = (int)(((size_t)SMEM_LIMIT - fixed) / ((size_t)(th + 2) * BC * 128u));
     return st > MAX_IN_STAGES ? MAX_IN_STAGES : st;
@@ -422,15 +448,22 @@ int dwpw_plan(const fce_dwpw_desc* d, DwpwParams& p) {
     if (d->dw_act != FCE_ACT_SILU && d->dw_act != FCE_ACT_NONE) return 0;
     if (d->pw_act != FCE_ACT_SILU && d->pw_act != FCE_ACT_NONE && d->pw_act != FCE_ACT_SIGMOID) return 0;
     if (d->H > 32000 || d->W > 32000) return 0;
+    // Weights parked for the life of the CTA where they fit next to at least three input stages (two being consumed, one in
+    // flight); otherwise chunk c of the weights is streamed with input chunk c (m scale: the 512 -> 256 blocks, 256 KB of
+    // weights - 32 KB per chunk and unit from L2, 13 B / clk / SM next to a depthwise stage that takes ~2 k cycles).
     int TH = 0, stages = 0;
-    for (int th = 8; th >= 7 && !TH; --th) {  // at least three input stages: two being consumed, one in flight
-        const int st = dwpw_stages(d, th);
-        if (st >= 3) {
-            TH = th;
-            stages = st;
+    bool stream = false;
+    for (int pass = 0; pass < 2 && !TH; ++pass)
+        for (int th = 8; th >= 7 && !TH; --th) {
+            const int st = dwpw_stages(d, th, pass == 1);
+            if (st >= 3) {
+                TH = th;
+                stages = st;
+                stream = pass == 1;
+            }
         }
-    }
     if (!TH) return 0;
+    p.w_stream = stream ? 1 : 0;
     p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.Cout = d->Cout;
     p.chunks = d->C / KC;
     p.w_chunk = (uint32_t)d->Cout * 128u;

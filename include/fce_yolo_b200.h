@@ -180,9 +180,9 @@ int fce_dwconv3x3(const fce_dwconv_desc* d, const void* x, const float* w, const
  * depthwise result (rounded to bf16, as the two-launch route stores it) goes straight into the shared-memory A operand
  * of the 1x1 on the tensor cores and never exists in HBM; results are bit-identical to fce_dwconv3x3 + fce_conv2d.
  * bf16 NHWC views in and out; w_dw fp32 [9][C] (tap-major), b_dw fp32 [C], w_pw bf16 [Cout][C], b_pw fp32 [Cout].
- * Shapes: C % 64 == 0, Cout % 16 == 0, Cout <= 256, and the [Cout, C] weights must fit shared memory next to the
- * pipeline (C * Cout <= 64 Ki elements); anything else returns FCE_ERR_UNSUPPORTED and the caller issues the two
- * launches.  fce_dwpw_route answers that question without launching (1 = this entry point takes the shape, 0 = not;
+ * Shapes: C % 64 == 0, Cout % 16 == 0, Cout <= 256 (the [Cout, C] weights are parked in shared memory where they fit next
+ * to the pipeline - C * Cout <= 64 Ki elements - and streamed chunk by chunk otherwise); anything else returns
+ * FCE_ERR_UNSUPPORTED and the caller issues the two launches.  fce_dwpw_route answers that question without launching (1 = this entry point takes the shape, 0 = not;
  * pure function of the descriptor). */
 typedef struct {
     int32_t B, H, W;

@@ -34,7 +34,9 @@ SHAPES = [(2, 80, 80, 256, 256), (3, 40, 40, 256, 256), (2, 20, 20, 256, 256), (
           (40, 40, 40, 128, 128), (1, 160, 160, 64, 64),
           # 64 Ki weight elements (the largest the kernel parks: 7-row units, three input stages), an odd number of units,
           # one column tile
-          (1, 8, 48, 256, 256), (3, 9, 16, 512, 128)]
+          (1, 8, 48, 256, 256), (3, 9, 16, 512, 128),
+          # weights too large to park (m-scale P4 / P5 first block, 256 KB): streamed chunk by chunk with the input
+          (2, 40, 40, 512, 256), (3, 20, 20, 512, 256), (1, 24, 40, 768, 192)]
 
 
 @pytest.mark.parametrize("B,H,W,Cc,Cout", SHAPES)
@@ -86,10 +88,10 @@ def test_dwpw_equals_two_launches(lib, B, H, W, Cc, Cout, acts, sliced):
 
 def test_dwpw_route_rejects(lib):
     """Shapes outside the kernel (the plan compiler then issues the two launches): channel counts off the 64 / 16 grid,
-    more than 256 outputs, weights that do not fit shared memory next to the pipeline."""
+    more than 256 outputs."""
     l, L = lib
     base = dict(B=1, H=40, W=40, in_off=0, out_off=0, dw_act=1, pw_act=1)
-    for Cc, Cout in [(80, 80), (64, 40), (384, 384), (512, 256), (768, 384)]:
+    for Cc, Cout in [(80, 80), (64, 40), (384, 384), (768, 384), (512, 264)]:
         d = L.DwpwDesc(C=Cc, Cout=Cout, in_pitch=Cc, out_pitch=Cout, **base)
         assert l.fce_dwpw_route(C.byref(d)) == 0
     d = L.DwpwDesc(C=256, Cout=256, in_pitch=256, out_pitch=256, **base)
