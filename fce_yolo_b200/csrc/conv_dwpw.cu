@@ -149,7 +149,7 @@ conv_dwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int chunks = p.chunks, units = p.units;
+    const int chunks = p.chunks;
     auto unit_coords = [&](int u, int& b, int& h0, int& w0) {
         const int tw = u % p.tiles_w;
         const int r = u / p.tiles_w;
