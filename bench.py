@@ -265,7 +265,7 @@ def kernel_table(pred, name):
     wpk = write_only_peak(pred.device)
     for (fn, args, n), ms in zip(ex._calls, acc):
         # the fused Detect epilogues are launches of the same tcgen05 conv kernel: one class
-        cls = "fce_conv2d" if n.fn == "fce_conv2d_detect" else n.fn
+        cls = "fce_conv2d" if n.fn in ("fce_conv2d_detect", "fce_conv1x1_chain") else n.fn  # dense convs on the tensor cores
         c = classes.setdefault(cls, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, ideal=0.0, wbytes=0.0, ideal_w=0.0))
         c["ms"] += ms
         # this launch's own roofline: the slower of its tensor time and its HBM time

@@ -59,6 +59,11 @@ class DwpwDesc(C.Structure):
                                    "pw_act")]
 
 
+class ChainDesc(C.Structure):
+    _fields_ = [(n, i32) for n in ("B", "H", "W", "c1", "cm", "c2", "Cout", "x1_pitch", "x1_off", "x2_pitch", "x2_off",
+                                   "out_pitch", "out_off", "act1", "act2")]
+
+
 class SppfDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "H", "W", "C", "pitch", "off", "dtype")]
 
@@ -130,6 +135,8 @@ _SIGS = {
     "fce_dwconv3x3": (C.c_int, [C.POINTER(DwconvDesc), _P, _P, _P, _P, _P, _P]),
     "fce_dwpw_conv": (C.c_int, [C.POINTER(DwpwDesc), _P, _P, _P, _P, _P, _P, _P]),
     "fce_dwpw_route": (C.c_int, [C.POINTER(DwpwDesc)]),
+    "fce_conv1x1_chain": (C.c_int, [C.POINTER(ChainDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fce_conv1x1_chain_route": (C.c_int, [C.POINTER(ChainDesc)]),
     "fce_sppf_pool": (C.c_int, [C.POINTER(SppfDesc), _P, _P]),
     "fce_upsample2x": (C.c_int, [C.POINTER(UpsampleDesc), _P, _P, _P]),
     "fce_bifpn_fuse": (C.c_int, [C.POINTER(BifpnDesc), _P, _P, _P, _P, _P]),

@@ -131,6 +131,8 @@ class Plan:
     FUSED_SUM = os.environ.get("FCE_FUSED_SUM", "1") != "0"
     FUSED_COORDATT_MLP = True  # False: cv1 / cv_h / cv_w as three strip convs (A/B timing, cross-check)
     FUSED_C3K_IN = True  # False: C3k.cv1 and C3k.cv2 as two launches (A/B timing, cross-check)
+    # False (or FCE_FUSED_C3K_TAIL=0): the last C3k's cv3 and C3k2's cv2 as two launches (A/B timing, cross-check)
+    FUSED_C3K_TAIL = os.environ.get("FCE_FUSED_C3K_TAIL", "1") != "0"
     # False (or FCE_FUSED_DWPW=0): Detect's DWConv + 1x1 blocks as two launches (A/B timing, cross-check)
     FUSED_DWPW = os.environ.get("FCE_FUSED_DWPW", "1") != "0"
     # False (or FCE_FUSED_STEM2=0): the first two convs as two launches (A/B timing, cross-check)
@@ -409,14 +411,19 @@ class Plan:
         t = self.conv(m.cv1, x, tag=tag + ".cv1")
         return self.conv(m.cv2, t, dst=dst, res=x if m.add else None, tag=tag + ".cv2")
 
-    def c3k(self, m, x: View, dst=None, tag="") -> View:
+    def _c3k_in_fused(self, m) -> bool:
+        p1, p2 = self.conv_params(m.cv1), self.conv_params(m.cv2)
+        return bool(self.FUSED_C3K_IN and p1[2:] == p2[2:] and p1[2:5] == (1, 1, 1) and p1[0].shape == p2[0].shape
+                    and m.cv1.conv.out_channels % 8 == 0)
+
+    def c3k(self, m, x: View, dst=None, tag="", defer_cv3=False) -> View:
+        """defer_cv3: everything but cv3; returns cv3's INPUT view (the caller chains cv3 into its own 1x1, c3k2())."""
         c_ = m.cv1.conv.out_channels
         blocks = list(m.m)
         if not blocks:
             raise PlanError("C3k without bottlenecks")
         p1, p2 = self.conv_params(m.cv1), self.conv_params(m.cv2)
-        if (self.FUSED_C3K_IN and p1[2:] == p2[2:] and p1[2:5] == (1, 1, 1) and p1[0].shape == p2[0].shape
-                and c_ % 8 == 0):
+        if self._c3k_in_fused(m):
             # cv1 and cv2 are 1x1 convs of the SAME input (block.py:338-340): ONE launch with the weights stacked reads x
             # once instead of twice (both layers sit left of the ridge: HBM-bound).  Buffer layout [chain out | cv2(x) |
             # cv1(x)]: the stacked conv writes channels [c_, 3c_), the bottleneck chain reads the last slice and ends in the
@@ -427,6 +434,8 @@ class Plan:
             a = buf.ch(2 * c_, 3 * c_)
             for j, blk in enumerate(blocks):
                 a = self.bottleneck(blk, a, dst=buf.ch(0, c_) if j == len(blocks) - 1 else None, tag=f"{tag}.m.{j}")
+            if defer_cv3:
+                return buf.ch(0, 2 * c_)
             return self.conv(m.cv3, buf.ch(0, 2 * c_), dst=dst, tag=tag + ".cv3")
         cat = self.new_buf(x.H, x.W, 2 * c_)
         a = self.conv(m.cv1, x, tag=tag + ".cv1")
@@ -434,17 +443,45 @@ class Plan:
             a = self.bottleneck(blk, a, dst=cat.ch(0, c_) if j == len(blocks) - 1 else None, tag=f"{tag}.m.{j}")
         with self.branch():  # independent of the bottleneck chain: same input, its own half of the concat buffer
             self.conv(m.cv2, x, dst=cat.ch(c_, 2 * c_), tag=tag + ".cv2")
+        if defer_cv3:
+            return cat
         return self.conv(m.cv3, cat, dst=dst, tag=tag + ".cv3")
+
+    def _c3k_tail_desc(self, m, H, W, B, dst):
+        """Descriptor of fce_conv1x1_chain for C3k2 `m` (its last block's cv3 chained into cv2) if that kernel takes the block,
+        else None."""
+        c, n = m.c, len(m.m)
+        if not (self.FUSED_C3K_TAIL and self.act_dt == L.BF16 and self.impl in (0, 2) and n >= 1
+                and type(m.m[-1]).__name__ == "C3k" and list(m.m[-1].m)):
+            return None
+        p3, p2 = self.conv_params(m.m[-1].cv3), self.conv_params(m.cv2)
+        Cout = p2[0].shape[0]
+        if p3[2:5] != (1, 1, 1) or p2[2:5] != (1, 1, 1) or tuple(p3[0].shape[:2]) != (c, c) or p2[0].shape[1] != (2 + n) * c:
+            return None
+        if dst is not None and dst.dtype != L.BF16:
+            return None
+        c_ = m.m[-1].cv1.conv.out_channels
+        x1_pitch = 3 * c_ if self._c3k_in_fused(m.m[-1]) else 2 * c_
+        d = L.ChainDesc(B=B, H=H, W=W, c1=c, cm=c, c2=(1 + n) * c, Cout=Cout, x1_pitch=x1_pitch, x1_off=0,
+                        x2_pitch=(1 + n) * c, x2_off=0, out_pitch=dst.pitch if dst is not None else Cout, out_off=0,
+                        act1=p3[5], act2=p2[5])
+        return d if L.load().fce_conv1x1_chain_route(ctypes.byref(d)) == 1 else None
 
     def c3k2(self, m, x, dst=None, tag="") -> View:
         c, n = m.c, len(m.m)
-        cat = self.new_buf(x.H, x.W, (2 + n) * c)
+        chain = self._c3k_tail_desc(m, x.H, x.W, getattr(x, "B", self.B), dst)
+        cat = self.new_buf(x.H, x.W, ((1 if chain is not None else 2) + n) * c)
         if isinstance(x, LazySum):  # BiFPN node in front: folded into cv1
             self.conv_of_sum(m.cv1, x, dst=cat.ch(0, 2 * c), tag=tag + ".cv1")
         else:
             self.conv(m.cv1, x, dst=cat.ch(0, 2 * c), tag=tag + ".cv1")
         prev = cat.ch(c, 2 * c)
         for j, blk in enumerate(m.m):
+            if chain is not None and j == n - 1:
+                # the last C3k's cv3 output t is only ever read by cv2: ONE launch computes t = cv3(..) tile by tile into shared
+                # memory and uses it as the last K slice of cv2 (fce_conv1x1_chain) - the concat buffer has no slot for it
+                x1 = self.c3k(blk, prev, tag=f"{tag}.m.{j}", defer_cv3=True)
+                return self._chain(blk.cv3, m.cv2, chain, x1, cat, dst, tag=f"{tag}.m.{j}.cv3+cv2")
             out = cat.ch((2 + j) * c, (3 + j) * c)
             if type(blk).__name__ == "C3k":
                 self.c3k(blk, prev, dst=out, tag=f"{tag}.m.{j}")
@@ -452,6 +489,23 @@ class Plan:
                 self.bottleneck(blk, prev, dst=out, tag=f"{tag}.m.{j}")
             prev = out
         return self.conv(m.cv2, cat, dst=dst, tag=tag + ".cv2")
+
+    def _chain(self, m1, m2, d, x1: View, x2: View, dst, tag="") -> View:
+        w1, b1 = self.conv_params(m1)[:2]
+        w2, b2 = self.conv_params(m2)[:2]
+        if (x1.C, x2.C, x1.pitch, x2.pitch) != (d.c1, d.c2, d.x1_pitch, d.x2_pitch) or x1.dtype != L.BF16 or x2.dtype != L.BF16:
+            raise PlanError(f"{tag}: views do not match the chain descriptor")
+        if dst is None:
+            dst = self.new_buf(x2.H, x2.W, d.Cout)
+        if (dst.H, dst.W, dst.C, dst.B, dst.pitch) != (x2.H, x2.W, d.Cout, x2.B, d.out_pitch):
+            raise PlanError(f"{tag}: chain output does not fit its destination")
+        ptrs = [x1, self._w(w1.view(d.cm, d.c1), torch.bfloat16), self._w(b1), x2,
+                self._w(w2.view(d.Cout, d.c2 + d.cm), torch.bfloat16), self._w(b2), dst]
+        px = x2.B * x2.H * x2.W
+        self.add(Node("fce_conv1x1_chain", d, ptrs, reads=[x1, x2], writes=[dst], tag=tag,
+                      flops=2.0 * px * (d.cm * d.c1 + d.Cout * (d.c2 + d.cm)),
+                      bytes=px * (d.c1 + d.c2 + d.Cout) * 2.0 + (d.cm * d.c1 + d.Cout * (d.c2 + d.cm)) * 2.0))
+        return dst
 
     def sppf(self, m, x: View, dst=None, tag="") -> View:
         k = m.m.kernel_size if isinstance(m.m.kernel_size, int) else m.m.kernel_size[0]

@@ -194,6 +194,26 @@ int fce_dwpw_conv(const fce_dwpw_desc* d, const void* x, const float* w_dw, cons
                   const float* b_pw, void* y, void* stream);
 int fce_dwpw_route(const fce_dwpw_desc* d);
 
+/* Two chained 1x1 convs in one pass - the tail of a C3k2 block whose last inner block is a C3k:
+ *     t = act1(W1 * x1 + b1)          C3k.cv3   (block.py:338-340; Conv.forward_fuse conv.py:80-89)
+ *     y = act2(W2 * [x2 ; t] + b2)    C3k2.cv2 over the concat [y0, y1, ..., t]   (block.py:303-307)
+ * t (rounded to bf16, as the two-launch route stores it) is written by the first GEMM's epilogue into the shared-memory
+ * A operand of the second GEMM and never exists in HBM; results are bit-identical to two fce_conv2d launches.
+ * bf16 NHWC views: x1 [M, c1], x2 [M, c2], y [M, Cout] (M = B*H*W); w1 bf16 [cm][c1], w2 bf16 [Cout][c2 + cm] (the t
+ * columns last, as the concat orders them), b1 fp32 [cm], b2 fp32 [Cout].
+ * Shapes: c1 % 64 == 0, c2 % 64 == 0, cm in {64, 128}, Cout % 128 == 0; anything else returns FCE_ERR_UNSUPPORTED and the
+ * caller issues the two launches.  fce_conv1x1_chain_route answers that without launching (1 / 0, pure function of the
+ * descriptor). */
+typedef struct {
+    int32_t B, H, W;
+    int32_t c1, cm, c2, Cout;
+    int32_t x1_pitch, x1_off, x2_pitch, x2_off, out_pitch, out_off;
+    int32_t act1, act2;          /* fce_act of the first / second conv */
+} fce_chain_desc;
+int fce_conv1x1_chain(const fce_chain_desc* d, const void* x1, const void* w1, const float* b1, const void* x2,
+                      const void* w2, const float* b2, void* y, void* stream);
+int fce_conv1x1_chain_route(const fce_chain_desc* d);
+
 /* SPPF pyramid: three chained 5x5/s1/p2 max-pools (= 5x5, 9x9, 13x13 windows) of slice 0 of the
  * concat buffer written to slices 1..3 (block.py:228-232).  buf has 4*C channels. */
 typedef struct {

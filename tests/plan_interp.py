@@ -100,6 +100,15 @@ class Interp(Arena):
         o = _act(F.conv2d(t, wp.float().view(d.Cout, d.C, 1, 1), bp.float()), d.pw_act)
         self.t(y).copy_(o.permute(0, 2, 3, 1))
 
+    def _fce_conv1x1_chain(self, d, p):
+        x1, w1, b1, x2, w2, b2, y = p
+        a1 = self.t(x1).permute(0, 3, 1, 2).float()
+        t = _act(F.conv2d(a1, w1.float().view(d.cm, d.c1, 1, 1), b1.float()), d.act1)
+        t = t.to(self.t(y).dtype).float()  # the intermediate is rounded to the activation dtype, as the two launches store it
+        a2 = torch.cat([self.t(x2).permute(0, 3, 1, 2).float(), t], 1)
+        o = _act(F.conv2d(a2, w2.float().view(d.Cout, d.c2 + d.cm, 1, 1), b2.float()), d.act2)
+        self.t(y).copy_(o.permute(0, 2, 3, 1))
+
     def _fce_sppf_pool(self, d, p):
         cat = p[0]
         cur = self.t(cat.ch(0, d.C)).permute(0, 3, 1, 2).float()

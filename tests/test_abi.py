@@ -30,7 +30,8 @@ def test_desc_struct_sizes_match_header():
              "fce_upsample_desc": L.UpsampleDesc, "fce_bifpn_desc": L.BifpnDesc, "fce_copy_desc": L.CopyDesc,
              "fce_pool_desc": L.PoolDesc, "fce_strip_attn_desc": L.StripAttnDesc, "fce_gate_desc": L.GateDesc,
              "fce_psa_desc": L.PsaDesc, "fce_decode_desc": L.DecodeDesc, "fce_nms_desc": L.NmsDesc,
-             "fce_coordatt_mlp_desc": L.CoordAttMlpDesc, "fce_detect_epi_desc": L.DetectEpiDesc}
+             "fce_coordatt_mlp_desc": L.CoordAttMlpDesc, "fce_detect_epi_desc": L.DetectEpiDesc, "fce_dwpw_desc": L.DwpwDesc,
+             "fce_chain_desc": L.ChainDesc}
     src = '#include <stdio.h>\n#include "fce_yolo_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:

@@ -7,7 +7,7 @@ import json
 import re
 import sys
 
-CLASS = [("conv_tc_kernel|conv_halo_kernel|strip_gemm_kernel|conv_simt|conv_direct", "fce_conv2d"),
+CLASS = [("conv_tc_kernel|conv_halo_kernel|conv_chain_kernel|strip_gemm_kernel|conv_simt|conv_direct", "fce_conv2d"),
          ("conv_dwpw_kernel", "fce_dwpw_conv"), ("conv_stem2_kernel", "fce_stem2_conv"),
          ("dwconv", "fce_dwconv3x3"), ("stem_fused", "fce_stem_conv"), ("decode_kernel", "fce_detect_decode"),
          ("gate_", "fce_gate_apply"), ("bifpn_kernel", "fce_bifpn_fuse"), ("coord_pool", "fce_coord_pool"),
