@@ -11,6 +11,7 @@ CUDA graph (350-590 eager ATen launches in the reference become one graph launch
 from __future__ import annotations
 
 import ctypes as C
+import gc
 import os
 import weakref
 
@@ -259,6 +260,25 @@ class Executor(Arena):
             self._cap_stream = torch.cuda.Stream(self.device)
         return self._cap_stream
 
+    def _capture(self, lo: int, hi: int):
+        """One CUDA graph of the nodes [lo, hi).  Python's cycle collector must not run inside the capture window: it may
+        finalize DEAD executors of the same process (they sit in reference cycles), and destroying their CUDA graphs is a call
+        CUDA forbids while a capture is open - the destructor only warns ("operation not permitted when stream is capturing
+        (function reset)"), but the open capture is invalidated and its next launch fails with "operation failed due to a
+        previous error during capture" (seen in a 650-test process; torch.cuda.graph no longer collects before capturing).
+        So: collect now, outside the window, and keep the collector off until the capture has ended."""
+        g = torch.cuda.CUDAGraph()
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(g, stream=self._capture_stream()):
+                self._launch_branched(lo, hi)
+        finally:
+            if gc_was_on:
+                gc.enable()
+        return g
+
     def run(self):
         stream = torch.cuda.current_stream(self.device)
         if not self._warm:
@@ -266,10 +286,7 @@ class Executor(Arena):
             stream.synchronize()
             self._warm = True
             if self.use_graph:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self._capture_stream()):
-                    self._launch_branched(0, len(self._calls))
-                self.graph = g
+                self.graph = self._capture(0, len(self._calls))
                 self.graph.replay()  # outputs of this call come from the replayed graph
             return
         if self.graph is not None:
@@ -310,10 +327,7 @@ class Executor(Arena):
             n = len(self._calls)
             self._segs = []
             for lo, hi in ((0, k), (k, n - 1), (n - 1, n)):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self._capture_stream()):
-                    self._launch_branched(lo, hi)
-                self._segs.append(g)
+                self._segs.append(self._capture(lo, hi))
             self.nms_done.record(stream)
         self.overlap = True
 

@@ -396,3 +396,54 @@ def test_fused_producer_nodes_in_u8_plans(name):
         it.run()
         ys[f] = it.outputs()[0].float()
     assert rel_max(ys[True], ys[False]) < 1e-5  # the interpreter runs the same fp32 arithmetic with the same bf16 roundings
+
+
+def test_capture_keeps_the_cycle_collector_out(monkeypatch):
+    """Executor._capture: a full collection BEFORE the capture window, the collector off inside it (finalizing a dead executor
+    there would destroy its CUDA graphs - forbidden during capture, it invalidates the open one), back on afterwards, also
+    when the capture raises.  CUDA-free: torch.cuda.CUDAGraph / torch.cuda.graph are replaced by recorders."""
+    import gc
+
+    from fce_yolo_b200 import engine
+
+    log = []
+
+    class FakeGraph:
+        pass
+
+    class FakeCtx:
+        def __init__(self, g, stream=None):
+            log.append(("ctx", isinstance(g, FakeGraph), stream))
+
+        def __enter__(self):
+            log.append(("enter", gc.isenabled()))
+
+        def __exit__(self, *exc):
+            log.append(("exit", gc.isenabled()))
+
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", FakeCtx)
+    collected = []
+    monkeypatch.setattr(engine.gc, "collect", lambda *a: collected.append(gc.isenabled()) or 0)
+    ex = object.__new__(engine.Executor)
+    ex._capture_stream = lambda: "cap"
+    ex._launch_branched = lambda lo, hi: log.append(("launch", lo, hi, gc.isenabled()))
+    assert gc.isenabled()
+    g = ex._capture(3, 7)
+    assert isinstance(g, FakeGraph) and collected == [True] and gc.isenabled()
+    assert log == [("ctx", True, "cap"), ("enter", False), ("launch", 3, 7, False), ("exit", False)]
+
+    def boom(lo, hi):
+        raise RuntimeError("launch failed")
+
+    ex._launch_branched = boom
+    with pytest.raises(RuntimeError):
+        ex._capture(0, 1)
+    assert gc.isenabled()
+    gc.disable()  # a host application that runs with the collector off keeps it off
+    try:
+        ex._launch_branched = lambda lo, hi: None
+        ex._capture(0, 1)
+        assert not gc.isenabled()
+    finally:
+        gc.enable()
