@@ -13,7 +13,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
 # full-set capture: the first conv launches of the step (stem .. layer 6: pair 3x3/s2, 1x1, strip kernels) + every non-conv kernel
 python tools/profile_step.py --batch $PB --nodes gpurun_out/nodes_$TAG.csv > gpurun_out/profile_step_$TAG.log 2>&1 && \
 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k regex:'conv_tc|conv_halo|conv_dwpw|conv_stem2' -c 34 -f -o /tmp/conv_$TAG python tools/profile_step.py --batch $PB \
+  -k regex:'conv_tc|conv_halo|conv_dwpw|conv_stem2|conv_chain' -c 34 -f -o /tmp/conv_$TAG python tools/profile_step.py --batch $PB \
   > gpurun_out/ncu_conv_$TAG.log 2>&1; echo "ncu conv rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
   -k regex:'dwconv|psa|nms|coord_pool|coordatt_mlp|gate|bifpn|stem|decode|sppf|upsample|strip_attn|simt' -c 40 -f -o /tmp/bw_$TAG \
