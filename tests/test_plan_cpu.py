@@ -398,6 +398,52 @@ def test_fused_producer_nodes_in_u8_plans(name):
     assert rel_max(ys[True], ys[False]) < 1e-5  # the interpreter runs the same fp32 arithmetic with the same bf16 roundings
 
 
+@pytest.mark.parametrize("name", ["m_bifpn_64", "n_fce_64", "x_fce_64", "s_coordatt_64"])
+def test_c3k_tail_chained_into_c3k2_cv2(name):
+    """bf16 plans: where a C3k2 block's last inner block is a C3k with 64 / 128 hidden channels and cv2 has a multiple of 128
+    outputs, C3k.cv3 and C3k2.cv2 become ONE fce_conv1x1_chain node and the concat buffer loses the slot of the C3k output
+    (m scale: layers 2, 4, 16; n scale: 6, 8, 22; s scale: 6; wider C3k blocks, the x-scale widths 96 / 192 and the
+    plain-bottleneck blocks stay as they are); the interpreted plan gives the predictions of the two-launch plan."""
+    from fce_yolo_b200.plan import Plan
+
+    case = FORWARD_CASES[name]
+    cfg, scale = load_cfg(case)
+    model = DetectionModel(cfg, scale=scale).fuse().eval()
+    load_synthetic(model, case["seed"])
+    B, S = case["batch"], case["size"]
+    x = synth_images(case["img_seed"], B, S, S)
+    saved = Plan.FUSED_C3K_TAIL
+    plans = {}
+    try:
+        for fused in (False, True):
+            Plan.FUSED_C3K_TAIL = fused
+            plans[fused] = compile_model(model, B, S, S, "bf16", torch.device("cpu"))
+    finally:
+        Plan.FUSED_C3K_TAIL = saved
+    tags = {f: [n.tag for n in p.nodes] for f, p in plans.items()}
+    chains = [n for n in plans[True].nodes if n.fn == "fce_conv1x1_chain"]
+    assert not any(n.fn == "fce_conv1x1_chain" for n in plans[False].nodes)
+    expect = 0
+    for i, m in enumerate(model.model):
+        if type(m).__name__ == "C3k2" and len(m.m) and type(m.m[-1]).__name__ == "C3k":
+            expect += m.c in (64, 128) and m.cv2.conv.out_channels % 128 == 0
+    assert len(chains) == expect and len(tags[True]) == len(tags[False]) - expect
+    assert expect == {"m_bifpn_64": 3, "n_fce_64": 3, "s_coordatt_64": 1, "x_fce_64": 0}[name]
+    for n in chains:
+        d, base = n.desc, n.tag[:-len(".cv3+cv2")]
+        assert base + ".cv3" in tags[False] and base + ".cv3" not in tags[True]
+        assert (d.c1, d.cm) == (d.cm, d.c1) and d.c2 % d.cm == 0 and d.x2_pitch == d.c2  # no slot for t in the concat buffer
+        x1, x2 = n.ptrs[0], n.ptrs[3]
+        assert (x1.C, x1.pitch, x2.C, x2.pitch) == (d.c1, d.x1_pitch, d.c2, d.x2_pitch) and n.reads == [x1, x2]
+    ys = {}
+    for f, plan in plans.items():
+        it = Interp(plan, reuse_memory=True)
+        it.input_tensor().copy_(x.permute(0, 2, 3, 1) if it.input_tensor().shape[-1] == 3 else x)
+        it.run()
+        ys[f] = it.outputs()[0].float()
+    assert rel_max(ys[True], ys[False]) < 1e-5  # the interpreter runs the same fp32 arithmetic with the same bf16 roundings
+
+
 def test_capture_keeps_the_cycle_collector_out(monkeypatch):
     """Executor._capture: a full collection BEFORE the capture window, the collector off inside it (finalizing a dead executor
     there would destroy its CUDA graphs - forbidden during capture, it invalidates the open one), back on afterwards, also
