@@ -309,6 +309,8 @@ def kernel_table(pred, name):
                 roof["traffic"] = round(tc["dram_bytes_per_step"] / c["launches"], 1)
                 roof["traffic_unit"] = "bytes per launch (ncu dram__bytes_read+write, profiles/traffic.json)"
                 roof["algorithmic_bytes_per_launch"] = round(c["bytes"] / c["launches"], 1)
+                if tj.get("note"):
+                    roof["traffic_note"] = tj["note"]
         except (OSError, ValueError, KeyError):
             tj = {}
     roof["write_only_peak_GB/s"] = round(wpk, 1)
